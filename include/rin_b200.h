@@ -1,0 +1,169 @@
+/* rin_b200 — C-ABI of the B200-native per-tetrahedron engine.
+ *
+ * This is the drop-in boundary for the hot path of Robust-Implicit-Surface-Networks:
+ * function evaluation -> vertex signs -> per-tet active-function filter -> per-tet
+ * arrangement -> mesh extraction (+ xyz).  Plain pointers and sizes only; every call
+ * returns 0 on success and a negative code on failure (text via rin_last_error()).
+ * No exceptions cross this boundary and there is NO CPU fallback: every entry point
+ * that computes requires a CUDA device (RIN_ERR_NO_DEVICE otherwise).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   rin_eval_functions*        load_functions()            app/implicit_arrangement.cpp:57-64
+ *                                                          (un-vendored implicit_functions lib)
+ *   rin_generate_grid          generate_tet_mesh()         src/io.cpp:95-152
+ *   rin_run(IA)                implicit_arrangement() stages "func signs", "filter",
+ *                              "simp_arr*", "extract mesh", "compute xyz"
+ *                                                          src/implicit_arrangement.cpp:53-402
+ *                              + compute_arrangement()     (un-vendored simplicial_arrangement)
+ *                              + extract_iso_mesh()        src/extract_mesh.cpp:10-265
+ *                              + compute_iso_vert_xyz()    src/extract_mesh.cpp:1446-1538
+ *   rin_run(MI)                material_interface() stages "highest func", "filter", "MI*",
+ *                              "extract mesh", "compute xyz" src/material_interface.cpp:53-447
+ *                              + extract_MI_mesh()         src/extract_mesh.cpp:569-986
+ *                              + compute_MI_vert_xyz()     src/extract_mesh.cpp:1541-1637
+ *   rin_get_complexes          cut_results[cut_result_index[tet]] as consumed by
+ *                              src/pair_faces.cpp:138-238, src/topo_ray_shooting.cpp:56-57
+ */
+#ifndef RIN_B200_H
+#define RIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rin_ctx rin_ctx;
+
+enum {
+    RIN_OK = 0,
+    RIN_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product never falls back to CPU */
+    RIN_ERR_CUDA = -2,
+    RIN_ERR_ARG = -3,
+    RIN_ERR_CAPACITY = -4,    /* a per-tet complex exceeded the kernel's fixed capacity */
+    RIN_ERR_ARRANGEMENT = -5, /* per-tet computation failed (reference: std::runtime_error) */
+    RIN_ERR_STATE = -6
+};
+
+/* function kinds (JSON "type" of the reference's function files) */
+enum { RIN_FN_PLANE = 0, RIN_FN_SPHERE = 1, RIN_FN_CYLINDER = 2, RIN_FN_ZERO = 3, RIN_FN_TORUS = 4 };
+
+/* parameters, by kind:
+ *  PLANE    p[0..2] point, p[3..5] normal                      value  n.(x-point)
+ *  SPHERE   p[0..2] center, p[3] radius, p[4] squared(0/1)     value  r-|x-c|  or  r^2-|x-c|^2
+ *  CYLINDER p[0..2] axis_point, p[3..5] axis_vector (unit), p[6] radius    value r-dist(x,axis)
+ *  TORUS    p[0..2] center, p[3..5] axis_vector (unit), p[6] major, p[7] minor
+ *  ZERO     -                                                  value  0
+ *  flip != 0 negates the value ("is_flipped").
+ */
+typedef struct rin_func_desc {
+    int32_t type;
+    int32_t flip;
+    double p[10];
+} rin_func_desc;
+
+enum { RIN_MODE_IA = 0, RIN_MODE_MI = 1 };
+enum {
+    RIN_FLAG_USE_LOOKUP = 1,           /* use_lookup            (src/implicit_arrangement.cpp:15) */
+    RIN_FLAG_USE_SECONDARY_LOOKUP = 2, /* use_secondary_lookup  (:16, :38-40)                     */
+    RIN_FLAG_NEGATE = 4                /* csg(): funcVals *= -1 (src/csg.cpp:37)                  */
+};
+
+/* stats.json fields produced by the hot path (src/implicit_arrangement.cpp:46-393,
+ * src/material_interface.cpp:45-438) */
+typedef struct rin_counts {
+    uint64_t num_pts, num_tets, num_funcs;
+    uint64_t num_degenerate_vertex; /* IA: (vertex,function) pairs with value == 0; MI: #vertices with tied maxima */
+    uint64_t num_intersecting_tet;
+    uint64_t num_k1, num_k2, num_kmore; /* IA: 1 / 2 / >=3 functions; MI: 2 / 3 / >=4 materials */
+    uint64_t num_verts, num_faces;      /* iso (MI) vertices / faces after deduplication */
+    uint64_t num_face_verts;            /* total length of the face vertex lists */
+    uint64_t num_face_tets;             /* total (tet, local face) pairs */
+    uint64_t num_general_tets;          /* tets that took the general (non-table) kernel */
+    uint64_t num_exact_fallbacks;       /* predicate evaluations that needed exact arithmetic */
+    uint64_t num_active_funcs;          /* length of func_in_tet */
+} rin_counts;
+
+/* host-side views filled by rin_download_mesh (caller allocates; sizes from rin_counts).
+ * Any pointer may be NULL to skip that array.  Mesh_None is written as UINT64_MAX / UINT32_MAX. */
+typedef struct rin_mesh_out {
+    /* vertices (IsoVert / MI_Vert, src/mesh.h:28-57) */
+    uint32_t* vert_tet;          /* [num_verts]     tet_index */
+    uint8_t*  vert_local;        /* [num_verts]     tet_vert_index */
+    uint8_t*  vert_simplex_size; /* [num_verts]     1..4 */
+    uint32_t* vert_simplex;      /* [num_verts*4]   simplex_vert_indices (unused slots UINT32_MAX) */
+    uint32_t* vert_funcs;        /* [num_verts*4]   func_indices[3] (IA) / material_indices[4] (MI) */
+    double*   vert_xyz;          /* [num_verts*3] */
+    /* faces (PolygonFace, src/mesh.h:15-25) */
+    uint32_t* face_offsets;      /* [num_faces+1]   into face_verts */
+    uint32_t* face_verts;        /* [num_face_verts] */
+    uint32_t* face_tet_offsets;  /* [num_faces+1]   into face_tets */
+    uint32_t* face_tets;         /* [num_face_tets*2] (tet, local face id) pairs */
+    uint32_t* face_funcs;        /* [num_faces*2]   func_index.first / .second */
+} rin_mesh_out;
+
+const char* rin_last_error(void);
+int rin_device_count(void);
+
+int rin_create(int device, rin_ctx** out);
+void rin_destroy(rin_ctx* ctx);
+
+/* ---- inputs ---------------------------------------------------------------------------- */
+/* explicit mesh, host pointers (pts: V*3 doubles; tets: T*4 indices, 64-bit as in the
+ * reference's std::array<size_t,4>, or 32-bit) */
+int rin_set_mesh_host(rin_ctx*, const double* pts, uint64_t n_pts, const void* tets,
+                      uint64_t n_tets, int index_bytes /* 4 or 8 */);
+/* generate_tet_mesh() on the device (same vertex and tet order as src/io.cpp:95-152) */
+int rin_generate_grid(rin_ctx*, uint32_t resolution, const double bbox_min[3], const double bbox_max[3]);
+/* restrict the run to tets [first, first+count) (slab sharding); count==0 means all */
+int rin_set_tet_range(rin_ctx*, uint64_t first, uint64_t count);
+
+/* function values: either parametric (evaluated on the device) ... */
+int rin_set_functions(rin_ctx*, const rin_func_desc* funcs, uint32_t n_funcs);
+/* ... or given by the caller as the reference's row-major V x F matrix (host pointer) */
+int rin_set_values_host(rin_ctx*, const double* vals_rowmajor, uint64_t n_pts, uint32_t n_funcs);
+
+/* ---- run -------------------------------------------------------------------------------- */
+int rin_run(rin_ctx*, int mode, uint32_t flags);
+int rin_get_counts(const rin_ctx*, rin_counts* out);
+int rin_download_mesh(rin_ctx*, rin_mesh_out* out);
+/* func_in_tet / start_index_of_tet (src/implicit_arrangement.cpp:84-85) for the tet range:
+ * start has count+1 entries; either pointer may be NULL */
+int rin_download_active(rin_ctx*, uint32_t* func_in_tet, uint64_t* start_index_of_tet);
+/* row-major V x F function values as evaluated on the device */
+int rin_download_values(rin_ctx*, double* vals_rowmajor);
+int rin_download_grid(rin_ctx*, double* pts, uint32_t* tets);
+/* per-stage device times of the last run in milliseconds (CUDA events); names via rin_stage_name */
+int rin_get_stage_times(const rin_ctx*, float* ms, int capacity);
+const char* rin_stage_name(int i);
+int rin_num_stages(void);
+
+/* ---- per-tet complexes on demand (host topology stages need O(#chains+#components) tets) --- */
+/* Serialises the full complexes of the given tets.  Layout per tet (uint32 words):
+ *  IA: nv, nf, nc, n_unique(0 if all planes unique), then nv*3 plane ids, then per face
+ *      [supporting_plane, positive_cell, negative_cell, n, v_0..v_{n-1}], per cell [n, f_0..],
+ *      then if n_unique: np, np group ids, np orientation flags.
+ *  MI: nv, nf, nc, n_unique, nv*4 material ids, per face [pos_label, neg_label, n, v..],
+ *      per cell [material_label, n, f..], then if n_unique: nm, nm group ids.
+ * offsets[i]..offsets[i+1] delimit tet i in `words`.  Call with words==NULL to get the size. */
+int rin_get_complexes(rin_ctx*, int mode, uint32_t flags, const uint64_t* tet_ids, uint64_t n,
+                      uint64_t* offsets, uint32_t* words, uint64_t* n_words);
+
+/* ---- one-shot host entry (what the C++ drop-in drivers call) ---------------------------- */
+int rin_run_host(rin_ctx*, int mode, uint32_t flags, const double* pts, uint64_t n_pts,
+                 const void* tets, uint64_t n_tets, int index_bytes,
+                 const double* vals_rowmajor, uint32_t n_funcs, rin_counts* counts);
+
+/* ---- slab-boundary exchange for multi-GPU runs (one process per GPU) -------------------- */
+/* After rin_run on every rank: export the keys of this rank's unique vertices whose simplex
+ * lies entirely in vertices >= min_shared_vertex (device pointer to 16-byte keys + local ids). */
+int rin_export_boundary(rin_ctx*, uint32_t min_shared_vertex, void** d_keys, void** d_ids, uint64_t* n);
+/* Import the lower neighbour's boundary keys (device pointers); vertices of this rank that
+ * match are dropped and remapped.  Updates counts and the downloadable mesh. */
+int rin_import_boundary(rin_ctx*, const void* d_keys, const void* d_ids, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIN_B200_H */

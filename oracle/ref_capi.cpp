@@ -1,0 +1,242 @@
+// ORACLE (test infrastructure, NOT product code).
+//
+// "Hybrid reference": the reference's OWN sources (/root/reference/src/{implicit_arrangement,
+// material_interface,csg,extract_mesh,mesh_connectivity,pair_faces,topo_ray_shooting,
+// cell_connectivity}.cpp) compiled in place (never copied) against shim headers and the restated
+// per-tet engine (oracle/sa), exposed to Python through a flat C interface.  Used to (1) replay
+// the reference's golden tests (tests/test_implicit_networks.cpp) through the restated engine,
+// (2) validate the port's filter/extract/xyz against the reference's actual code, (3) time the
+// reference's CPU path (bench.py --impl reference, cpu_baseline.kind = "reference").
+#include <simplicial_arrangement/lookup_table.h>
+#include <simplicial_arrangement/simplicial_arrangement.h>
+
+#include "csg.h"
+#include "implicit_arrangement.h"
+#include "material_interface.h"
+
+#include "result_bag.h"
+
+#include <iostream>
+
+namespace {
+struct CoutMute
+{
+    std::streambuf* old;
+    explicit CoutMute(bool on) : old(nullptr)
+    {
+        if (on) old = std::cout.rdbuf(nullptr);
+    }
+    ~CoutMute()
+    {
+        if (old) {
+            std::cout.rdbuf(old);
+            std::cout.clear();
+        }
+    }
+};
+
+void pack_crs(ResultBag* bag, const std::string& name, const std::vector<std::vector<size_t>>& v)
+{
+    auto& off = bag->i64[name + "_offsets"];
+    auto& dat = bag->i64[name];
+    off.push_back(0);
+    for (auto& l : v) {
+        for (auto x : l) dat.push_back(x == Mesh_None ? -1 : int64_t(x));
+        off.push_back(int64_t(dat.size()));
+    }
+}
+
+void pack_mesh(ResultBag* bag, const std::vector<std::array<double, 3>>& pts,
+    const std::vector<PolygonFace>& faces)
+{
+    auto& xyz = bag->f64["vert_xyz"];
+    for (auto& p : pts) xyz.insert(xyz.end(), p.begin(), p.end());
+    auto& foff = bag->i64["face_offsets"];
+    auto& fv = bag->i64["face_verts"];
+    auto& ftoff = bag->i64["face_tet_offsets"];
+    auto& ft = bag->i64["face_tets"];
+    auto& ff = bag->i64["face_funcs"];
+    foff.push_back(0);
+    ftoff.push_back(0);
+    for (auto& f : faces) {
+        for (auto v : f.vert_indices) fv.push_back(int64_t(v));
+        foff.push_back(int64_t(fv.size()));
+        for (auto& p : f.tet_face_indices) {
+            ft.push_back(int64_t(p.first));
+            ft.push_back(int64_t(p.second));
+        }
+        ftoff.push_back(int64_t(ft.size() / 2));
+        ff.push_back(int64_t(f.func_index.first));
+        ff.push_back(int64_t(f.func_index.second));
+    }
+}
+
+void pack_labels(ResultBag* bag, const std::vector<std::string>& tl, const std::vector<double>& t,
+    const std::vector<std::string>& sl, const std::vector<size_t>& s)
+{
+    std::string names;
+    for (auto& l : tl) names += l + "\n";
+    bag->error = ""; // not an error; labels travel in i64/f64 + a joined string below
+    bag->f64["timings"] = t;
+    auto& st = bag->i64["stats"];
+    for (auto x : s) st.push_back(int64_t(x));
+    bag->i64["timing_label_bytes"].assign(names.begin(), names.end());
+    std::string sn;
+    for (auto& l : sl) sn += l + "\n";
+    bag->i64["stats_label_bytes"].assign(sn.begin(), sn.end());
+}
+} // namespace
+
+extern "C" {
+
+// flags: bit0 robust_test, bit1 use_lookup, bit2 use_secondary_lookup, bit3 use_topo_ray_shooting,
+// bit4 quiet (mute std::cout)
+void* ref_ia_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint64_t T,
+    const double* vals, uint32_t F, uint32_t flags)
+{
+    auto* bag = new ResultBag;
+    CoutMute mute(flags & 16);
+    std::vector<std::array<double, 3>> pts(V);
+    for (uint64_t i = 0; i < V; ++i) pts[i] = {pts_in[3 * i], pts_in[3 * i + 1], pts_in[3 * i + 2]};
+    std::vector<std::array<size_t, 4>> tets(T);
+    for (uint64_t i = 0; i < T; ++i)
+        tets[i] = {tets_in[4 * i], tets_in[4 * i + 1], tets_in[4 * i + 2], tets_in[4 * i + 3]};
+    Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> fv(V, F);
+    std::copy(vals, vals + V * F, fv.data());
+    bool use_lookup = flags & 2;
+    if (use_lookup) { // app/implicit_arrangement.cpp:29-42
+        simplicial_arrangement::load_lookup_table(simplicial_arrangement::ARRANGEMENT);
+        simplicial_arrangement::enable_lookup_table();
+    } else
+        simplicial_arrangement::disable_lookup_table();
+    std::vector<std::array<double, 3>> iso_pts;
+    std::vector<PolygonFace> iso_faces;
+    std::vector<std::vector<size_t>> patches, chains, nme, shells, cells;
+    std::vector<size_t> patch_label;
+    std::vector<Edge> edges;
+    std::vector<std::vector<bool>> cell_label;
+    std::vector<std::string> tl, sl;
+    std::vector<double> tm;
+    std::vector<size_t> st;
+    bool ok = false;
+    try {
+        ok = implicit_arrangement(flags & 1, use_lookup, flags & 4, flags & 8, pts, tets, fv, iso_pts,
+            iso_faces, patches, patch_label, edges, chains, nme, shells, cells, cell_label, tl, tm, sl, st);
+    } catch (std::exception& e) {
+        bag->i64["threw"] = {1};
+        pack_labels(bag, tl, tm, sl, st);
+        bag->error = e.what();
+        return bag;
+    }
+    pack_labels(bag, tl, tm, sl, st);
+    bag->i64["success"] = {ok ? 1 : 0};
+    pack_mesh(bag, iso_pts, iso_faces);
+    pack_crs(bag, "patches", patches);
+    pack_crs(bag, "chains", chains);
+    pack_crs(bag, "non_manifold_edges_of_vert", nme);
+    pack_crs(bag, "shells", shells);
+    pack_crs(bag, "cells", cells);
+    auto& pl = bag->i64["patch_function_label"];
+    for (auto x : patch_label) pl.push_back(int64_t(x));
+    auto& ed = bag->i64["edges"];
+    for (auto& e : edges) {
+        ed.push_back(int64_t(e.v1));
+        ed.push_back(int64_t(e.v2));
+    }
+    auto& cl = bag->i64["cell_function_label"]; // cells x F, row-major 0/1
+    for (auto& row : cell_label)
+        for (bool b : row) cl.push_back(b ? 1 : 0);
+    return bag;
+}
+
+void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint64_t T,
+    const double* vals, uint32_t F, uint32_t flags)
+{
+    auto* bag = new ResultBag;
+    CoutMute mute(flags & 16);
+    std::vector<std::array<double, 3>> pts(V);
+    for (uint64_t i = 0; i < V; ++i) pts[i] = {pts_in[3 * i], pts_in[3 * i + 1], pts_in[3 * i + 2]};
+    std::vector<std::array<size_t, 4>> tets(T);
+    for (uint64_t i = 0; i < T; ++i)
+        tets[i] = {tets_in[4 * i], tets_in[4 * i + 1], tets_in[4 * i + 2], tets_in[4 * i + 3]};
+    Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> fv(V, F);
+    std::copy(vals, vals + V * F, fv.data());
+    bool use_lookup = flags & 2;
+    if (use_lookup) { // app/material_interface.cpp:32-45
+        simplicial_arrangement::load_lookup_table(simplicial_arrangement::MATERIAL_INTERFACE);
+        simplicial_arrangement::enable_lookup_table();
+    } else
+        simplicial_arrangement::disable_lookup_table();
+    std::vector<std::array<double, 3>> mi_pts;
+    std::vector<PolygonFace> mi_faces;
+    std::vector<std::vector<size_t>> patches, chains, nme, shells, cells;
+    std::vector<std::pair<size_t, size_t>> patch_label;
+    std::vector<Edge> edges;
+    std::vector<size_t> cell_label;
+    std::vector<std::string> tl, sl;
+    std::vector<double> tm;
+    std::vector<size_t> st;
+    bool ok = false;
+    try {
+        ok = material_interface(flags & 1, use_lookup, flags & 4, flags & 8, pts, tets, fv, mi_pts,
+            mi_faces, patches, patch_label, edges, chains, nme, shells, cells, cell_label, tl, tm, sl, st);
+    } catch (std::exception& e) {
+        bag->i64["threw"] = {1};
+        pack_labels(bag, tl, tm, sl, st);
+        bag->error = e.what();
+        return bag;
+    }
+    pack_labels(bag, tl, tm, sl, st);
+    bag->i64["success"] = {ok ? 1 : 0};
+    pack_mesh(bag, mi_pts, mi_faces);
+    pack_crs(bag, "patches", patches);
+    pack_crs(bag, "chains", chains);
+    pack_crs(bag, "non_manifold_edges_of_vert", nme);
+    pack_crs(bag, "shells", shells);
+    pack_crs(bag, "cells", cells);
+    auto& pl = bag->i64["patch_function_label"];
+    for (auto& x : patch_label) {
+        pl.push_back(int64_t(x.first));
+        pl.push_back(int64_t(x.second));
+    }
+    auto& ed = bag->i64["edges"];
+    for (auto& e : edges) {
+        ed.push_back(int64_t(e.v1));
+        ed.push_back(int64_t(e.v2));
+    }
+    auto& cl = bag->i64["cell_function_label"];
+    for (auto x : cell_label) cl.push_back(x == Mesh_None ? -1 : int64_t(x));
+    return bag;
+}
+
+const int64_t* ref_i64(void* h, const char* name, uint64_t* n)
+{
+    auto* b = static_cast<ResultBag*>(h);
+    auto it = b->i64.find(name);
+    if (it == b->i64.end()) {
+        *n = 0;
+        return nullptr;
+    }
+    *n = it->second.size();
+    return it->second.data();
+}
+const double* ref_f64(void* h, const char* name, uint64_t* n)
+{
+    auto* b = static_cast<ResultBag*>(h);
+    auto it = b->f64.find(name);
+    if (it == b->f64.end()) {
+        *n = 0;
+        return nullptr;
+    }
+    *n = it->second.size();
+    return it->second.data();
+}
+const char* ref_error(void* h)
+{
+    return static_cast<ResultBag*>(h)->error.c_str();
+}
+void ref_free(void* h)
+{
+    delete static_cast<ResultBag*>(h);
+}
+}
