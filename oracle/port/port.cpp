@@ -344,7 +344,11 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
             if (!is_iso_f[f]) continue;
             std::vector<int64_t> fv;
             for (size_t v : ar.faces[f].vertices) fv.push_back(int64_t(gid[v]));
-            int64_t fn = func_in_tet[s0 + int64_t(ar.faces[f].supporting_plane) - 4];
+            // QUIRK kept from the reference (:249,:258): for an iso-face coplanar with a tet
+            // face the supporting plane is a boundary plane (< 4) and `supporting_plane - 4 +
+            // start_index` wraps to an EARLIER entry of func_in_tet; out of range (UB there) -> None.
+            int64_t fidx = s0 + int64_t(ar.faces[f].supporting_plane) - 4;
+            int64_t fn = fidx >= 0 ? func_in_tet[fidx] : NONE64;
             if (ar.faces[f].negative_cell == Arrangement<3>::None) { // on the tet boundary
                 auto k3 = min2_max_key(fv);
                 std::array<uint64_t, 7> key;

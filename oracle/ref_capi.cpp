@@ -125,6 +125,7 @@ void* ref_ia_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
     } catch (std::exception& e) {
         bag->i64["threw"] = {1};
         pack_labels(bag, tl, tm, sl, st);
+        pack_mesh(bag, iso_pts, iso_faces); // the hot-path outputs exist before host topology throws
         bag->error = e.what();
         return bag;
     }
@@ -183,6 +184,7 @@ void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
     } catch (std::exception& e) {
         bag->i64["threw"] = {1};
         pack_labels(bag, tl, tm, sl, st);
+        pack_mesh(bag, mi_pts, mi_faces);
         bag->error = e.what();
         return bag;
     }

@@ -1,0 +1,80 @@
+// Shared device helpers: decoupled look-back tile scan, hashing, record format.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rin {
+
+constexpr uint32_t NONE32 = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Iso record: the part of a per-tet complex that the mesh extraction consumes
+// (/root/reference/src/extract_mesh.cpp:60-261 reads only iso vertices and iso faces).
+//   byte 0      n_iso_verts
+//   byte 1      n_iso_faces
+//   byte 2,3    total number of face-vertex entries (u16 LE)
+//   n_iso_verts x { local vertex id, plane0, plane1, plane2 }            (planes ascending)
+//   n_iso_faces x { local face id lo, hi, supporting plane, flags, n, n x iso-vertex rank }
+//                   flags bit0: face lies on the tet boundary (negative_cell == None)
+// IA plane ids / MI material ids: 0..3 simplex faces, 4+j the j-th active function of the tet.
+// MI records carry 4 material ids per vertex and {pos label, neg label} instead of
+// {supporting plane}: see mi_complex.cuh.
+// ---------------------------------------------------------------------------------------------
+constexpr int REC_HDR = 4;
+
+__host__ __device__ inline uint32_t rec_size_ia(int nv, int nf, int nfv)
+{
+    return uint32_t(REC_HDR + 4 * nv + 5 * nf + nfv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoupled look-back over tiles for a PAIR of 31-bit partial sums packed with a 2-bit flag in
+// one 64-bit word, so that flag and value are published atomically.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_PRE = 2ull << 62;
+
+__device__ __forceinline__ unsigned long long st_pack(unsigned long long flag, uint32_t a, uint32_t b)
+{
+    return flag | ((unsigned long long)(a & 0x7fffffffu) << 31) | (unsigned long long)(b & 0x7fffffffu);
+}
+
+// Called by ONE thread of the tile.  Publishes this tile's aggregate, sums the predecessors and
+// publishes the inclusive prefix.  Returns the exclusive prefix in (ea, eb).
+__device__ __forceinline__ void tile_lookback(
+    volatile unsigned long long* st, int tile, uint32_t a, uint32_t b, uint32_t& ea, uint32_t& eb)
+{
+    ea = 0;
+    eb = 0;
+    if (tile > 0) {
+        st[tile] = st_pack(ST_AGG, a, b);
+        for (int p = tile - 1; p >= 0; --p) {
+            unsigned long long w;
+            do {
+                w = st[p];
+            } while ((w >> 62) == 0);
+            ea += uint32_t((w >> 31) & 0x7fffffffu);
+            eb += uint32_t(w & 0x7fffffffu);
+            if ((w >> 62) == 2) break;
+        }
+    }
+    st[tile] = st_pack(ST_PRE, ea + a, eb + b);
+}
+
+__device__ __forceinline__ uint32_t hash4(uint4 k)
+{
+    uint32_t h = k.x * 0x9E3779B1u;
+    h = (h ^ (h >> 15)) + k.y * 0x85EBCA77u;
+    h = (h ^ (h >> 13)) + k.z * 0xC2B2AE3Du;
+    h = (h ^ (h >> 16)) + k.w * 0x27D4EB2Fu;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h;
+}
+
+__device__ __forceinline__ bool key_eq(uint4 a, uint4 b)
+{
+    return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
+}
+
+} // namespace rin

@@ -1,0 +1,918 @@
+// sm_100a kernels of the implicit-arrangement hot path (K1..K7 of SURVEY.md section 2-D).
+// Bounds: K1/K2 stream V*F doubles and T index quadruples (HBM); K3/K5/K6/K7 touch only the
+// ~7 % active tets; K4 is latency / local-memory bound.  No tensor cores: nothing is a contraction.
+#pragma once
+#include "../../include/rin_b200.h"
+#include "common.cuh"
+#include "ia_complex.cuh"
+
+namespace rin {
+
+// ---------------------------------------------------------------------------------------------
+// K0: generate_tet_mesh on the device (/root/reference/src/io.cpp:95-152)
+// ---------------------------------------------------------------------------------------------
+__global__ void grid_points_kernel(uint32_t N, double3 bmin, double3 bmax, double* __restrict__ pts)
+{
+    uint64_t n = (uint64_t)N * N * N;
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n;
+         v += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t k = v % N, j = (v / N) % N, i = v / ((uint64_t)N * N);
+        double d = double(N - 1);
+        // t * (max - min) + min with t = i / (N-1)   (src/io.cpp:104-113)
+        pts[3 * v + 0] = (double(i) / d) * (bmax.x - bmin.x) + bmin.x;
+        pts[3 * v + 1] = (double(j) / d) * (bmax.y - bmin.y) + bmin.y;
+        pts[3 * v + 2] = (double(k) / d) * (bmax.z - bmin.z) + bmin.z;
+    }
+}
+
+__constant__ uint8_t c_grid_even[5][4] = {{4, 6, 1, 3}, {6, 3, 4, 7}, {1, 3, 0, 4}, {3, 1, 2, 6}, {4, 1, 6, 5}};
+__constant__ uint8_t c_grid_odd[5][4] = {{7, 0, 2, 5}, {2, 3, 0, 7}, {5, 7, 0, 4}, {7, 2, 6, 5}, {0, 1, 2, 5}};
+
+__global__ void grid_tets_kernel(uint32_t R, uint4* __restrict__ tets)
+{
+    const uint32_t N = R + 1;
+    uint64_t n = (uint64_t)R * R * R * 5;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t cube = t / 5;
+        uint32_t s = t % 5;
+        uint32_t k = cube % R, j = (cube / R) % R, i = cube / ((uint64_t)R * R);
+        const uint8_t* tab = ((i + j + k) & 1) ? c_grid_odd[s] : c_grid_even[s];
+        uint32_t v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t q = tab[c];
+            // corner q of the cube, numbered like v0..v7 at src/io.cpp:126-133
+            uint32_t di = ((q & 3) == 1 || (q & 3) == 2), dj = ((q & 3) >= 2), dk = (q >> 2);
+            v[c] = (i + di) * N * N + (j + dj) * N + (k + dk);
+        }
+        tets[t] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void narrow_tets_kernel(const uint64_t* __restrict__ in, uint64_t n, uint4* __restrict__ out)
+{
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 4 * t);
+        ulonglong2 a = p[0], b = p[1];
+        out[t] = make_uint4((uint32_t)a.x, (uint32_t)a.y, (uint32_t)b.x, (uint32_t)b.y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: evaluate every function at every vertex (SoA double[F][V]) + per-vertex sign bit masks.
+// Replaces load_functions (app/implicit_arrangement.cpp:57-64) and the "func signs" loop
+// (src/implicit_arrangement.cpp:61-77).  vmask[w*V + v] = (P bits, N bits) of functions 32w..32w+31.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double eval_func(const rin_func_desc& f, double x, double y, double z)
+{
+    double v = 0.0;
+    switch (f.type) {
+    case RIN_FN_PLANE: {
+        double dx = x - f.p[0], dy = y - f.p[1], dz = z - f.p[2];
+        v = (f.p[3] * dx + f.p[4] * dy) + f.p[5] * dz;
+        break;
+    }
+    case RIN_FN_SPHERE: {
+        double dx = x - f.p[0], dy = y - f.p[1], dz = z - f.p[2];
+        double s = (dx * dx + dy * dy) + dz * dz;
+        v = (f.p[4] != 0.0) ? f.p[3] * f.p[3] - s : f.p[3] - sqrt(s);
+        break;
+    }
+    case RIN_FN_CYLINDER: {
+        double dx = x - f.p[0], dy = y - f.p[1], dz = z - f.p[2];
+        double t = (f.p[3] * dx + f.p[4] * dy) + f.p[5] * dz;
+        double px = dx - t * f.p[3], py = dy - t * f.p[4], pz = dz - t * f.p[5];
+        v = f.p[6] - sqrt((px * px + py * py) + pz * pz);
+        break;
+    }
+    case RIN_FN_TORUS: {
+        double dx = x - f.p[0], dy = y - f.p[1], dz = z - f.p[2];
+        double t = (f.p[3] * dx + f.p[4] * dy) + f.p[5] * dz;
+        double px = dx - t * f.p[3], py = dy - t * f.p[4], pz = dz - t * f.p[5];
+        double rho = sqrt((px * px + py * py) + pz * pz) - f.p[6];
+        v = f.p[7] - sqrt(rho * rho + t * t);
+        break;
+    }
+    default: break;
+    }
+    return f.flip ? -v : v;
+}
+
+__global__ void __launch_bounds__(256) eval_functions_kernel(const double* __restrict__ pts,
+    uint32_t v_first, uint32_t v_count, uint32_t V, const rin_func_desc* __restrict__ funcs, uint32_t F,
+    int negate, double* __restrict__ vals, uint2* __restrict__ vmask,
+    unsigned long long* __restrict__ n_zero)
+{
+    extern __shared__ rin_func_desc s_funcs[];
+    for (uint32_t i = threadIdx.x; i < F * (sizeof(rin_func_desc) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(s_funcs)[i] = reinterpret_cast<const double*>(funcs)[i];
+    __syncthreads();
+    unsigned zeros = 0;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < v_count;
+         idx += gridDim.x * blockDim.x) {
+        const uint32_t v = v_first + idx;
+        const double x = pts[3 * (size_t)v], y = pts[3 * (size_t)v + 1], z = pts[3 * (size_t)v + 2];
+        for (uint32_t w = 0; w * 32 < F; ++w) {
+            uint32_t P = 0, Nn = 0;
+            const uint32_t fe = min(F, w * 32 + 32);
+            for (uint32_t f = w * 32; f < fe; ++f) {
+                double val = eval_func(s_funcs[f], x, y, z);
+                if (negate) val = val * -1; // csg(): funcVals * -1 (src/csg.cpp:37)
+                vals[(size_t)f * V + v] = val;
+                P |= (val > 0 ? 1u : 0u) << (f & 31);
+                Nn |= (val < 0 ? 1u : 0u) << (f & 31);
+            }
+            vmask[(size_t)w * V + v] = make_uint2(P, Nn);
+            zeros += (fe - w * 32) - __popc(P | Nn);
+        }
+    }
+    // num_degenerate_vertex counts (vertex, function) pairs with value 0 (:69-73)
+    for (int o = 16; o; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(n_zero, (unsigned long long)zeros);
+}
+
+// values supplied by the caller as the reference's row-major V x F matrix: transpose to SoA and
+// build the sign masks (the "func signs" loop).
+__global__ void __launch_bounds__(256) ingest_values_kernel(const double* __restrict__ rowmajor,
+    uint32_t v_first, uint32_t v_count, uint32_t V, uint32_t F, int negate, double* __restrict__ vals,
+    uint2* __restrict__ vmask, unsigned long long* __restrict__ n_zero)
+{
+    unsigned zeros = 0;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < v_count;
+         idx += gridDim.x * blockDim.x) {
+        const uint32_t v = v_first + idx;
+        for (uint32_t w = 0; w * 32 < F; ++w) {
+            uint32_t P = 0, Nn = 0;
+            const uint32_t fe = min(F, w * 32 + 32);
+            for (uint32_t f = w * 32; f < fe; ++f) {
+                double val = rowmajor[(size_t)v * F + f];
+                if (negate) val = val * -1;
+                vals[(size_t)f * V + v] = val;
+                P |= (val > 0 ? 1u : 0u) << (f & 31);
+                Nn |= (val < 0 ? 1u : 0u) << (f & 31);
+            }
+            vmask[(size_t)w * V + v] = make_uint2(P, Nn);
+            zeros += (fe - w * 32) - __popc(P | Nn);
+        }
+    }
+    for (int o = 16; o; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(n_zero, (unsigned long long)zeros);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: per-tet active-function filter + ordered stream compaction.
+// Replaces the "filter" loop (src/implicit_arrangement.cpp:86-116): function j is active in a tet
+// iff it is neither positive at all four vertices nor negative at all four (pos<4 && neg<4, :106).
+// Output: active tets in tet order with their W-word function masks.
+// Single pass over the 16-byte index records; tile offsets by decoupled look-back.
+// ---------------------------------------------------------------------------------------------
+constexpr int FILT_THREADS = 256;
+constexpr int FILT_ITEMS = 4;
+constexpr int FILT_TILE = FILT_THREADS * FILT_ITEMS;
+
+struct FilterCounters
+{
+    unsigned tile_counter;
+    unsigned n_active;
+    unsigned n_k1, n_k2, n_kmore;
+    unsigned n_funcs; // sum of popcounts = |func_in_tet|
+};
+
+template <int W>
+__global__ void __launch_bounds__(FILT_THREADS) filter_ia_kernel(const uint4* __restrict__ tets,
+    uint32_t t_first, uint32_t t_count, const uint2* __restrict__ vmask, uint32_t V, uint32_t last_mask,
+    uint32_t* __restrict__ act_tet, uint32_t* __restrict__ act_mask, uint32_t cap,
+    volatile unsigned long long* __restrict__ status, FilterCounters* __restrict__ ctr)
+{
+    __shared__ unsigned s_tile;
+    __shared__ unsigned s_cnt[FILT_ITEMS][FILT_THREADS / 32];
+    __shared__ unsigned s_base;
+    __shared__ unsigned s_k[3];
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(&ctr->tile_counter, 1u);
+        s_k[0] = s_k[1] = s_k[2] = 0;
+    }
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const uint32_t base = tile * FILT_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t m[FILT_ITEMS][W];
+    unsigned ball[FILT_ITEMS];
+    unsigned k1 = 0, k2 = 0, km = 0, kf = 0;
+#pragma unroll
+    for (int j = 0; j < FILT_ITEMS; ++j) {
+        const uint32_t i = base + j * FILT_THREADS + threadIdx.x;
+        bool act = false;
+#pragma unroll
+        for (int w = 0; w < W; ++w) m[j][w] = 0;
+        if (i < t_count) {
+            const uint4 tv = __ldg(&tets[t_first + i]);
+            int k = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const uint2 a = __ldg(&vmask[(size_t)w * V + tv.x]);
+                const uint2 b = __ldg(&vmask[(size_t)w * V + tv.y]);
+                const uint2 c = __ldg(&vmask[(size_t)w * V + tv.z]);
+                const uint2 d = __ldg(&vmask[(size_t)w * V + tv.w]);
+                uint32_t mm = ~((a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y));
+                if (w == W - 1) mm &= last_mask;
+                m[j][w] = mm;
+                k += __popc(mm);
+            }
+            act = k > 0;
+            k1 += (k == 1);
+            k2 += (k == 2);
+            km += (k > 2);
+            kf += k;
+        }
+        ball[j] = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) s_cnt[j][warp] = __popc(ball[j]);
+    }
+    for (int o = 16; o; o >>= 1) {
+        k1 += __shfl_xor_sync(0xffffffffu, k1, o);
+        k2 += __shfl_xor_sync(0xffffffffu, k2, o);
+        km += __shfl_xor_sync(0xffffffffu, km, o);
+        kf += __shfl_xor_sync(0xffffffffu, kf, o);
+    }
+    if (lane == 0) {
+        if (k1) atomicAdd(&s_k[0], k1);
+        if (k2) atomicAdd(&s_k[1], k2);
+        if (km) atomicAdd(&s_k[2], km);
+    }
+    // kf goes through the look-back as the second lane (it is the CRS length prefix)
+    __shared__ unsigned s_kf[FILT_THREADS / 32];
+    if (lane == 0) s_kf[warp] = kf;
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive prefix over the (item, warp) sequence: 4 x 8 = 32 entries, one per lane
+        const int j = lane / (FILT_THREADS / 32), w = lane % (FILT_THREADS / 32);
+        unsigned c = s_cnt[j][w], x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        s_cnt[j][w] = x - c;
+        unsigned total = __shfl_sync(0xffffffffu, x, 31);
+        unsigned kft = (lane < FILT_THREADS / 32) ? s_kf[lane] : 0;
+        for (int o = 16; o; o >>= 1) kft += __shfl_xor_sync(0xffffffffu, kft, o);
+        if (lane == 0) {
+            uint32_t ea, eb;
+            tile_lookback(status, (int)tile, total, kft, ea, eb);
+            s_base = ea;
+            if (total) {
+                atomicAdd(&ctr->n_active, total);
+                atomicAdd(&ctr->n_funcs, kft);
+                if (s_k[0]) atomicAdd(&ctr->n_k1, s_k[0]);
+                if (s_k[1]) atomicAdd(&ctr->n_k2, s_k[1]);
+                if (s_k[2]) atomicAdd(&ctr->n_kmore, s_k[2]);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned gbase = s_base;
+#pragma unroll
+    for (int j = 0; j < FILT_ITEMS; ++j) {
+        if ((ball[j] >> lane) & 1) {
+            const unsigned pos = gbase + s_cnt[j][warp] + __popc(ball[j] & ((1u << lane) - 1));
+            if (pos < cap) {
+                act_tet[pos] = t_first + base + j * FILT_THREADS + threadIdx.x;
+#pragma unroll
+                for (int w = 0; w < W; ++w) act_mask[(size_t)w * cap + pos] = m[j][w];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: classify active tets: table hit (record offset in the LUT blob) or general work list.
+// Dispatch rules of src/implicit_arrangement.cpp:276-284: tables serve 1 function, and 2
+// functions when the secondary lookup is on; any zero value at a tet vertex, coincident crossing
+// points or a missing table entry go to the general kernel.
+// rec_ref[a]: bit31 = general (payload filled by K4), else 4-byte-unit offset into the LUT blob.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t REF_GENERAL = 0x80000000u;
+constexpr uint16_t LUT_MISS = 0xffffu;
+
+struct LutView
+{
+    const uint16_t* lut1; // [16]   record offset (4-byte units) per vertex-sign pattern
+    const uint16_t* lut2; // [256*64] outer | inner<<8
+    const uint8_t* blob;
+    uint32_t blob_bytes;
+};
+
+__device__ __forceinline__ int nth_set_bit(const uint32_t* m, int W, int n)
+{
+    for (int w = 0; w < W; ++w) {
+        int c = __popc(m[w]);
+        if (n < c) return w * 32 + __fns(m[w], 0, n + 1);
+        n -= c;
+    }
+    return -1;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    uint32_t n_active, const uint2* __restrict__ vmask, const double* __restrict__ vals, uint32_t V,
+    LutView lut, int use_lookup, int use_secondary, uint32_t* __restrict__ rec_ref,
+    uint32_t* __restrict__ general_list, unsigned* __restrict__ n_general, unsigned* __restrict__ n_exact,
+    int* __restrict__ key_out)
+{
+    __shared__ uint16_t s_lut2[256 * 64];
+    __shared__ uint16_t s_lut1[16];
+    if (use_lookup) {
+        for (int i = threadIdx.x; i < 256 * 64; i += blockDim.x) s_lut2[i] = lut.lut2[i];
+        if (threadIdx.x < 16) s_lut1[threadIdx.x] = lut.lut1[threadIdx.x];
+    }
+    __syncthreads();
+    unsigned exact = 0;
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        uint32_t m[W];
+        int k = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            m[w] = act_mask[(size_t)w * cap + a];
+            k += __popc(m[w]);
+        }
+        uint32_t ref = REF_GENERAL;
+        int key = -1;
+        if (use_lookup && (k == 1 || (k == 2 && (use_secondary || key_out)))) {
+            const uint4 tv = __ldg(&tets[act_tet[a]]);
+            const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
+            const int f0 = nth_set_bit(m, W, 0);
+            const int f1 = (k == 2) ? nth_set_bit(m, W, 1) : f0;
+            int s0 = 0, s1 = 0;
+            bool nonzero = true;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint2 a0 = __ldg(&vmask[(size_t)(f0 >> 5) * V + vv[c]]);
+                s0 |= ((a0.x >> (f0 & 31)) & 1) << c;
+                nonzero &= (((a0.x | a0.y) >> (f0 & 31)) & 1) != 0;
+                if (k == 2) {
+                    const uint2 a1 = __ldg(&vmask[(size_t)(f1 >> 5) * V + vv[c]]);
+                    s1 |= ((a1.x >> (f1 & 31)) & 1) << c;
+                    nonzero &= (((a1.x | a1.y) >> (f1 & 31)) & 1) != 0;
+                }
+            }
+            if (nonzero) {
+                if (k == 1) {
+                    key = s0;
+                    ref = s_lut1[s0];
+                } else {
+                    key = s0 | (s1 << 4);
+                    double p0[4], p1[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        p0[c] = __ldg(&vals[(size_t)f0 * V + vv[c]]);
+                        p1[c] = __ldg(&vals[(size_t)f1 * V + vv[c]]);
+                    }
+                    int e = 0;
+                    for (int x = 0; x < 4 && key >= 0; ++x)
+                        for (int y = x + 1; y < 4; ++y, ++e) {
+                            bool c0 = ((s0 >> x) & 1) != ((s0 >> y) & 1);
+                            bool c1 = ((s1 >> x) & 1) != ((s1 >> y) & 1);
+                            if (!(c0 && c1)) continue;
+                            // order of the two crossing points on edge (x,y)
+                            int s = det2_sign(p0[x], p0[y], p1[x], p1[y], &exact);
+                            if (s == 0) {
+                                key = -1;
+                                break;
+                            }
+                            if (s > 0) key |= 1 << (8 + e);
+                        }
+                    if (key >= 0 && use_secondary) {
+                        uint16_t off = s_lut2[key];
+                        ref = (off == LUT_MISS) ? REF_GENERAL : off;
+                    }
+                }
+            }
+        }
+        if (key_out) key_out[a] = key;
+        if (ref & REF_GENERAL) {
+            unsigned g = atomicAdd(n_general, 1u);
+            general_list[g] = a;
+        }
+        rec_ref[a] = ref;
+    }
+    if (exact) atomicAdd(n_exact, exact);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: general arrangement kernel: one thread per tet, complex in local memory, iso record out.
+// ---------------------------------------------------------------------------------------------
+struct GeneralCounters
+{
+    unsigned n_general;
+    unsigned arena_top; // bytes
+    unsigned n_exact;
+    int err;            // first error code (RIN_ERR_*)
+    unsigned err_tet;
+    unsigned arena_overflow;
+};
+
+// serialises the iso part of a finished complex into `buf`; returns the size in bytes (0 on overflow)
+template <class Caps>
+__device__ int ia_write_iso_record(const IAComplex<Caps>& cx, uint8_t* buf, int cap)
+{
+    uint8_t rank_of[Caps::MAXV];
+    uint32_t isov[Caps::MAXV / 32];
+    for (int i = 0; i < Caps::MAXV / 32; ++i) isov[i] = 0;
+    int nfi = 0, nfv = 0;
+    for (int f = 0; f < cx.nf; ++f)
+        if (cx.is_iso_face(f)) {
+            ++nfi;
+            nfv += cx.flen[f];
+            for (int k = 0; k < cx.flen[f]; ++k) {
+                int v = cx.fv[cx.foff[f] + k];
+                isov[v >> 5] |= 1u << (v & 31);
+            }
+        }
+    int nvi = 0;
+    for (int v = 0; v < cx.nv; ++v)
+        if ((isov[v >> 5] >> (v & 31)) & 1) rank_of[v] = (uint8_t)nvi++;
+    if (nvi > 255 || nfi > 255 || (int)rec_size_ia(nvi, nfi, nfv) > cap) return 0;
+    int p = 0;
+    buf[p++] = (uint8_t)nvi;
+    buf[p++] = (uint8_t)nfi;
+    buf[p++] = (uint8_t)(nfv & 255);
+    buf[p++] = (uint8_t)(nfv >> 8);
+    for (int v = 0; v < cx.nv; ++v)
+        if ((isov[v >> 5] >> (v & 31)) & 1) {
+            buf[p++] = (uint8_t)v;
+            buf[p++] = cx.vp[v][0];
+            buf[p++] = cx.vp[v][1];
+            buf[p++] = cx.vp[v][2];
+        }
+    for (int f = 0; f < cx.nf; ++f)
+        if (cx.is_iso_face(f)) {
+            buf[p++] = (uint8_t)(f & 255);
+            buf[p++] = (uint8_t)(f >> 8);
+            buf[p++] = cx.fplane[f];
+            buf[p++] = (cx.fneg[f] == N8) ? 1 : 0;
+            buf[p++] = cx.flen[f];
+            for (int k = 0; k < cx.flen[f]; ++k) buf[p++] = rank_of[cx.fv[cx.foff[f] + k]];
+        }
+    return p;
+}
+
+constexpr int GEN_THREADS = 64;
+constexpr int GEN_REC_CAP = 4096;
+
+template <int W>
+__global__ void __launch_bounds__(GEN_THREADS) general_ia_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    const uint32_t* __restrict__ general_list, const double* __restrict__ vals, uint32_t V,
+    uint8_t* __restrict__ arena, uint32_t arena_cap, uint32_t* __restrict__ rec_ref,
+    GeneralCounters* __restrict__ gc)
+{
+    const uint32_t n = gc->n_general;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const uint32_t a = general_list[g];
+        const uint4 tv = __ldg(&tets[act_tet[a]]);
+        IAComplex<IACaps> cx;
+        cx.init();
+        for (int w = 0; w < W; ++w) {
+            uint32_t mm = act_mask[(size_t)w * cap + a];
+            while (mm) {
+                int f = w * 32 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                double pv[4];
+                pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
+                pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
+                pv[2] = __ldg(&vals[(size_t)f * V + tv.z]);
+                pv[3] = __ldg(&vals[(size_t)f * V + tv.w]);
+                cx.insert(pv);
+            }
+        }
+        uint8_t buf[GEN_REC_CAP];
+        int sz = 0;
+        if (!cx.err) {
+            sz = ia_write_iso_record(cx, buf, GEN_REC_CAP);
+            if (sz == 0) cx.err = 1;
+        }
+        if (cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
+        if (cx.err) {
+            if (atomicCAS(&gc->err, 0, cx.err == 1 ? RIN_ERR_CAPACITY : RIN_ERR_ARRANGEMENT) == 0)
+                gc->err_tet = act_tet[a];
+            rec_ref[a] = REF_GENERAL; // offset 0: the arena starts with an empty record
+            continue;
+        }
+        const uint32_t szal = (uint32_t(sz) + 3u) & ~3u;
+        const uint32_t off = atomicAdd(&gc->arena_top, szal);
+        if (off + szal > arena_cap) {
+            gc->arena_overflow = 1;
+            rec_ref[a] = REF_GENERAL;
+            continue;
+        }
+        for (int i = 0; i < sz; ++i) arena[off + i] = buf[i];
+        rec_ref[a] = REF_GENERAL | (off >> 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5a: per-active-tet output counts + exclusive scan (4 lanes: iso verts, iso faces, face-vertex
+// entries, active functions).  offs[a] = (vert offset, face offset, face-vertex offset, CRS offset)
+// ---------------------------------------------------------------------------------------------
+struct ScanTotals
+{
+    unsigned tile_counter;
+    unsigned n_cand, n_faces, n_fv, n_funcs;
+};
+
+__device__ __forceinline__ const uint8_t* record_ptr(uint32_t ref, const uint8_t* lut_blob, const uint8_t* arena)
+{
+    return (ref & REF_GENERAL) ? arena + (size_t)(ref & ~REF_GENERAL) * 4 : lut_blob + (size_t)ref * 4;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restrict__ rec_ref,
+    const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active,
+    const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena, uint4* __restrict__ offs,
+    volatile unsigned long long* __restrict__ statusA, volatile unsigned long long* __restrict__ statusB,
+    ScanTotals* __restrict__ tot)
+{
+    __shared__ unsigned s_tile;
+    __shared__ uint4 s_warp[8];
+    __shared__ uint4 s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&tot->tile_counter, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const uint32_t a = tile * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 c = make_uint4(0, 0, 0, 0);
+    if (a < n_active) {
+        const uint8_t* r = record_ptr(rec_ref[a], lut_blob, arena);
+        const uint32_t h = *reinterpret_cast<const uint32_t*>(r);
+        c.x = h & 255;
+        c.y = (h >> 8) & 255;
+        c.z = h >> 16;
+        for (int w = 0; w < W; ++w) c.w += __popc(act_mask[(size_t)w * cap + a]);
+    }
+    uint4 x = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint4 y;
+        y.x = __shfl_up_sync(0xffffffffu, x.x, o);
+        y.y = __shfl_up_sync(0xffffffffu, x.y, o);
+        y.z = __shfl_up_sync(0xffffffffu, x.z, o);
+        y.w = __shfl_up_sync(0xffffffffu, x.w, o);
+        if (lane >= o) {
+            x.x += y.x;
+            x.y += y.y;
+            x.z += y.z;
+            x.w += y.w;
+        }
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint4 run = make_uint4(0, 0, 0, 0);
+        for (int w = 0; w < 8; ++w) {
+            uint4 t = s_warp[w];
+            s_warp[w] = run;
+            run.x += t.x;
+            run.y += t.y;
+            run.z += t.z;
+            run.w += t.w;
+        }
+        uint32_t e0, e1, e2, e3;
+        tile_lookback(statusA, (int)tile, run.x, run.y, e0, e1);
+        tile_lookback(statusB, (int)tile, run.z, run.w, e2, e3);
+        s_base = make_uint4(e0, e1, e2, e3);
+        if (tile == (n_active + 255) / 256 - 1) {
+            tot->n_cand = e0 + run.x;
+            tot->n_faces = e1 + run.y;
+            tot->n_fv = e2 + run.z;
+            tot->n_funcs = e3 + run.w;
+        }
+    }
+    __syncthreads();
+    if (a < n_active) {
+        const uint4 b = s_base, wv = s_warp[warp];
+        offs[a] = make_uint4(b.x + wv.x + x.x - c.x, b.y + wv.y + x.y - c.y, b.z + wv.z + x.z - c.z,
+            b.w + wv.w + x.w - c.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5b: emit vertex candidates (canonical keys) and face records.
+// Replaces the body of extract_iso_mesh (src/extract_mesh.cpp:93-261): classification of an iso
+// vertex by the number of simplex-boundary planes among its three planes and the keys
+//   on tet vertex (v)                :197-225        on tet edge (vmin, vmax, fn)       :113-151
+//   on tet face (v0<=v1<=v2, fa, fb) :153-183        interior: never shared             :185-195
+// cand_key  = (v0, v1, v2, fa | fb<<16) with unused slots 0xffffffff / 0xffff
+// cand_pay  = (tet, local | simplex_size<<8 | dedup<<16, f0 | f1<<16, f2)
+// face_hdr  = (tet, local face | n<<16 | boundary<<24, function id, face-vertex offset)
+// ---------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    uint32_t n_active, const uint32_t* __restrict__ rec_ref, const uint4* __restrict__ offs,
+    const uint8_t* __restrict__ lut_blob, uint32_t lut_bytes, const uint8_t* __restrict__ arena,
+    uint4* __restrict__ cand_key, uint4* __restrict__ cand_pay, uint4* __restrict__ face_hdr,
+    uint32_t* __restrict__ fv_ref, unsigned* __restrict__ n_bndry_faces)
+{
+    extern __shared__ __align__(16) uint8_t s_blob[];
+    for (uint32_t i = threadIdx.x; i < lut_bytes / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(s_blob)[i] = reinterpret_cast<const uint32_t*>(lut_blob)[i];
+    __syncthreads();
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        const uint32_t ref = rec_ref[a];
+        const uint8_t* r = (ref & REF_GENERAL) ? arena + (size_t)(ref & ~REF_GENERAL) * 4 : s_blob + ref * 4;
+        const int nv = r[0], nf = r[1];
+        if (nv == 0 && nf == 0) continue;
+        const uint32_t t = act_tet[a];
+        const uint4 tv4 = __ldg(&tets[t]);
+        const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
+        uint32_t m[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) m[w] = act_mask[(size_t)w * cap + a];
+        const uint4 o = offs[a];
+        const uint8_t* p = r + REC_HDR;
+        for (int i = 0; i < nv; ++i, p += 4) {
+            const int local = p[0];
+            uint32_t fn[3] = {0xffffu, 0xffffu, 0xffffu};
+            uint32_t corners[4];
+            int ni = 0, nb = 0;
+            unsigned on_b = 0;
+#pragma unroll
+            for (int k = 1; k <= 3; ++k) {
+                const int pl = p[k];
+                if (pl > 3)
+                    fn[ni++] = (uint32_t)nth_set_bit(m, W, pl - 4);
+                else {
+                    on_b |= 1u << pl;
+                    ++nb;
+                }
+            }
+            int ncn = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (!((on_b >> c) & 1)) corners[ncn++] = tv[c];
+            uint4 key, pay;
+            pay.x = t;
+            if (nb == 0) {
+                key = make_uint4(tv[0], tv[1], tv[2], tv[3]); // unused: interior vertices are unique
+                pay.y = (uint32_t)local | (4u << 8);
+            } else {
+                // sort the (<= 3) corners ascending
+                if (ncn >= 2 && corners[0] > corners[1]) {
+                    uint32_t s = corners[0];
+                    corners[0] = corners[1];
+                    corners[1] = s;
+                }
+                if (ncn == 3) {
+                    if (corners[1] > corners[2]) {
+                        uint32_t s = corners[1];
+                        corners[1] = corners[2];
+                        corners[2] = s;
+                    }
+                    if (corners[0] > corners[1]) {
+                        uint32_t s = corners[0];
+                        corners[0] = corners[1];
+                        corners[1] = s;
+                    }
+                }
+                key.x = corners[0];
+                key.y = ncn >= 2 ? corners[1] : NONE32;
+                key.z = ncn >= 3 ? corners[2] : NONE32;
+                key.w = fn[0] | (fn[1] << 16); // function ids in plane-triple order (:138,:167-168)
+                pay.y = (uint32_t)local | ((uint32_t)ncn << 8) | (1u << 16);
+            }
+            pay.z = fn[0] | (fn[1] << 16);
+            pay.w = fn[2];
+            cand_key[o.x + i] = key;
+            cand_pay[o.x + i] = pay;
+        }
+        uint32_t fvo = o.z;
+        unsigned nbf = 0;
+        for (int j = 0; j < nf; ++j) {
+            const uint32_t local = p[0] | (p[1] << 8);
+            const int sp = p[2], bnd = p[3] & 1, n = p[4];
+            // func_index.first = func_in_tet[supporting_plane - 4 + start] (:249,:258); for a face
+            // coplanar with a tet face sp < 4 and the reference's index wraps to an earlier CRS
+            // entry: resolved in finalize_faces (needs the CRS), flagged here by fn = 0xfffffff0|sp
+            const uint32_t f = (sp > 3) ? (uint32_t)nth_set_bit(m, W, sp - 4) : (0xfffffff0u | sp);
+            face_hdr[o.y + j] = make_uint4(t, local | ((uint32_t)n << 16) | ((uint32_t)bnd << 24), f, fvo);
+            for (int k = 0; k < n; ++k) fv_ref[fvo + k] = o.x + p[5 + k];
+            fvo += n;
+            nbf += bnd;
+            p += 5 + n;
+        }
+        if (nbf) atomicAdd(n_bndry_faces, nbf);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: deduplication with first-occurrence numbering.
+// The reference's try_emplace(key, next id) (src/extract_mesh.cpp:139,169,214,244) gives a shared
+// vertex the id of its FIRST candidate in (tet, local index) order.  Here: every candidate
+// atomicMin's its index into an open-addressing table slot owned by its key -> the slot ends up
+// holding the first candidate (order independent, hence deterministic); representatives are
+// flagged and ranked by an exclusive scan in candidate order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hash_insert_kernel(const uint4* __restrict__ keys,
+    const uint4* __restrict__ pay, uint32_t n, uint32_t* __restrict__ table, uint32_t mask,
+    uint32_t* __restrict__ slot_of)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        if (!((pay[c].y >> 16) & 1)) {
+            slot_of[c] = NONE32;
+            continue;
+        }
+        const uint4 k = keys[c];
+        uint32_t h = hash4(k) & mask;
+        for (;;) {
+            uint32_t cur = table[h];
+            if (cur == NONE32) {
+                cur = atomicCAS(&table[h], NONE32, c);
+                if (cur == NONE32) break;
+            }
+            if (key_eq(keys[cur], k)) {
+                atomicMin(&table[h], c);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+        slot_of[c] = h;
+    }
+}
+
+// rep[c] = first candidate with the same key; single-lane look-back scan of the representative
+// flags gives vid[c] (valid at representatives).
+__global__ void __launch_bounds__(256) rank_reps_kernel(const uint32_t* __restrict__ table,
+    const uint32_t* __restrict__ slot_of, uint32_t n, uint32_t* __restrict__ rep, uint32_t* __restrict__ vid,
+    volatile unsigned long long* __restrict__ status, unsigned* __restrict__ tile_counter,
+    unsigned* __restrict__ n_unique)
+{
+    __shared__ unsigned s_tile, s_base;
+    __shared__ unsigned s_warp[8];
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ITEMS = 4;
+    const uint32_t base = tile * 256 * ITEMS + threadIdx.x * ITEMS;
+    uint32_t r[ITEMS];
+    unsigned cnt = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t c = base + j;
+        r[j] = NONE32;
+        if (c < n) {
+            const uint32_t s = slot_of[c];
+            r[j] = (s == NONE32) ? c : table[s];
+            cnt += (r[j] == c);
+        }
+    }
+    unsigned x = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int w = 0; w < 8; ++w) {
+            unsigned t = s_warp[w];
+            s_warp[w] = run;
+            run += t;
+        }
+        uint32_t e0, e1;
+        tile_lookback(status, (int)tile, run, 0, e0, e1);
+        s_base = e0;
+        if (tile == (n + 256 * ITEMS - 1) / (256 * ITEMS) - 1) *n_unique = e0 + run;
+    }
+    __syncthreads();
+    unsigned id = s_base + s_warp[warp] + x - cnt;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t c = base + j;
+        if (c < n) {
+            rep[c] = r[j];
+            vid[c] = (r[j] == c) ? id++ : NONE32;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: write the unique vertices (IsoVert fields) and their coordinates.
+// compute_iso_vert_xyz (src/extract_mesh.cpp:1446-1538) with compute_barycentric_coords
+// (src/extract_mesh.h:111-159): same operation order, no FMA contraction (-fmad=false).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) write_verts_ia_kernel(const uint4* __restrict__ cand_key,
+    const uint4* __restrict__ cand_pay, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ vid,
+    uint32_t n, const uint4* __restrict__ tets, const double* __restrict__ vals, uint32_t V,
+    const double* __restrict__ pts, uint32_t* __restrict__ v_tet, uint8_t* __restrict__ v_local,
+    uint8_t* __restrict__ v_size, uint4* __restrict__ v_simplex, uint4* __restrict__ v_funcs,
+    double* __restrict__ v_xyz)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        if (rep[c] != c) continue;
+        const uint32_t id = vid[c];
+        const uint4 pay = cand_pay[c];
+        const int size = (pay.y >> 8) & 255;
+        uint32_t sv[4];
+        if (size == 4) {
+            const uint4 tv = __ldg(&tets[pay.x]);
+            sv[0] = tv.x;
+            sv[1] = tv.y;
+            sv[2] = tv.z;
+            sv[3] = tv.w;
+        } else {
+            const uint4 k = cand_key[c];
+            sv[0] = k.x;
+            sv[1] = k.y;
+            sv[2] = k.z;
+            sv[3] = NONE32;
+        }
+        uint32_t fi[3] = {pay.z & 0xffffu, pay.z >> 16, pay.w & 0xffffu};
+        for (int q = 0; q < 3; ++q)
+            if (fi[q] == 0xffffu) fi[q] = NONE32;
+        v_tet[id] = pay.x;
+        v_local[id] = (uint8_t)(pay.y & 255);
+        v_size[id] = (uint8_t)size;
+        v_simplex[id] = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+        v_funcs[id] = make_uint4(fi[0], fi[1], fi[2], NONE32);
+        double out[3];
+#define PT(v, c) pts[3 * (size_t)(v) + (c)]
+#define FV(v, f) vals[(size_t)(f) * V + (v)]
+        if (size == 1) {
+            for (int d = 0; d < 3; ++d) out[d] = PT(sv[0], d);
+        } else if (size == 2) {
+            const double f1 = FV(sv[0], fi[0]), f2 = FV(sv[1], fi[0]);
+            const double b0 = f2 / (f2 - f1), b1 = 1 - b0;
+            for (int d = 0; d < 3; ++d) out[d] = b0 * PT(sv[0], d) + b1 * PT(sv[1], d);
+        } else if (size == 3) {
+            double p1[3], p2[3];
+            for (int k = 0; k < 3; ++k) {
+                p1[k] = FV(sv[k], fi[0]);
+                p2[k] = FV(sv[k], fi[1]);
+            }
+            const double n1 = p1[2] * p2[1] - p1[1] * p2[2];
+            const double n2 = p1[0] * p2[2] - p1[2] * p2[0];
+            const double n3 = p1[1] * p2[0] - p1[0] * p2[1];
+            const double dd = n1 + n2 + n3;
+            const double w0 = n1 / dd, w1 = n2 / dd, w2 = n3 / dd;
+            for (int d = 0; d < 3; ++d) out[d] = w0 * PT(sv[0], d) + w1 * PT(sv[1], d) + w2 * PT(sv[2], d);
+        } else {
+            double p1[4], p2[4], p3[4];
+            for (int k = 0; k < 4; ++k) {
+                p1[k] = FV(sv[k], fi[0]);
+                p2[k] = FV(sv[k], fi[1]);
+                p3[k] = FV(sv[k], fi[2]);
+            }
+            const double n1 = p1[3] * (p2[2] * p3[1] - p2[1] * p3[2]) + p1[2] * (p2[1] * p3[3] - p2[3] * p3[1]) +
+                              p1[1] * (p2[3] * p3[2] - p2[2] * p3[3]);
+            const double n2 = p1[3] * (p2[0] * p3[2] - p2[2] * p3[0]) + p1[2] * (p2[3] * p3[0] - p2[0] * p3[3]) +
+                              p1[0] * (p2[2] * p3[3] - p2[3] * p3[2]);
+            const double n3 = p1[3] * (p2[1] * p3[0] - p2[0] * p3[1]) + p1[1] * (p2[0] * p3[3] - p2[3] * p3[0]) +
+                              p1[0] * (p2[3] * p3[1] - p2[1] * p3[3]);
+            const double n4 = p1[2] * (p2[0] * p3[1] - p2[1] * p3[0]) + p1[1] * (p2[2] * p3[0] - p2[0] * p3[2]) +
+                              p1[0] * (p2[1] * p3[2] - p2[2] * p3[1]);
+            const double dd = n1 + n2 + n3 + n4;
+            const double w0 = n1 / dd, w1 = n2 / dd, w2 = n3 / dd, w3 = n4 / dd;
+            for (int d = 0; d < 3; ++d)
+                out[d] = w0 * PT(sv[0], d) + w1 * PT(sv[1], d) + w2 * PT(sv[2], d) + w3 * PT(sv[3], d);
+        }
+#undef PT
+#undef FV
+        v_xyz[3 * (size_t)id + 0] = out[0];
+        v_xyz[3 * (size_t)id + 1] = out[1];
+        v_xyz[3 * (size_t)id + 2] = out[2];
+    }
+}
+
+// face vertex references -> final vertex ids
+__global__ void __launch_bounds__(256) remap_face_verts_kernel(const uint32_t* __restrict__ fv_ref,
+    uint32_t n, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ vid, uint32_t* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = vid[rep[fv_ref[i]]];
+}
+
+// generic (no iso-face on a tet boundary): one output face per face record
+__global__ void __launch_bounds__(256) write_faces_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    uint32_t n_fv, uint32_t* __restrict__ f_off, uint32_t* __restrict__ f_toff, uint32_t* __restrict__ f_tets,
+    uint32_t* __restrict__ f_funcs)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+        if (i == n) {
+            f_off[n] = n_fv;
+            f_toff[n] = n;
+            continue;
+        }
+        const uint4 h = face_hdr[i];
+        f_off[i] = h.w;
+        f_toff[i] = i;
+        f_tets[2 * (size_t)i] = h.x;
+        f_tets[2 * (size_t)i + 1] = h.y & 0xffffu;
+        f_funcs[2 * (size_t)i] = h.z;
+        f_funcs[2 * (size_t)i + 1] = NONE32;
+    }
+}
+
+} // namespace rin

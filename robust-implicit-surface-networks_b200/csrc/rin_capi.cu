@@ -1,0 +1,875 @@
+// C-ABI implementation (include/rin_b200.h): context, device buffers, stage orchestration.
+// Host code here only sizes buffers and launches kernels; all per-vertex / per-tet work is in
+// kernels_*.cuh.  There is no CPU fallback: without a CUDA device every entry point fails.
+#include "../../include/rin_b200.h"
+#include "kernels_ia.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace rin;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(RIN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const
+    {
+        return static_cast<T*>(p);
+    }
+};
+
+enum Stage {
+    ST_EVAL = 0,   // function evaluation + signs          (load_functions + "func signs")
+    ST_FILTER,     // active-function filter               ("filter")
+    ST_CLASSIFY,   // table dispatch                       ("simp_arr(1 func)", "(2 func)")
+    ST_GENERAL,    // general per-tet kernel               ("simp_arr(>=3 func)")
+    ST_SCAN,       // output counts + offsets              ("extract mesh")
+    ST_EMIT,       //                                      ("extract mesh")
+    ST_DEDUP,      //                                      ("extract mesh")
+    ST_VERTS,      // unique vertices + coordinates        ("compute xyz")
+    ST_FACES,      //                                      ("extract mesh")
+    ST_COUNT
+};
+const char* kStageNames[ST_COUNT] = {"eval+signs", "filter", "classify(lookup)", "general", "count+scan",
+    "emit", "dedup", "verts+xyz", "faces"};
+
+struct Lut
+{
+    DevBuf lut1, lut2, blob;
+    uint32_t blob_bytes = 0;
+    bool built = false;
+    // host copies (tests / introspection)
+    std::vector<uint16_t> h_lut1, h_lut2;
+    std::vector<uint8_t> h_blob;
+};
+
+} // namespace
+
+struct rin_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // mesh
+    uint64_t V = 0, T = 0;
+    DevBuf pts, tets;
+    uint64_t t_first = 0, t_count = 0;
+    // functions / values
+    uint32_t F = 0;
+    DevBuf funcs;
+    bool have_funcs = false, have_values = false;
+    DevBuf rowmajor; // caller-provided values (device copy)
+    DevBuf vals, vmask;
+    // work buffers
+    DevBuf counters; // small zeroed block: FilterCounters | GeneralCounters | ScanTotals | misc
+    DevBuf status;   // look-back status words
+    DevBuf act_tet, act_mask, rec_ref, general_list, arena, offs;
+    DevBuf cand_key, cand_pay, face_hdr, fv_ref;
+    DevBuf table, slot_of, rep, vid;
+    // outputs
+    DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz;
+    DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
+    uint32_t act_cap = 0;
+    Lut lut_ia;
+    rin_counts counts{};
+    int last_mode = -1;
+    uint32_t last_flags = 0;
+    float stage_ms[ST_COUNT] = {};
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    bool ran = false;
+};
+
+namespace {
+
+struct Counters
+{
+    FilterCounters filt;
+    GeneralCounters gen;
+    ScanTotals scan;
+    unsigned rank_tile, n_unique, n_bndry_faces, n_exact_classify;
+    unsigned long long n_zero;
+};
+
+int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8)
+{
+    uint64_t b = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sm_count * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(b, cap));
+}
+
+uint32_t words_for(uint32_t F)
+{
+    return (F + 31) / 32;
+}
+
+template <int W>
+int run_ia_w(rin_ctx* c, uint32_t flags);
+
+int build_ia_tables(rin_ctx* c);
+
+} // namespace
+
+extern "C" {
+
+const char* rin_last_error(void)
+{
+    return g_err.c_str();
+}
+
+int rin_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int rin_create(int device, rin_ctx** out)
+{
+    if (!out) return fail(RIN_ERR_ARG, "rin_create: null out");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail(RIN_ERR_NO_DEVICE, "rin_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(RIN_ERR_ARG, "rin_create: bad device index");
+    CK(cudaSetDevice(device));
+    auto* c = new rin_ctx;
+    c->device = device;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    *out = c;
+    return RIN_OK;
+}
+
+void rin_destroy(rin_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->counters,
+        &c->status, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->arena, &c->offs,
+        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid,
+        &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->f_off, &c->f_verts,
+        &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob};
+    for (auto* b : bufs) b->release();
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void* tets, uint64_t n_tets,
+    int index_bytes)
+{
+    if (!c || !pts || !tets) return fail(RIN_ERR_ARG, "rin_set_mesh_host: null argument");
+    if (index_bytes != 4 && index_bytes != 8) return fail(RIN_ERR_ARG, "index_bytes must be 4 or 8");
+    if (n_pts >= 0xffffffffull || n_tets >= 0x7fffffffull)
+        return fail(RIN_ERR_ARG, "mesh too large for 32-bit device indices");
+    CK(cudaSetDevice(c->device));
+    CK(c->pts.ensure(n_pts * 24));
+    CK(c->tets.ensure(n_tets * 16));
+    CK(cudaMemcpyAsync(c->pts.p, pts, n_pts * 24, cudaMemcpyHostToDevice, c->stream));
+    if (index_bytes == 4) {
+        CK(cudaMemcpyAsync(c->tets.p, tets, n_tets * 16, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // the reference hands std::array<size_t,4>: upload raw, narrow on the device
+        CK(c->rowmajor.ensure(n_tets * 32));
+        CK(cudaMemcpyAsync(c->rowmajor.p, tets, n_tets * 32, cudaMemcpyHostToDevice, c->stream));
+        narrow_tets_kernel<<<grid_for(n_tets, 256, c->sm_count), 256, 0, c->stream>>>(
+            c->rowmajor.as<uint64_t>(), n_tets, c->tets.as<uint4>());
+        CK(cudaGetLastError());
+    }
+    c->V = n_pts;
+    c->T = n_tets;
+    c->t_first = 0;
+    c->t_count = n_tets;
+    c->have_values = false;
+    c->ran = false;
+    return RIN_OK;
+}
+
+int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double bmax[3])
+{
+    if (!c || R == 0) return fail(RIN_ERR_ARG, "rin_generate_grid: bad argument");
+    const uint64_t N = (uint64_t)R + 1;
+    const uint64_t V = N * N * N, T = (uint64_t)R * R * R * 5;
+    if (V >= 0xffffffffull || T >= 0x7fffffffull) return fail(RIN_ERR_ARG, "grid too large");
+    CK(cudaSetDevice(c->device));
+    CK(c->pts.ensure(V * 24));
+    CK(c->tets.ensure(T * 16));
+    grid_points_kernel<<<grid_for(V, 256, c->sm_count), 256, 0, c->stream>>>((uint32_t)N,
+        make_double3(bmin[0], bmin[1], bmin[2]), make_double3(bmax[0], bmax[1], bmax[2]), c->pts.as<double>());
+    grid_tets_kernel<<<grid_for(T, 256, c->sm_count), 256, 0, c->stream>>>(R, c->tets.as<uint4>());
+    CK(cudaGetLastError());
+    c->V = V;
+    c->T = T;
+    c->t_first = 0;
+    c->t_count = T;
+    c->have_values = false;
+    c->ran = false;
+    return RIN_OK;
+}
+
+int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (count == 0) count = c->T - first;
+    if (first + count > c->T) return fail(RIN_ERR_ARG, "tet range out of bounds");
+    c->t_first = first;
+    c->t_count = count;
+    return RIN_OK;
+}
+
+int rin_set_functions(rin_ctx* c, const rin_func_desc* funcs, uint32_t F)
+{
+    if (!c || !funcs || F == 0) return fail(RIN_ERR_ARG, "rin_set_functions: bad argument");
+    if (F > 65534) return fail(RIN_ERR_ARG, "too many functions");
+    CK(cudaSetDevice(c->device));
+    CK(c->funcs.ensure(F * sizeof(rin_func_desc)));
+    CK(cudaMemcpyAsync(c->funcs.p, funcs, F * sizeof(rin_func_desc), cudaMemcpyHostToDevice, c->stream));
+    c->F = F;
+    c->have_funcs = true;
+    c->have_values = false;
+    return RIN_OK;
+}
+
+int rin_set_values_host(rin_ctx* c, const double* vals, uint64_t n_pts, uint32_t F)
+{
+    if (!c || !vals || F == 0) return fail(RIN_ERR_ARG, "rin_set_values_host: bad argument");
+    if (n_pts != c->V) return fail(RIN_ERR_ARG, "rin_set_values_host: row count != number of points");
+    if (F > 65534) return fail(RIN_ERR_ARG, "too many functions");
+    CK(cudaSetDevice(c->device));
+    CK(c->rowmajor.ensure(n_pts * F * 8));
+    CK(cudaMemcpyAsync(c->rowmajor.p, vals, n_pts * F * 8, cudaMemcpyHostToDevice, c->stream));
+    c->F = F;
+    c->have_values = true;
+    c->have_funcs = false;
+    return RIN_OK;
+}
+
+int rin_run(rin_ctx* c, int mode, uint32_t flags)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (c->T == 0 || c->V == 0) return fail(RIN_ERR_STATE, "rin_run: no mesh");
+    if (!c->have_funcs && !c->have_values) return fail(RIN_ERR_STATE, "rin_run: no functions / values");
+    CK(cudaSetDevice(c->device));
+    if (!(flags & RIN_FLAG_USE_LOOKUP)) flags &= ~RIN_FLAG_USE_SECONDARY_LOOKUP; // :38-40
+    if (mode == RIN_MODE_IA) {
+        if ((flags & RIN_FLAG_USE_LOOKUP) && !c->lut_ia.built) {
+            int rc = build_ia_tables(c);
+            if (rc) return rc;
+        }
+        int rc;
+        switch (words_for(c->F)) {
+        case 1: rc = run_ia_w<1>(c, flags); break;
+        case 2: rc = run_ia_w<2>(c, flags); break;
+        case 3: rc = run_ia_w<3>(c, flags); break;
+        case 4: rc = run_ia_w<4>(c, flags); break;
+        default: return fail(RIN_ERR_ARG, "more than 128 functions are not supported by this build");
+        }
+        if (rc == RIN_OK) {
+            c->last_mode = mode;
+            c->last_flags = flags;
+            c->ran = true;
+        }
+        return rc;
+    }
+    return fail(RIN_ERR_ARG, "rin_run: material interface mode is not built yet");
+}
+
+int rin_get_counts(const rin_ctx* c, rin_counts* out)
+{
+    if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
+    *out = c->counts;
+    return RIN_OK;
+}
+
+int rin_download_mesh(rin_ctx* c, rin_mesh_out* o)
+{
+    if (!c || !o) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
+    CK(cudaSetDevice(c->device));
+    const rin_counts& n = c->counts;
+    auto dl = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
+        if (!dst || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
+    CK(dl(o->vert_tet, c->v_tet, n.num_verts * 4));
+    CK(dl(o->vert_local, c->v_local, n.num_verts));
+    CK(dl(o->vert_simplex_size, c->v_size, n.num_verts));
+    CK(dl(o->vert_simplex, c->v_simplex, n.num_verts * 16));
+    CK(dl(o->vert_funcs, c->v_funcs, n.num_verts * 16));
+    CK(dl(o->vert_xyz, c->v_xyz, n.num_verts * 24));
+    CK(dl(o->face_offsets, c->f_off, (n.num_faces + 1) * 4));
+    CK(dl(o->face_verts, c->f_verts, n.num_face_verts * 4));
+    CK(dl(o->face_tet_offsets, c->f_toff, (n.num_faces + 1) * 4));
+    CK(dl(o->face_tets, c->f_tets, n.num_face_tets * 8));
+    CK(dl(o->face_funcs, c->f_funcs, n.num_faces * 8));
+    CK(cudaStreamSynchronize(c->stream));
+    return RIN_OK;
+}
+
+int rin_download_active(rin_ctx* c, uint32_t* func_in_tet, uint64_t* start)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
+    CK(cudaSetDevice(c->device));
+    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet, W = words_for(c->F);
+    std::vector<uint32_t> at(A), am((size_t)A * W);
+    if (A) {
+        CK(cudaMemcpyAsync(at.data(), c->act_tet.p, (size_t)A * 4, cudaMemcpyDeviceToHost, c->stream));
+        for (uint32_t w = 0; w < W; ++w)
+            CK(cudaMemcpyAsync(am.data() + (size_t)w * A, c->act_mask.as<uint32_t>() + (size_t)w * c->act_cap,
+                (size_t)A * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    // format conversion only: expand the compact (tet, mask) list into the reference's CRS arrays
+    uint64_t pos = 0, a = 0;
+    for (uint64_t t = 0; t < c->t_count; ++t) {
+        if (start) start[t] = pos;
+        if (a < A && at[a] == c->t_first + t) {
+            for (uint32_t w = 0; w < W; ++w) {
+                uint32_t m = am[(size_t)w * A + a];
+                while (m) {
+                    int b = __builtin_ctz(m);
+                    m &= m - 1;
+                    if (func_in_tet) func_in_tet[pos] = w * 32 + b;
+                    ++pos;
+                }
+            }
+            ++a;
+        }
+    }
+    if (start) start[c->t_count] = pos;
+    return RIN_OK;
+}
+
+int rin_download_values(rin_ctx* c, double* out)
+{
+    if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
+    CK(cudaSetDevice(c->device));
+    std::vector<double> soa((size_t)c->V * c->F);
+    CK(cudaMemcpyAsync(soa.data(), c->vals.p, soa.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint64_t v = 0; v < c->V; ++v)
+        for (uint32_t f = 0; f < c->F; ++f) out[v * c->F + f] = soa[(size_t)f * c->V + v];
+    return RIN_OK;
+}
+
+int rin_download_grid(rin_ctx* c, double* pts, uint32_t* tets)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (pts) CK(cudaMemcpyAsync(pts, c->pts.p, c->V * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (tets) CK(cudaMemcpyAsync(tets, c->tets.p, c->T * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RIN_OK;
+}
+
+int rin_get_stage_times(const rin_ctx* c, float* ms, int capacity)
+{
+    if (!c || !ms) return fail(RIN_ERR_ARG, "null argument");
+    for (int i = 0; i < capacity && i < ST_COUNT; ++i) ms[i] = c->stage_ms[i];
+    return RIN_OK;
+}
+const char* rin_stage_name(int i)
+{
+    return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : "";
+}
+int rin_num_stages(void)
+{
+    return ST_COUNT;
+}
+
+int rin_run_host(rin_ctx* c, int mode, uint32_t flags, const double* pts, uint64_t n_pts, const void* tets,
+    uint64_t n_tets, int index_bytes, const double* vals, uint32_t F, rin_counts* counts)
+{
+    int rc = rin_set_mesh_host(c, pts, n_pts, tets, n_tets, index_bytes);
+    if (rc) return rc;
+    rc = rin_set_values_host(c, vals, n_pts, F);
+    if (rc) return rc;
+    rc = rin_run(c, mode, flags);
+    if (rc) return rc;
+    if (counts) *counts = c->counts;
+    return RIN_OK;
+}
+
+int rin_get_complexes(rin_ctx*, int, uint32_t, const uint64_t*, uint64_t, uint64_t*, uint32_t*, uint64_t*)
+{
+    return fail(RIN_ERR_STATE, "rin_get_complexes: not built yet");
+}
+int rin_export_boundary(rin_ctx*, uint32_t, void**, void**, uint64_t*)
+{
+    return fail(RIN_ERR_STATE, "rin_export_boundary: not built yet");
+}
+int rin_import_boundary(rin_ctx*, const void*, const void*, uint64_t)
+{
+    return fail(RIN_ERR_STATE, "rin_import_boundary: not built yet");
+}
+
+// introspection for tests: host copy of the IA tables
+int rin_debug_ia_tables(rin_ctx* c, const uint16_t** lut1, const uint16_t** lut2, const uint8_t** blob,
+    uint32_t* blob_bytes)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->lut_ia.built) {
+        CK(cudaSetDevice(c->device));
+        int rc = build_ia_tables(c);
+        if (rc) return rc;
+    }
+    *lut1 = c->lut_ia.h_lut1.data();
+    *lut2 = c->lut_ia.h_lut2.data();
+    *blob = c->lut_ia.h_blob.data();
+    *blob_bytes = c->lut_ia.blob_bytes;
+    return RIN_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// One implicit-arrangement pass over tets [t_first, t_first + t_count).
+// ------------------------------------------------------------------------------------------------
+template <int W>
+int run_ia_w(rin_ctx* c, uint32_t flags)
+{
+    const uint32_t V = (uint32_t)c->V, F = c->F;
+    const uint32_t T = (uint32_t)c->t_count, t_first = (uint32_t)c->t_first;
+    const int use_lookup = (flags & RIN_FLAG_USE_LOOKUP) ? 1 : 0;
+    const int use_secondary = (flags & RIN_FLAG_USE_SECONDARY_LOOKUP) ? 1 : 0;
+    const int negate = (flags & RIN_FLAG_NEGATE) ? 1 : 0;
+    cudaStream_t s = c->stream;
+    const int sm = c->sm_count;
+
+    CK(c->counters.ensure(sizeof(Counters)));
+    Counters* dctr = c->counters.as<Counters>();
+    Counters h{};
+
+    // ---- K1: values + sign masks.  The vertex range is restricted to what the tet range can touch
+    // only for generated grids by the caller (rin_set_tet_range keeps all V by default).
+    CK(c->vals.ensure((size_t)V * F * 8));
+    CK(c->vmask.ensure((size_t)V * W * 8));
+    CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
+    CK(cudaEventRecord(c->ev[ST_EVAL], s));
+    if (c->have_funcs) {
+        size_t smem = F * sizeof(rin_func_desc);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_functions_kernel<<<grid_for(V, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), 0, V, V,
+            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+    } else {
+        ingest_values_kernel<<<grid_for(V, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), 0, V, V, F,
+            negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+    }
+    CK(cudaGetLastError());
+
+    // ---- K2: filter + ordered compaction
+    CK(cudaEventRecord(c->ev[ST_FILTER], s));
+    const uint32_t n_tiles = (T + FILT_TILE - 1) / FILT_TILE;
+    const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
+    for (int attempt = 0;; ++attempt) {
+        if (c->act_cap == 0) c->act_cap = std::max<uint32_t>(1u << 16, T / 4);
+        c->act_cap = std::min<uint32_t>(c->act_cap, std::max<uint32_t>(T, 1));
+        CK(c->act_tet.ensure((size_t)c->act_cap * 4));
+        CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
+        CK(c->status.ensure((size_t)std::max<uint32_t>(n_tiles, 1) * 8 * 2 + 64));
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)n_tiles * 8, s));
+        filter_ia_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
+            c->vmask.as<uint2>(), V, last_mask, c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(),
+            c->act_cap, c->status.as<unsigned long long>(), &dctr->filt);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h.filt.n_active <= c->act_cap) break;
+        if (attempt > 0) return fail(RIN_ERR_STATE, "filter: active list overflow after regrow");
+        // regrow and redo the filter (the counters of this pass are discarded)
+        c->act_cap = h.filt.n_active + h.filt.n_active / 16 + 1024;
+        Counters z{};
+        z.n_zero = h.n_zero;
+        CK(cudaMemcpyAsync(dctr, &z, sizeof(Counters), cudaMemcpyHostToDevice, s));
+    }
+    const uint32_t A = h.filt.n_active;
+
+    rin_counts& n = c->counts;
+    n = rin_counts{};
+    n.num_pts = c->V;
+    n.num_tets = c->t_count;
+    n.num_funcs = F;
+    n.num_degenerate_vertex = h.n_zero;
+    n.num_intersecting_tet = A;
+    n.num_k1 = h.filt.n_k1;
+    n.num_k2 = h.filt.n_k2;
+    n.num_kmore = h.filt.n_kmore;
+    n.num_active_funcs = h.filt.n_funcs;
+
+    // ---- K3: classify
+    CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
+    CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
+    CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
+    CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
+    LutView lv{c->lut_ia.lut1.as<uint16_t>(), c->lut_ia.lut2.as<uint16_t>(), c->lut_ia.blob.as<uint8_t>(),
+        c->lut_ia.blob_bytes};
+    // without tables the blob is a single empty record so that offsets stay valid
+    if (A) {
+        classify_ia_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
+            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vmask.as<uint2>(),
+            c->vals.as<double>(), V, lv, use_lookup, use_secondary, c->rec_ref.as<uint32_t>(),
+            c->general_list.as<uint32_t>(), &dctr->gen.n_general, &dctr->n_exact_classify, nullptr);
+        CK(cudaGetLastError());
+    }
+
+    // ---- K4: general kernel (arena grows on overflow)
+    CK(cudaEventRecord(c->ev[ST_GENERAL], s));
+    if (A) {
+        for (int attempt = 0;; ++attempt) {
+            if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
+            const unsigned top0 = 4;
+            CK(cudaMemsetAsync(c->arena.p, 0, 4, s));
+            CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
+            general_ia_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(), c->act_tet.as<uint32_t>(),
+                c->act_mask.as<uint32_t>(), c->act_cap, c->general_list.as<uint32_t>(), c->vals.as<double>(),
+                V, c->arena.as<uint8_t>(), (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u),
+                c->rec_ref.as<uint32_t>(), &dctr->gen);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&h.gen, &dctr->gen, sizeof(GeneralCounters), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h.gen.err)
+                return fail(h.gen.err, "per-tet arrangement failed in tet " + std::to_string(h.gen.err_tet) +
+                                           (h.gen.err == RIN_ERR_CAPACITY ? " (complex exceeds kernel capacity)"
+                                                                         : " (degenerate input plane)"));
+            if (!h.gen.arena_overflow) break;
+            if (attempt > 2) return fail(RIN_ERR_STATE, "general kernel: arena overflow after regrow");
+            CK(c->arena.ensure((size_t)h.gen.arena_top + h.gen.arena_top / 8 + 4096));
+            GeneralCounters z{};
+            z.n_general = h.gen.n_general;
+            CK(cudaMemcpyAsync(&dctr->gen, &z, sizeof(GeneralCounters), cudaMemcpyHostToDevice, s));
+        }
+    }
+    n.num_general_tets = h.gen.n_general;
+
+    // ---- K5a: counts + offsets
+    CK(cudaEventRecord(c->ev[ST_SCAN], s));
+    const uint32_t a_tiles = (A + 255) / 256;
+    if (A) {
+        CK(c->status.ensure((size_t)a_tiles * 16 + 64));
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
+        count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
+            c->act_cap, A, c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
+            c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h.scan, &dctr->scan, sizeof(ScanTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
+
+    // ---- K5b: emit
+    CK(cudaEventRecord(c->ev[ST_EMIT], s));
+    CK(c->cand_key.ensure((size_t)std::max(NC, 1u) * 16));
+    CK(c->cand_pay.ensure((size_t)std::max(NC, 1u) * 16));
+    CK(c->face_hdr.ensure((size_t)std::max(NFc, 1u) * 16));
+    CK(c->fv_ref.ensure((size_t)std::max(NFV, 1u) * 4));
+    if (A) {
+        const size_t smem = (c->lut_ia.blob_bytes + 3) & ~3u;
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(emit_ia_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        emit_ia_kernel<W><<<grid_for(A, 256, sm, 4), 256, smem, s>>>(c->tets.as<uint4>(),
+            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(),
+            c->offs.as<uint4>(), c->lut_ia.blob.as<uint8_t>(), (uint32_t)smem, c->arena.as<uint8_t>(),
+            c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>(),
+            &dctr->n_bndry_faces);
+        CK(cudaGetLastError());
+    }
+
+    // ---- K6: dedup (hash-min + rank)
+    CK(cudaEventRecord(c->ev[ST_DEDUP], s));
+    uint32_t NV = 0;
+    if (NC) {
+        uint32_t tsize = 1024;
+        while (tsize < 2 * NC) tsize <<= 1;
+        CK(c->table.ensure((size_t)tsize * 4));
+        CK(c->slot_of.ensure((size_t)NC * 4));
+        CK(c->rep.ensure((size_t)NC * 4));
+        CK(c->vid.ensure((size_t)NC * 4));
+        CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
+        hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
+            c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
+        const uint32_t r_tiles = (NC + 1023) / 1024;
+        CK(c->status.ensure((size_t)r_tiles * 8 + 64));
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)r_tiles * 8, s));
+        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NC,
+            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
+            &dctr->n_unique);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        NV = h.n_unique;
+    }
+
+    // ---- K7: unique vertices + xyz
+    CK(cudaEventRecord(c->ev[ST_VERTS], s));
+    CK(c->v_tet.ensure((size_t)std::max(NV, 1u) * 4));
+    CK(c->v_local.ensure(std::max(NV, 1u)));
+    CK(c->v_size.ensure(std::max(NV, 1u)));
+    CK(c->v_simplex.ensure((size_t)std::max(NV, 1u) * 16));
+    CK(c->v_funcs.ensure((size_t)std::max(NV, 1u) * 16));
+    CK(c->v_xyz.ensure((size_t)std::max(NV, 1u) * 24));
+    if (NC) {
+        write_verts_ia_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
+            c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
+            c->vals.as<double>(), V, c->pts.as<double>(), c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(),
+            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>());
+        CK(cudaGetLastError());
+    }
+
+    // ---- faces
+    CK(cudaEventRecord(c->ev[ST_FACES], s));
+    CK(c->f_off.ensure((size_t)(NFc + 1) * 4));
+    CK(c->f_verts.ensure((size_t)std::max(NFV, 1u) * 4));
+    CK(c->f_toff.ensure((size_t)(NFc + 1) * 4));
+    CK(c->f_tets.ensure((size_t)std::max(NFc, 1u) * 8));
+    CK(c->f_funcs.ensure((size_t)std::max(NFc, 1u) * 8));
+    if (h.n_bndry_faces)
+        return fail(RIN_ERR_STATE, "iso-faces on tet boundaries (degenerate input): dedup path not built yet");
+    if (NFV)
+        remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
+            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
+    write_faces_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, NFV,
+        c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[ST_COUNT], s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+
+    n.num_verts = NV;
+    n.num_faces = NFc;
+    n.num_face_verts = NFV;
+    n.num_face_tets = NFc;
+    n.num_exact_fallbacks = (uint64_t)h.gen.n_exact + h.n_exact_classify;
+    return RIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lookup tables (1 and 2 functions), generated by THIS library's general kernel on witness tets:
+// one witness per vertex-sign pattern (1 function) and per (sign pattern, crossing order) key
+// (2 functions).  A key that no witness realises stays LUT_MISS and takes the general kernel.
+// ------------------------------------------------------------------------------------------------
+uint64_t splitmix(uint64_t& s)
+{
+    uint64_t z = (s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+double urand(uint64_t& s)
+{
+    return (splitmix(s) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+int build_ia_tables(rin_ctx* c)
+{
+    cudaStream_t s = c->stream;
+    const int sm = c->sm_count;
+    Lut& L = c->lut_ia;
+    // witnesses: tet w has private vertices 4w..4w+3; functions 0,1
+    const uint32_t NW1 = 16, NW2 = 1u << 18, NWT = NW1 + NW2;
+    const uint32_t Vw = 4 * NWT;
+    std::vector<double> vals((size_t)2 * Vw, 0.0);
+    uint64_t seed = 0x5eed1a2b3c4dULL;
+    for (uint32_t w = 0; w < NW1; ++w)
+        for (int cidx = 0; cidx < 4; ++cidx) {
+            vals[4 * w + cidx] = (((w >> cidx) & 1) ? 1.0 : -1.0) * (0.5 + urand(seed));
+            vals[(size_t)Vw + 4 * w + cidx] = 1.0; // second function inactive (all positive)
+        }
+    for (uint32_t w = NW1; w < NWT; ++w) {
+        uint32_t outer = (uint32_t)(splitmix(seed) & 255);
+        for (int cidx = 0; cidx < 4; ++cidx) {
+            vals[4 * w + cidx] = (((outer >> cidx) & 1) ? 1.0 : -1.0) * (0.02 + urand(seed));
+            vals[(size_t)Vw + 4 * w + cidx] = (((outer >> (4 + cidx)) & 1) ? 1.0 : -1.0) * (0.02 + urand(seed));
+        }
+    }
+    std::vector<uint4> tets(NWT);
+    for (uint32_t w = 0; w < NWT; ++w) tets[w] = make_uint4(4 * w, 4 * w + 1, 4 * w + 2, 4 * w + 3);
+    // masks
+    std::vector<uint2> vm(Vw);
+    for (uint32_t v = 0; v < Vw; ++v) {
+        uint32_t P = 0, N = 0;
+        for (int f = 0; f < 2; ++f) {
+            double x = vals[(size_t)f * Vw + v];
+            P |= (x > 0 ? 1u : 0u) << f;
+            N |= (x < 0 ? 1u : 0u) << f;
+        }
+        vm[v] = make_uint2(P, N);
+    }
+    DevBuf d_vals, d_tets, d_vm, d_act_tet, d_act_mask, d_ref, d_gl, d_keys, d_ctr, d_arena, d_l1, d_l2;
+    auto cleanup = [&]() {
+        for (DevBuf* b : {&d_vals, &d_tets, &d_vm, &d_act_tet, &d_act_mask, &d_ref, &d_gl, &d_keys, &d_ctr,
+                 &d_arena, &d_l1, &d_l2})
+            b->release();
+    };
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup();                                                                             \
+            return fail(RIN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                          \
+    } while (0)
+    CKC(d_vals.ensure(vals.size() * 8));
+    CKC(d_tets.ensure((size_t)NWT * 16));
+    CKC(d_vm.ensure((size_t)Vw * 8));
+    CKC(d_act_tet.ensure((size_t)NWT * 4));
+    CKC(d_act_mask.ensure((size_t)NWT * 4));
+    CKC(d_ref.ensure((size_t)NWT * 4));
+    CKC(d_gl.ensure((size_t)NWT * 4));
+    CKC(d_keys.ensure((size_t)NWT * 4));
+    CKC(d_ctr.ensure(sizeof(Counters)));
+    CKC(d_l1.ensure(32));
+    CKC(d_l2.ensure(256 * 64 * 2));
+    CKC(cudaMemcpyAsync(d_vals.p, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_tets.p, tets.data(), (size_t)NWT * 16, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_vm.p, vm.data(), (size_t)Vw * 8, cudaMemcpyHostToDevice, s));
+    // every witness is "active"; mask = functions crossing it
+    std::vector<uint32_t> at(NWT), am(NWT);
+    for (uint32_t w = 0; w < NWT; ++w) {
+        at[w] = w;
+        am[w] = (w < NW1) ? 1u : 3u;
+    }
+    CKC(cudaMemcpyAsync(d_act_tet.p, at.data(), (size_t)NWT * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_act_mask.p, am.data(), (size_t)NWT * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemsetAsync(d_ctr.p, 0, sizeof(Counters), s));
+    CKC(cudaMemsetAsync(d_l1.p, 0xff, 32, s));
+    CKC(cudaMemsetAsync(d_l2.p, 0xff, 256 * 64 * 2, s));
+    Counters* dctr = d_ctr.as<Counters>();
+    // pass 1: keys of all witnesses (tables are all-miss, so nothing is looked up)
+    LutView lv{d_l1.as<uint16_t>(), d_l2.as<uint16_t>(), nullptr, 0};
+    classify_ia_kernel<1><<<grid_for(NWT, 256, sm, 4), 256, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
+        d_act_mask.as<uint32_t>(), NWT, NWT, d_vm.as<uint2>(), d_vals.as<double>(), Vw, lv, 1, 0,
+        d_ref.as<uint32_t>(), d_gl.as<uint32_t>(), &dctr->gen.n_general, &dctr->n_exact_classify,
+        d_keys.as<int>());
+    CKC(cudaGetLastError());
+    std::vector<int> keys(NWT);
+    CKC(cudaMemcpyAsync(keys.data(), d_keys.p, (size_t)NWT * 4, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    // first witness of every key
+    std::vector<uint32_t> chosen;
+    std::vector<int> chosen_key;
+    {
+        std::vector<char> seen1(16, 0), seen2(256 * 64, 0);
+        for (uint32_t w = 0; w < NWT; ++w) {
+            int k = keys[w];
+            if (k < 0) continue;
+            char& sn = (w < NW1) ? seen1[k] : seen2[k];
+            if (sn) continue;
+            sn = 1;
+            chosen.push_back(w);
+            chosen_key.push_back(w < NW1 ? k : (k | (1 << 20)));
+        }
+    }
+    // pass 2: general kernel on the chosen witnesses
+    const uint32_t NCH = (uint32_t)chosen.size();
+    CKC(cudaMemcpyAsync(d_gl.p, chosen.data(), (size_t)NCH * 4, cudaMemcpyHostToDevice, s));
+    GeneralCounters g0{};
+    g0.n_general = NCH;
+    g0.arena_top = 4;
+    CKC(cudaMemcpyAsync(&dctr->gen, &g0, sizeof(g0), cudaMemcpyHostToDevice, s));
+    CKC(d_arena.ensure((size_t)NCH * 256 + 4096));
+    CKC(cudaMemsetAsync(d_arena.p, 0, 4, s));
+    general_ia_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
+        d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), d_vals.as<double>(), Vw, d_arena.as<uint8_t>(),
+        (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
+    CKC(cudaGetLastError());
+    GeneralCounters g1;
+    CKC(cudaMemcpyAsync(&g1, &dctr->gen, sizeof(g1), cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    if (g1.err || g1.arena_overflow) {
+        cleanup();
+        return fail(RIN_ERR_STATE, "table generation failed");
+    }
+    std::vector<uint8_t> arena(g1.arena_top);
+    std::vector<uint32_t> refs(NWT);
+    CKC(cudaMemcpyAsync(arena.data(), d_arena.p, g1.arena_top, cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemcpyAsync(refs.data(), d_ref.p, (size_t)NWT * 4, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    // pack: blob = [empty record][records in (table, key) order]
+    L.h_lut1.assign(16, LUT_MISS);
+    L.h_lut2.assign(256 * 64, LUT_MISS);
+    L.h_blob.assign(4, 0);
+    std::map<int, uint32_t> order; // key (with table tag) -> witness
+    for (uint32_t i = 0; i < NCH; ++i) order[chosen_key[i]] = chosen[i];
+    for (auto& kv : order) {
+        const uint32_t w = kv.second;
+        const uint8_t* r = arena.data() + (size_t)(refs[w] & ~REF_GENERAL) * 4;
+        const int nv = r[0], nf = r[1], nfv = r[2] | (r[3] << 8);
+        const uint32_t sz = rec_size_ia(nv, nf, nfv);
+        const uint32_t off = (uint32_t)L.h_blob.size() / 4;
+        if (off >= LUT_MISS) {
+            cleanup();
+            return fail(RIN_ERR_STATE, "table blob too large");
+        }
+        L.h_blob.insert(L.h_blob.end(), r, r + sz);
+        while (L.h_blob.size() % 4) L.h_blob.push_back(0);
+        if (kv.first & (1 << 20))
+            L.h_lut2[kv.first & 0xfffff] = (uint16_t)off;
+        else
+            L.h_lut1[kv.first] = (uint16_t)off;
+    }
+    L.blob_bytes = (uint32_t)L.h_blob.size();
+    CKC(L.lut1.ensure(32));
+    CKC(L.lut2.ensure(256 * 64 * 2));
+    CKC(L.blob.ensure(L.blob_bytes));
+    CKC(cudaMemcpyAsync(L.lut1.p, L.h_lut1.data(), 32, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(L.lut2.p, L.h_lut2.data(), 256 * 64 * 2, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(L.blob.p, L.h_blob.data(), L.blob_bytes, cudaMemcpyHostToDevice, s));
+    CKC(cudaStreamSynchronize(s));
+    cleanup();
+    L.built = true;
+    return RIN_OK;
+#undef CKC
+}
+
+} // namespace

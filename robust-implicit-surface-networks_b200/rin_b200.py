@@ -1,0 +1,190 @@
+"""ctypes binding of librin_b200.so (the C-ABI declared in include/rin_b200.h).
+
+Used by tests/, bench.py and __graft_entry__.py.  There is no CPU path behind this module: if the
+CUDA library is missing it raises, and every computing call needs a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librin_b200.so")
+
+MODE_IA, MODE_MI = 0, 1
+FLAG_LOOKUP, FLAG_SECONDARY, FLAG_NEGATE = 1, 2, 4
+
+FUNC_DESC = np.dtype([("type", "<i4"), ("flip", "<i4"), ("p", "<f8", (10,))])
+
+
+class Counts(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "num_pts", "num_tets", "num_funcs", "num_degenerate_vertex", "num_intersecting_tet",
+        "num_k1", "num_k2", "num_kmore", "num_verts", "num_faces", "num_face_verts",
+        "num_face_tets", "num_general_tets", "num_exact_fallbacks", "num_active_funcs")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class MeshOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "vert_tet", "vert_local", "vert_simplex_size", "vert_simplex", "vert_funcs", "vert_xyz",
+        "face_offsets", "face_verts", "face_tet_offsets", "face_tets", "face_funcs")]
+
+
+class RinError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rin_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "librin_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.rin_last_error.restype = C.c_char_p
+        L.rin_stage_name.restype = C.c_char_p
+        L.rin_stage_name.argtypes = [C.c_int]
+        L.rin_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.rin_destroy.argtypes = [C.c_void_p]
+        L.rin_set_mesh_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
+        L.rin_generate_grid.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.rin_set_tet_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.rin_set_functions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.rin_set_values_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        L.rin_run.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.rin_get_counts.argtypes = [C.c_void_p, C.POINTER(Counts)]
+        L.rin_download_mesh.argtypes = [C.c_void_p, C.POINTER(MeshOut)]
+        L.rin_download_active.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rin_download_values.argtypes = [C.c_void_p, C.c_void_p]
+        L.rin_download_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rin_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                   C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Counts)]
+        L.rin_get_complexes.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                        C.c_void_p, C.POINTER(C.c_uint64)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Context:
+    """One engine instance bound to one GPU (mirrors rin_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._check(lib().rin_create(device, C.byref(self._h)))
+        self._keep = []
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RinError(rc, lib().rin_last_error().decode())
+
+    def close(self):
+        if self._h:
+            lib().rin_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs
+    def set_mesh(self, pts, tets):
+        pts = np.ascontiguousarray(pts, np.float64)
+        if tets.dtype not in (np.uint32, np.uint64):
+            tets = tets.astype(np.uint64)
+        tets = np.ascontiguousarray(tets)
+        self._check(lib().rin_set_mesh_host(self._h, pts.ctypes.data, len(pts), tets.ctypes.data, len(tets),
+                                            tets.dtype.itemsize))
+
+    def generate_grid(self, R, bmin=(-1, -1, -1), bmax=(1, 1, 1)):
+        a = np.asarray(bmin, np.float64)
+        b = np.asarray(bmax, np.float64)
+        self._check(lib().rin_generate_grid(self._h, R, a.ctypes.data, b.ctypes.data))
+        self.grid_R = R
+
+    def set_tet_range(self, first, count):
+        self._check(lib().rin_set_tet_range(self._h, first, count))
+
+    def set_functions(self, funcs):
+        funcs = np.ascontiguousarray(funcs, FUNC_DESC)
+        self._check(lib().rin_set_functions(self._h, funcs.ctypes.data, len(funcs)))
+
+    def set_values(self, vals):
+        vals = np.ascontiguousarray(vals, np.float64)
+        self._check(lib().rin_set_values_host(self._h, vals.ctypes.data, vals.shape[0], vals.shape[1]))
+
+    # ---- run
+    def run(self, mode=MODE_IA, flags=FLAG_LOOKUP | FLAG_SECONDARY):
+        self._check(lib().rin_run(self._h, mode, flags))
+        return self.counts()
+
+    def run_host(self, mode, flags, pts, tets, vals):
+        cnt = Counts()
+        self._check(lib().rin_run_host(self._h, mode, flags, pts.ctypes.data, len(pts), tets.ctypes.data,
+                                       len(tets), tets.dtype.itemsize, vals.ctypes.data, vals.shape[1],
+                                       C.byref(cnt)))
+        return cnt
+
+    def counts(self):
+        cnt = Counts()
+        self._check(lib().rin_get_counts(self._h, C.byref(cnt)))
+        return cnt
+
+    def download_mesh(self, into=None):
+        n = self.counts()
+        if into is None:
+            into = {
+                "vert_tet": np.empty(n.num_verts, np.uint32),
+                "vert_local": np.empty(n.num_verts, np.uint8),
+                "vert_simplex_size": np.empty(n.num_verts, np.uint8),
+                "vert_simplex": np.empty((n.num_verts, 4), np.uint32),
+                "vert_funcs": np.empty((n.num_verts, 4), np.uint32),
+                "vert_xyz": np.empty((n.num_verts, 3), np.float64),
+                "face_offsets": np.empty(n.num_faces + 1, np.uint32),
+                "face_verts": np.empty(n.num_face_verts, np.uint32),
+                "face_tet_offsets": np.empty(n.num_faces + 1, np.uint32),
+                "face_tets": np.empty((n.num_face_tets, 2), np.uint32),
+                "face_funcs": np.empty((n.num_faces, 2), np.uint32),
+            }
+        mo = MeshOut(**{k: _ptr(v) for k, v in into.items()})
+        self._check(lib().rin_download_mesh(self._h, C.byref(mo)))
+        return into
+
+    def download_active(self):
+        n = self.counts()
+        fit = np.empty(n.num_active_funcs, np.uint32)
+        start = np.empty(n.num_tets + 1, np.uint64)
+        self._check(lib().rin_download_active(self._h, fit.ctypes.data, start.ctypes.data))
+        return fit, start
+
+    def download_values(self):
+        n = self.counts()
+        out = np.empty((n.num_pts, n.num_funcs), np.float64)
+        self._check(lib().rin_download_values(self._h, out.ctypes.data))
+        return out
+
+    def download_grid(self, V, T):
+        pts = np.empty((V, 3), np.float64)
+        tets = np.empty((T, 4), np.uint32)
+        self._check(lib().rin_download_grid(self._h, pts.ctypes.data, tets.ctypes.data))
+        return pts, tets
+
+    def stage_times(self):
+        k = lib().rin_num_stages()
+        ms = np.zeros(k, np.float32)
+        self._check(lib().rin_get_stage_times(self._h, ms.ctypes.data, k))
+        return {lib().rin_stage_name(i).decode(): float(ms[i]) for i in range(k)}
