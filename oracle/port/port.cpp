@@ -20,6 +20,7 @@
 
 #include "../../include/rin_b200.h"
 #include "../result_bag.h"
+#include "../sa/exact_arith.h"
 
 #include <algorithm>
 #include <array>
@@ -539,6 +540,12 @@ int orc_get_complex(void* h, uint64_t t, uint32_t* words, uint64_t cap, uint64_t
     *n_words = w.size();
     if (words && cap >= w.size()) std::memcpy(words, w.data(), 4 * w.size());
     return 0;
+}
+
+// exact determinant sign (n <= 4, row-major) and the vertex-orientation predicate, for unit tests
+int orc_det_sign(int n, const double* m)
+{
+    return sa_oracle::det_sign(n, m, nullptr);
 }
 
 // one per-tet arrangement, for unit tests of the engine: planes = k*4 doubles

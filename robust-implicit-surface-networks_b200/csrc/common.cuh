@@ -60,6 +60,43 @@ __device__ __forceinline__ void tile_lookback(
     st[tile] = st_pack(ST_PRE, ea + a, eb + b);
 }
 
+// Warp-parallel variant: called by all 32 lanes of ONE warp with the same (a, b); each step
+// inspects 32 predecessors at once.  Returns the exclusive prefix in every lane.
+__device__ __forceinline__ void tile_lookback_warp(
+    volatile unsigned long long* st, int tile, uint32_t a, uint32_t b, uint32_t& ea, uint32_t& eb)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t sa = 0, sb = 0;
+    if (tile > 0) {
+        if (lane == 0) st[tile] = st_pack(ST_AGG, a, b);
+        int p = tile - 1;
+        for (;;) {
+            const int idx = p - lane;
+            unsigned long long w = ST_PRE; // before the first tile: prefix 0
+            if (idx >= 0) {
+                do {
+                    w = st[idx];
+                } while ((w >> 62) == 0);
+            }
+            const unsigned pre = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+            const int upto = pre ? (__ffs(pre) - 1) : 31; // nearest predecessor holding a prefix
+            uint32_t va = (lane <= upto) ? uint32_t((w >> 31) & 0x7fffffffu) : 0u;
+            uint32_t vb = (lane <= upto) ? uint32_t(w & 0x7fffffffu) : 0u;
+            for (int o = 16; o; o >>= 1) {
+                va += __shfl_xor_sync(0xffffffffu, va, o);
+                vb += __shfl_xor_sync(0xffffffffu, vb, o);
+            }
+            sa += va;
+            sb += vb;
+            if (pre) break;
+            p -= 32;
+        }
+    }
+    ea = sa;
+    eb = sb;
+    if (lane == 0) st[tile] = st_pack(ST_PRE, ea + a, eb + b);
+}
+
 __device__ __forceinline__ uint32_t hash4(uint4 k)
 {
     uint32_t h = k.x * 0x9E3779B1u;

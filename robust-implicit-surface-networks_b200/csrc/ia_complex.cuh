@@ -11,9 +11,11 @@
 
 namespace rin {
 
+// Big tier: per-thread local memory, 16-bit indices.
 struct IACaps
 {
-    static constexpr int MAXP = 68;   // planes incl. the 4 simplex faces
+    using idx = uint16_t;
+    static constexpr int MAXK = 64;   // input planes
     static constexpr int MAXV = 256;
     static constexpr int MAXE = 640;
     static constexpr int MAXF = 448;
@@ -22,34 +24,49 @@ struct IACaps
     static constexpr int MAXCF = 1024; // cell face pool
     static constexpr int MAXLOOP = 48;
 };
+// Small tier (<= 4 functions, the common non-table case): 8-bit indices, ~3.9 KB, lives in
+// shared memory.  Capacities cover the transient state inside one insertion step.
+struct IACapsSmall
+{
+    using idx = uint8_t;
+    static constexpr int MAXK = 4;
+    static constexpr int MAXV = 48;
+    static constexpr int MAXE = 128;
+    static constexpr int MAXF = 96;
+    static constexpr int MAXC = 32;
+    static constexpr int MAXFE = 384;
+    static constexpr int MAXCF = 160;
+    static constexpr int MAXLOOP = 12;
+};
 
-constexpr uint16_t N16 = 0xffff;
 constexpr uint8_t N8 = 0xff;
 
 template <class Caps>
 struct IAComplex
 {
-    // geometry: plane p -> values at the 4 simplex corners (rows 0..3 are the unit planes)
-    double pl[Caps::MAXP][4];
+    using I = typename Caps::idx;
+    static constexpr I NI = (I)~(I)0; // "none"
+    // geometry: input plane j (plane id 4+j) -> values at the 4 simplex corners
+    double plv[Caps::MAXK][4];
     int np;
     // combinatorics
     int nv, ne, nf, nc, nfe, ncf;
     uint8_t vp[Caps::MAXV][3];
     int8_t vo[Caps::MAXV];
-    uint16_t ev0[Caps::MAXE], ev1[Caps::MAXE];
+    I ev0[Caps::MAXE], ev1[Caps::MAXE];
     uint8_t ep0[Caps::MAXE], ep1[Caps::MAXE];
-    uint16_t ec_pos[Caps::MAXE], ec_neg[Caps::MAXE], ec_x[Caps::MAXE]; // also reused as edge remap
+    I ec_pos[Caps::MAXE], ec_neg[Caps::MAXE], ec_x[Caps::MAXE]; // also reused as edge remap
     uint8_t ec_split[Caps::MAXE];
     uint16_t foff[Caps::MAXF];
     uint8_t flen[Caps::MAXF], fplane[Caps::MAXF], fpos[Caps::MAXF], fneg[Caps::MAXF];
-    uint16_t fc_pos[Caps::MAXF], fc_neg[Caps::MAXF], fc_cut[Caps::MAXF]; // fc_pos reused as face remap
+    I fc_pos[Caps::MAXF], fc_neg[Caps::MAXF], fc_cut[Caps::MAXF]; // fc_pos reused as face remap
     uint8_t fc_split[Caps::MAXF];
-    uint16_t fv[Caps::MAXFE], fe[Caps::MAXFE];
+    I fv[Caps::MAXFE], fe[Caps::MAXFE];
     uint16_t coff[Caps::MAXC];
     uint8_t clen[Caps::MAXC], c_split[Caps::MAXC], cmap[Caps::MAXC];
-    uint16_t cf[Caps::MAXCF];
+    I cf[Caps::MAXCF];
     // unique-plane bookkeeping
-    uint8_t upi[Caps::MAXP]; // plane -> group
+    uint8_t upi[Caps::MAXK + 4]; // plane -> group
     int n_groups;
     bool has_coplanar;
     int err; // 0 ok, 1 capacity, 2 degenerate input
@@ -57,8 +74,6 @@ struct IAComplex
 
     __device__ void init()
     {
-        for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 4; ++j) pl[i][j] = (i == j) ? 1.0 : 0.0;
         np = 4;
         err = 0;
         n_exact = 0;
@@ -103,7 +118,8 @@ struct IAComplex
         has_coplanar = false;
     }
 
-    // exact sign of plane q at the point where the three planes of vertex v meet
+    // exact sign of plane q at the point where the three planes of vertex v meet:
+    // q(X) = det[impl; q] / det[impl; 1] restricted to the corners not fixed by boundary planes
     __device__ int orient_vertex(int v, const double* q)
     {
         const double* impl[3];
@@ -114,7 +130,7 @@ struct IAComplex
             if (p < 4)
                 fixed |= 1u << p;
             else
-                impl[ni++] = pl[p];
+                impl[ni++] = plv[p - 4];
         }
         int idx[4], n = 0;
         for (int c = 0; c < 4; ++c)
@@ -123,16 +139,38 @@ struct IAComplex
             double x = q[idx[0]];
             return x > 0 ? 1 : (x < 0 ? -1 : 0);
         }
-        double mq[16], md[16];
-        for (int r = 0; r < ni; ++r)
-            for (int c = 0; c < n; ++c) mq[r * n + c] = md[r * n + c] = impl[r][idx[c]];
-        for (int c = 0; c < n; ++c) {
-            mq[ni * n + c] = q[idx[c]];
-            md[ni * n + c] = 1.0;
+        int sq, sd;
+        if (n == 2) {
+            const double a = impl[0][idx[0]], b = impl[0][idx[1]];
+            sq = det2_sign(a, b, q[idx[0]], q[idx[1]], &n_exact);
+            if (sq == 0) return 0;
+            sd = (a > b) - (a < b); // det[[a,b],[1,1]]
+        } else if (n == 3) {
+            double m[9];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                m[c] = impl[0][idx[c]];
+                m[3 + c] = impl[1][idx[c]];
+                m[6 + c] = q[idx[c]];
+            }
+            sq = det3_sign(m, &n_exact);
+            if (sq == 0) return 0;
+            m[6] = m[7] = m[8] = 1.0;
+            sd = det3_sign(m, &n_exact);
+        } else {
+            double m[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                m[c] = impl[0][c];
+                m[4 + c] = impl[1][c];
+                m[8 + c] = impl[2][c];
+                m[12 + c] = q[c];
+            }
+            sq = det4_sign(m, &n_exact);
+            if (sq == 0) return 0;
+            m[12] = m[13] = m[14] = m[15] = 1.0;
+            sd = det4_sign(m, &n_exact);
         }
-        int sq = detn_sign(n, mq, &n_exact);
-        if (sq == 0) return 0;
-        int sd = detn_sign(n, md, &n_exact);
         if (sd == 0) err = 2;
         return sq * sd;
     }
@@ -148,7 +186,7 @@ struct IAComplex
     // insert plane `pid` (values already stored in pl[pid]); returns coplanar plane id or -1
     __device__ int add_plane(int pid)
     {
-        const double* q = pl[pid];
+        const double* q = plv[pid - 4];
         // ---- 1. vertices
         bool any = false;
         for (int v = 0; v < nv; ++v) {
@@ -164,7 +202,7 @@ struct IAComplex
         const int nE = ne;
         for (int e = 0; e < nE; ++e) {
             int o0 = vo[ev0[e]], o1 = vo[ev1[e]];
-            ec_pos[e] = ec_neg[e] = ec_x[e] = N16;
+            ec_pos[e] = ec_neg[e] = ec_x[e] = NI;
             ec_split[e] = 0;
             if (o0 == 0 && o1 == 0) continue;
             if (o0 == 0)
@@ -214,7 +252,7 @@ struct IAComplex
                 npos += (o > 0);
                 nneg += (o < 0);
             }
-            fc_pos[f] = fc_neg[f] = fc_cut[f] = N16;
+            fc_pos[f] = fc_neg[f] = fc_cut[f] = NI;
             fc_split[f] = 0;
             if (npos == 0 && nneg == 0) {
                 if (coplanar < 0) coplanar = fplane[f];
@@ -312,8 +350,8 @@ struct IAComplex
             bool has_pos = false, has_neg = false;
             for (int k = 0; k < clen[c]; ++k) {
                 int f = cf[coff[c] + k];
-                has_pos |= (fc_pos[f] != N16);
-                has_neg |= (fc_neg[f] != N16);
+                has_pos |= (fc_pos[f] != NI);
+                has_neg |= (fc_neg[f] != NI);
             }
             if (!(has_pos && has_neg)) continue;
             c_split[c] = 1;
@@ -322,7 +360,7 @@ struct IAComplex
                 return -1;
             }
             // collect the boundary edges of the cut polygon
-            uint16_t cut_e[Caps::MAXLOOP];
+            I cut_e[Caps::MAXLOOP];
             int n_cut = 0;
             int first_a = -1, first_b = -1;
             auto add_cut_edge = [&](int e, int da, int db, bool inward, bool on_neg_side) {
@@ -332,7 +370,7 @@ struct IAComplex
                     err = 1;
                     return;
                 }
-                cut_e[n_cut++] = (uint16_t)e;
+                cut_e[n_cut++] = (I)e;
                 if (first_a >= 0) return;
                 int oa = inward ? db : da, ob = inward ? da : db;
                 if (on_neg_side) {
@@ -350,14 +388,14 @@ struct IAComplex
             coff[cp] = ncf;
             for (int k = 0; k < clen[c]; ++k) {
                 int f = cf[coff[c] + k];
-                if (fc_pos[f] != N16) cf[ncf++] = fc_pos[f];
+                if (fc_pos[f] != NI) cf[ncf++] = fc_pos[f];
             }
             const int gpos_slot = ncf++;
             clen[cp] = ncf - coff[cp];
             coff[cn] = ncf;
             for (int k = 0; k < clen[c]; ++k) {
                 int f = cf[coff[c] + k];
-                if (fc_neg[f] != N16) cf[ncf++] = fc_neg[f];
+                if (fc_neg[f] != NI) cf[ncf++] = fc_neg[f];
             }
             const int gneg_slot = ncf++;
             clen[cn] = ncf - coff[cn];
@@ -367,19 +405,19 @@ struct IAComplex
                 if (fc_split[f]) {
                     int ce = fc_cut[f];
                     add_cut_edge(ce, ev0[ce], ev1[ce], inward, true);
-                } else if (fc_pos[f] != N16 || fc_neg[f] != N16) {
+                } else if (fc_pos[f] != NI || fc_neg[f] != NI) {
                     const int n = flen[f], off = foff[f];
                     for (int j = 0; j < n; ++j) {
                         int a = fv[off + j], b = fv[off + ((j + 1) % n)];
                         if (vo[a] == 0 && vo[b] == 0)
-                            add_cut_edge(fe[off + j], a, b, inward, fc_neg[f] != N16);
+                            add_cut_edge(fe[off + j], a, b, inward, fc_neg[f] != NI);
                     }
                 }
             }
             if (err) return -1;
             // new face G: chain the cut edges into a loop starting first_a -> first_b
             const int G = nf++;
-            fc_pos[G] = fc_neg[G] = fc_cut[G] = N16;
+            fc_pos[G] = fc_neg[G] = fc_cut[G] = NI;
             fc_split[G] = 0;
             fplane[G] = (uint8_t)pid;
             fpos[G] = (uint8_t)cp;
@@ -414,8 +452,8 @@ struct IAComplex
                     }
                     used |= 1ull << pick;
                     int e = cut_e[pick];
-                    fv[nfe] = (uint16_t)cur;
-                    fe[nfe] = (uint16_t)e;
+                    fv[nfe] = (I)cur;
+                    fe[nfe] = (I)e;
                     ++nfe;
                     cur = (ev0[e] == cur) ? ev1[e] : ev0[e];
                 }
@@ -443,7 +481,7 @@ struct IAComplex
             int k = 0;
             for (int e = 0; e < ne; ++e) {
                 bool dead = (e < nE) && ec_split[e];
-                ec_pos[e] = dead ? N16 : (uint16_t)k; // reuse as edge remap
+                ec_pos[e] = dead ? NI : (I)k; // reuse as edge remap
                 if (!dead) {
                     ev0[k] = ev0[e];
                     ev1[k] = ev1[e];
@@ -459,7 +497,7 @@ struct IAComplex
             for (int f = 0; f < nf; ++f) {
                 bool dead = (f < nF) && fc_split[f];
                 if (dead) {
-                    fc_pos[f] = N16;
+                    fc_pos[f] = NI;
                     continue;
                 }
                 int off = foff[f], n = flen[f];
@@ -495,12 +533,12 @@ struct IAComplex
     __device__ void insert(const double v[4])
     {
         if (err) return;
-        if (np >= Caps::MAXP) {
+        if (np >= Caps::MAXK + 4) {
             err = 1;
             return;
         }
         int pid = np++;
-        for (int c = 0; c < 4; ++c) pl[pid][c] = v[c];
+        for (int c = 0; c < 4; ++c) plv[pid - 4][c] = v[c];
         int cop = add_plane(pid);
         if (err) return;
         if (cop < 0)
@@ -523,8 +561,10 @@ struct IAComplex
     {
         int r = group_first(p);
         if (r == p) return true;
+        // p = c * r as linear functions; r < 4 is the unit plane e_r
+        if (r < 4) return plv[p - 4][r] > 0;
         for (int k = 0; k < 4; ++k)
-            if (pl[r][k] != 0) return (pl[r][k] > 0) == (pl[p][k] > 0);
+            if (plv[r - 4][k] != 0) return (plv[r - 4][k] > 0) == (plv[p - 4][k] > 0);
         return true;
     }
 

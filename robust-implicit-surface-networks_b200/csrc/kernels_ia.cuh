@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) ingest_values_kernel(const double* __rest
 // Single pass over the 16-byte index records; tile offsets by decoupled look-back.
 // ---------------------------------------------------------------------------------------------
 constexpr int FILT_THREADS = 256;
-constexpr int FILT_ITEMS = 4;
+constexpr int FILT_ITEMS = 8;
 constexpr int FILT_TILE = FILT_THREADS * FILT_ITEMS;
 
 struct FilterCounters
@@ -246,20 +246,26 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_ia_kernel(const uint4* __
     if (lane == 0) s_kf[warp] = kf;
     __syncthreads();
     if (warp == 0) {
-        // exclusive prefix over the (item, warp) sequence: 4 x 8 = 32 entries, one per lane
-        const int j = lane / (FILT_THREADS / 32), w = lane % (FILT_THREADS / 32);
-        unsigned c = s_cnt[j][w], x = c;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+        // exclusive prefix over the (item, warp) sequence, FILT_ITEMS * 8 entries, 32 per round
+        unsigned run = 0;
+#pragma unroll
+        for (int r = 0; r < FILT_ITEMS * (FILT_THREADS / 32) / 32; ++r) {
+            const int e = r * 32 + lane;
+            const int j = e / (FILT_THREADS / 32), w = e % (FILT_THREADS / 32);
+            unsigned c = s_cnt[j][w], x = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            s_cnt[j][w] = run + x - c;
+            run += __shfl_sync(0xffffffffu, x, 31);
         }
-        s_cnt[j][w] = x - c;
-        unsigned total = __shfl_sync(0xffffffffu, x, 31);
+        const unsigned total = run;
         unsigned kft = (lane < FILT_THREADS / 32) ? s_kf[lane] : 0;
         for (int o = 16; o; o >>= 1) kft += __shfl_xor_sync(0xffffffffu, kft, o);
+        uint32_t ea, eb;
+        tile_lookback_warp(status, (int)tile, total, kft, ea, eb);
         if (lane == 0) {
-            uint32_t ea, eb;
-            tile_lookback(status, (int)tile, total, kft, ea, eb);
             s_base = ea;
             if (total) {
                 atomicAdd(&ctr->n_active, total);
@@ -292,6 +298,19 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_ia_kernel(const uint4* __
 // points or a missing table entry go to the general kernel.
 // rec_ref[a]: bit31 = general (payload filled by K4), else 4-byte-unit offset into the LUT blob.
 // ---------------------------------------------------------------------------------------------
+struct GeneralCounters
+{
+    unsigned n_general; // all tets that take a general kernel
+    unsigned n_small;   // ... of which <= IACapsSmall::MAXK functions (shared-memory tier)
+    unsigned n_big;     // ... big tier (more functions)
+    unsigned n_ovf;     // small-tier capacity overflows, re-queued for the big tier
+    unsigned arena_top; // bytes
+    unsigned n_exact;
+    int err;            // first error code (RIN_ERR_*)
+    unsigned err_tet;
+    unsigned arena_overflow;
+};
+
 constexpr uint32_t REF_GENERAL = 0x80000000u;
 constexpr uint16_t LUT_MISS = 0xffffu;
 
@@ -318,8 +337,8 @@ __global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restric
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     uint32_t n_active, const uint2* __restrict__ vmask, const double* __restrict__ vals, uint32_t V,
     LutView lut, int use_lookup, int use_secondary, uint32_t* __restrict__ rec_ref,
-    uint32_t* __restrict__ general_list, unsigned* __restrict__ n_general, unsigned* __restrict__ n_exact,
-    int* __restrict__ key_out)
+    uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list, GeneralCounters* __restrict__ gc,
+    unsigned* __restrict__ n_exact, int* __restrict__ key_out)
 {
     __shared__ uint16_t s_lut2[256 * 64];
     __shared__ uint16_t s_lut1[16];
@@ -392,8 +411,11 @@ __global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restric
         }
         if (key_out) key_out[a] = key;
         if (ref & REF_GENERAL) {
-            unsigned g = atomicAdd(n_general, 1u);
-            general_list[g] = a;
+            atomicAdd(&gc->n_general, 1u);
+            if (k <= IACapsSmall::MAXK)
+                small_list[atomicAdd(&gc->n_small, 1u)] = a;
+            else
+                big_list[atomicAdd(&gc->n_big, 1u)] = a;
         }
         rec_ref[a] = ref;
     }
@@ -403,112 +425,152 @@ __global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restric
 // ---------------------------------------------------------------------------------------------
 // K4: general arrangement kernel: one thread per tet, complex in local memory, iso record out.
 // ---------------------------------------------------------------------------------------------
-struct GeneralCounters
+
+// iso part of a finished complex: counts, then serialisation straight into the arena
+template <class Caps>
+struct IsoScan
 {
-    unsigned n_general;
-    unsigned arena_top; // bytes
-    unsigned n_exact;
-    int err;            // first error code (RIN_ERR_*)
-    unsigned err_tet;
-    unsigned arena_overflow;
+    uint32_t isov[(Caps::MAXV + 31) / 32];
+    int nvi, nfi, nfv;
+    __device__ void run(const IAComplex<Caps>& cx)
+    {
+        for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) isov[i] = 0;
+        nfi = 0;
+        nfv = 0;
+        for (int f = 0; f < cx.nf; ++f)
+            if (cx.is_iso_face(f)) {
+                ++nfi;
+                nfv += cx.flen[f];
+                for (int k = 0; k < cx.flen[f]; ++k) {
+                    int v = cx.fv[cx.foff[f] + k];
+                    isov[v >> 5] |= 1u << (v & 31);
+                }
+            }
+        nvi = 0;
+        for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) nvi += __popc(isov[i]);
+    }
+    __device__ int rank(int v) const
+    {
+        int r = __popc(isov[v >> 5] & ((1u << (v & 31)) - 1u));
+        for (int i = 0; i < (v >> 5); ++i) r += __popc(isov[i]);
+        return r;
+    }
+    __device__ void write(const IAComplex<Caps>& cx, uint8_t* buf) const
+    {
+        int p = 0;
+        buf[p++] = (uint8_t)nvi;
+        buf[p++] = (uint8_t)nfi;
+        buf[p++] = (uint8_t)(nfv & 255);
+        buf[p++] = (uint8_t)(nfv >> 8);
+        for (int v = 0; v < cx.nv; ++v)
+            if ((isov[v >> 5] >> (v & 31)) & 1) {
+                buf[p++] = (uint8_t)v;
+                buf[p++] = cx.vp[v][0];
+                buf[p++] = cx.vp[v][1];
+                buf[p++] = cx.vp[v][2];
+            }
+        for (int f = 0; f < cx.nf; ++f)
+            if (cx.is_iso_face(f)) {
+                buf[p++] = (uint8_t)(f & 255);
+                buf[p++] = (uint8_t)(f >> 8);
+                buf[p++] = cx.fplane[f];
+                buf[p++] = (cx.fneg[f] == N8) ? 1 : 0;
+                buf[p++] = cx.flen[f];
+                for (int k = 0; k < cx.flen[f]; ++k) buf[p++] = (uint8_t)rank(cx.fv[cx.foff[f] + k]);
+            }
+    }
 };
 
-// serialises the iso part of a finished complex into `buf`; returns the size in bytes (0 on overflow)
-template <class Caps>
-__device__ int ia_write_iso_record(const IAComplex<Caps>& cx, uint8_t* buf, int cap)
+// One general tet: gather the active functions' values, build the complex, publish the record.
+// Returns false when the complex did not fit this tier (caller re-queues it for the big tier).
+template <class Caps, int W>
+__device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier)
 {
-    uint8_t rank_of[Caps::MAXV];
-    uint32_t isov[Caps::MAXV / 32];
-    for (int i = 0; i < Caps::MAXV / 32; ++i) isov[i] = 0;
-    int nfi = 0, nfv = 0;
-    for (int f = 0; f < cx.nf; ++f)
-        if (cx.is_iso_face(f)) {
-            ++nfi;
-            nfv += cx.flen[f];
-            for (int k = 0; k < cx.flen[f]; ++k) {
-                int v = cx.fv[cx.foff[f] + k];
-                isov[v >> 5] |= 1u << (v & 31);
-            }
+    const uint4 tv = __ldg(&tets[act_tet[a]]);
+    cx.init();
+    for (int w = 0; w < W; ++w) {
+        uint32_t mm = act_mask[(size_t)w * cap + a];
+        while (mm) {
+            int f = w * 32 + __ffs(mm) - 1;
+            mm &= mm - 1;
+            double pv[4];
+            pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
+            pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
+            pv[2] = __ldg(&vals[(size_t)f * V + tv.z]);
+            pv[3] = __ldg(&vals[(size_t)f * V + tv.w]);
+            cx.insert(pv);
         }
-    int nvi = 0;
-    for (int v = 0; v < cx.nv; ++v)
-        if ((isov[v >> 5] >> (v & 31)) & 1) rank_of[v] = (uint8_t)nvi++;
-    if (nvi > 255 || nfi > 255 || (int)rec_size_ia(nvi, nfi, nfv) > cap) return 0;
-    int p = 0;
-    buf[p++] = (uint8_t)nvi;
-    buf[p++] = (uint8_t)nfi;
-    buf[p++] = (uint8_t)(nfv & 255);
-    buf[p++] = (uint8_t)(nfv >> 8);
-    for (int v = 0; v < cx.nv; ++v)
-        if ((isov[v >> 5] >> (v & 31)) & 1) {
-            buf[p++] = (uint8_t)v;
-            buf[p++] = cx.vp[v][0];
-            buf[p++] = cx.vp[v][1];
-            buf[p++] = cx.vp[v][2];
-        }
-    for (int f = 0; f < cx.nf; ++f)
-        if (cx.is_iso_face(f)) {
-            buf[p++] = (uint8_t)(f & 255);
-            buf[p++] = (uint8_t)(f >> 8);
-            buf[p++] = cx.fplane[f];
-            buf[p++] = (cx.fneg[f] == N8) ? 1 : 0;
-            buf[p++] = cx.flen[f];
-            for (int k = 0; k < cx.flen[f]; ++k) buf[p++] = rank_of[cx.fv[cx.foff[f] + k]];
-        }
-    return p;
+    }
+    IsoScan<Caps> iso;
+    if (!cx.err) {
+        iso.run(cx);
+        if (iso.nvi > 255 || iso.nfi > 255 || iso.nfv > 65535) cx.err = 1;
+    }
+    if (cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
+    if (cx.err == 1 && !last_tier) return false;
+    if (cx.err) {
+        if (atomicCAS(&gc->err, 0, cx.err == 1 ? RIN_ERR_CAPACITY : RIN_ERR_ARRANGEMENT) == 0)
+            gc->err_tet = act_tet[a];
+        rec_ref[a] = REF_GENERAL; // offset 0: the arena starts with an empty record
+        return true;
+    }
+    const uint32_t sz = rec_size_ia(iso.nvi, iso.nfi, iso.nfv);
+    const uint32_t szal = (sz + 3u) & ~3u;
+    const uint32_t off = atomicAdd(&gc->arena_top, szal);
+    if (off + szal > arena_cap) {
+        gc->arena_overflow = 1;
+        rec_ref[a] = REF_GENERAL;
+        return true;
+    }
+    iso.write(cx, arena + off);
+    rec_ref[a] = REF_GENERAL | (off >> 2);
+    return true;
 }
 
-constexpr int GEN_THREADS = 64;
-constexpr int GEN_REC_CAP = 4096;
-
+// Small tier: complexes in shared memory, `lanes` active lanes per warp (few lanes = little
+// divergence when there are only a handful of general tets, the usual case).
+constexpr int GEN_SMALL_WARPS = 4;
 template <int W>
-__global__ void __launch_bounds__(GEN_THREADS) general_ia_kernel(const uint4* __restrict__ tets,
-    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
-    const uint32_t* __restrict__ general_list, const double* __restrict__ vals, uint32_t V,
+__global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_ia_small_kernel(
+    const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet,
+    const uint32_t* __restrict__ act_mask, uint32_t cap, const uint32_t* __restrict__ small_list,
+    uint32_t* __restrict__ ovf_list, int lanes, const double* __restrict__ vals, uint32_t V,
     uint8_t* __restrict__ arena, uint32_t arena_cap, uint32_t* __restrict__ rec_ref,
     GeneralCounters* __restrict__ gc)
 {
-    const uint32_t n = gc->n_general;
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    IAComplex<IACapsSmall>* s_cx = reinterpret_cast<IAComplex<IACapsSmall>*>(s_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= lanes) return;
+    const uint32_t n = gc->n_small;
+    const uint32_t slots = gridDim.x * GEN_SMALL_WARPS * lanes;
+    IAComplex<IACapsSmall>& cx = s_cx[warp * lanes + lane];
+    for (uint32_t g = (blockIdx.x * GEN_SMALL_WARPS + warp) * lanes + lane; g < n; g += slots) {
+        const uint32_t a = small_list[g];
+        if (!general_ia_one<IACapsSmall, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap,
+                rec_ref, gc, false))
+            ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
+    }
+}
+
+// Big tier: complexes in per-thread local memory.
+constexpr int GEN_THREADS = 64;
+template <int W>
+__global__ void __launch_bounds__(GEN_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ ovf_list,
+    const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc)
+{
+    const uint32_t nb = gc->n_big, n = nb + gc->n_ovf;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
-        const uint32_t a = general_list[g];
-        const uint4 tv = __ldg(&tets[act_tet[a]]);
         IAComplex<IACaps> cx;
-        cx.init();
-        for (int w = 0; w < W; ++w) {
-            uint32_t mm = act_mask[(size_t)w * cap + a];
-            while (mm) {
-                int f = w * 32 + __ffs(mm) - 1;
-                mm &= mm - 1;
-                double pv[4];
-                pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
-                pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
-                pv[2] = __ldg(&vals[(size_t)f * V + tv.z]);
-                pv[3] = __ldg(&vals[(size_t)f * V + tv.w]);
-                cx.insert(pv);
-            }
-        }
-        uint8_t buf[GEN_REC_CAP];
-        int sz = 0;
-        if (!cx.err) {
-            sz = ia_write_iso_record(cx, buf, GEN_REC_CAP);
-            if (sz == 0) cx.err = 1;
-        }
-        if (cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
-        if (cx.err) {
-            if (atomicCAS(&gc->err, 0, cx.err == 1 ? RIN_ERR_CAPACITY : RIN_ERR_ARRANGEMENT) == 0)
-                gc->err_tet = act_tet[a];
-            rec_ref[a] = REF_GENERAL; // offset 0: the arena starts with an empty record
-            continue;
-        }
-        const uint32_t szal = (uint32_t(sz) + 3u) & ~3u;
-        const uint32_t off = atomicAdd(&gc->arena_top, szal);
-        if (off + szal > arena_cap) {
-            gc->arena_overflow = 1;
-            rec_ref[a] = REF_GENERAL;
-            continue;
-        }
-        for (int i = 0; i < sz; ++i) arena[off + i] = buf[i];
-        rec_ref[a] = REF_GENERAL | (off >> 2);
+        const uint32_t a = g < nb ? big_list[g] : ovf_list[g - nb];
+        general_ia_one<IACaps, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref, gc,
+            true);
     }
 }
 
@@ -567,25 +629,39 @@ __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restr
     }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint4 run = make_uint4(0, 0, 0, 0);
-        for (int w = 0; w < 8; ++w) {
-            uint4 t = s_warp[w];
-            s_warp[w] = run;
-            run.x += t.x;
-            run.y += t.y;
-            run.z += t.z;
-            run.w += t.w;
+    if (warp == 0) {
+        // exclusive prefix of the 8 warp totals (lanes 0..7), block total in lane 7
+        uint4 t = (lane < 8) ? s_warp[lane] : make_uint4(0, 0, 0, 0), x8 = t;
+        for (int o = 1; o < 8; o <<= 1) {
+            uint4 y;
+            y.x = __shfl_up_sync(0xffffffffu, x8.x, o);
+            y.y = __shfl_up_sync(0xffffffffu, x8.y, o);
+            y.z = __shfl_up_sync(0xffffffffu, x8.z, o);
+            y.w = __shfl_up_sync(0xffffffffu, x8.w, o);
+            if (lane >= o) {
+                x8.x += y.x;
+                x8.y += y.y;
+                x8.z += y.z;
+                x8.w += y.w;
+            }
         }
+        if (lane < 8) s_warp[lane] = make_uint4(x8.x - t.x, x8.y - t.y, x8.z - t.z, x8.w - t.w);
+        uint4 run;
+        run.x = __shfl_sync(0xffffffffu, x8.x, 7);
+        run.y = __shfl_sync(0xffffffffu, x8.y, 7);
+        run.z = __shfl_sync(0xffffffffu, x8.z, 7);
+        run.w = __shfl_sync(0xffffffffu, x8.w, 7);
         uint32_t e0, e1, e2, e3;
-        tile_lookback(statusA, (int)tile, run.x, run.y, e0, e1);
-        tile_lookback(statusB, (int)tile, run.z, run.w, e2, e3);
-        s_base = make_uint4(e0, e1, e2, e3);
-        if (tile == (n_active + 255) / 256 - 1) {
-            tot->n_cand = e0 + run.x;
-            tot->n_faces = e1 + run.y;
-            tot->n_fv = e2 + run.z;
-            tot->n_funcs = e3 + run.w;
+        tile_lookback_warp(statusA, (int)tile, run.x, run.y, e0, e1);
+        tile_lookback_warp(statusB, (int)tile, run.z, run.w, e2, e3);
+        if (lane == 0) {
+            s_base = make_uint4(e0, e1, e2, e3);
+            if (tile == (n_active + 255) / 256 - 1) {
+                tot->n_cand = e0 + run.x;
+                tot->n_faces = e1 + run.y;
+                tot->n_fv = e2 + run.z;
+                tot->n_funcs = e3 + run.w;
+            }
         }
     }
     __syncthreads();
@@ -692,9 +768,30 @@ __global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ 
             const uint32_t local = p[0] | (p[1] << 8);
             const int sp = p[2], bnd = p[3] & 1, n = p[4];
             // func_index.first = func_in_tet[supporting_plane - 4 + start] (:249,:258); for a face
-            // coplanar with a tet face sp < 4 and the reference's index wraps to an earlier CRS
-            // entry: resolved in finalize_faces (needs the CRS), flagged here by fn = 0xfffffff0|sp
-            const uint32_t f = (sp > 3) ? (uint32_t)nth_set_bit(m, W, sp - 4) : (0xfffffff0u | sp);
+            // coplanar with a tet face sp < 4 and the reference's index wraps to an earlier CRS entry
+            uint32_t f;
+            if (sp > 3)
+                f = (uint32_t)nth_set_bit(m, W, sp - 4);
+            else {
+                // QUIRK kept from the reference: CRS entry (start + sp - 4) belongs to an earlier tet
+                f = NONE32;
+                int back = 4 - sp; // how many CRS entries before this tet's start
+                for (uint32_t ap = a; ap > 0 && back > 0;) {
+                    --ap;
+                    uint32_t mp[W];
+                    int kp = 0;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        mp[w] = act_mask[(size_t)w * cap + ap];
+                        kp += __popc(mp[w]);
+                    }
+                    if (back <= kp) {
+                        f = (uint32_t)nth_set_bit(mp, W, kp - back);
+                        back = 0;
+                    } else
+                        back -= kp;
+                }
+            }
             face_hdr[o.y + j] = make_uint4(t, local | ((uint32_t)n << 16) | ((uint32_t)bnd << 24), f, fvo);
             for (int k = 0; k < n; ++k) fv_ref[fvo + k] = o.x + p[5 + k];
             fvo += n;
@@ -774,17 +871,20 @@ __global__ void __launch_bounds__(256) rank_reps_kernel(const uint32_t* __restri
     }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned run = 0;
-        for (int w = 0; w < 8; ++w) {
-            unsigned t = s_warp[w];
-            s_warp[w] = run;
-            run += t;
+    if (warp == 0) {
+        unsigned t = (lane < 8) ? s_warp[lane] : 0, x8 = t;
+        for (int o = 1; o < 8; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x8, o);
+            if (lane >= o) x8 += y;
         }
+        if (lane < 8) s_warp[lane] = x8 - t;
+        const unsigned run = __shfl_sync(0xffffffffu, x8, 7);
         uint32_t e0, e1;
-        tile_lookback(status, (int)tile, run, 0, e0, e1);
-        s_base = e0;
-        if (tile == (n + 256 * ITEMS - 1) / (256 * ITEMS) - 1) *n_unique = e0 + run;
+        tile_lookback_warp(status, (int)tile, run, 0, e0, e1);
+        if (lane == 0) {
+            s_base = e0;
+            if (tile == (n + 256 * ITEMS - 1) / (256 * ITEMS) - 1) *n_unique = e0 + run;
+        }
     }
     __syncthreads();
     unsigned id = s_base + s_warp[warp] + x - cnt;
@@ -912,6 +1012,179 @@ __global__ void __launch_bounds__(256) write_faces_kernel(const uint4* __restric
         f_tets[2 * (size_t)i + 1] = h.y & 0xffffu;
         f_funcs[2 * (size_t)i] = h.z;
         f_funcs[2 * (size_t)i + 1] = NONE32;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Degenerate inputs only: iso-faces lying on a tet boundary are shared by two tets and are
+// deduplicated by (smallest, second smallest, largest) vertex id; the first tet keeps the face and
+// collects the (tet, local face) pairs of the others (src/extract_mesh.cpp:240-253,
+// compute_iso_face_key src/extract_mesh.h:68-92).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bface_keys_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    const uint32_t* __restrict__ fverts, uint4* __restrict__ fkeys)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = face_hdr[i];
+        if (!((h.y >> 24) & 1)) continue;
+        const int nv = (h.y >> 16) & 255;
+        uint32_t mn = fverts[h.w], mx = mn;
+        int mn_pos = 0;
+        for (int k = 1; k < nv; ++k) {
+            uint32_t v = fverts[h.w + k];
+            if (v < mn) {
+                mn = v;
+                mn_pos = k;
+            } else if (v > mx)
+                mx = v;
+        }
+        uint32_t second = mx + 1;
+        for (int k = 0; k < nv; ++k) {
+            uint32_t v = fverts[h.w + k];
+            if (k != mn_pos && v < second) second = v;
+        }
+        fkeys[i] = make_uint4(mn, second, mx, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) bface_insert_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    const uint4* __restrict__ fkeys, uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ slot_of)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        if (!((face_hdr[c].y >> 24) & 1)) {
+            slot_of[c] = NONE32;
+            continue;
+        }
+        const uint4 k = fkeys[c];
+        uint32_t h = hash4(k) & mask;
+        for (;;) {
+            uint32_t cur = table[h];
+            if (cur == NONE32) {
+                cur = atomicCAS(&table[h], NONE32, c);
+                if (cur == NONE32) break;
+            }
+            if (key_eq(fkeys[cur], k)) {
+                atomicMin(&table[h], c);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+        slot_of[c] = h;
+    }
+}
+
+// frep[i] = representative face; ndup[rep] counts the later duplicates
+__global__ void __launch_bounds__(256) bface_reps_kernel(const uint32_t* __restrict__ table,
+    const uint32_t* __restrict__ slot_of, uint32_t n, uint32_t* __restrict__ frep, uint32_t* __restrict__ ndup)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = slot_of[i];
+        const uint32_t r = (s == NONE32) ? i : table[s];
+        frep[i] = r;
+        if (r != i) atomicAdd(&ndup[r], 1u);
+    }
+}
+
+// single-block exclusive scan of (kept, kept ? nverts : 0, kept ? 1 + ndup : 0) -> pos[i]
+__global__ void __launch_bounds__(1024) bface_scan_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    const uint32_t* __restrict__ frep, const uint32_t* __restrict__ ndup, uint4* __restrict__ pos,
+    uint32_t* __restrict__ totals)
+{
+    __shared__ uint32_t s_w[32][3];
+    __shared__ uint32_t s_run[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 3) s_run[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t c[3] = {0, 0, 0};
+        if (i < n && frep[i] == i) {
+            c[0] = 1;
+            c[1] = (face_hdr[i].y >> 16) & 255;
+            c[2] = 1 + ndup[i];
+        }
+        uint32_t x[3] = {c[0], c[1], c[2]};
+        for (int o = 1; o < 32; o <<= 1)
+            for (int q = 0; q < 3; ++q) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, x[q], o);
+                if (lane >= o) x[q] += y;
+            }
+        if (lane == 31)
+            for (int q = 0; q < 3; ++q) s_w[warp][q] = x[q];
+        __syncthreads();
+        if (warp == 0) {
+            for (int q = 0; q < 3; ++q) {
+                uint32_t t = s_w[lane][q], y = t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t z = __shfl_up_sync(0xffffffffu, y, o);
+                    if (lane >= o) y += z;
+                }
+                s_w[lane][q] = y - t;
+            }
+        }
+        __syncthreads();
+        if (i < n)
+            pos[i] = make_uint4(s_run[0] + s_w[warp][0] + x[0] - c[0], s_run[1] + s_w[warp][1] + x[1] - c[1],
+                s_run[2] + s_w[warp][2] + x[2] - c[2], 0);
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            for (int q = 0; q < 3; ++q) s_run[q] += s_w[31][q] + x[q];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) totals[threadIdx.x] = s_run[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) bface_write_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    const uint32_t* __restrict__ fverts_in, const uint32_t* __restrict__ frep, const uint4* __restrict__ pos,
+    uint32_t* __restrict__ cursor, const uint32_t* __restrict__ totals, uint32_t* __restrict__ f_off,
+    uint32_t* __restrict__ f_verts, uint32_t* __restrict__ f_toff, uint32_t* __restrict__ f_tets,
+    uint32_t* __restrict__ f_funcs)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+        if (i == n) {
+            f_off[totals[0]] = totals[1];
+            f_toff[totals[0]] = totals[2];
+            continue;
+        }
+        const uint4 h = face_hdr[i];
+        const uint32_t r = frep[i];
+        if (r == i) {
+            const uint4 p = pos[i];
+            const int nv = (h.y >> 16) & 255;
+            f_off[p.x] = p.y;
+            for (int k = 0; k < nv; ++k) f_verts[p.y + k] = fverts_in[h.w + k];
+            f_toff[p.x] = p.z;
+            f_tets[2 * (size_t)p.z] = h.x;
+            f_tets[2 * (size_t)p.z + 1] = h.y & 0xffffu;
+            f_funcs[2 * (size_t)p.x] = h.z;
+            f_funcs[2 * (size_t)p.x + 1] = NONE32;
+        } else {
+            const uint4 p = pos[r];
+            const uint32_t slot = p.z + 1 + atomicAdd(&cursor[r], 1u);
+            f_tets[2 * (size_t)slot] = h.x;
+            f_tets[2 * (size_t)slot + 1] = h.y & 0xffffu;
+        }
+    }
+}
+
+// duplicates were appended in arbitrary order: restore (tet, local face) order per face
+__global__ void __launch_bounds__(256) bface_sort_pairs_kernel(uint32_t n_faces, const uint32_t* __restrict__ f_toff,
+    uint32_t* __restrict__ f_tets)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_faces; j += gridDim.x * blockDim.x) {
+        const uint32_t b = f_toff[j] + 1, e = f_toff[j + 1];
+        for (uint32_t x = b + 1; x < e; ++x) {
+            uint32_t t0 = f_tets[2 * (size_t)x], t1 = f_tets[2 * (size_t)x + 1];
+            uint32_t y = x;
+            while (y > b && (f_tets[2 * (size_t)(y - 1)] > t0 ||
+                                (f_tets[2 * (size_t)(y - 1)] == t0 && f_tets[2 * (size_t)(y - 1) + 1] > t1))) {
+                f_tets[2 * (size_t)y] = f_tets[2 * (size_t)(y - 1)];
+                f_tets[2 * (size_t)y + 1] = f_tets[2 * (size_t)(y - 1) + 1];
+                --y;
+            }
+            f_tets[2 * (size_t)y] = t0;
+            f_tets[2 * (size_t)y + 1] = t1;
+        }
     }
 }
 

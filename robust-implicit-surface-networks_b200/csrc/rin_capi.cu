@@ -104,9 +104,10 @@ struct rin_ctx
     // work buffers
     DevBuf counters; // small zeroed block: FilterCounters | GeneralCounters | ScanTotals | misc
     DevBuf status;   // look-back status words
-    DevBuf act_tet, act_mask, rec_ref, general_list, arena, offs;
+    DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
+    DevBuf tmp_fverts, fkeys, frep, fdup, fpos; // degenerate boundary-face dedup
     // outputs
     DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
@@ -189,8 +190,8 @@ void rin_destroy(rin_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->counters,
-        &c->status, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->arena, &c->offs,
-        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid,
+        &c->status, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
+        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->fkeys, &c->frep, &c->fdup, &c->fpos,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob};
     for (auto* b : bufs) b->release();
@@ -551,6 +552,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
     CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
     CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
+    CK(c->big_list.ensure((size_t)std::max(A, 1u) * 8)); // [big | small-tier overflow]
     CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
     LutView lv{c->lut_ia.lut1.as<uint16_t>(), c->lut_ia.lut2.as<uint16_t>(), c->lut_ia.blob.as<uint8_t>(),
         c->lut_ia.blob_bytes};
@@ -559,21 +561,33 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         classify_ia_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
             c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vmask.as<uint2>(),
             c->vals.as<double>(), V, lv, use_lookup, use_secondary, c->rec_ref.as<uint32_t>(),
-            c->general_list.as<uint32_t>(), &dctr->gen.n_general, &dctr->n_exact_classify, nullptr);
+            c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_exact_classify,
+            nullptr);
         CK(cudaGetLastError());
     }
 
-    // ---- K4: general kernel (arena grows on overflow)
+    // ---- K4: general kernels (arena grows on overflow)
     CK(cudaEventRecord(c->ev[ST_GENERAL], s));
     if (A) {
+        const uint32_t est =
+            use_lookup ? (use_secondary ? h.filt.n_kmore : h.filt.n_kmore + h.filt.n_k2) : A;
+        const int small_blocks = (int)std::max<uint32_t>(
+            1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
+        const size_t small_smem = GEN_SMALL_WARPS * sizeof(IAComplex<IACapsSmall>);
         for (int attempt = 0;; ++attempt) {
             if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
+            const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
             const unsigned top0 = 4;
             CK(cudaMemsetAsync(c->arena.p, 0, 4, s));
             CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
-            general_ia_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(), c->act_tet.as<uint32_t>(),
-                c->act_mask.as<uint32_t>(), c->act_cap, c->general_list.as<uint32_t>(), c->vals.as<double>(),
-                V, c->arena.as<uint8_t>(), (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u),
+            // small tier: one tet per warp, complex in shared memory; capacity overflow -> ovf list
+            general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
+                c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
+                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A, 1, c->vals.as<double>(), V,
+                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
+            general_ia_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
+                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
+                c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
                 c->rec_ref.as<uint32_t>(), &dctr->gen);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(&h.gen, &dctr->gen, sizeof(GeneralCounters), cudaMemcpyDeviceToHost, s));
@@ -587,6 +601,8 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             CK(c->arena.ensure((size_t)h.gen.arena_top + h.gen.arena_top / 8 + 4096));
             GeneralCounters z{};
             z.n_general = h.gen.n_general;
+            z.n_small = h.gen.n_small;
+            z.n_big = h.gen.n_big;
             CK(cudaMemcpyAsync(&dctr->gen, &z, sizeof(GeneralCounters), cudaMemcpyHostToDevice, s));
         }
     }
@@ -673,22 +689,65 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(c->f_toff.ensure((size_t)(NFc + 1) * 4));
     CK(c->f_tets.ensure((size_t)std::max(NFc, 1u) * 8));
     CK(c->f_funcs.ensure((size_t)std::max(NFc, 1u) * 8));
-    if (h.n_bndry_faces)
-        return fail(RIN_ERR_STATE, "iso-faces on tet boundaries (degenerate input): dedup path not built yet");
-    if (NFV)
+    uint32_t NF = NFc, NFVout = NFV, NFT = NFc;
+    if (!h.n_bndry_faces) {
+        if (NFV)
+            remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
+                c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
+        write_faces_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
+            NFV, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(),
+            c->f_funcs.as<uint32_t>());
+        CK(cudaGetLastError());
+    } else {
+        // degenerate input: iso-faces on tet boundaries are shared between two tets
+        uint32_t tsize = 1024;
+        while (tsize < 2 * NFc) tsize <<= 1;
+        CK(c->table.ensure((size_t)tsize * 4));
+        CK(c->slot_of.ensure((size_t)NFc * 4));
+        CK(c->tmp_fverts.ensure((size_t)NFV * 4));
+        CK(c->fkeys.ensure((size_t)NFc * 16));
+        CK(c->frep.ensure((size_t)NFc * 4));
+        CK(c->fdup.ensure((size_t)NFc * 8 + 16)); // ndup | cursor | totals
+        CK(c->fpos.ensure((size_t)NFc * 16));
+        uint32_t* ndup = c->fdup.as<uint32_t>();
+        uint32_t* cursor = ndup + NFc;
+        uint32_t* totals = cursor + NFc;
+        CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
+        CK(cudaMemsetAsync(c->fdup.p, 0, (size_t)NFc * 8 + 16, s));
+        const int g = grid_for(NFc, 256, sm, 8);
         remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
-            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
-    write_faces_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, NFV,
-        c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>());
-    CK(cudaGetLastError());
+            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->tmp_fverts.as<uint32_t>());
+        bface_keys_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->tmp_fverts.as<uint32_t>(),
+            c->fkeys.as<uint4>());
+        bface_insert_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->fkeys.as<uint4>(),
+            c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
+        bface_reps_kernel<<<g, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NFc,
+            c->frep.as<uint32_t>(), ndup);
+        bface_scan_kernel<<<1, 1024, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
+            c->fpos.as<uint4>(), totals);
+        bface_write_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
+            c->tmp_fverts.as<uint32_t>(), c->frep.as<uint32_t>(), c->fpos.as<uint4>(), cursor, totals,
+            c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(),
+            c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>());
+        CK(cudaGetLastError());
+        uint32_t ht[3];
+        CK(cudaMemcpyAsync(ht, totals, 12, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        NF = ht[0];
+        NFVout = ht[1];
+        NFT = ht[2];
+        bface_sort_pairs_kernel<<<grid_for(NF, 256, sm, 8), 256, 0, s>>>(NF, c->f_toff.as<uint32_t>(),
+            c->f_tets.as<uint32_t>());
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(c->ev[ST_COUNT], s));
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
 
     n.num_verts = NV;
-    n.num_faces = NFc;
-    n.num_face_verts = NFV;
-    n.num_face_tets = NFc;
+    n.num_faces = NF;
+    n.num_face_verts = NFVout;
+    n.num_face_tets = NFT;
     n.num_exact_fallbacks = (uint64_t)h.gen.n_exact + h.n_exact_classify;
     return RIN_OK;
 }
@@ -789,7 +848,7 @@ int build_ia_tables(rin_ctx* c)
     LutView lv{d_l1.as<uint16_t>(), d_l2.as<uint16_t>(), nullptr, 0};
     classify_ia_kernel<1><<<grid_for(NWT, 256, sm, 4), 256, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
         d_act_mask.as<uint32_t>(), NWT, NWT, d_vm.as<uint2>(), d_vals.as<double>(), Vw, lv, 1, 0,
-        d_ref.as<uint32_t>(), d_gl.as<uint32_t>(), &dctr->gen.n_general, &dctr->n_exact_classify,
+        d_ref.as<uint32_t>(), d_gl.as<uint32_t>(), d_gl.as<uint32_t>(), &dctr->gen, &dctr->n_exact_classify,
         d_keys.as<int>());
     CKC(cudaGetLastError());
     std::vector<int> keys(NWT);
@@ -815,13 +874,14 @@ int build_ia_tables(rin_ctx* c)
     CKC(cudaMemcpyAsync(d_gl.p, chosen.data(), (size_t)NCH * 4, cudaMemcpyHostToDevice, s));
     GeneralCounters g0{};
     g0.n_general = NCH;
+    g0.n_big = NCH;
     g0.arena_top = 4;
     CKC(cudaMemcpyAsync(&dctr->gen, &g0, sizeof(g0), cudaMemcpyHostToDevice, s));
     CKC(d_arena.ensure((size_t)NCH * 256 + 4096));
     CKC(cudaMemsetAsync(d_arena.p, 0, 4, s));
-    general_ia_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
-        d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), d_vals.as<double>(), Vw, d_arena.as<uint8_t>(),
-        (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
+    general_ia_big_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
+        d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), d_gl.as<uint32_t>(), d_vals.as<double>(), Vw,
+        d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
     CKC(cudaGetLastError());
     GeneralCounters g1;
     CKC(cudaMemcpyAsync(&g1, &dctr->gen, sizeof(g1), cudaMemcpyDeviceToHost, s));
