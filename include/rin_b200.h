@@ -137,6 +137,8 @@ int rin_download_grid(rin_ctx*, double* pts, uint32_t* tets);
 /* per-stage device times of the last run in milliseconds (CUDA events); names via rin_stage_name */
 int rin_get_stage_times(const rin_ctx*, float* ms, int capacity);
 const char* rin_stage_name(int i);
+/* CUDA-event durations of the last run: the eval and filter kernels alone, and the whole pass */
+int rin_get_kernel_times(const rin_ctx*, float* eval_ms, float* filter_ms, float* total_ms);
 int rin_num_stages(void);
 
 /* ---- per-tet complexes on demand (host topology stages need O(#chains+#components) tets) --- */

@@ -60,6 +60,26 @@ __global__ void narrow_tets_kernel(const uint64_t* __restrict__ in, uint64_t n, 
     }
 }
 
+// min / max vertex id referenced by a tet range (slab sharding evaluates only that vertex range)
+__global__ void vertex_range_kernel(const uint4* __restrict__ tets, uint32_t t_first, uint32_t n,
+    uint32_t* __restrict__ minmax)
+{
+    uint32_t lo = 0xffffffffu, hi = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 t = tets[t_first + i];
+        lo = min(min(lo, t.x), min(min(t.y, t.z), t.w));
+        hi = max(max(hi, t.x), max(max(t.y, t.z), t.w));
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[0], lo);
+        atomicMax(&minmax[1], hi);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: evaluate every function at every vertex (SoA double[F][V]) + per-vertex sign bit masks.
 // Replaces load_functions (app/implicit_arrangement.cpp:57-64) and the "func signs" loop

@@ -86,6 +86,17 @@ struct Lut
 
 } // namespace
 
+namespace {
+struct Counters
+{
+    FilterCounters filt;
+    GeneralCounters gen;
+    ScanTotals scan;
+    unsigned rank_tile, n_unique, n_bndry_faces, n_exact_classify;
+    unsigned long long n_zero;
+};
+} // namespace
+
 struct rin_ctx
 {
     int device = 0;
@@ -118,19 +129,15 @@ struct rin_ctx
     uint32_t last_flags = 0;
     float stage_ms[ST_COUNT] = {};
     cudaEvent_t ev[ST_COUNT + 1] = {};
+    cudaEvent_t kev[4] = {}; // tight brackets around the eval and filter kernels
+    float kernel_ms[2] = {};
+    float total_ms = 0;
+    uint32_t v_first = 0, v_count = 0; // vertex range touched by the tet range
     bool ran = false;
 };
 
 namespace {
 
-struct Counters
-{
-    FilterCounters filt;
-    GeneralCounters gen;
-    ScanTotals scan;
-    unsigned rank_tile, n_unique, n_bndry_faces, n_exact_classify;
-    unsigned long long n_zero;
-};
 
 int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8)
 {
@@ -180,6 +187,7 @@ int rin_create(int device, rin_ctx** out)
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    for (auto& e : c->kev) CK(cudaEventCreate(&e));
     *out = c;
     return RIN_OK;
 }
@@ -196,6 +204,8 @@ void rin_destroy(rin_ctx* c)
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob};
     for (auto* b : bufs) b->release();
     for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -226,6 +236,7 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
     c->T = n_tets;
     c->t_first = 0;
     c->t_count = n_tets;
+    c->v_first = c->v_count = 0;
     c->have_values = false;
     c->ran = false;
     return RIN_OK;
@@ -248,6 +259,7 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     c->T = T;
     c->t_first = 0;
     c->t_count = T;
+    c->v_first = c->v_count = 0;
     c->have_values = false;
     c->ran = false;
     return RIN_OK;
@@ -260,6 +272,23 @@ int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
     if (first + count > c->T) return fail(RIN_ERR_ARG, "tet range out of bounds");
     c->t_first = first;
     c->t_count = count;
+    c->v_first = 0;
+    c->v_count = 0;
+    if (first != 0 || count != c->T) {
+        // vertex id range referenced by the tet range: only these vertices are evaluated
+        CK(cudaSetDevice(c->device));
+        CK(c->counters.ensure(sizeof(Counters)));
+        uint32_t init[2] = {0xffffffffu, 0u};
+        uint32_t* d = c->counters.as<uint32_t>();
+        CK(cudaMemcpyAsync(d, init, 8, cudaMemcpyHostToDevice, c->stream));
+        vertex_range_kernel<<<grid_for(count, 256, c->sm_count), 256, 0, c->stream>>>(c->tets.as<uint4>(),
+            (uint32_t)first, (uint32_t)count, d);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(init, d, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->v_first = init[0];
+        c->v_count = init[1] - init[0] + 1;
+    }
     return RIN_OK;
 }
 
@@ -417,6 +446,14 @@ int rin_get_stage_times(const rin_ctx* c, float* ms, int capacity)
     for (int i = 0; i < capacity && i < ST_COUNT; ++i) ms[i] = c->stage_ms[i];
     return RIN_OK;
 }
+int rin_get_kernel_times(const rin_ctx* c, float* eval_ms, float* filter_ms, float* total_ms)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (eval_ms) *eval_ms = c->kernel_ms[0];
+    if (filter_ms) *filter_ms = c->kernel_ms[1];
+    if (total_ms) *total_ms = c->total_ms;
+    return RIN_OK;
+}
 const char* rin_stage_name(int i)
 {
     return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : "";
@@ -497,16 +534,19 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(c->vmask.ensure((size_t)V * W * 8));
     CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
     CK(cudaEventRecord(c->ev[ST_EVAL], s));
+    const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
+    CK(cudaEventRecord(c->kev[0], s));
     if (c->have_funcs) {
         size_t smem = F * sizeof(rin_func_desc);
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eval_functions_kernel<<<grid_for(V, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), 0, V, V,
+        eval_functions_kernel<<<grid_for(vc, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), vf, vc, V,
             c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
     } else {
-        ingest_values_kernel<<<grid_for(V, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), 0, V, V, F,
+        ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
             negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
     }
+    CK(cudaEventRecord(c->kev[1], s));
     CK(cudaGetLastError());
 
     // ---- K2: filter + ordered compaction
@@ -520,9 +560,11 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
         CK(c->status.ensure((size_t)std::max<uint32_t>(n_tiles, 1) * 8 * 2 + 64));
         CK(cudaMemsetAsync(c->status.p, 0, (size_t)n_tiles * 8, s));
+        CK(cudaEventRecord(c->kev[2], s));
         filter_ia_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
             c->vmask.as<uint2>(), V, last_mask, c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(),
             c->act_cap, c->status.as<unsigned long long>(), &dctr->filt);
+        CK(cudaEventRecord(c->kev[3], s));
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -743,6 +785,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventRecord(c->ev[ST_COUNT], s));
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
+    CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+    CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
     n.num_verts = NV;
     n.num_faces = NF;

@@ -66,6 +66,8 @@ def lib():
         L.rin_download_values.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_download_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rin_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.rin_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float)]
         L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Counts)]
         L.rin_get_complexes.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -182,6 +184,11 @@ class Context:
         tets = np.empty((T, 4), np.uint32)
         self._check(lib().rin_download_grid(self._h, pts.ctypes.data, tets.ctypes.data))
         return pts, tets
+
+    def kernel_times(self):
+        e, f, t = C.c_float(), C.c_float(), C.c_float()
+        self._check(lib().rin_get_kernel_times(self._h, C.byref(e), C.byref(f), C.byref(t)))
+        return {"eval_ms": e.value, "filter_ms": f.value, "total_ms": t.value}
 
     def stage_times(self):
         k = lib().rin_num_stages()
