@@ -319,7 +319,7 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
             for (int c = 0; c < 4; ++c)
                 if (!on_bndry[c]) corners.push_back(tv[c]);
             if (nb == 0) { // interior: never shared (:185-195), corners in tet order
-                gid[j] = new_vert(t, j, 4,
+                gid[j] = new_vert(t + tet_first, j, 4,
                     {int64_t(tv[0]), int64_t(tv[1]), int64_t(tv[2]), int64_t(tv[3])}, fi);
                 continue;
             }
@@ -336,7 +336,7 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
                 for (size_t c = 0; c < corners.size(); ++c) sv[c] = int64_t(corners[c]);
                 std::array<int64_t, 3> fstore = {NONE64, NONE64, NONE64};
                 if (nb != 3) fstore = fi; // on-vertex case leaves func_indices untouched (:216-222)
-                new_vert(t, j, int(corners.size()), sv, fstore);
+                new_vert(t + tet_first, j, int(corners.size()), sv, fstore);
             }
             gid[j] = ins.first->second;
         }
@@ -359,13 +359,13 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
                 key[2] = uint64_t(k3[2]);
                 auto ins = face_map.try_emplace(key, face_vlist.size());
                 if (!ins.second) {
-                    face_tlist[ins.first->second].push_back(int64_t(t));
+                    face_tlist[ins.first->second].push_back(int64_t(t + tet_first));
                     face_tlist[ins.first->second].push_back(int64_t(f));
                     continue;
                 }
             }
             face_vlist.push_back(fv);
-            face_tlist.push_back({int64_t(t), int64_t(f)});
+            face_tlist.push_back({int64_t(t + tet_first), int64_t(f)});
             ffunc.push_back(fn);
             ffunc.push_back(NONE64);
         }

@@ -10,21 +10,17 @@ constexpr uint32_t NONE32 = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------
 // Iso record: the part of a per-tet complex that the mesh extraction consumes
 // (/root/reference/src/extract_mesh.cpp:60-261 reads only iso vertices and iso faces).
-//   byte 0      n_iso_verts
-//   byte 1      n_iso_faces
-//   byte 2,3    total number of face-vertex entries (u16 LE)
-//   n_iso_verts x { local vertex id, plane0, plane1, plane2 }            (planes ascending)
-//   n_iso_faces x { local face id lo, hi, supporting plane, flags, n, n x iso-vertex rank }
-//                   flags bit0: face lies on the tet boundary (negative_cell == None)
-// IA plane ids / MI material ids: 0..3 simplex faces, 4+j the j-th active function of the tet.
-// MI records carry 4 material ids per vertex and {pos label, neg label} instead of
-// {supporting plane}: see mi_complex.cuh.
+// A sequence of 32-bit words (records are 4-byte aligned so that one load fetches one entry):
+//   word 0                 n_iso_verts | n_iso_faces << 8 | n_face_vertex_entries << 16
+//   n_iso_verts words      local vertex id | plane0 << 8 | plane1 << 16 | plane2 << 24  (ascending)
+//   per iso face           local face id (16) | supporting plane << 16 | n << 24 | boundary << 31
+//                          followed by ceil(n/4) words of iso-vertex ranks, one byte each
+// boundary: the face lies on the tet boundary (negative_cell == None).
+// Plane ids: 0..3 simplex faces, 4+j the j-th active function of the tet.
 // ---------------------------------------------------------------------------------------------
-constexpr int REC_HDR = 4;
-
-__host__ __device__ inline uint32_t rec_size_ia(int nv, int nf, int nfv)
+__host__ __device__ inline uint32_t rec_face_words(int n)
 {
-    return uint32_t(REC_HDR + 4 * nv + 5 * nf + nfv);
+    return 1u + uint32_t(n + 3) / 4u;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -186,10 +186,13 @@ __global__ void __launch_bounds__(256) ingest_values_kernel(const double* __rest
 // Replaces the "filter" loop (src/implicit_arrangement.cpp:86-116): function j is active in a tet
 // iff it is neither positive at all four vertices nor negative at all four (pos<4 && neg<4, :106).
 // Output: active tets in tet order with their W-word function masks.
-// Single pass over the 16-byte index records; tile offsets by decoupled look-back.
+// One streaming pass over the 16-byte index records writes tile-local compacted slots (no
+// inter-block dependency, hence no spinning warps); a one-block scan of the tile totals and a
+// gather over the ~7 % active tets produce the ordered list.
 // ---------------------------------------------------------------------------------------------
 constexpr int FILT_THREADS = 256;
 constexpr int FILT_ITEMS = 8;
+constexpr int FILT_BATCH = 4;
 constexpr int FILT_TILE = FILT_THREADS * FILT_ITEMS;
 
 struct FilterCounters
@@ -200,55 +203,68 @@ struct FilterCounters
     unsigned n_funcs; // sum of popcounts = |func_in_tet|
 };
 
+// Pass 1 (streams the index records): per-tile compaction into tile-local slots
+// tl_tet / tl_mask [tile * FILT_TILE + rank] and per-tile totals.  No inter-block dependency.
 template <int W>
-__global__ void __launch_bounds__(FILT_THREADS) filter_ia_kernel(const uint4* __restrict__ tets,
+__global__ void __launch_bounds__(FILT_THREADS) filter_tiles_kernel(const uint4* __restrict__ tets,
     uint32_t t_first, uint32_t t_count, const uint2* __restrict__ vmask, uint32_t V, uint32_t last_mask,
-    uint32_t* __restrict__ act_tet, uint32_t* __restrict__ act_mask, uint32_t cap,
-    volatile unsigned long long* __restrict__ status, FilterCounters* __restrict__ ctr)
+    uint32_t* __restrict__ tl_tet, uint32_t* __restrict__ tl_mask, size_t tl_stride,
+    uint2* __restrict__ tile_cnt, FilterCounters* __restrict__ ctr)
 {
-    __shared__ unsigned s_tile;
     __shared__ unsigned s_cnt[FILT_ITEMS][FILT_THREADS / 32];
-    __shared__ unsigned s_base;
+    __shared__ unsigned s_kf[FILT_THREADS / 32];
     __shared__ unsigned s_k[3];
-    if (threadIdx.x == 0) {
-        s_tile = atomicAdd(&ctr->tile_counter, 1u);
-        s_k[0] = s_k[1] = s_k[2] = 0;
-    }
-    __syncthreads();
-    const unsigned tile = s_tile;
+    const unsigned tile = blockIdx.x;
     const uint32_t base = tile * FILT_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 3) s_k[threadIdx.x] = 0;
     uint32_t m[FILT_ITEMS][W];
     unsigned ball[FILT_ITEMS];
     unsigned k1 = 0, k2 = 0, km = 0, kf = 0;
+    // batches of FILT_BATCH items: all index loads of a batch are issued before the first
+    // dependent mask gather, all gathers before the first use (memory-level parallelism)
 #pragma unroll
-    for (int j = 0; j < FILT_ITEMS; ++j) {
-        const uint32_t i = base + j * FILT_THREADS + threadIdx.x;
-        bool act = false;
+    for (int j0 = 0; j0 < FILT_ITEMS; j0 += FILT_BATCH) {
+        uint4 tv[FILT_BATCH];
 #pragma unroll
-        for (int w = 0; w < W; ++w) m[j][w] = 0;
-        if (i < t_count) {
-            const uint4 tv = __ldg(&tets[t_first + i]);
-            int k = 0;
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const uint2 a = __ldg(&vmask[(size_t)w * V + tv.x]);
-                const uint2 b = __ldg(&vmask[(size_t)w * V + tv.y]);
-                const uint2 c = __ldg(&vmask[(size_t)w * V + tv.z]);
-                const uint2 d = __ldg(&vmask[(size_t)w * V + tv.w]);
-                uint32_t mm = ~((a.x & b.x & c.x & d.x) | (a.y & b.y & c.y & d.y));
-                if (w == W - 1) mm &= last_mask;
-                m[j][w] = mm;
-                k += __popc(mm);
-            }
-            act = k > 0;
-            k1 += (k == 1);
-            k2 += (k == 2);
-            km += (k > 2);
-            kf += k;
+        for (int j = 0; j < FILT_BATCH; ++j) {
+            const uint32_t i = base + (j0 + j) * FILT_THREADS + threadIdx.x;
+            tv[j] = __ldg(&tets[t_first + min(i, t_count - 1)]);
         }
-        ball[j] = __ballot_sync(0xffffffffu, act);
-        if (lane == 0) s_cnt[j][warp] = __popc(ball[j]);
+        int kk[FILT_BATCH];
+#pragma unroll
+        for (int j = 0; j < FILT_BATCH; ++j) kk[j] = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            uint2 g[FILT_BATCH][4];
+#pragma unroll
+            for (int j = 0; j < FILT_BATCH; ++j) {
+                g[j][0] = __ldg(&vmask[(size_t)w * V + tv[j].x]);
+                g[j][1] = __ldg(&vmask[(size_t)w * V + tv[j].y]);
+                g[j][2] = __ldg(&vmask[(size_t)w * V + tv[j].z]);
+                g[j][3] = __ldg(&vmask[(size_t)w * V + tv[j].w]);
+            }
+#pragma unroll
+            for (int j = 0; j < FILT_BATCH; ++j) {
+                uint32_t mm = ~((g[j][0].x & g[j][1].x & g[j][2].x & g[j][3].x) |
+                                (g[j][0].y & g[j][1].y & g[j][2].y & g[j][3].y));
+                if (w == W - 1) mm &= last_mask;
+                const uint32_t i = base + (j0 + j) * FILT_THREADS + threadIdx.x;
+                if (i >= t_count) mm = 0;
+                m[j0 + j][w] = mm;
+                kk[j] += __popc(mm);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < FILT_BATCH; ++j) {
+            const int kq = kk[j];
+            k1 += (kq == 1);
+            k2 += (kq == 2);
+            km += (kq > 2);
+            kf += kq;
+            ball[j0 + j] = __ballot_sync(0xffffffffu, kq > 0);
+            if (lane == 0) s_cnt[j0 + j][warp] = __popc(ball[j0 + j]);
+        }
     }
     for (int o = 16; o; o >>= 1) {
         k1 += __shfl_xor_sync(0xffffffffu, k1, o);
@@ -256,58 +272,124 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_ia_kernel(const uint4* __
         km += __shfl_xor_sync(0xffffffffu, km, o);
         kf += __shfl_xor_sync(0xffffffffu, kf, o);
     }
+    if (lane == 0) s_kf[warp] = kf;
+    __syncthreads();
     if (lane == 0) {
         if (k1) atomicAdd(&s_k[0], k1);
         if (k2) atomicAdd(&s_k[1], k2);
         if (km) atomicAdd(&s_k[2], km);
     }
-    // kf goes through the look-back as the second lane (it is the CRS length prefix)
-    __shared__ unsigned s_kf[FILT_THREADS / 32];
-    if (lane == 0) s_kf[warp] = kf;
-    __syncthreads();
-    if (warp == 0) {
-        // exclusive prefix over the (item, warp) sequence, FILT_ITEMS * 8 entries, 32 per round
-        unsigned run = 0;
+    // every warp derives the exclusive prefix over the (item, warp) sequence it needs by itself
+    unsigned my_off[FILT_ITEMS];
+    unsigned run = 0;
 #pragma unroll
-        for (int r = 0; r < FILT_ITEMS * (FILT_THREADS / 32) / 32; ++r) {
-            const int e = r * 32 + lane;
-            const int j = e / (FILT_THREADS / 32), w = e % (FILT_THREADS / 32);
-            unsigned c = s_cnt[j][w], x = c;
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            s_cnt[j][w] = run + x - c;
-            run += __shfl_sync(0xffffffffu, x, 31);
+    for (int r = 0; r < FILT_ITEMS * (FILT_THREADS / 32) / 32; ++r) {
+        const int e = r * 32 + lane;
+        const unsigned c = s_cnt[e / (FILT_THREADS / 32)][e % (FILT_THREADS / 32)];
+        unsigned x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
         }
-        const unsigned total = run;
-        unsigned kft = (lane < FILT_THREADS / 32) ? s_kf[lane] : 0;
-        for (int o = 16; o; o >>= 1) kft += __shfl_xor_sync(0xffffffffu, kft, o);
-        uint32_t ea, eb;
-        tile_lookback_warp(status, (int)tile, total, kft, ea, eb);
-        if (lane == 0) {
-            s_base = ea;
-            if (total) {
-                atomicAdd(&ctr->n_active, total);
-                atomicAdd(&ctr->n_funcs, kft);
-                if (s_k[0]) atomicAdd(&ctr->n_k1, s_k[0]);
-                if (s_k[1]) atomicAdd(&ctr->n_k2, s_k[1]);
-                if (s_k[2]) atomicAdd(&ctr->n_kmore, s_k[2]);
-            }
+        const unsigned excl = run + x - c;
+        // entry (j, warp) lives in lane (j * 8 + warp) % 32 of round (j * 8 + warp) / 32
+#pragma unroll
+        for (int j = 0; j < FILT_ITEMS; ++j) {
+            const int idx = j * (FILT_THREADS / 32) + warp;
+            if (idx / 32 == r) my_off[j] = __shfl_sync(0xffffffffu, excl, idx % 32);
         }
+        run += __shfl_sync(0xffffffffu, x, 31);
     }
-    __syncthreads();
-    const unsigned gbase = s_base;
+    const size_t tbase = (size_t)tile * FILT_TILE;
 #pragma unroll
     for (int j = 0; j < FILT_ITEMS; ++j) {
         if ((ball[j] >> lane) & 1) {
-            const unsigned pos = gbase + s_cnt[j][warp] + __popc(ball[j] & ((1u << lane) - 1));
-            if (pos < cap) {
-                act_tet[pos] = t_first + base + j * FILT_THREADS + threadIdx.x;
+            const size_t pos = tbase + my_off[j] + __popc(ball[j] & ((1u << lane) - 1));
+            tl_tet[pos] = t_first + base + j * FILT_THREADS + threadIdx.x;
 #pragma unroll
-                for (int w = 0; w < W; ++w) act_mask[(size_t)w * cap + pos] = m[j][w];
+            for (int w = 0; w < W; ++w) tl_mask[(size_t)w * tl_stride + pos] = m[j][w];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned kft = 0;
+        for (int w = 0; w < FILT_THREADS / 32; ++w) kft += s_kf[w];
+        tile_cnt[tile] = make_uint2(run, kft);
+        if (s_k[0]) atomicAdd(&ctr->n_k1, s_k[0]);
+        if (s_k[1]) atomicAdd(&ctr->n_k2, s_k[1]);
+        if (s_k[2]) atomicAdd(&ctr->n_kmore, s_k[2]);
+    }
+}
+
+// Pass 2 (one block): exclusive scan of the per-tile totals -> tile_off[tile] = (first active
+// index, first CRS index); tile_off[n_tiles] = totals.
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(const uint2* __restrict__ tile_cnt, uint32_t n_tiles,
+    uint2* __restrict__ tile_off, FilterCounters* __restrict__ ctr)
+{
+    __shared__ uint2 s_w[32];
+    __shared__ uint2 s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = make_uint2(0, 0);
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n_tiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint2 c = (i < n_tiles) ? tile_cnt[i] : make_uint2(0, 0);
+        uint2 x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y0 = __shfl_up_sync(0xffffffffu, x.x, o), y1 = __shfl_up_sync(0xffffffffu, x.y, o);
+            if (lane >= o) {
+                x.x += y0;
+                x.y += y1;
             }
         }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint2 t = s_w[lane], y = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned z0 = __shfl_up_sync(0xffffffffu, y.x, o), z1 = __shfl_up_sync(0xffffffffu, y.y, o);
+                if (lane >= o) {
+                    y.x += z0;
+                    y.y += z1;
+                }
+            }
+            s_w[lane] = make_uint2(y.x - t.x, y.y - t.y);
+        }
+        __syncthreads();
+        const uint2 r = s_run, wv = s_w[warp];
+        if (i < n_tiles) tile_off[i] = make_uint2(r.x + wv.x + x.x - c.x, r.y + wv.y + x.y - c.y);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = make_uint2(r.x + wv.x + x.x, r.y + wv.y + x.y);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tile_off[n_tiles] = s_run;
+        ctr->n_active = s_run.x;
+        ctr->n_funcs = s_run.y;
+    }
+}
+
+// Pass 3: ordered gather of the tile-local slots into the compact active list (7 % of the tets)
+template <int W>
+__global__ void __launch_bounds__(256) compact_active_kernel(const uint32_t* __restrict__ tl_tet,
+    const uint32_t* __restrict__ tl_mask, size_t tl_stride, const uint2* __restrict__ tile_off,
+    uint32_t n_tiles, uint32_t n_active, uint32_t* __restrict__ act_tet, uint32_t* __restrict__ act_mask,
+    uint32_t cap)
+{
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        // tile = last one with tile_off.x <= a
+        uint32_t lo = 0, hi = n_tiles;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&tile_off[mid].x) <= a)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const size_t pos = (size_t)lo * FILT_TILE + (a - __ldg(&tile_off[lo].x));
+        act_tet[a] = tl_tet[pos];
+#pragma unroll
+        for (int w = 0; w < W; ++w) act_mask[(size_t)w * cap + a] = tl_mask[(size_t)w * tl_stride + pos];
     }
 }
 
@@ -451,16 +533,19 @@ template <class Caps>
 struct IsoScan
 {
     uint32_t isov[(Caps::MAXV + 31) / 32];
-    int nvi, nfi, nfv;
+    int nvi, nfi, nfv, nfw; // nfw: words used by the face entries
     __device__ void run(const IAComplex<Caps>& cx)
     {
         for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) isov[i] = 0;
         nfi = 0;
         nfv = 0;
+        nfw = 0;
         for (int f = 0; f < cx.nf; ++f)
             if (cx.is_iso_face(f)) {
                 ++nfi;
                 nfv += cx.flen[f];
+                if (cx.flen[f] > 127) nfv = 1 << 20; // loop too long for the record format -> capacity error
+                nfw += rec_face_words(cx.flen[f]);
                 for (int k = 0; k < cx.flen[f]; ++k) {
                     int v = cx.fv[cx.foff[f] + k];
                     isov[v >> 5] |= 1u << (v & 31);
@@ -475,28 +560,26 @@ struct IsoScan
         for (int i = 0; i < (v >> 5); ++i) r += __popc(isov[i]);
         return r;
     }
-    __device__ void write(const IAComplex<Caps>& cx, uint8_t* buf) const
+    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + nvi + nfw); }
+    __device__ void write(const IAComplex<Caps>& cx, uint32_t* w) const
     {
         int p = 0;
-        buf[p++] = (uint8_t)nvi;
-        buf[p++] = (uint8_t)nfi;
-        buf[p++] = (uint8_t)(nfv & 255);
-        buf[p++] = (uint8_t)(nfv >> 8);
+        w[p++] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
         for (int v = 0; v < cx.nv; ++v)
-            if ((isov[v >> 5] >> (v & 31)) & 1) {
-                buf[p++] = (uint8_t)v;
-                buf[p++] = cx.vp[v][0];
-                buf[p++] = cx.vp[v][1];
-                buf[p++] = cx.vp[v][2];
-            }
+            if ((isov[v >> 5] >> (v & 31)) & 1)
+                w[p++] = (uint32_t)v | ((uint32_t)cx.vp[v][0] << 8) | ((uint32_t)cx.vp[v][1] << 16) |
+                         ((uint32_t)cx.vp[v][2] << 24);
         for (int f = 0; f < cx.nf; ++f)
             if (cx.is_iso_face(f)) {
-                buf[p++] = (uint8_t)(f & 255);
-                buf[p++] = (uint8_t)(f >> 8);
-                buf[p++] = cx.fplane[f];
-                buf[p++] = (cx.fneg[f] == N8) ? 1 : 0;
-                buf[p++] = cx.flen[f];
-                for (int k = 0; k < cx.flen[f]; ++k) buf[p++] = (uint8_t)rank(cx.fv[cx.foff[f] + k]);
+                const int n = cx.flen[f];
+                w[p++] = (uint32_t)f | ((uint32_t)cx.fplane[f] << 16) | ((uint32_t)n << 24) |
+                         ((cx.fneg[f] == N8) ? 0x80000000u : 0u);
+                for (int k0 = 0; k0 < n; k0 += 4) {
+                    uint32_t x = 0;
+                    for (int k = k0; k < n && k < k0 + 4; ++k)
+                        x |= (uint32_t)rank(cx.fv[cx.foff[f] + k]) << (8 * (k - k0));
+                    w[p++] = x;
+                }
             }
     }
 };
@@ -527,7 +610,7 @@ __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __r
     IsoScan<Caps> iso;
     if (!cx.err) {
         iso.run(cx);
-        if (iso.nvi > 255 || iso.nfi > 255 || iso.nfv > 65535) cx.err = 1;
+        if (iso.nvi > 255 || iso.nfi > 255 || iso.nfv > 65535 || cx.nf > 65535) cx.err = 1;
     }
     if (cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
     if (cx.err == 1 && !last_tier) return false;
@@ -537,15 +620,14 @@ __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __r
         rec_ref[a] = REF_GENERAL; // offset 0: the arena starts with an empty record
         return true;
     }
-    const uint32_t sz = rec_size_ia(iso.nvi, iso.nfi, iso.nfv);
-    const uint32_t szal = (sz + 3u) & ~3u;
+    const uint32_t szal = iso.size_bytes();
     const uint32_t off = atomicAdd(&gc->arena_top, szal);
     if (off + szal > arena_cap) {
         gc->arena_overflow = 1;
         rec_ref[a] = REF_GENERAL;
         return true;
     }
-    iso.write(cx, arena + off);
+    iso.write(cx, reinterpret_cast<uint32_t*>(arena + off));
     rec_ref[a] = REF_GENERAL | (off >> 2);
     return true;
 }
@@ -716,8 +798,11 @@ __global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ 
     __syncthreads();
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         const uint32_t ref = rec_ref[a];
-        const uint8_t* r = (ref & REF_GENERAL) ? arena + (size_t)(ref & ~REF_GENERAL) * 4 : s_blob + ref * 4;
-        const int nv = r[0], nf = r[1];
+        const uint32_t* r = (ref & REF_GENERAL)
+                                ? reinterpret_cast<const uint32_t*>(arena) + (size_t)(ref & ~REF_GENERAL)
+                                : reinterpret_cast<const uint32_t*>(s_blob) + ref;
+        const uint32_t hdr = r[0];
+        const int nv = hdr & 255, nf = (hdr >> 8) & 255;
         if (nv == 0 && nf == 0) continue;
         const uint32_t t = act_tet[a];
         const uint4 tv4 = __ldg(&tets[t]);
@@ -725,73 +810,83 @@ __global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ 
         uint32_t m[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) m[w] = act_mask[(size_t)w * cap + a];
-        const uint4 o = offs[a];
-        const uint8_t* p = r + REC_HDR;
-        for (int i = 0; i < nv; ++i, p += 4) {
-            const int local = p[0];
-            uint32_t fn[3] = {0xffffu, 0xffffu, 0xffffu};
-            uint32_t corners[4];
-            int ni = 0, nb = 0;
-            unsigned on_b = 0;
+        // the first four active functions in registers (tables never need more)
+        uint32_t fl[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};
+        {
+            int q = 0;
 #pragma unroll
-            for (int k = 1; k <= 3; ++k) {
-                const int pl = p[k];
-                if (pl > 3)
-                    fn[ni++] = (uint32_t)nth_set_bit(m, W, pl - 4);
-                else {
-                    on_b |= 1u << pl;
-                    ++nb;
+            for (int w = 0; w < W; ++w) {
+                uint32_t mm = m[w];
+                while (mm && q < 4) {
+                    fl[q++] = w * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1;
                 }
             }
-            int ncn = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (!((on_b >> c) & 1)) corners[ncn++] = tv[c];
+        }
+        auto func_of = [&](int pl) -> uint32_t { // plane id (>= 4) -> global function id
+            const int j = pl - 4;
+            return j < 4 ? fl[j] : (uint32_t)nth_set_bit(m, W, j);
+        };
+        const uint4 o = offs[a];
+        const uint32_t* p = r + 1;
+        for (int i = 0; i < nv; ++i) {
+            const uint32_t e = p[i];
+            const int local = e & 255;
+            const int p0 = (e >> 8) & 255, p1 = (e >> 16) & 255, p2 = e >> 24;
+            // planes ascend: boundary planes (< 4) come first
+            const int nb = (p0 < 4) + (p1 < 4) + (p2 < 4);
             uint4 key, pay;
             pay.x = t;
+            uint32_t f0 = 0xffffu, f1 = 0xffffu, f2 = 0xffffu;
             if (nb == 0) {
+                f0 = func_of(p0);
+                f1 = func_of(p1);
+                f2 = func_of(p2);
                 key = make_uint4(tv[0], tv[1], tv[2], tv[3]); // unused: interior vertices are unique
                 pay.y = (uint32_t)local | (4u << 8);
             } else {
-                // sort the (<= 3) corners ascending
-                if (ncn >= 2 && corners[0] > corners[1]) {
-                    uint32_t s = corners[0];
-                    corners[0] = corners[1];
-                    corners[1] = s;
+                uint32_t c0, c1 = NONE32, c2 = NONE32;
+                int ncn;
+                if (nb == 3) { // on the tet corner not listed
+                    c0 = tv[6 - p0 - p1 - p2];
+                    ncn = 1;
+                } else if (nb == 2) { // on the tet edge between the two corners not listed
+                    f0 = func_of(p2);
+                    const unsigned rest = 0xfu & ~((1u << p0) | (1u << p1));
+                    const int a0 = __ffs(rest) - 1, a1 = 31 - __clz(rest);
+                    c0 = min(tv[a0], tv[a1]);
+                    c1 = max(tv[a0], tv[a1]);
+                    ncn = 2;
+                } else { // on the tet face opposite corner p0
+                    f0 = func_of(p1);
+                    f1 = func_of(p2);
+                    const uint32_t x = tv[p0 == 0 ? 1 : 0], y = tv[p0 <= 1 ? 2 : 1], z = tv[p0 == 3 ? 2 : 3];
+                    const uint32_t lo = min(x, min(y, z)), hi = max(x, max(y, z));
+                    c0 = lo;
+                    c1 = x ^ y ^ z ^ lo ^ hi; // the middle one
+                    c2 = hi;
+                    ncn = 3;
                 }
-                if (ncn == 3) {
-                    if (corners[1] > corners[2]) {
-                        uint32_t s = corners[1];
-                        corners[1] = corners[2];
-                        corners[2] = s;
-                    }
-                    if (corners[0] > corners[1]) {
-                        uint32_t s = corners[0];
-                        corners[0] = corners[1];
-                        corners[1] = s;
-                    }
-                }
-                key.x = corners[0];
-                key.y = ncn >= 2 ? corners[1] : NONE32;
-                key.z = ncn >= 3 ? corners[2] : NONE32;
-                key.w = fn[0] | (fn[1] << 16); // function ids in plane-triple order (:138,:167-168)
+                key = make_uint4(c0, c1, c2, f0 | (f1 << 16)); // function ids in plane order (:138,:167-168)
                 pay.y = (uint32_t)local | ((uint32_t)ncn << 8) | (1u << 16);
             }
-            pay.z = fn[0] | (fn[1] << 16);
-            pay.w = fn[2];
+            pay.z = f0 | (f1 << 16);
+            pay.w = f2;
             cand_key[o.x + i] = key;
             cand_pay[o.x + i] = pay;
         }
+        p += nv;
         uint32_t fvo = o.z;
         unsigned nbf = 0;
         for (int j = 0; j < nf; ++j) {
-            const uint32_t local = p[0] | (p[1] << 8);
-            const int sp = p[2], bnd = p[3] & 1, n = p[4];
+            const uint32_t e = *p++;
+            const uint32_t local = e & 0xffffu;
+            const int sp = (e >> 16) & 255, n = (e >> 24) & 127, bnd = e >> 31;
             // func_index.first = func_in_tet[supporting_plane - 4 + start] (:249,:258); for a face
             // coplanar with a tet face sp < 4 and the reference's index wraps to an earlier CRS entry
             uint32_t f;
             if (sp > 3)
-                f = (uint32_t)nth_set_bit(m, W, sp - 4);
+                f = func_of(sp);
             else {
                 // QUIRK kept from the reference: CRS entry (start + sp - 4) belongs to an earlier tet
                 f = NONE32;
@@ -813,10 +908,12 @@ __global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ 
                 }
             }
             face_hdr[o.y + j] = make_uint4(t, local | ((uint32_t)n << 16) | ((uint32_t)bnd << 24), f, fvo);
-            for (int k = 0; k < n; ++k) fv_ref[fvo + k] = o.x + p[5 + k];
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                const uint32_t x = *p++;
+                for (int k = k0; k < n && k < k0 + 4; ++k) fv_ref[fvo + k] = o.x + ((x >> (8 * (k - k0))) & 255);
+            }
             fvo += n;
             nbf += bnd;
-            p += 5 + n;
         }
         if (nbf) atomicAdd(n_bndry_faces, nbf);
     }

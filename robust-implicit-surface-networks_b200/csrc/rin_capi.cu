@@ -115,6 +115,7 @@ struct rin_ctx
     // work buffers
     DevBuf counters; // small zeroed block: FilterCounters | GeneralCounters | ScanTotals | misc
     DevBuf status;   // look-back status words
+    DevBuf tl_tet, tl_mask, tile_cnt, tile_off; // tile-local filter output
     DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
@@ -198,7 +199,7 @@ void rin_destroy(rin_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->counters,
-        &c->status, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
+        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->fkeys, &c->frep, &c->fdup, &c->fpos,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob};
@@ -549,34 +550,34 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventRecord(c->kev[1], s));
     CK(cudaGetLastError());
 
-    // ---- K2: filter + ordered compaction
+    // ---- K2: filter (tile-local compaction) + tile scan + ordered gather
     CK(cudaEventRecord(c->ev[ST_FILTER], s));
     const uint32_t n_tiles = (T + FILT_TILE - 1) / FILT_TILE;
     const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
-    for (int attempt = 0;; ++attempt) {
-        if (c->act_cap == 0) c->act_cap = std::max<uint32_t>(1u << 16, T / 4);
-        c->act_cap = std::min<uint32_t>(c->act_cap, std::max<uint32_t>(T, 1));
-        CK(c->act_tet.ensure((size_t)c->act_cap * 4));
-        CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
-        CK(c->status.ensure((size_t)std::max<uint32_t>(n_tiles, 1) * 8 * 2 + 64));
-        CK(cudaMemsetAsync(c->status.p, 0, (size_t)n_tiles * 8, s));
-        CK(cudaEventRecord(c->kev[2], s));
-        filter_ia_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
-            c->vmask.as<uint2>(), V, last_mask, c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(),
-            c->act_cap, c->status.as<unsigned long long>(), &dctr->filt);
-        CK(cudaEventRecord(c->kev[3], s));
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (h.filt.n_active <= c->act_cap) break;
-        if (attempt > 0) return fail(RIN_ERR_STATE, "filter: active list overflow after regrow");
-        // regrow and redo the filter (the counters of this pass are discarded)
-        c->act_cap = h.filt.n_active + h.filt.n_active / 16 + 1024;
-        Counters z{};
-        z.n_zero = h.n_zero;
-        CK(cudaMemcpyAsync(dctr, &z, sizeof(Counters), cudaMemcpyHostToDevice, s));
-    }
+    const size_t tl_stride = (size_t)n_tiles * FILT_TILE;
+    CK(c->tl_tet.ensure(tl_stride * 4));
+    CK(c->tl_mask.ensure(tl_stride * 4 * W));
+    CK(c->tile_cnt.ensure((size_t)n_tiles * 8));
+    CK(c->tile_off.ensure((size_t)(n_tiles + 1) * 8));
+    CK(cudaEventRecord(c->kev[2], s));
+    filter_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
+        c->vmask.as<uint2>(), V, last_mask, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(), tl_stride,
+        c->tile_cnt.as<uint2>(), &dctr->filt);
+    CK(cudaEventRecord(c->kev[3], s));
+    scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     const uint32_t A = h.filt.n_active;
+    c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 16 + 1024);
+    CK(c->act_tet.ensure((size_t)c->act_cap * 4));
+    CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
+    if (A) {
+        compact_active_kernel<W><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tl_tet.as<uint32_t>(),
+            c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, A, c->act_tet.as<uint32_t>(),
+            c->act_mask.as<uint32_t>(), c->act_cap);
+        CK(cudaGetLastError());
+    }
 
     rin_counts& n = c->counts;
     n = rin_counts{};
@@ -949,8 +950,11 @@ int build_ia_tables(rin_ctx* c)
     for (auto& kv : order) {
         const uint32_t w = kv.second;
         const uint8_t* r = arena.data() + (size_t)(refs[w] & ~REF_GENERAL) * 4;
-        const int nv = r[0], nf = r[1], nfv = r[2] | (r[3] << 8);
-        const uint32_t sz = rec_size_ia(nv, nf, nfv);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(r);
+        const int nv = rw[0] & 255, nf = (rw[0] >> 8) & 255;
+        uint32_t words = 1 + nv;
+        for (int f = 0; f < nf; ++f) words += rec_face_words((rw[words] >> 24) & 127);
+        const uint32_t sz = 4 * words;
         const uint32_t off = (uint32_t)L.h_blob.size() / 4;
         if (off >= LUT_MISS) {
             cleanup();
