@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <limits>
+#include <map>
 #include <cmath>
 #include <cstring>
 #include <set>
@@ -451,6 +453,347 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
     return bag;
 }
 
+// material_interface hot path (src/material_interface.cpp:53-447).
+void* orc_mi_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64_t T_all,
+    const double* vals, uint32_t F, uint32_t flags, uint64_t tet_first, uint64_t tet_count)
+{
+    auto* bag = new ResultBag;
+    bool use_lookup = flags & RIN_FLAG_USE_LOOKUP;
+    bool use_secondary = (flags & RIN_FLAG_USE_SECONDARY_LOOKUP) && use_lookup;
+    if (use_lookup) {
+        load_lookup_table(MATERIAL_INTERFACE);
+        enable_lookup_table();
+    } else
+        disable_lookup_table(); // app/material_interface.cpp:42-45
+    const uint64_t* tets = tets_all + 4 * tet_first;
+    const uint64_t T = tet_count ? tet_count : T_all - tet_first;
+    auto& tm = bag->f64["timings"];
+    auto Fv = [&](uint64_t v, uint64_t f) { return vals[v * F + f]; };
+
+    // ---- "highest func" :59-92
+    double t0 = now_s();
+    std::vector<uint32_t> highest(V);
+    std::vector<char> degenerate(V, 0);
+    std::unordered_map<uint64_t, std::vector<uint32_t>> highest_all;
+    int64_t num_degenerate = 0;
+    for (uint64_t i = 0; i < V; ++i) {
+        double mx = Fv(i, 0);
+        uint32_t id = 0, cnt = 1;
+        for (uint32_t j = 1; j < F; ++j) {
+            if (Fv(i, j) > mx) {
+                mx = Fv(i, j);
+                id = j;
+                cnt = 1;
+            } else if (Fv(i, j) == mx)
+                ++cnt;
+        }
+        highest[i] = id;
+        if (cnt > 1) {
+            degenerate[i] = 1;
+            ++num_degenerate;
+            auto& l = highest_all[i];
+            for (uint32_t j = 0; j < F; ++j)
+                if (Fv(i, j) == mx) l.push_back(j);
+        }
+    }
+    tm.push_back(now_s() - t0);
+
+    // ---- "filter" :99-152
+    t0 = now_s();
+    auto& mat_in_tet = bag->i64["func_in_tet"];
+    auto& start = bag->i64["start_index_of_tet"];
+    start.push_back(0);
+    int64_t num_intersecting = 0;
+    {
+        std::set<uint32_t> ms;
+        for (uint64_t t = 0; t < T; ++t) {
+            const uint64_t* tv = tets + 4 * t;
+            ms.clear();
+            for (int c = 0; c < 4; ++c) {
+                if (degenerate[tv[c]]) {
+                    const auto& l = highest_all[tv[c]];
+                    ms.insert(l.begin(), l.end());
+                } else
+                    ms.insert(highest[tv[c]]);
+            }
+            if (ms.size() < 2) {
+                start.push_back(int64_t(mat_in_tet.size()));
+                continue;
+            }
+            double min_h[4];
+            for (int c = 0; c < 4; ++c) {
+                min_h[c] = std::numeric_limits<double>::max();
+                for (uint32_t m : ms)
+                    if (Fv(tv[c], m) < min_h[c]) min_h[c] = Fv(tv[c], m);
+            }
+            for (uint32_t j = 0; j < F; ++j) {
+                int greater = 0;
+                for (int c = 0; c < 4; ++c) greater += (Fv(tv[c], j) > min_h[c]);
+                if (greater > 1) ms.insert(j);
+            }
+            ++num_intersecting;
+            mat_in_tet.insert(mat_in_tet.end(), ms.begin(), ms.end());
+            start.push_back(int64_t(mat_in_tet.size()));
+        }
+    }
+    tm.push_back(now_s() - t0);
+
+    // ---- per-tet material interfaces :288-351
+    t0 = now_s();
+    std::vector<MaterialInterface<3>> cuts;
+    std::vector<int64_t> cut_index(T, NONE64);
+    int64_t n2 = 0, n3 = 0, nmore = 0;
+    try {
+        std::vector<Material<double, 3>> mats;
+        for (uint64_t t = 0; t < T; ++t) {
+            int64_t k = start[t + 1] - start[t];
+            if (k == 0) continue;
+            const uint64_t* tv = tets + 4 * t;
+            mats.resize(k);
+            for (int64_t j = 0; j < k; ++j)
+                for (int c = 0; c < 4; ++c) mats[j][c] = Fv(tv[c], mat_in_tet[start[t] + j]);
+            cut_index[t] = int64_t(cuts.size());
+            if (use_lookup && !use_secondary && k == 3) {
+                disable_lookup_table();
+                cuts.emplace_back(compute_material_interface(mats));
+                enable_lookup_table();
+            } else
+                cuts.emplace_back(compute_material_interface(mats));
+            (k == 2 ? n2 : (k == 3 ? n3 : nmore))++;
+        }
+    } catch (std::runtime_error& e) {
+        bag->error = e.what();
+        return bag;
+    }
+    tm.push_back(now_s() - t0);
+
+    // ---- "extract mesh": extract_MI_mesh, src/extract_mesh.cpp:569-986
+    t0 = now_s();
+    auto& vrec = bag->i64["vert_rec"]; // 11 per vertex: tet, local, size, sv[4], mi[4]
+    auto& ffunc = bag->i64["face_funcs"];
+    std::vector<std::vector<int64_t>> face_vlist, face_tlist;
+    KeyMap vert_map;
+    size_t n_verts = 0;
+    std::vector<int> vsize; // simplex size per MI vertex
+    std::vector<int64_t> vsimplex0;
+    auto new_vert = [&](uint64_t tet, size_t local, int size, std::array<int64_t, 4> sv, std::array<int64_t, 4> mi) {
+        vrec.push_back(int64_t(tet));
+        vrec.push_back(int64_t(local));
+        vrec.push_back(size);
+        for (auto x : sv) vrec.push_back(x);
+        for (auto x : mi) vrec.push_back(x);
+        vsize.push_back(size);
+        vsimplex0.push_back(sv[0]);
+        return n_verts++;
+    };
+    // boundary-face matching state (:603-605): face key -> material label(s) of the first side
+    std::map<std::array<int64_t, 3>, std::vector<int64_t>> open_bfaces;
+    std::vector<int64_t> lid;
+    std::vector<char> is_mi_v, is_mi_f;
+    for (uint64_t t = 0; t < T; ++t) {
+        if (cut_index[t] == NONE64) continue;
+        const auto& mi = cuts[cut_index[t]];
+        const uint64_t* tv = tets + 4 * t;
+        const int64_t s0 = start[t];
+        const uint64_t tg = t + tet_first;
+        is_mi_v.assign(mi.vertices.size(), 0);
+        is_mi_f.assign(mi.faces.size(), 0);
+        for (size_t f = 0; f < mi.faces.size(); ++f)
+            if (mi.faces[f].positive_material_label > 3) { // :641-651
+                is_mi_f[f] = 1;
+                for (size_t v : mi.faces[f].vertices) is_mi_v[v] = 1;
+            }
+        lid.assign(mi.vertices.size(), 0);
+        for (size_t j = 0; j < mi.vertices.size(); ++j) {
+            std::array<int64_t, 4> ms = {NONE64, NONE64, NONE64, NONE64};
+            bool on_b[4] = {false, false, false, false};
+            int nb = 0, nm = 0;
+            for (size_t m : mi.vertices[j]) {
+                if (m > 3)
+                    ms[nm++] = mat_in_tet[s0 + int64_t(m) - 4];
+                else {
+                    on_b[m] = true;
+                    ++nb;
+                }
+            }
+            std::vector<uint64_t> corners;
+            for (int c = 0; c < 4; ++c)
+                if (!on_b[c]) corners.push_back(tv[c]);
+            if (!is_mi_v[j]) { // a tet vertex that is not on the interface: encoded -(id)-1 (:670-687)
+                lid[j] = -int64_t(corners[0]) - 1;
+                continue;
+            }
+            if (nb == 0) { // :775-786
+                lid[j] = int64_t(new_vert(tg, j, 4,
+                    {int64_t(tv[0]), int64_t(tv[1]), int64_t(tv[2]), int64_t(tv[3])}, ms));
+                continue;
+            }
+            std::sort(corners.begin(), corners.end());
+            std::sort(ms.begin(), ms.begin() + nm); // material ids sorted in the key AND the record (:713-735,:751)
+            std::array<uint64_t, 7> key;
+            key.fill(~0ULL);
+            key[0] = corners.size();
+            for (size_t c = 0; c < corners.size(); ++c) key[1 + c] = corners[c];
+            if (nb != 3)
+                for (int q = 0; q < nm; ++q) key[4 + q] = uint64_t(ms[q]);
+            auto ins = vert_map.try_emplace(key, n_verts);
+            if (ins.second) {
+                std::array<int64_t, 4> sv = {NONE64, NONE64, NONE64, NONE64};
+                for (size_t c = 0; c < corners.size(); ++c) sv[c] = int64_t(corners[c]);
+                std::array<int64_t, 4> mstore = {NONE64, NONE64, NONE64, NONE64};
+                if (nb != 3) mstore = ms;
+                new_vert(tg, j, int(corners.size()), sv, mstore);
+            }
+            lid[j] = int64_t(ins.first->second);
+        }
+        for (size_t f = 0; f < mi.faces.size(); ++f) {
+            const auto& face = mi.faces[f];
+            if (is_mi_f[f]) { // :823-832
+                std::vector<int64_t> fv;
+                for (size_t v : face.vertices) fv.push_back(lid[v]);
+                face_vlist.push_back(fv);
+                face_tlist.push_back({int64_t(tg), int64_t(f)});
+                ffunc.push_back(mat_in_tet[s0 + int64_t(face.positive_material_label) - 4]);
+                ffunc.push_back(mat_in_tet[s0 + int64_t(face.negative_material_label) - 4]);
+                continue;
+            }
+            // simplex boundary face: match with the neighbouring tet (:833-950)
+            std::vector<int64_t> bv;
+            for (size_t v : face.vertices) {
+                if (lid[v] >= 0 && vsize[lid[v]] == 1)
+                    bv.push_back(-vsimplex0[lid[v]] - 1);
+                else
+                    bv.push_back(lid[v]);
+            }
+            auto key = min2_max_key(bv);
+            std::vector<int64_t> labels;
+            size_t nl = face.negative_material_label;
+            if (mi.unique_materials.empty() || mi.unique_materials[mi.unique_material_indices[nl]].size() == 1)
+                labels.push_back(mat_in_tet[s0 + int64_t(nl) - 4]);
+            else
+                for (size_t m : mi.unique_materials[mi.unique_material_indices[nl]])
+                    labels.push_back(mat_in_tet[s0 + int64_t(m) - 4]);
+            auto it = open_bfaces.find(key);
+            if (it == open_bfaces.end()) {
+                open_bfaces.emplace(key, labels);
+                continue;
+            }
+            bool common = false;
+            for (auto a : it->second)
+                for (auto b : labels) common |= (a == b);
+            if (common) {
+                open_bfaces.erase(it); // same material on both sides: not an interface
+                continue;
+            }
+            // different materials on the two sides: the second tet emits the face (:952-981)
+            std::vector<int64_t> fv;
+            for (size_t k = 0; k < face.vertices.size(); ++k) {
+                if (bv[k] < 0) {
+                    uint64_t vid = uint64_t(-bv[k] - 1);
+                    std::array<uint64_t, 7> vk;
+                    vk.fill(~0ULL);
+                    vk[0] = 1;
+                    vk[1] = vid;
+                    auto ins = vert_map.try_emplace(vk, n_verts);
+                    if (ins.second)
+                        new_vert(tg, face.vertices[k], 1, {int64_t(vid), NONE64, NONE64, NONE64},
+                            {NONE64, NONE64, NONE64, NONE64});
+                    fv.push_back(int64_t(ins.first->second));
+                } else
+                    fv.push_back(lid[face.vertices[k]]);
+            }
+            face_vlist.push_back(fv);
+            face_tlist.push_back({int64_t(tg), int64_t(f)});
+            // QUIRK kept from the reference (:979): positive label < 4 indexes BEFORE this tet's entries
+            int64_t fidx = s0 + int64_t(face.positive_material_label) - 4;
+            ffunc.push_back(fidx >= 0 ? mat_in_tet[fidx] : NONE64);
+            ffunc.push_back(mat_in_tet[s0 + int64_t(nl) - 4]);
+        }
+    }
+    auto& foff = bag->i64["face_offsets"];
+    auto& fverts = bag->i64["face_verts"];
+    auto& ftoff = bag->i64["face_tet_offsets"];
+    auto& ftets = bag->i64["face_tets"];
+    foff.push_back(0);
+    ftoff.push_back(0);
+    for (size_t f = 0; f < face_vlist.size(); ++f) {
+        fverts.insert(fverts.end(), face_vlist[f].begin(), face_vlist[f].end());
+        foff.push_back(int64_t(fverts.size()));
+        ftets.insert(ftets.end(), face_tlist[f].begin(), face_tlist[f].end());
+        ftoff.push_back(int64_t(ftets.size() / 2));
+    }
+    tm.push_back(now_s() - t0);
+
+    // ---- "compute xyz": compute_MI_vert_xyz, src/extract_mesh.cpp:1541-1637
+    t0 = now_s();
+    auto& xyz = bag->f64["vert_xyz"];
+    xyz.resize(3 * n_verts);
+    auto P = [&](int64_t v, int c) { return pts[3 * v + c]; };
+    for (size_t i = 0; i < n_verts; ++i) {
+        const int64_t* r = &vrec[11 * i];
+        const int64_t* sv = r + 3;
+        const int64_t* m = r + 7;
+        double* o = &xyz[3 * i];
+        switch (r[2]) {
+        case 1:
+            for (int c = 0; c < 3; ++c) o[c] = P(sv[0], c);
+            break;
+        case 2: {
+            double f1 = Fv(sv[0], m[0]) - Fv(sv[0], m[1]);
+            double f2 = Fv(sv[1], m[0]) - Fv(sv[1], m[1]);
+            double b0 = f2 / (f2 - f1), b1 = 1 - b0;
+            for (int c = 0; c < 3; ++c) o[c] = b0 * P(sv[0], c) + b1 * P(sv[1], c);
+            break;
+        }
+        case 3: {
+            double a[3], b[3];
+            for (int k = 0; k < 3; ++k) {
+                a[k] = Fv(sv[k], m[0]) - Fv(sv[k], m[1]);
+                b[k] = Fv(sv[k], m[1]) - Fv(sv[k], m[2]);
+            }
+            double n1 = a[2] * b[1] - a[1] * b[2];
+            double n2_ = a[0] * b[2] - a[2] * b[0];
+            double n3_ = a[1] * b[0] - a[0] * b[1];
+            double d = n1 + n2_ + n3_;
+            double w0 = n1 / d, w1 = n2_ / d, w2 = n3_ / d;
+            for (int c = 0; c < 3; ++c) o[c] = w0 * P(sv[0], c) + w1 * P(sv[1], c) + w2 * P(sv[2], c);
+            break;
+        }
+        case 4: {
+            double p1[4], p2[4], p3[4];
+            for (int k = 0; k < 4; ++k) {
+                p1[k] = Fv(sv[k], m[0]) - Fv(sv[k], m[1]);
+                p2[k] = Fv(sv[k], m[1]) - Fv(sv[k], m[2]);
+                p3[k] = Fv(sv[k], m[2]) - Fv(sv[k], m[3]);
+            }
+            double n1 = p1[3] * (p2[2] * p3[1] - p2[1] * p3[2]) + p1[2] * (p2[1] * p3[3] - p2[3] * p3[1]) +
+                        p1[1] * (p2[3] * p3[2] - p2[2] * p3[3]);
+            double n2_ = p1[3] * (p2[0] * p3[2] - p2[2] * p3[0]) + p1[2] * (p2[3] * p3[0] - p2[0] * p3[3]) +
+                         p1[0] * (p2[2] * p3[3] - p2[3] * p3[2]);
+            double n3_ = p1[3] * (p2[1] * p3[0] - p2[0] * p3[1]) + p1[1] * (p2[0] * p3[3] - p2[3] * p3[0]) +
+                         p1[0] * (p2[3] * p3[1] - p2[1] * p3[3]);
+            double n4 = p1[2] * (p2[0] * p3[1] - p2[1] * p3[0]) + p1[1] * (p2[2] * p3[0] - p2[0] * p3[2]) +
+                        p1[0] * (p2[1] * p3[2] - p2[2] * p3[1]);
+            double d = n1 + n2_ + n3_ + n4;
+            double w[4] = {n1 / d, n2_ / d, n3_ / d, n4 / d};
+            for (int c = 0; c < 3; ++c)
+                o[c] = w[0] * P(sv[0], c) + w[1] * P(sv[1], c) + w[2] * P(sv[2], c) + w[3] * P(sv[3], c);
+            break;
+        }
+        default: break;
+        }
+    }
+    tm.push_back(now_s() - t0);
+
+    auto es = engine_stats();
+    bag->i64["stats"] = {int64_t(V), int64_t(T), num_degenerate, num_intersecting, n2, n3, nmore, int64_t(n_verts),
+        int64_t(face_vlist.size())};
+    bag->i64["engine"] = {int64_t(es.lookups), int64_t(es.general), int64_t(es.exact_fallbacks)};
+    bag->cuts_mi = std::move(cuts);
+    bag->cut_index = std::move(cut_index);
+    return bag;
+}
+
 const int64_t* orc_i64(void* h, const char* name, uint64_t* n)
 {
     auto* b = static_cast<ResultBag*>(h);
@@ -563,6 +906,27 @@ int orc_compute_arrangement(const double* planes, uint32_t k, int use_lookup, ui
         for (uint32_t j = 0; j < k; ++j)
             for (int c = 0; c < 4; ++c) p[j][c] = planes[4 * j + c];
         b.cuts_ia.push_back(compute_arrangement(p));
+        b.cut_index = {0};
+    } catch (std::runtime_error&) {
+        return -5;
+    }
+    return orc_get_complex(&b, 0, words, cap, n_words);
+}
+
+int orc_compute_material_interface(const double* mats, uint32_t k, int use_lookup, uint32_t* words,
+    uint64_t cap, uint64_t* n_words)
+{
+    ResultBag b;
+    try {
+        if (use_lookup) {
+            load_lookup_table(MATERIAL_INTERFACE);
+            enable_lookup_table();
+        } else
+            disable_lookup_table();
+        std::vector<Material<double, 3>> m(k);
+        for (uint32_t j = 0; j < k; ++j)
+            for (int c = 0; c < 4; ++c) m[j][c] = mats[4 * j + c];
+        b.cuts_mi.push_back(compute_material_interface(m));
         b.cut_index = {0};
     } catch (std::runtime_error&) {
         return -5;

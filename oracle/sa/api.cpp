@@ -125,6 +125,7 @@ static void generate_ia_tables()
 
 void generate_mi_tables(std::map<int, simplicial_arrangement::MaterialInterface<3>>& mi2,
     std::map<int, simplicial_arrangement::MaterialInterface<3>>& mi3);
+int mi_lookup_key_2(const double* a, const double* b);
 
 } // namespace sa_oracle
 
@@ -184,6 +185,22 @@ Arrangement<3> compute_arrangement(const std::vector<Plane<double, 3>>& planes)
     }
     ++sa_oracle::stats().general;
     return sa_oracle::compute_arrangement_general(planes);
+}
+
+MaterialInterface<3> compute_material_interface(const std::vector<Material<double, 3>>& materials)
+{
+    auto& t = sa_oracle::g_tables;
+    // upstream: 2 materials -> first table, 3 materials -> secondary table; here only the first
+    // table is materialised, the 3-material case runs the general algorithm (same results)
+    if (t.enabled && t.mi_loaded && materials.size() == 2) {
+        int key = sa_oracle::mi_lookup_key_2(materials[0].data(), materials[1].data());
+        if (key >= 0) {
+            ++sa_oracle::stats().lookups;
+            return t.mi2[key];
+        }
+    }
+    ++sa_oracle::stats().general;
+    return sa_oracle::compute_material_interface_general(materials);
 }
 
 } // namespace simplicial_arrangement

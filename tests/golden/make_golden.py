@@ -42,6 +42,22 @@ EXPECTED_IA = {
 }
 
 
+# material interface goldens (tests/test_implicit_networks.cpp:475-731)
+EXPECTED_MI = {
+    "1-sphere": (0, 0, 1, [], [0]),
+    "2-planesphere": (1, 0, 2, [[1, 0]], [1, 0]),
+    "2-sphere": (1, 0, 2, [[1, 0]], [1, 0]),
+    "3-sphere-1": (3, 1, 3, [[2, 0], [2, 1], [1, 0]], [2, 0, 1]),
+    "3-sphere-4": (0, 0, 1, [], [2]),
+}
+EXPECTED_MI_8SPHERE = {
+    "shells": 8, "cells": 8, "corners": 6,
+    "patch_function_label": [[3, 1], [7, 3], [7, 6], [3, 2], [6, 2], [6, 4], [5, 4], [5, 1], [7, 5], [4, 0], [2, 0],
+                             [1, 0], [7, 1], [7, 4], [5, 0], [6, 0], [3, 0], [7, 2], [7, 0]],
+    "cell_function_label": [3, 1, 7, 6, 2, 4, 5, 0],
+}
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -96,6 +112,46 @@ def main():
     with open(os.path.join(HERE, "c1_golden.json"), "w") as f:
         json.dump(c1, f, indent=1, sort_keys=True)
     print("C1", b.stats)
+
+    # ---- material interface
+    mi_out = {}
+    for name, (npatch, nchain, ncell, plabel, clabel) in EXPECTED_MI.items():
+        with open(os.path.join(REF_EX, "tests", name + ".json")) as f:
+            spec = json.load(f)
+        vals = orc_eval(make_funcs(spec), pts)
+        b = ref_run("mi", pts, tets, vals)
+        got = (len(crs(b, "patches")), len(crs(b, "chains")), len(crs(b, "cells")),
+               b["patch_function_label"].reshape(-1, 2).tolist(), b["cell_function_label"].tolist())
+        assert got == (npatch, nchain, ncell, plabel, clabel), (name, got)
+        d = mesh_digest(b)
+        d["face_funcs"] = sha(b["face_funcs"])
+        mi_out[name] = {"grid": 101, "reference_test_expectation": {
+            "patches": npatch, "chains": nchain, "cells": ncell, "patch_function_label": plabel,
+            "cell_function_label": clabel}, "stats": b.stats, "digest": d}
+        print("MI", name, "golden reproduced", b.stats["num_MI_verts"], b.stats["num_MI_faces"])
+    with open(os.path.join(REF_EX, "tests", "mesh.json")) as f:
+        m = json.load(f)
+    m_pts = np.asarray(m[0], np.float64)
+    m_tets = np.asarray(m[1], np.uint32)
+    with open(os.path.join(REF_EX, "tests", "8-sphere.json")) as f:
+        spec = json.load(f)
+    with open(os.path.join(HERE, "functions", "8-sphere.json"), "w") as f:
+        json.dump(spec, f)
+    vals = orc_eval(make_funcs(spec), m_pts)
+    b = ref_run("mi", m_pts, m_tets, vals)
+    corners = sum(1 for l in crs(b, "non_manifold_edges_of_vert") if len(l) > 2)
+    got = {"shells": len(crs(b, "shells")), "cells": len(crs(b, "cells")), "corners": corners,
+           "patch_function_label": b["patch_function_label"].reshape(-1, 2).tolist(),
+           "cell_function_label": b["cell_function_label"].tolist()}
+    assert got == EXPECTED_MI_8SPHERE, got
+    np.savez_compressed(os.path.join(HERE, "mi_8sphere_inputs.npz"), pts=m_pts, tets=m_tets)
+    d = mesh_digest(b)
+    d["face_funcs"] = sha(b["face_funcs"])
+    mi_out["8-sphere"] = {"mesh": "examples/tests/mesh.json", "reference_test_expectation": EXPECTED_MI_8SPHERE,
+                          "stats": b.stats, "digest": d}
+    print("MI 8-sphere golden reproduced", b.stats)
+    with open(os.path.join(HERE, "mi_goldens.json"), "w") as f:
+        json.dump(mi_out, f, indent=1, sort_keys=True)
 
     # small cases with full arrays (reference extract + xyz code on the restated engine)
     small = {}

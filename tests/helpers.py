@@ -54,6 +54,7 @@ def oracle_lib():
                                         C.POINTER(C.c_uint64)]
         lib.orc_compute_arrangement.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p,
                                                 C.c_uint64, C.POINTER(C.c_uint64)]
+        lib.orc_compute_material_interface.argtypes = lib.orc_compute_arrangement.argtypes
         _oracle = lib
     return _oracle
 
