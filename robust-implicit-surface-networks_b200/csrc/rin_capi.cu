@@ -2,7 +2,7 @@
 // Host code here only sizes buffers and launches kernels; all per-vertex / per-tet work is in
 // kernels_*.cuh.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "../../include/rin_b200.h"
-#include "kernels_ia.cuh"
+#include "kernels_mi.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -92,7 +92,7 @@ struct Counters
     FilterCounters filt;
     GeneralCounters gen;
     ScanTotals scan;
-    unsigned rank_tile, n_unique, n_bndry_faces, n_exact_classify;
+    unsigned rank_tile, n_unique, n_bndry_faces, n_exact_classify, n_tie_faces;
     unsigned long long n_zero;
 };
 } // namespace
@@ -124,7 +124,7 @@ struct rin_ctx
     DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
     uint32_t act_cap = 0;
-    Lut lut_ia;
+    Lut lut_ia, lut_mi;
     rin_counts counts{};
     int last_mode = -1;
     uint32_t last_flags = 0;
@@ -154,8 +154,11 @@ uint32_t words_for(uint32_t F)
 
 template <int W>
 int run_ia_w(rin_ctx* c, uint32_t flags);
+template <int W>
+int run_mi_w(rin_ctx* c, uint32_t flags);
 
 int build_ia_tables(rin_ctx* c);
+int build_mi_tables(rin_ctx* c);
 
 } // namespace
 
@@ -202,7 +205,8 @@ void rin_destroy(rin_ctx* c)
         &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->fkeys, &c->frep, &c->fdup, &c->fpos,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->f_off, &c->f_verts,
-        &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob};
+        &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob,
+        &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -347,7 +351,28 @@ int rin_run(rin_ctx* c, int mode, uint32_t flags)
         }
         return rc;
     }
-    return fail(RIN_ERR_ARG, "rin_run: material interface mode is not built yet");
+    if (mode == RIN_MODE_MI) {
+        if (c->F > 1023) return fail(RIN_ERR_ARG, "material interface: more than 1023 materials");
+        if ((flags & RIN_FLAG_USE_LOOKUP) && !c->lut_mi.built) {
+            int rc = build_mi_tables(c);
+            if (rc) return rc;
+        }
+        int rc;
+        switch (words_for(c->F)) {
+        case 1: rc = run_mi_w<1>(c, flags); break;
+        case 2: rc = run_mi_w<2>(c, flags); break;
+        case 3: rc = run_mi_w<3>(c, flags); break;
+        case 4: rc = run_mi_w<4>(c, flags); break;
+        default: return fail(RIN_ERR_ARG, "more than 128 materials are not supported by this build");
+        }
+        if (rc == RIN_OK) {
+            c->last_mode = mode;
+            c->last_flags = flags;
+            c->ran = true;
+        }
+        return rc;
+    }
+    return fail(RIN_ERR_ARG, "rin_run: unknown mode");
 }
 
 int rin_get_counts(const rin_ctx* c, rin_counts* out)
@@ -799,6 +824,251 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
 }
 
 // ------------------------------------------------------------------------------------------------
+// One material-interface pass over tets [t_first, t_first + t_count).
+// ------------------------------------------------------------------------------------------------
+template <int W>
+int run_mi_w(rin_ctx* c, uint32_t flags)
+{
+    const uint32_t V = (uint32_t)c->V, F = c->F;
+    const uint32_t T = (uint32_t)c->t_count, t_first = (uint32_t)c->t_first;
+    const int use_lookup = (flags & RIN_FLAG_USE_LOOKUP) ? 1 : 0;
+    const int use_secondary = (flags & RIN_FLAG_USE_SECONDARY_LOOKUP) ? 1 : 0;
+    const int negate = (flags & RIN_FLAG_NEGATE) ? 1 : 0;
+    cudaStream_t s = c->stream;
+    const int sm = c->sm_count;
+
+    CK(c->counters.ensure(sizeof(Counters)));
+    Counters* dctr = c->counters.as<Counters>();
+    Counters h{};
+
+    // ---- K1: values + sign masks.  The vertex range is restricted to what the tet range can touch
+    // only for generated grids by the caller (rin_set_tet_range keeps all V by default).
+    CK(c->vals.ensure((size_t)V * F * 8));
+    CK(c->vmask.ensure((size_t)V * W * 8));
+    CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
+    CK(cudaEventRecord(c->ev[ST_EVAL], s));
+    const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
+    CK(cudaEventRecord(c->kev[0], s));
+    if (c->have_funcs) {
+        size_t smem = F * sizeof(rin_func_desc);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_functions_kernel<<<grid_for(vc, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), vf, vc, V,
+            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+    } else {
+        ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
+            negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+    }
+    // "highest func": masks of the maximal materials replace the sign masks
+    CK(cudaMemsetAsync(&dctr->n_zero, 0, 8, s));
+    highest_material_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->vals.as<double>(), vf, vc, V, F,
+        c->vmask.as<uint2>(), &dctr->n_zero);
+    CK(cudaEventRecord(c->kev[1], s));
+    CK(cudaGetLastError());
+
+    // ---- K2: filter (tile-local compaction) + tile scan + ordered gather
+    CK(cudaEventRecord(c->ev[ST_FILTER], s));
+    const uint32_t n_tiles = (T + FILT_TILE - 1) / FILT_TILE;
+    const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
+    const size_t tl_stride = (size_t)n_tiles * FILT_TILE;
+    CK(c->tl_tet.ensure(tl_stride * 4));
+    CK(c->tl_mask.ensure(tl_stride * 4 * W));
+    CK(c->tile_cnt.ensure((size_t)n_tiles * 8));
+    CK(c->tile_off.ensure((size_t)(n_tiles + 1) * 8));
+    CK(cudaEventRecord(c->kev[2], s));
+    (void)last_mask;
+    filter_mi_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
+        c->vmask.as<uint2>(), c->vals.as<double>(), V, F, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
+        tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt, &dctr->n_tie_faces);
+    CK(cudaEventRecord(c->kev[3], s));
+    scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h.n_tie_faces)
+        return fail(RIN_ERR_STATE, "material interface: materials tie exactly on whole tet faces (" +
+                                       std::to_string(h.n_tie_faces) +
+                                       " candidate tets); the degenerate boundary-face matching of "
+                                       "src/extract_mesh.cpp:833-981 is not built on the device yet");
+    const uint32_t A = h.filt.n_active;
+    c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 16 + 1024);
+    CK(c->act_tet.ensure((size_t)c->act_cap * 4));
+    CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
+    if (A) {
+        compact_active_kernel<W><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tl_tet.as<uint32_t>(),
+            c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, A, c->act_tet.as<uint32_t>(),
+            c->act_mask.as<uint32_t>(), c->act_cap);
+        CK(cudaGetLastError());
+    }
+
+    rin_counts& n = c->counts;
+    n = rin_counts{};
+    n.num_pts = c->V;
+    n.num_tets = c->t_count;
+    n.num_funcs = F;
+    n.num_degenerate_vertex = h.n_zero;
+    n.num_intersecting_tet = A;
+    n.num_k1 = h.filt.n_k1;
+    n.num_k2 = h.filt.n_k2;
+    n.num_kmore = h.filt.n_kmore;
+    n.num_active_funcs = h.filt.n_funcs;
+
+    // ---- K3: classify
+    CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
+    CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
+    CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
+    CK(c->big_list.ensure((size_t)std::max(A, 1u) * 8)); // [big | small-tier overflow]
+    CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
+    if (A) {
+        classify_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
+            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vals.as<double>(), V,
+            c->lut_mi.lut1.as<uint16_t>(), use_lookup, c->rec_ref.as<uint32_t>(), c->general_list.as<uint32_t>(),
+            c->big_list.as<uint32_t>(), &dctr->gen);
+        CK(cudaGetLastError());
+    }
+    (void)use_secondary;
+
+    // ---- K4: general kernels (arena grows on overflow)
+    CK(cudaEventRecord(c->ev[ST_GENERAL], s));
+    if (A) {
+        const uint32_t est = use_lookup ? (h.filt.n_kmore + h.filt.n_k2) : A;
+        const int small_blocks = (int)std::max<uint32_t>(
+            1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
+        const size_t small_smem = GEN_SMALL_WARPS * sizeof(MIComplex<MICapsSmall>);
+        for (int attempt = 0;; ++attempt) {
+            if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
+            const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
+            const unsigned top0 = 4;
+            CK(cudaMemsetAsync(c->arena.p, 0, 4, s));
+            CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
+            // small tier: one tet per warp, complex in shared memory; capacity overflow -> ovf list
+            general_mi_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
+                c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
+                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V,
+                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
+            general_mi_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
+                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
+                c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
+                c->rec_ref.as<uint32_t>(), &dctr->gen);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&h.gen, &dctr->gen, sizeof(GeneralCounters), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h.gen.err)
+                return fail(h.gen.err, "per-tet arrangement failed in tet " + std::to_string(h.gen.err_tet) +
+                                           (h.gen.err == RIN_ERR_CAPACITY ? " (complex exceeds kernel capacity)"
+                                                                         : " (degenerate input)"));
+            if (!h.gen.arena_overflow) break;
+            if (attempt > 2) return fail(RIN_ERR_STATE, "general kernel: arena overflow after regrow");
+            CK(c->arena.ensure((size_t)h.gen.arena_top + h.gen.arena_top / 8 + 4096));
+            GeneralCounters z{};
+            z.n_general = h.gen.n_general;
+            z.n_small = h.gen.n_small;
+            z.n_big = h.gen.n_big;
+            CK(cudaMemcpyAsync(&dctr->gen, &z, sizeof(GeneralCounters), cudaMemcpyHostToDevice, s));
+        }
+    }
+    n.num_general_tets = h.gen.n_general;
+
+    // ---- K5a: counts + offsets
+    CK(cudaEventRecord(c->ev[ST_SCAN], s));
+    const uint32_t a_tiles = (A + 255) / 256;
+    if (A) {
+        CK(c->status.ensure((size_t)a_tiles * 16 + 64));
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
+        count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
+            c->act_cap, A, c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
+            c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h.scan, &dctr->scan, sizeof(ScanTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
+
+    // ---- K5b: emit
+    CK(cudaEventRecord(c->ev[ST_EMIT], s));
+    CK(c->cand_key.ensure((size_t)std::max(NC, 1u) * 16));
+    CK(c->cand_pay.ensure((size_t)std::max(NC, 1u) * 16));
+    CK(c->face_hdr.ensure((size_t)std::max(NFc, 1u) * 16));
+    CK(c->fv_ref.ensure((size_t)std::max(NFV, 1u) * 4));
+    if (A) {
+        emit_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(), c->act_tet.as<uint32_t>(),
+            c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(),
+            c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->cand_key.as<uint4>(),
+            c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>());
+        CK(cudaGetLastError());
+    }
+
+    // ---- K6: dedup (hash-min + rank)
+    CK(cudaEventRecord(c->ev[ST_DEDUP], s));
+    uint32_t NV = 0;
+    if (NC) {
+        uint32_t tsize = 1024;
+        while (tsize < 2 * NC) tsize <<= 1;
+        CK(c->table.ensure((size_t)tsize * 4));
+        CK(c->slot_of.ensure((size_t)NC * 4));
+        CK(c->rep.ensure((size_t)NC * 4));
+        CK(c->vid.ensure((size_t)NC * 4));
+        CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
+        hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
+            c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
+        const uint32_t r_tiles = (NC + 1023) / 1024;
+        CK(c->status.ensure((size_t)r_tiles * 8 + 64));
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)r_tiles * 8, s));
+        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NC,
+            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
+            &dctr->n_unique);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        NV = h.n_unique;
+    }
+
+    // ---- K7: unique vertices + xyz
+    CK(cudaEventRecord(c->ev[ST_VERTS], s));
+    CK(c->v_tet.ensure((size_t)std::max(NV, 1u) * 4));
+    CK(c->v_local.ensure(std::max(NV, 1u)));
+    CK(c->v_size.ensure(std::max(NV, 1u)));
+    CK(c->v_simplex.ensure((size_t)std::max(NV, 1u) * 16));
+    CK(c->v_funcs.ensure((size_t)std::max(NV, 1u) * 16));
+    CK(c->v_xyz.ensure((size_t)std::max(NV, 1u) * 24));
+    if (NC) {
+        write_verts_mi_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
+            c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
+            c->vals.as<double>(), V, c->pts.as<double>(), c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(),
+            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>());
+        CK(cudaGetLastError());
+    }
+
+    // ---- faces
+    CK(cudaEventRecord(c->ev[ST_FACES], s));
+    CK(c->f_off.ensure((size_t)(NFc + 1) * 4));
+    CK(c->f_verts.ensure((size_t)std::max(NFV, 1u) * 4));
+    CK(c->f_toff.ensure((size_t)(NFc + 1) * 4));
+    CK(c->f_tets.ensure((size_t)std::max(NFc, 1u) * 8));
+    CK(c->f_funcs.ensure((size_t)std::max(NFc, 1u) * 8));
+    uint32_t NF = NFc, NFVout = NFV, NFT = NFc;
+    if (NFV)
+        remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
+            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
+    write_faces_mi_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, NFV,
+        c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[ST_COUNT], s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+    CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
+    CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+    CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
+
+    n.num_verts = NV;
+    n.num_faces = NF;
+    n.num_face_verts = NFVout;
+    n.num_face_tets = NFT;
+    n.num_exact_fallbacks = (uint64_t)h.gen.n_exact + h.n_exact_classify;
+    return RIN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Lookup tables (1 and 2 functions), generated by THIS library's general kernel on witness tets:
 // one witness per vertex-sign pattern (1 function) and per (sign pattern, crossing order) key
 // (2 functions).  A key that no witness realises stays LUT_MISS and takes the general kernel.
@@ -973,6 +1243,98 @@ int build_ia_tables(rin_ctx* c)
     CKC(L.blob.ensure(L.blob_bytes));
     CKC(cudaMemcpyAsync(L.lut1.p, L.h_lut1.data(), 32, cudaMemcpyHostToDevice, s));
     CKC(cudaMemcpyAsync(L.lut2.p, L.h_lut2.data(), 256 * 64 * 2, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(L.blob.p, L.h_blob.data(), L.blob_bytes, cudaMemcpyHostToDevice, s));
+    CKC(cudaStreamSynchronize(s));
+    cleanup();
+    L.built = true;
+    return RIN_OK;
+#undef CKC
+}
+
+// 16-entry table for two materials (sign pattern of m0 - m1 at the corners), generated by this
+// library's general MI kernel on witness tets.
+int build_mi_tables(rin_ctx* c)
+{
+    cudaStream_t s = c->stream;
+    const int sm = c->sm_count;
+    Lut& L = c->lut_mi;
+    const uint32_t NW = 16, Vw = 4 * NW;
+    std::vector<double> vals((size_t)2 * Vw);
+    for (uint32_t w = 0; w < NW; ++w)
+        for (int i = 0; i < 4; ++i) {
+            const double a = 0.25 * i;
+            vals[4 * w + i] = a;
+            vals[(size_t)Vw + 4 * w + i] = a + (((w >> i) & 1) ? -1.0 : 1.0) * (0.5 + 0.125 * i);
+        }
+    std::vector<uint4> tets(NW);
+    std::vector<uint32_t> at(NW), am(NW, 3u), gl(NW);
+    for (uint32_t w = 0; w < NW; ++w) {
+        tets[w] = make_uint4(4 * w, 4 * w + 1, 4 * w + 2, 4 * w + 3);
+        at[w] = gl[w] = w;
+    }
+    DevBuf d_vals, d_tets, d_at, d_am, d_ref, d_gl, d_ctr, d_arena;
+    auto cleanup = [&]() {
+        for (DevBuf* b : {&d_vals, &d_tets, &d_at, &d_am, &d_ref, &d_gl, &d_ctr, &d_arena}) b->release();
+    };
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup();                                                                             \
+            return fail(RIN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                          \
+    } while (0)
+    CKC(d_vals.ensure(vals.size() * 8));
+    CKC(d_tets.ensure(NW * 16));
+    CKC(d_at.ensure(NW * 4));
+    CKC(d_am.ensure(NW * 4));
+    CKC(d_ref.ensure(NW * 4));
+    CKC(d_gl.ensure(NW * 4));
+    CKC(d_ctr.ensure(sizeof(Counters)));
+    CKC(d_arena.ensure(1 << 16));
+    CKC(cudaMemcpyAsync(d_vals.p, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_tets.p, tets.data(), NW * 16, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_at.p, at.data(), NW * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_am.p, am.data(), NW * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemcpyAsync(d_gl.p, gl.data(), NW * 4, cudaMemcpyHostToDevice, s));
+    CKC(cudaMemsetAsync(d_ctr.p, 0, sizeof(Counters), s));
+    CKC(cudaMemsetAsync(d_arena.p, 0, 4, s));
+    Counters* dctr = d_ctr.as<Counters>();
+    GeneralCounters g0{};
+    g0.n_general = g0.n_big = NW;
+    g0.arena_top = 4;
+    CKC(cudaMemcpyAsync(&dctr->gen, &g0, sizeof(g0), cudaMemcpyHostToDevice, s));
+    general_mi_big_kernel<1><<<sm, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_at.as<uint32_t>(), d_am.as<uint32_t>(),
+        NW, d_gl.as<uint32_t>(), d_gl.as<uint32_t>(), d_vals.as<double>(), Vw, d_arena.as<uint8_t>(), 1 << 16,
+        d_ref.as<uint32_t>(), &dctr->gen);
+    CKC(cudaGetLastError());
+    GeneralCounters g1;
+    std::vector<uint32_t> refs(NW);
+    CKC(cudaMemcpyAsync(&g1, &dctr->gen, sizeof(g1), cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemcpyAsync(refs.data(), d_ref.p, NW * 4, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    if (g1.err || g1.arena_overflow) {
+        cleanup();
+        return fail(RIN_ERR_STATE, "MI table generation failed");
+    }
+    std::vector<uint8_t> arena(g1.arena_top);
+    CKC(cudaMemcpyAsync(arena.data(), d_arena.p, g1.arena_top, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    L.h_lut1.assign(16, 0);
+    L.h_blob.assign(4, 0);
+    for (uint32_t w = 0; w < NW; ++w) {
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(arena.data() + (size_t)(refs[w] & ~REF_GENERAL) * 4);
+        const int nv = rw[0] & 255, nf = (rw[0] >> 8) & 255;
+        uint32_t words = 1 + 2 * nv;
+        for (int f = 0; f < nf; ++f) words += 1 + rec_face_words((rw[words] >> 24) & 127);
+        L.h_lut1[w] = (uint16_t)(L.h_blob.size() / 4);
+        const uint8_t* r = reinterpret_cast<const uint8_t*>(rw);
+        L.h_blob.insert(L.h_blob.end(), r, r + 4 * words);
+    }
+    L.blob_bytes = (uint32_t)L.h_blob.size();
+    CKC(L.lut1.ensure(32));
+    CKC(L.blob.ensure(L.blob_bytes));
+    CKC(cudaMemcpyAsync(L.lut1.p, L.h_lut1.data(), 32, cudaMemcpyHostToDevice, s));
     CKC(cudaMemcpyAsync(L.blob.p, L.h_blob.data(), L.blob_bytes, cudaMemcpyHostToDevice, s));
     CKC(cudaStreamSynchronize(s));
     cleanup();
