@@ -78,10 +78,8 @@ def grid_resolution(n_gpus):
 
 
 def slab_range(R, rank, world):
-    """Contiguous tet range of x-slabs [i0, i1): cubes are i-major (src/io.cpp:122-125)."""
-    i0, i1 = R * rank // world, R * (rank + 1) // world
-    per_slab = 5 * R * R
-    return i0 * per_slab, (i1 - i0) * per_slab
+    import sharding
+    return sharding.slab_range(R, rank, world)
 
 
 def cpu_reference_run(config, seconds_budget=20.0):
@@ -192,16 +190,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    import sharding
+    gather = sharding.torch_gather(dist, torch.device("cuda", local)) if dist is not None else None
+
+    def step():
+        """One pass: local hot path on this rank's slab, then (N > 1) the slab-boundary key
+        exchange over NCCL and the rewrite to global vertex ids."""
+        c = ctx.run(mode, flags)
+        if dist is not None:
+            sharding.exchange(ctx, rank, world, gather, c.num_faces)
+        return c
+
     # ---- value: inputs resident in HBM ---------------------------------------------------------
     for _ in range(args.warmup):
-        ctx.run(mode, flags)
+        step()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     dev_ms, eval_ms, filt_ms = [], [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cnt = ctx.run(mode, flags)
+        cnt = step()
         kt = ctx.kernel_times()
         dev_ms.append(kt["total_ms"])
         eval_ms.append(kt["eval_ms"])

@@ -157,13 +157,27 @@ int rin_run_host(rin_ctx*, int mode, uint32_t flags, const double* pts, uint64_t
                  const void* tets, uint64_t n_tets, int index_bytes,
                  const double* vals_rowmajor, uint32_t n_funcs, rin_counts* counts);
 
-/* ---- slab-boundary exchange for multi-GPU runs (one process per GPU) -------------------- */
-/* After rin_run on every rank: export the keys of this rank's unique vertices whose simplex
- * lies entirely in vertices >= min_shared_vertex (device pointer to 16-byte keys + local ids). */
-int rin_export_boundary(rin_ctx*, uint32_t min_shared_vertex, void** d_keys, void** d_ids, uint64_t* n);
-/* Import the lower neighbour's boundary keys (device pointers); vertices of this rank that
- * match are dropped and remapped.  Updates counts and the downloadable mesh. */
-int rin_import_boundary(rin_ctx*, const void* d_keys, const void* d_ids, uint64_t n);
+/* ---- slab-boundary exchange for multi-GPU runs (one process per GPU) ----------------------
+ * Every rank runs rin_run on its own contiguous tet range (rin_set_tet_range).  Vertices whose
+ * minimal simplex lies in the vertex range shared with another rank are found by both; the rank
+ * with the LOWER tet range owns them (it is the first occurrence in tet order).  Protocol, with
+ * the collectives done by the caller (NCCL all-gather of a few KB):
+ *   1. rin_boundary_export(own_only = 0, [lo, hi]) on every rank -> keys of shared candidates
+ *   2. all-gather the keys; rin_mark_foreign(keys of all LOWER ranks) -> n_own
+ *   3. all-gather n_own -> this rank's global vertex offset
+ *   4. rin_boundary_export(own_only = 1) -> (key, own index) of the owned shared vertices;
+ *      all-gather (key, offset + own index)
+ *   5. rin_finalize_sharded(offset, foreign keys, foreign global ids): vertex arrays keep the
+ *      owned vertices (first-occurrence order), face vertex lists are rewritten to global ids.
+ * A key is four 32-bit words: sorted simplex vertex ids (unused 0xffffffff) and the packed
+ * function / material ids. */
+int rin_boundary_export(rin_ctx*, int own_only, uint32_t v_lo, uint32_t v_hi, uint32_t* keys, uint32_t* ids,
+                        uint64_t capacity, uint64_t* n);
+int rin_mark_foreign(rin_ctx*, const uint32_t* keys, uint64_t n_keys, uint64_t* n_own);
+int rin_finalize_sharded(rin_ctx*, uint64_t vert_offset, const uint32_t* keys, const uint32_t* global_ids,
+                         uint64_t n_keys);
+/* vertex id range referenced by the current tet range */
+int rin_get_vertex_range(const rin_ctx*, uint32_t* v_lo, uint32_t* v_hi);
 
 #ifdef __cplusplus
 }

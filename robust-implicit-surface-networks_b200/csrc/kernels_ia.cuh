@@ -1025,12 +1025,13 @@ __global__ void __launch_bounds__(256) write_verts_ia_kernel(const uint4* __rest
     uint32_t n, const uint4* __restrict__ tets, const double* __restrict__ vals, uint32_t V,
     const double* __restrict__ pts, uint32_t* __restrict__ v_tet, uint8_t* __restrict__ v_local,
     uint8_t* __restrict__ v_size, uint4* __restrict__ v_simplex, uint4* __restrict__ v_funcs,
-    double* __restrict__ v_xyz)
+    double* __restrict__ v_xyz, uint4* __restrict__ v_key)
 {
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         if (rep[c] != c) continue;
         const uint32_t id = vid[c];
         const uint4 pay = cand_pay[c];
+        v_key[id] = cand_key[c];
         const int size = (pay.y >> 8) & 255;
         uint32_t sv[4];
         if (size == 4) {
@@ -1302,6 +1303,163 @@ __global__ void __launch_bounds__(256) bface_sort_pairs_kernel(uint32_t n_faces,
             f_tets[2 * (size_t)y] = t0;
             f_tets[2 * (size_t)y + 1] = t1;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slab-boundary exchange (multi-GPU): vertices whose minimal simplex lies in the vertex range
+// shared with another rank.
+// ---------------------------------------------------------------------------------------------
+// appends (key, id) of the unique vertices with simplex inside [lo, hi]; id = local id, or the own
+// index when own_only (foreign vertices are skipped)
+__global__ void __launch_bounds__(256) boundary_select_kernel(const uint4* __restrict__ v_key,
+    const uint8_t* __restrict__ v_size, uint32_t n, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ own_idx,
+    uint4* __restrict__ out_keys, uint32_t* __restrict__ out_ids, uint32_t cap, unsigned* __restrict__ n_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int sz = v_size[i];
+        if (sz >= 4) continue;
+        const uint4 k = v_key[i];
+        bool in = k.x >= lo && k.x <= hi;
+        if (sz >= 2) in &= k.y >= lo && k.y <= hi;
+        if (sz >= 3) in &= k.z >= lo && k.z <= hi;
+        if (!in) continue;
+        uint32_t id = i;
+        if (own_idx) {
+            id = own_idx[i];
+            if (id == NONE32) continue;
+        }
+        const unsigned p = atomicAdd(n_out, 1u);
+        if (p < cap) {
+            out_keys[p] = k;
+            out_ids[p] = id;
+        }
+    }
+}
+
+// open-addressing set of foreign keys: table[h] = index into fkeys
+__global__ void __launch_bounds__(256) foreign_insert_kernel(const uint4* __restrict__ fkeys, uint32_t m,
+    uint32_t* __restrict__ table, uint32_t mask)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
+        const uint4 k = fkeys[c];
+        uint32_t h = hash4(k) & mask;
+        for (;;) {
+            uint32_t cur = atomicCAS(&table[h], NONE32, c);
+            if (cur == NONE32 || key_eq(fkeys[cur], k)) break;
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t foreign_lookup(const uint4* fkeys, const uint32_t* table, uint32_t mask, uint4 k)
+{
+    uint32_t h = hash4(k) & mask;
+    for (;;) {
+        const uint32_t cur = table[h];
+        if (cur == NONE32) return NONE32;
+        if (key_eq(fkeys[cur], k)) return cur;
+        h = (h + 1) & mask;
+    }
+}
+
+// flag[i] = 1 when vertex i is owned by this rank (not found among the lower ranks' keys)
+__global__ void __launch_bounds__(256) mark_foreign_kernel(const uint4* __restrict__ v_key,
+    const uint8_t* __restrict__ v_size, uint32_t n, const uint4* __restrict__ fkeys,
+    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ own_flag)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t own = 1;
+        if (v_size[i] < 4 && mask && foreign_lookup(fkeys, table, mask, v_key[i]) != NONE32) own = 0;
+        own_flag[i] = own;
+    }
+}
+
+// single-block exclusive scan of 0/1 flags -> own_idx (NONE32 where the flag is 0); total in *n_own
+__global__ void __launch_bounds__(1024) own_scan_kernel(const uint32_t* __restrict__ flag, uint32_t n,
+    uint32_t* __restrict__ own_idx, unsigned* __restrict__ n_own)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < n; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t c = (i < n) ? flag[i] : 0;
+        uint32_t x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t t = s_w[lane], y = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t z = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= o) y += z;
+            }
+            s_w[lane] = y - t;
+        }
+        __syncthreads();
+        const uint32_t r = s_run, wv = s_w[warp];
+        if (i < n) own_idx[i] = c ? (r + wv + x - c) : NONE32;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = r + wv + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_own = s_run;
+}
+
+// gid[i] = global id of local vertex i: offset + own index, or the owner's id for foreign vertices
+__global__ void __launch_bounds__(256) global_ids_kernel(const uint4* __restrict__ v_key,
+    const uint32_t* __restrict__ own_idx, uint32_t n, uint32_t offset, const uint4* __restrict__ fkeys,
+    const uint32_t* __restrict__ fgids, const uint32_t* __restrict__ table, uint32_t mask,
+    uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t o = own_idx[i];
+        if (o != NONE32) {
+            gid[i] = offset + o;
+            continue;
+        }
+        const uint32_t f = mask ? foreign_lookup(fkeys, table, mask, v_key[i]) : NONE32;
+        if (f == NONE32) {
+            atomicAdd(n_unresolved, 1u);
+            gid[i] = NONE32;
+        } else
+            gid[i] = fgids[f];
+    }
+}
+
+__global__ void __launch_bounds__(256) apply_gids_kernel(uint32_t* __restrict__ f_verts, uint32_t n,
+    const uint32_t* __restrict__ gid)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        f_verts[i] = gid[f_verts[i]];
+}
+
+// keep the owned vertices (order preserved)
+__global__ void __launch_bounds__(256) compact_own_verts_kernel(const uint32_t* __restrict__ own_idx, uint32_t n,
+    const uint32_t* __restrict__ v_tet, const uint8_t* __restrict__ v_local, const uint8_t* __restrict__ v_size,
+    const uint4* __restrict__ v_simplex, const uint4* __restrict__ v_funcs, const double* __restrict__ v_xyz,
+    const uint4* __restrict__ v_key, uint32_t* __restrict__ o_tet, uint8_t* __restrict__ o_local,
+    uint8_t* __restrict__ o_size, uint4* __restrict__ o_simplex, uint4* __restrict__ o_funcs,
+    double* __restrict__ o_xyz, uint4* __restrict__ o_key)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t d = own_idx[i];
+        if (d == NONE32) continue;
+        o_tet[d] = v_tet[i];
+        o_local[d] = v_local[i];
+        o_size[d] = v_size[i];
+        o_simplex[d] = v_simplex[i];
+        o_funcs[d] = v_funcs[i];
+        o_xyz[3 * (size_t)d] = v_xyz[3 * (size_t)i];
+        o_xyz[3 * (size_t)d + 1] = v_xyz[3 * (size_t)i + 1];
+        o_xyz[3 * (size_t)d + 2] = v_xyz[3 * (size_t)i + 2];
+        o_key[d] = v_key[i];
     }
 }
 

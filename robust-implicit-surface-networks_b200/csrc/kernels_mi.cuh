@@ -514,12 +514,13 @@ __global__ void __launch_bounds__(256) write_verts_mi_kernel(const uint4* __rest
     uint32_t n, const uint4* __restrict__ tets, const double* __restrict__ vals, uint32_t V,
     const double* __restrict__ pts, uint32_t* __restrict__ v_tet, uint8_t* __restrict__ v_local,
     uint8_t* __restrict__ v_size, uint4* __restrict__ v_simplex, uint4* __restrict__ v_funcs,
-    double* __restrict__ v_xyz)
+    double* __restrict__ v_xyz, uint4* __restrict__ v_key)
 {
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         if (rep[c] != c) continue;
         const uint32_t id = vid[c];
         const uint4 pay = cand_pay[c];
+        v_key[id] = cand_key[c];
         const int size = (pay.y >> 8) & 255;
         uint32_t sv[4];
         if (size == 4) {

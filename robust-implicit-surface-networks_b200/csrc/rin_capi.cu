@@ -119,9 +119,14 @@ struct rin_ctx
     DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
-    DevBuf tmp_fverts, fkeys, frep, fdup, fpos; // degenerate boundary-face dedup
+    DevBuf tmp_fverts, bfkeys, frep, fdup, fpos; // degenerate boundary-face dedup
     // outputs
-    DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz;
+    DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz, v_key;
+    // sharded runs
+    DevBuf o_tet, o_local, o_size, o_simplex, o_funcs, o_xyz, o_key, own_flag, own_idx, gid, fkeys, fgids, ftable,
+        bkeys, bids;
+    bool marked = false, finalized = false;
+    uint32_t n_local_verts = 0, n_own = 0;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
     uint32_t act_cap = 0;
     Lut lut_ia, lut_mi;
@@ -203,8 +208,10 @@ void rin_destroy(rin_ctx* c)
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->counters,
         &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
-        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->fkeys, &c->frep, &c->fdup, &c->fpos,
-        &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->f_off, &c->f_verts,
+        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos,
+        &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
+        &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
+        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob,
         &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
@@ -506,13 +513,156 @@ int rin_get_complexes(rin_ctx*, int, uint32_t, const uint64_t*, uint64_t, uint64
 {
     return fail(RIN_ERR_STATE, "rin_get_complexes: not built yet");
 }
-int rin_export_boundary(rin_ctx*, uint32_t, void**, void**, uint64_t*)
+int rin_get_vertex_range(const rin_ctx* c, uint32_t* lo, uint32_t* hi)
 {
-    return fail(RIN_ERR_STATE, "rin_export_boundary: not built yet");
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (lo) *lo = c->v_count ? c->v_first : 0;
+    if (hi) *hi = c->v_count ? c->v_first + c->v_count - 1 : (uint32_t)c->V - 1;
+    return RIN_OK;
 }
-int rin_import_boundary(rin_ctx*, const void*, const void*, uint64_t)
+
+int rin_boundary_export(rin_ctx* c, int own_only, uint32_t lo, uint32_t hi, uint32_t* keys, uint32_t* ids,
+    uint64_t capacity, uint64_t* n_out)
 {
-    return fail(RIN_ERR_STATE, "rin_import_boundary: not built yet");
+    if (!c || !n_out) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
+    if (own_only && !c->marked) return fail(RIN_ERR_STATE, "rin_boundary_export(own_only): call rin_mark_foreign first");
+    if (c->finalized) return fail(RIN_ERR_STATE, "run already finalized");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t NV = c->n_local_verts;
+    CK(c->counters.ensure(sizeof(Counters)));
+    unsigned* d_n = &c->counters.as<Counters>()->n_unique;
+    CK(cudaMemsetAsync(d_n, 0, 4, s));
+    const uint32_t cap = (uint32_t)std::max<uint64_t>(NV, 1);
+    CK(c->bkeys.ensure((size_t)cap * 16));
+    CK(c->bids.ensure((size_t)cap * 4));
+    if (NV) {
+        boundary_select_kernel<<<grid_for(NV, 256, c->sm_count), 256, 0, s>>>(c->v_key.as<uint4>(),
+            c->v_size.as<uint8_t>(), NV, lo, hi, own_only ? c->own_idx.as<uint32_t>() : nullptr,
+            c->bkeys.as<uint4>(), c->bids.as<uint32_t>(), cap, d_n);
+        CK(cudaGetLastError());
+    }
+    unsigned n = 0;
+    CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *n_out = n;
+    if (keys && ids) {
+        if (capacity < n) return fail(RIN_ERR_ARG, "rin_boundary_export: capacity too small");
+        if (n) {
+            CK(cudaMemcpyAsync(keys, c->bkeys.p, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(ids, c->bids.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+    }
+    return RIN_OK;
+}
+
+namespace {
+int upload_foreign(rin_ctx* c, const uint32_t* keys, const uint32_t* gids, uint64_t m, uint32_t* mask_out)
+{
+    cudaStream_t s = c->stream;
+    *mask_out = 0;
+    if (m == 0) return RIN_OK;
+    uint32_t tsize = 64;
+    while (tsize < 2 * m) tsize <<= 1;
+    CK(c->fkeys.ensure(m * 16));
+    CK(c->ftable.ensure((size_t)tsize * 4));
+    CK(cudaMemcpyAsync(c->fkeys.p, keys, m * 16, cudaMemcpyHostToDevice, s));
+    if (gids) {
+        CK(c->fgids.ensure(m * 4));
+        CK(cudaMemcpyAsync(c->fgids.p, gids, m * 4, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemsetAsync(c->ftable.p, 0xff, (size_t)tsize * 4, s));
+    foreign_insert_kernel<<<grid_for(m, 256, c->sm_count), 256, 0, s>>>(c->fkeys.as<uint4>(), (uint32_t)m,
+        c->ftable.as<uint32_t>(), tsize - 1);
+    CK(cudaGetLastError());
+    *mask_out = tsize - 1;
+    return RIN_OK;
+}
+} // namespace
+
+int rin_mark_foreign(rin_ctx* c, const uint32_t* keys, uint64_t m, uint64_t* n_own)
+{
+    if (!c || (m && !keys)) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran || c->finalized) return fail(RIN_ERR_STATE, "rin_mark_foreign: no fresh run");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t NV = c->n_local_verts;
+    uint32_t mask = 0;
+    int rc = upload_foreign(c, keys, nullptr, m, &mask);
+    if (rc) return rc;
+    CK(c->own_flag.ensure((size_t)std::max(NV, 1u) * 4));
+    CK(c->own_idx.ensure((size_t)std::max(NV, 1u) * 4));
+    unsigned* d_n = &c->counters.as<Counters>()->n_unique;
+    if (NV) {
+        mark_foreign_kernel<<<grid_for(NV, 256, c->sm_count), 256, 0, s>>>(c->v_key.as<uint4>(),
+            c->v_size.as<uint8_t>(), NV, c->fkeys.as<uint4>(), c->ftable.as<uint32_t>(), mask,
+            c->own_flag.as<uint32_t>());
+        own_scan_kernel<<<1, 1024, 0, s>>>(c->own_flag.as<uint32_t>(), NV, c->own_idx.as<uint32_t>(), d_n);
+        CK(cudaGetLastError());
+    } else
+        CK(cudaMemsetAsync(d_n, 0, 4, s));
+    unsigned n = 0;
+    CK(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->n_own = n;
+    c->marked = true;
+    if (n_own) *n_own = n;
+    return RIN_OK;
+}
+
+int rin_finalize_sharded(rin_ctx* c, uint64_t vert_offset, const uint32_t* keys, const uint32_t* gids, uint64_t m)
+{
+    if (!c || (m && (!keys || !gids))) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->marked || c->finalized) return fail(RIN_ERR_STATE, "rin_finalize_sharded: call rin_mark_foreign first");
+    if (vert_offset + c->n_own >= 0xffffffffull) return fail(RIN_ERR_ARG, "global vertex ids exceed 32 bits");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t NV = c->n_local_verts, NO = c->n_own;
+    uint32_t mask = 0;
+    int rc = upload_foreign(c, keys, gids, m, &mask);
+    if (rc) return rc;
+    CK(c->gid.ensure((size_t)std::max(NV, 1u) * 4));
+    unsigned* d_bad = &c->counters.as<Counters>()->n_bndry_faces;
+    CK(cudaMemsetAsync(d_bad, 0, 4, s));
+    if (NV) {
+        global_ids_kernel<<<grid_for(NV, 256, c->sm_count), 256, 0, s>>>(c->v_key.as<uint4>(),
+            c->own_idx.as<uint32_t>(), NV, (uint32_t)vert_offset, c->fkeys.as<uint4>(), c->fgids.as<uint32_t>(),
+            c->ftable.as<uint32_t>(), mask, c->gid.as<uint32_t>(), d_bad);
+        const uint32_t NFV = (uint32_t)c->counts.num_face_verts;
+        if (NFV)
+            apply_gids_kernel<<<grid_for(NFV, 256, c->sm_count), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
+                c->gid.as<uint32_t>());
+        const size_t no1 = std::max(NO, 1u);
+        CK(c->o_tet.ensure(no1 * 4));
+        CK(c->o_local.ensure(no1));
+        CK(c->o_size.ensure(no1));
+        CK(c->o_simplex.ensure(no1 * 16));
+        CK(c->o_funcs.ensure(no1 * 16));
+        CK(c->o_xyz.ensure(no1 * 24));
+        CK(c->o_key.ensure(no1 * 16));
+        compact_own_verts_kernel<<<grid_for(NV, 256, c->sm_count), 256, 0, s>>>(c->own_idx.as<uint32_t>(), NV,
+            c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(),
+            c->v_funcs.as<uint4>(), c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(),
+            c->o_local.as<uint8_t>(), c->o_size.as<uint8_t>(), c->o_simplex.as<uint4>(), c->o_funcs.as<uint4>(),
+            c->o_xyz.as<double>(), c->o_key.as<uint4>());
+        CK(cudaGetLastError());
+    }
+    unsigned bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (bad) return fail(RIN_ERR_STATE, "rin_finalize_sharded: " + std::to_string(bad) + " shared vertices have no owner id");
+    std::swap(c->v_tet, c->o_tet);
+    std::swap(c->v_local, c->o_local);
+    std::swap(c->v_size, c->o_size);
+    std::swap(c->v_simplex, c->o_simplex);
+    std::swap(c->v_funcs, c->o_funcs);
+    std::swap(c->v_xyz, c->o_xyz);
+    std::swap(c->v_key, c->o_key);
+    c->counts.num_verts = NO;
+    c->finalized = true;
+    return RIN_OK;
 }
 
 // introspection for tests: host copy of the IA tables
@@ -742,11 +892,13 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(c->v_simplex.ensure((size_t)std::max(NV, 1u) * 16));
     CK(c->v_funcs.ensure((size_t)std::max(NV, 1u) * 16));
     CK(c->v_xyz.ensure((size_t)std::max(NV, 1u) * 24));
+    CK(c->v_key.ensure((size_t)std::max(NV, 1u) * 16));
     if (NC) {
         write_verts_ia_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
             c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
             c->vals.as<double>(), V, c->pts.as<double>(), c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(),
-            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>());
+            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>(),
+            c->v_key.as<uint4>());
         CK(cudaGetLastError());
     }
 
@@ -773,7 +925,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         CK(c->table.ensure((size_t)tsize * 4));
         CK(c->slot_of.ensure((size_t)NFc * 4));
         CK(c->tmp_fverts.ensure((size_t)NFV * 4));
-        CK(c->fkeys.ensure((size_t)NFc * 16));
+        CK(c->bfkeys.ensure((size_t)NFc * 16));
         CK(c->frep.ensure((size_t)NFc * 4));
         CK(c->fdup.ensure((size_t)NFc * 8 + 16)); // ndup | cursor | totals
         CK(c->fpos.ensure((size_t)NFc * 16));
@@ -786,8 +938,8 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
             c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->tmp_fverts.as<uint32_t>());
         bface_keys_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->tmp_fverts.as<uint32_t>(),
-            c->fkeys.as<uint4>());
-        bface_insert_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->fkeys.as<uint4>(),
+            c->bfkeys.as<uint4>());
+        bface_insert_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->bfkeys.as<uint4>(),
             c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
         bface_reps_kernel<<<g, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NFc,
             c->frep.as<uint32_t>(), ndup);
@@ -815,6 +967,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
     CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
+    c->marked = c->finalized = false;
+    c->n_local_verts = NV;
+    c->n_own = NV;
     n.num_verts = NV;
     n.num_faces = NF;
     n.num_face_verts = NFVout;
@@ -1031,11 +1186,13 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->v_simplex.ensure((size_t)std::max(NV, 1u) * 16));
     CK(c->v_funcs.ensure((size_t)std::max(NV, 1u) * 16));
     CK(c->v_xyz.ensure((size_t)std::max(NV, 1u) * 24));
+    CK(c->v_key.ensure((size_t)std::max(NV, 1u) * 16));
     if (NC) {
         write_verts_mi_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
             c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
             c->vals.as<double>(), V, c->pts.as<double>(), c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(),
-            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>());
+            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>(),
+            c->v_key.as<uint4>());
         CK(cudaGetLastError());
     }
 
@@ -1060,6 +1217,9 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
     CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
+    c->marked = c->finalized = false;
+    c->n_local_verts = NV;
+    c->n_own = NV;
     n.num_verts = NV;
     n.num_faces = NF;
     n.num_face_verts = NFVout;

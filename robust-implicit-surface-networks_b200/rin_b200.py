@@ -68,6 +68,11 @@ def lib():
         L.rin_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.rin_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                            C.POINTER(C.c_float)]
+        L.rin_boundary_export.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_uint64, C.POINTER(C.c_uint64)]
+        L.rin_mark_foreign.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.rin_finalize_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.rin_get_vertex_range.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Counts)]
         L.rin_get_complexes.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -184,6 +189,34 @@ class Context:
         tets = np.empty((T, 4), np.uint32)
         self._check(lib().rin_download_grid(self._h, pts.ctypes.data, tets.ctypes.data))
         return pts, tets
+
+    # ---- slab-boundary exchange (see sharding.py for the protocol)
+    def vertex_range(self):
+        lo, hi = C.c_uint32(), C.c_uint32()
+        self._check(lib().rin_get_vertex_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def boundary_export(self, own_only, lo, hi):
+        n = C.c_uint64()
+        self._check(lib().rin_boundary_export(self._h, int(own_only), lo, hi, None, None, 0, C.byref(n)))
+        keys = np.empty((n.value, 4), np.uint32)
+        ids = np.empty(n.value, np.uint32)
+        if n.value:
+            self._check(lib().rin_boundary_export(self._h, int(own_only), lo, hi, keys.ctypes.data, ids.ctypes.data,
+                                                  n.value, C.byref(n)))
+        return keys, ids
+
+    def mark_foreign(self, keys):
+        keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 4)
+        n = C.c_uint64()
+        self._check(lib().rin_mark_foreign(self._h, keys.ctypes.data if len(keys) else None, len(keys), C.byref(n)))
+        return n.value
+
+    def finalize_sharded(self, offset, keys, gids):
+        keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 4)
+        gids = np.ascontiguousarray(gids, np.uint32)
+        self._check(lib().rin_finalize_sharded(self._h, offset, keys.ctypes.data if len(keys) else None,
+                                               gids.ctypes.data if len(keys) else None, len(keys)))
 
     def kernel_times(self):
         e, f, t = C.c_float(), C.c_float(), C.c_float()

@@ -1,0 +1,117 @@
+"""Slab sharding across GPUs: contiguous tet ranges per rank and the slab-boundary key exchange.
+
+Tets are independent through evaluation, filter, per-tet arrangement and candidate emission; the
+only cross-rank step is the identification of vertices found by two ranks on their shared vertex
+plane.  The rank holding the LOWER tet range owns such a vertex (it is the first occurrence in
+tet order, the numbering rule of /root/reference/src/extract_mesh.cpp:139,169,214), so that the
+concatenation of the ranks' vertex arrays equals the single-process result.
+
+`exchange()` is engine-agnostic: `engine` is a rin_b200.Context (device kernels behind the C-ABI)
+or any object with the same four methods; `gather(array) -> [array per rank]` is an all-gather
+(torch.distributed NCCL on the GPU box, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def slab_range(R, rank, world):
+    """Tet range of x-slabs [i0, i1) of a generated grid (cubes are i-major, src/io.cpp:122-125)."""
+    i0, i1 = R * rank // world, R * (rank + 1) // world
+    per_slab = 5 * R * R
+    return i0 * per_slab, (i1 - i0) * per_slab
+
+
+def exchange(engine, rank, world, gather, n_faces):
+    """Runs the boundary protocol.  Returns dict(vert_offset, face_offset, n_verts_total,
+    n_faces_total, n_own)."""
+    lo, hi = engine.vertex_range()
+    ranges = gather(np.array([lo, hi], np.int64))
+    # window covering every overlap of this rank's vertex range with another rank's
+    w_lo, w_hi = None, None
+    for s, (slo, shi) in enumerate(ranges):
+        if s == rank:
+            continue
+        a, b = max(lo, int(slo)), min(hi, int(shi))
+        if a <= b:
+            w_lo = a if w_lo is None else min(w_lo, a)
+            w_hi = b if w_hi is None else max(w_hi, b)
+    if w_lo is None:
+        w_lo, w_hi = 1, 0  # empty window
+    keys, _ = engine.boundary_export(False, w_lo, w_hi)
+    all_keys = gather(keys.reshape(-1).astype(np.int64))
+    lower = [k.reshape(-1, 4) for k in all_keys[:rank]]
+    lower = np.concatenate(lower).astype(np.uint32) if lower else np.zeros((0, 4), np.uint32)
+    n_own = engine.mark_foreign(lower)
+    counts = gather(np.array([n_own, n_faces], np.int64))
+    vert_offset = int(sum(int(c[0]) for c in counts[:rank]))
+    face_offset = int(sum(int(c[1]) for c in counts[:rank]))
+    keys2, own_idx = engine.boundary_export(True, w_lo, w_hi)
+    packed = np.concatenate([keys2.astype(np.int64), (own_idx.astype(np.int64) + vert_offset)[:, None]], axis=1)
+    allp = gather(packed.reshape(-1))
+    low = [p.reshape(-1, 5) for p in allp[:rank]]
+    low = np.concatenate(low) if low else np.zeros((0, 5), np.int64)
+    engine.finalize_sharded(vert_offset, low[:, :4].astype(np.uint32), low[:, 4].astype(np.uint32))
+    return {"vert_offset": vert_offset, "face_offset": face_offset, "n_own": n_own,
+            "n_verts_total": int(sum(int(c[0]) for c in counts)),
+            "n_faces_total": int(sum(int(c[1]) for c in counts))}
+
+
+def torch_gather(dist, device=None):
+    """all-gather of variable-length int64 vectors over torch.distributed."""
+    import torch
+
+    def gather(arr):
+        arr = np.ascontiguousarray(arr, np.int64).reshape(-1)
+        world = dist.get_world_size()
+        n = torch.tensor([arr.size], dtype=torch.int64, device=device)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(max(sizes), 1)
+        buf = torch.zeros(m, dtype=torch.int64, device=device)
+        if arr.size:
+            buf[:arr.size] = torch.from_numpy(arr).to(buf.device)
+        outs = [torch.zeros(m, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(outs, buf)
+        return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
+
+    return gather
+
+
+class NumpyEngine:
+    """The same four steps on host arrays (used by the CPU tests with the oracle as per-rank engine)."""
+
+    def __init__(self, keys, sizes, v_lo, v_hi):
+        self.keys = np.ascontiguousarray(keys, np.uint32).reshape(-1, 4)  # one per local vertex
+        self.sizes = np.asarray(sizes)
+        self.lo, self.hi = v_lo, v_hi
+        self.own_idx = None
+        self.gid = None
+
+    def vertex_range(self):
+        return self.lo, self.hi
+
+    def _in_window(self, lo, hi):
+        k, s = self.keys.astype(np.int64), self.sizes
+        ok = (s < 4) & (k[:, 0] >= lo) & (k[:, 0] <= hi)
+        ok &= (s < 2) | ((k[:, 1] >= lo) & (k[:, 1] <= hi))
+        ok &= (s < 3) | ((k[:, 2] >= lo) & (k[:, 2] <= hi))
+        return ok
+
+    def boundary_export(self, own_only, lo, hi):
+        sel = self._in_window(lo, hi)
+        if own_only:
+            sel &= self.own_idx >= 0
+            return self.keys[sel], self.own_idx[sel].astype(np.uint32)
+        return self.keys[sel], np.nonzero(sel)[0].astype(np.uint32)
+
+    def mark_foreign(self, keys):
+        foreign = {tuple(k) for k in np.asarray(keys).reshape(-1, 4).tolist()}
+        own = np.array([not (s < 4 and tuple(k) in foreign) for k, s in zip(self.keys.tolist(), self.sizes)],
+                       bool)
+        self.own_idx = np.where(own, np.cumsum(own) - 1, -1)
+        return int(own.sum())
+
+    def finalize_sharded(self, offset, keys, gids):
+        table = {tuple(k): int(g) for k, g in zip(np.asarray(keys).reshape(-1, 4).tolist(), gids)}
+        self.gid = np.array([offset + o if o >= 0 else table[tuple(k)]
+                             for o, k in zip(self.own_idx, self.keys.tolist())], np.int64)
