@@ -192,13 +192,14 @@ def main():
 
     import sharding
     gather = sharding.torch_gather(dist, torch.device("cuda", local)) if dist is not None else None
+    xstate = sharding.ExchangeState()
 
     def step():
         """One pass: local hot path on this rank's slab, then (N > 1) the slab-boundary key
         exchange over NCCL and the rewrite to global vertex ids."""
         c = ctx.run(mode, flags)
         if dist is not None:
-            sharding.exchange(ctx, rank, world, gather, c.num_faces)
+            sharding.exchange(ctx, rank, world, gather, c.num_faces, xstate)
         return c
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------

@@ -20,59 +20,85 @@ def slab_range(R, rank, world):
     return i0 * per_slab, (i1 - i0) * per_slab
 
 
-def exchange(engine, rank, world, gather, n_faces):
-    """Runs the boundary protocol.  Returns dict(vert_offset, face_offset, n_verts_total,
-    n_faces_total, n_own)."""
-    lo, hi = engine.vertex_range()
-    ranges = gather(np.array([lo, hi], np.int64))
-    # window covering every overlap of this rank's vertex range with another rank's
-    w_lo, w_hi = None, None
-    for s, (slo, shi) in enumerate(ranges):
-        if s == rank:
-            continue
-        a, b = max(lo, int(slo)), min(hi, int(shi))
-        if a <= b:
-            w_lo = a if w_lo is None else min(w_lo, a)
-            w_hi = b if w_hi is None else max(w_hi, b)
-    if w_lo is None:
-        w_lo, w_hi = 1, 0  # empty window
+class ExchangeState:
+    """Per-run cache: the shared vertex window does not change between passes over the same mesh."""
+
+    def __init__(self):
+        self.window = None
+
+
+def exchange(engine, rank, world, gather, n_faces, state=None):
+    """Runs the boundary protocol (two all-gathers per pass).  Returns dict(vert_offset,
+    face_offset, n_verts_total, n_faces_total, n_own)."""
+    if state is None:
+        state = ExchangeState()
+    if state.window is None:
+        lo, hi = engine.vertex_range()
+        ranges = gather(np.array([lo, hi], np.int64))
+        # window covering every overlap of this rank's vertex range with another rank's
+        w_lo, w_hi = None, None
+        for s, (slo, shi) in enumerate(ranges):
+            if s == rank:
+                continue
+            a, b = max(lo, int(slo)), min(hi, int(shi))
+            if a <= b:
+                w_lo = a if w_lo is None else min(w_lo, a)
+                w_hi = b if w_hi is None else max(w_hi, b)
+        state.window = (1, 0) if w_lo is None else (w_lo, w_hi)
+    w_lo, w_hi = state.window
+    # 1. keys of every candidate in the shared window; a key found by a lower rank is foreign
     keys, _ = engine.boundary_export(False, w_lo, w_hi)
     all_keys = gather(keys.reshape(-1).astype(np.int64))
     lower = [k.reshape(-1, 4) for k in all_keys[:rank]]
     lower = np.concatenate(lower).astype(np.uint32) if lower else np.zeros((0, 4), np.uint32)
     n_own = engine.mark_foreign(lower)
-    counts = gather(np.array([n_own, n_faces], np.int64))
-    vert_offset = int(sum(int(c[0]) for c in counts[:rank]))
-    face_offset = int(sum(int(c[1]) for c in counts[:rank]))
+    # 2. (n_own, n_faces) + owned shared keys with their own index; receivers add the owner's offset
     keys2, own_idx = engine.boundary_export(True, w_lo, w_hi)
-    packed = np.concatenate([keys2.astype(np.int64), (own_idx.astype(np.int64) + vert_offset)[:, None]], axis=1)
-    allp = gather(packed.reshape(-1))
-    low = [p.reshape(-1, 5) for p in allp[:rank]]
+    msg = np.concatenate([np.array([n_own, n_faces], np.int64),
+                          np.concatenate([keys2.astype(np.int64), own_idx.astype(np.int64)[:, None]],
+                                         axis=1).reshape(-1)])
+    allm = gather(msg)
+    n_owns = [int(m[0]) for m in allm]
+    n_fs = [int(m[1]) for m in allm]
+    offsets = np.concatenate([[0], np.cumsum(n_owns)])
+    low = []
+    for s in range(rank):
+        p = allm[s][2:].reshape(-1, 5).copy()
+        p[:, 4] += offsets[s]
+        low.append(p)
     low = np.concatenate(low) if low else np.zeros((0, 5), np.int64)
+    vert_offset = int(offsets[rank])
     engine.finalize_sharded(vert_offset, low[:, :4].astype(np.uint32), low[:, 4].astype(np.uint32))
-    return {"vert_offset": vert_offset, "face_offset": face_offset, "n_own": n_own,
-            "n_verts_total": int(sum(int(c[0]) for c in counts)),
-            "n_faces_total": int(sum(int(c[1]) for c in counts))}
+    return {"vert_offset": vert_offset, "face_offset": int(sum(n_fs[:rank])), "n_own": n_own,
+            "n_verts_total": int(offsets[-1]), "n_faces_total": int(sum(n_fs))}
 
 
 def torch_gather(dist, device=None):
-    """all-gather of variable-length int64 vectors over torch.distributed."""
+    """all-gather of variable-length int64 vectors over torch.distributed.  Buffers are padded to a
+    remembered capacity so that the usual pass needs ONE collective; the element count travels in
+    slot 0 and a pass whose payload outgrew the capacity is repeated with a larger one."""
     import torch
+
+    cap = {"n": 1024}
 
     def gather(arr):
         arr = np.ascontiguousarray(arr, np.int64).reshape(-1)
         world = dist.get_world_size()
-        n = torch.tensor([arr.size], dtype=torch.int64, device=device)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        sizes = [int(s.item()) for s in sizes]
-        m = max(max(sizes), 1)
-        buf = torch.zeros(m, dtype=torch.int64, device=device)
-        if arr.size:
-            buf[:arr.size] = torch.from_numpy(arr).to(buf.device)
-        outs = [torch.zeros(m, dtype=torch.int64, device=device) for _ in range(world)]
-        dist.all_gather(outs, buf)
-        return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
+        while True:
+            m = cap["n"]
+            host = np.zeros(m + 1, np.int64)
+            host[0] = arr.size
+            if arr.size <= m:
+                host[1:1 + arr.size] = arr
+            buf = torch.from_numpy(host).to(device) if device is not None else torch.from_numpy(host)
+            out = torch.empty((world, m + 1), dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(out, buf) if hasattr(dist, "all_gather_into_tensor") and device is not None \
+                else dist.all_gather(list(out.unbind(0)), buf)
+            res = out.cpu().numpy()
+            need = int(res[:, 0].max())
+            if need <= m:
+                return [res[r, 1:1 + int(res[r, 0])] for r in range(world)]
+            cap["n"] = int(need * 1.25) + 1024
 
     return gather
 
