@@ -193,13 +193,18 @@ def main():
     import sharding
     gather = sharding.torch_gather(dist, torch.device("cuda", local)) if dist is not None else None
     xstate = sharding.ExchangeState()
+    if dist is not None:
+        # NCCL communicator of the engine itself (device-side exchange): rank 0's id to everyone
+        uid = torch.from_numpy(rin.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        ctx.nccl_init(uid.cpu().numpy(), rank, world)
 
     def step():
         """One pass: local hot path on this rank's slab, then (N > 1) the slab-boundary key
         exchange over NCCL and the rewrite to global vertex ids."""
         c = ctx.run(mode, flags)
         if dist is not None:
-            sharding.exchange(ctx, rank, world, gather, c.num_faces, xstate)
+            ctx.exchange_nccl()
         return c
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------
@@ -227,6 +232,22 @@ def main():
     wall = float(wall_t.item())
     ms_per_step = 1e3 * wall / args.steps
     value = T_total / (wall / args.steps)
+
+    # ---- N > 1: the device-side NCCL exchange against the host-driven protocol of sharding.py -----
+    exchange_verified = None
+    if dist is not None:
+        ctx.run(mode, flags)
+        info_a = ctx.exchange_nccl()
+        mesh_a = ctx.download_mesh()
+        c_b = ctx.run(mode, flags)
+        info_b = sharding.exchange(ctx, rank, world, gather, c_b.num_faces, xstate)
+        mesh_b = ctx.download_mesh()
+        same = all(np.array_equal(mesh_a[k], mesh_b[k]) for k in mesh_a) and \
+            info_a["vert_offset"] == info_b["vert_offset"] and info_a["n_verts_total"] == info_b["n_verts_total"]
+        ok = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        exchange_verified = bool(ok.item())
+        n_verts_total = info_a["n_verts_total"]
 
     # ---- roofline of the dominant streaming kernel (filter: reads every tet's index record) -----
     peak, peak_src = measured_peak()
@@ -322,7 +343,10 @@ def main():
                                     ((16.0 * T_total + 88.0 * (R + 1) ** 3) / 1e6)},
                 "device_ms_per_step": float(np.mean(dev_ms)), "stage_ms": stage,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 12 * args.steps,
-                "clocks": sampler.summary(), "counts": cnt.as_dict()}
+                "clocks": sampler.summary(), "counts": cnt.as_dict(),
+                "exchange": None if dist is None else {
+                    "what": "slab-boundary vertex keys, 2 ncclAllGather per step (device-side, rin_exchange_nccl)",
+                    "verified_against_host_protocol": exchange_verified, "n_verts_total": n_verts_total}}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

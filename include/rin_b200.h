@@ -176,6 +176,13 @@ int rin_boundary_export(rin_ctx*, int own_only, uint32_t v_lo, uint32_t v_hi, ui
 int rin_mark_foreign(rin_ctx*, const uint32_t* keys, uint64_t n_keys, uint64_t* n_own);
 int rin_finalize_sharded(rin_ctx*, uint64_t vert_offset, const uint32_t* keys, const uint32_t* global_ids,
                          uint64_t n_keys);
+/* The same protocol entirely on the device: stream-ordered kernels around two ncclAllGather calls
+ * over NVLink / NVSwitch (NCCL is loaded at run time; env RIN_NCCL_LIB overrides the library name).
+ * rank 0 creates the id, the caller distributes its 128 bytes, every rank calls rin_nccl_init. */
+int rin_nccl_unique_id(uint8_t id[128]);
+int rin_nccl_init(rin_ctx*, const uint8_t id[128], int rank, int world);
+int rin_exchange_nccl(rin_ctx*, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
+                      uint64_t* n_faces_total);
 /* vertex id range referenced by the current tet range */
 int rin_get_vertex_range(const rin_ctx*, uint32_t* v_lo, uint32_t* v_hi);
 

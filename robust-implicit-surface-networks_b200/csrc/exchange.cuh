@@ -1,0 +1,193 @@
+// Device-side slab-boundary exchange over NCCL (NVLink / NVSwitch): the whole protocol of
+// sharding.py as stream-ordered kernels around two ncclAllGather calls, no host round trips
+// except the final read-back of the counts.
+#pragma once
+#include "kernels_ia.cuh"
+
+namespace rin {
+
+// message layout per rank (uint32 words): header[4] = {count, n_own, n_faces, 0},
+// keys[cap][4], ids[cap]
+__host__ __device__ inline size_t xmsg_words(uint32_t cap)
+{
+    return 4 + (size_t)cap * 5;
+}
+
+__global__ void x_header_kernel(uint32_t* msg, const unsigned* count, uint32_t cap, const unsigned* n_own,
+    uint32_t n_faces, unsigned* overflow)
+{
+    const unsigned c = *count;
+    msg[0] = c;
+    msg[1] = n_own ? *n_own : 0;
+    msg[2] = n_faces;
+    msg[3] = 0;
+    if (c > cap) *overflow = c;
+}
+
+// select into a message buffer (keys at msg+4, ids at msg+4+4*cap)
+__global__ void __launch_bounds__(256) x_select_kernel(const uint4* __restrict__ v_key,
+    const uint8_t* __restrict__ v_size, uint32_t n, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ own_idx,
+    uint32_t* __restrict__ msg, uint32_t cap, unsigned* __restrict__ n_out)
+{
+    uint4* out_keys = reinterpret_cast<uint4*>(msg + 4);
+    uint32_t* out_ids = msg + 4 + (size_t)cap * 4;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int sz = v_size[i];
+        if (sz >= 4) continue;
+        const uint4 k = v_key[i];
+        bool in = k.x >= lo && k.x <= hi;
+        if (sz >= 2) in &= k.y >= lo && k.y <= hi;
+        if (sz >= 3) in &= k.z >= lo && k.z <= hi;
+        if (!in) continue;
+        uint32_t id = i;
+        if (own_idx) {
+            id = own_idx[i];
+            if (id == NONE32) continue;
+        }
+        const unsigned p = atomicAdd(n_out, 1u);
+        if (p < cap) {
+            out_keys[p] = k;
+            out_ids[p] = id;
+        }
+    }
+}
+
+// inserts the keys of ranks [0, rank) of a gathered buffer into the foreign table;
+// table[h] = (s * cap + i) indexes the gathered buffer
+__global__ void __launch_bounds__(256) x_insert_kernel(const uint32_t* __restrict__ all, uint32_t cap, int rank,
+    uint32_t* __restrict__ table, uint32_t mask)
+{
+    const size_t stride = xmsg_words(cap);
+    const uint32_t total = (uint32_t)rank * cap;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
+        const uint32_t s = c / cap, i = c % cap;
+        const uint32_t* m = all + s * stride;
+        if (i >= min(m[0], cap)) continue;
+        const uint4 k = reinterpret_cast<const uint4*>(m + 4)[i];
+        uint32_t h = hash4(k) & mask;
+        for (;;) {
+            const uint32_t cur = atomicCAS(&table[h], NONE32, c);
+            if (cur == NONE32) break;
+            const uint4 kc = reinterpret_cast<const uint4*>(all + (cur / cap) * stride + 4)[cur % cap];
+            if (key_eq(kc, k)) break;
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t x_lookup(const uint32_t* all, uint32_t cap, const uint32_t* table, uint32_t mask,
+    uint4 k)
+{
+    const size_t stride = xmsg_words(cap);
+    uint32_t h = hash4(k) & mask;
+    for (;;) {
+        const uint32_t cur = table[h];
+        if (cur == NONE32) return NONE32;
+        const uint4 kc = reinterpret_cast<const uint4*>(all + (cur / cap) * stride + 4)[cur % cap];
+        if (key_eq(kc, k)) return cur;
+        h = (h + 1) & mask;
+    }
+}
+
+// own flag + ordered own index (decoupled look-back over tiles of 1024 vertices)
+__global__ void __launch_bounds__(256) x_mark_scan_kernel(const uint4* __restrict__ v_key,
+    const uint8_t* __restrict__ v_size, uint32_t n, const uint32_t* __restrict__ all, uint32_t cap,
+    const uint32_t* __restrict__ table, uint32_t mask, int rank, uint32_t* __restrict__ own_idx,
+    volatile unsigned long long* __restrict__ status, unsigned* __restrict__ tile_counter,
+    unsigned* __restrict__ n_own)
+{
+    __shared__ unsigned s_tile, s_base;
+    __shared__ unsigned s_warp[8];
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ITEMS = 4;
+    const uint32_t base = tile * 256 * ITEMS + threadIdx.x * ITEMS;
+    bool own[ITEMS];
+    unsigned cnt = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t i = base + j;
+        own[j] = false;
+        if (i < n) {
+            own[j] = true;
+            if (rank > 0 && v_size[i] < 4 && x_lookup(all, cap, table, mask, v_key[i]) != NONE32) own[j] = false;
+            cnt += own[j];
+        }
+    }
+    unsigned x = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned t = (lane < 8) ? s_warp[lane] : 0, x8 = t;
+        for (int o = 1; o < 8; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x8, o);
+            if (lane >= o) x8 += y;
+        }
+        if (lane < 8) s_warp[lane] = x8 - t;
+        const unsigned run = __shfl_sync(0xffffffffu, x8, 7);
+        uint32_t e0, e1;
+        tile_lookback_warp(status, (int)tile, run, 0, e0, e1);
+        if (lane == 0) {
+            s_base = e0;
+            if (tile == (n + 256 * ITEMS - 1) / (256 * ITEMS) - 1) *n_own = e0 + run;
+        }
+    }
+    __syncthreads();
+    unsigned id = s_base + s_warp[warp] + x - cnt;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t i = base + j;
+        if (i < n) own_idx[i] = own[j] ? id++ : NONE32;
+    }
+}
+
+// offsets[s] = sum of n_own of ranks < s; offsets[world] = total; face offsets likewise
+__global__ void x_offsets_kernel(const uint32_t* __restrict__ all, uint32_t cap, int world, uint32_t* __restrict__ voff,
+    uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const size_t stride = xmsg_words(cap);
+    uint32_t v = 0, f = 0;
+    for (int s = 0; s < world; ++s) {
+        voff[s] = v;
+        foff[s] = f;
+        const uint32_t* m = all + s * stride;
+        v += m[1];
+        f += m[2];
+        if (m[0] > cap) *overflow = max(*overflow, m[0]);
+    }
+    voff[world] = v;
+    foff[world] = f;
+}
+
+// global id of every local vertex: own -> offset + own index; foreign -> owner's offset + its own index
+__global__ void __launch_bounds__(256) x_global_ids_kernel(const uint4* __restrict__ v_key,
+    const uint32_t* __restrict__ own_idx, uint32_t n, int rank, const uint32_t* __restrict__ voff,
+    const uint32_t* __restrict__ all, uint32_t cap, const uint32_t* __restrict__ table, uint32_t mask,
+    uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved)
+{
+    const size_t stride = xmsg_words(cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t o = own_idx[i];
+        if (o != NONE32) {
+            gid[i] = voff[rank] + o;
+            continue;
+        }
+        const uint32_t f = x_lookup(all, cap, table, mask, v_key[i]);
+        if (f == NONE32) {
+            atomicAdd(n_unresolved, 1u);
+            gid[i] = NONE32;
+        } else {
+            const uint32_t s = f / cap, j = f % cap;
+            gid[i] = voff[s] + (all + s * stride + 4 + (size_t)cap * 4)[j];
+        }
+    }
+}
+
+} // namespace rin

@@ -3,6 +3,9 @@
 // kernels_*.cuh.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "../../include/rin_b200.h"
 #include "kernels_mi.cuh"
+#include "exchange.cuh"
+
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -74,6 +77,22 @@ enum Stage {
 const char* kStageNames[ST_COUNT] = {"eval+signs", "filter", "classify(lookup)", "general", "count+scan",
     "emit", "dedup", "verts+xyz", "faces"};
 
+
+struct NcclApi
+{
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, char[128], int) = nullptr; // ncclUniqueId is passed by value
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct UniqueId
+{
+    char internal[128];
+};
+NcclApi g_nccl;
+
 struct Lut
 {
     DevBuf lut1, lut2, blob;
@@ -126,6 +145,12 @@ struct rin_ctx
     DevBuf o_tet, o_local, o_size, o_simplex, o_funcs, o_xyz, o_key, own_flag, own_idx, gid, fkeys, fgids, ftable,
         bkeys, bids;
     bool marked = false, finalized = false;
+    // NCCL exchange
+    void* nccl_comm = nullptr;
+    int x_rank = 0, x_world = 1;
+    uint32_t x_cap = 0, x_lo = 1, x_hi = 0;
+    bool x_window = false;
+    DevBuf x_send, x_recv1, x_recv2, x_table, x_small;
     uint32_t n_local_verts = 0, n_own = 0;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
     uint32_t act_cap = 0;
@@ -211,7 +236,7 @@ void rin_destroy(rin_ctx* c)
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
-        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->f_off, &c->f_verts,
+        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob,
         &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
@@ -219,6 +244,7 @@ void rin_destroy(rin_ctx* c)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -286,6 +312,7 @@ int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
     c->t_count = count;
     c->v_first = 0;
     c->v_count = 0;
+    c->x_window = false;
     if (first != 0 || count != c->T) {
         // vertex id range referenced by the tet range: only these vertices are evaluated
         CK(cudaSetDevice(c->device));
@@ -663,6 +690,209 @@ int rin_finalize_sharded(rin_ctx* c, uint64_t vert_offset, const uint32_t* keys,
     c->counts.num_verts = NO;
     c->finalized = true;
     return RIN_OK;
+}
+
+// ---- NCCL (loaded at run time; the process normally has torch's bundled libnccl.so.2 mapped) ----
+namespace {
+
+
+int load_nccl()
+{
+    if (g_nccl.handle) return RIN_OK;
+    const char* env = getenv("RIN_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(RIN_ERR_STATE, "NCCL library not found (set RIN_NCCL_LIB)");
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    void* init = dlsym(h, "ncclCommInitRank");
+    if (!g_nccl.GetUniqueId || !g_nccl.AllGather || !init) return fail(RIN_ERR_STATE, "NCCL symbols missing");
+    memcpy(&g_nccl.CommInitRank, &init, sizeof(init));
+    g_nccl.handle = h;
+    return RIN_OK;
+}
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0)                                                                               \
+            return fail(RIN_ERR_CUDA, std::string(#call) + ": NCCL error " +                       \
+                                          (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
+    } while (0)
+} // namespace
+
+int rin_nccl_unique_id(uint8_t id[128])
+{
+    int rc = load_nccl();
+    if (rc) return rc;
+    NK(g_nccl.GetUniqueId(id));
+    return RIN_OK;
+}
+
+int rin_nccl_init(rin_ctx* c, const uint8_t id[128], int rank, int world)
+{
+    if (!c || !id) return fail(RIN_ERR_ARG, "null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    typedef int (*init_fn)(void**, int, UniqueId, int);
+    init_fn init;
+    memcpy(&init, &g_nccl.CommInitRank, sizeof(init));
+    UniqueId u;
+    memcpy(u.internal, id, 128);
+    NK(init(&c->nccl_comm, world, u, rank));
+    c->x_rank = rank;
+    c->x_world = world;
+    c->x_window = false;
+    return RIN_OK;
+}
+
+// The whole slab-boundary protocol on the device (see sharding.py): two ncclAllGather calls.
+int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
+    uint64_t* n_faces_total)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->nccl_comm) return fail(RIN_ERR_STATE, "rin_exchange_nccl: call rin_nccl_init first");
+    if (!c->ran || c->finalized) return fail(RIN_ERR_STATE, "rin_exchange_nccl: no fresh run");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int rank = c->x_rank, world = c->x_world, sm = c->sm_count;
+    const uint32_t NV = c->n_local_verts;
+    const uint32_t NFV = (uint32_t)c->counts.num_face_verts;
+    CK(c->x_small.ensure(4096));
+    uint32_t* small = c->x_small.as<uint32_t>(); // [0..15] counters, [16..16+2*world] ranges, [64..] offsets
+    if (!c->x_window) {
+        // shared vertex window: all-gather of the ranks' vertex ranges (once per mesh / range)
+        uint32_t lo = c->v_count ? c->v_first : 0, hi = c->v_count ? c->v_first + c->v_count - 1 : (uint32_t)c->V - 1;
+        uint32_t mine[2] = {lo, hi};
+        std::vector<uint32_t> all(2 * world);
+        CK(cudaMemcpyAsync(small + 16, mine, 8, cudaMemcpyHostToDevice, s));
+        NK(g_nccl.AllGather(small + 16, small + 32, 2, 3 /*ncclUint32*/, c->nccl_comm, s));
+        CK(cudaMemcpyAsync(all.data(), small + 32, 8 * world, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        bool any = false;
+        uint32_t wl = 0, wh = 0;
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            uint32_t a = std::max(lo, all[2 * r]), b = std::min(hi, all[2 * r + 1]);
+            if (a > b) continue;
+            wl = any ? std::min(wl, a) : a;
+            wh = any ? std::max(wh, b) : b;
+            any = true;
+        }
+        c->x_lo = any ? wl : 1;
+        c->x_hi = any ? wh : 0;
+        c->x_window = true;
+    }
+    if (c->x_cap == 0) c->x_cap = 4096;
+    for (int attempt = 0;; ++attempt) {
+        const uint32_t cap = c->x_cap;
+        const size_t words = xmsg_words(cap);
+        CK(c->x_send.ensure(words * 4));
+        CK(c->x_recv1.ensure(words * 4 * world));
+        CK(c->x_recv2.ensure(words * 4 * world));
+        uint32_t tsize = 64;
+        while (tsize < 2ull * cap * std::max(rank, 1)) tsize <<= 1;
+        CK(c->x_table.ensure((size_t)tsize * 4));
+        CK(c->own_idx.ensure((size_t)std::max(NV, 1u) * 4));
+        CK(c->gid.ensure((size_t)std::max(NV, 1u) * 4));
+        const uint32_t tiles = (NV + 1023) / 1024;
+        CK(c->status.ensure((size_t)std::max(tiles, 1u) * 8 + 64));
+        CK(cudaMemsetAsync(small, 0, 64, s));
+        unsigned* d_cnt1 = small + 0;
+        unsigned* d_cnt2 = small + 1;
+        unsigned* d_nown = small + 2;
+        unsigned* d_ovf = small + 3;
+        unsigned* d_tile = small + 4;
+        unsigned* d_bad = small + 5;
+        uint32_t* d_voff = small + 64;
+        uint32_t* d_foff = small + 64 + (world + 1);
+        uint32_t* msg = c->x_send.as<uint32_t>();
+        // 1. candidates in the shared window -> all ranks
+        if (NV)
+            x_select_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
+                c->x_lo, c->x_hi, nullptr, msg, cap, d_cnt1);
+        x_header_kernel<<<1, 1, 0, s>>>(msg, d_cnt1, cap, nullptr, 0, d_ovf);
+        NK(g_nccl.AllGather(msg, c->x_recv1.p, words, 3, c->nccl_comm, s));
+        // 2. keys of lower ranks are foreign; ordered own index
+        CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+        if (rank > 0)
+            x_insert_kernel<<<grid_for((uint64_t)rank * cap, 256, sm), 256, 0, s>>>(c->x_recv1.as<uint32_t>(), cap,
+                rank, c->x_table.as<uint32_t>(), tsize - 1);
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)std::max(tiles, 1u) * 8, s));
+        if (NV)
+            x_mark_scan_kernel<<<tiles, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
+                c->x_recv1.as<uint32_t>(), cap, c->x_table.as<uint32_t>(), tsize - 1, rank, c->own_idx.as<uint32_t>(),
+                c->status.as<unsigned long long>(), d_tile, d_nown);
+        // 3. owned shared keys with their own index + (n_own, n_faces) -> all ranks
+        if (NV)
+            x_select_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
+                c->x_lo, c->x_hi, c->own_idx.as<uint32_t>(), msg, cap, d_cnt2);
+        x_header_kernel<<<1, 1, 0, s>>>(msg, d_cnt2, cap, d_nown, (uint32_t)c->counts.num_faces, d_ovf);
+        NK(g_nccl.AllGather(msg, c->x_recv2.p, words, 3, c->nccl_comm, s));
+        x_offsets_kernel<<<1, 1, 0, s>>>(c->x_recv2.as<uint32_t>(), cap, world, d_voff, d_foff, d_ovf);
+        // 4. global ids, rewrite the face vertex lists, keep the owned vertices
+        CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+        if (rank > 0)
+            x_insert_kernel<<<grid_for((uint64_t)rank * cap, 256, sm), 256, 0, s>>>(c->x_recv2.as<uint32_t>(), cap,
+                rank, c->x_table.as<uint32_t>(), tsize - 1);
+        std::vector<uint32_t> hsmall(64 + 2 * (world + 1));
+        CK(cudaMemcpyAsync(hsmall.data(), small, hsmall.size() * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (hsmall[3]) { // a rank's payload outgrew the capacity: every rank sees it, redo larger
+            if (attempt > 3) return fail(RIN_ERR_STATE, "exchange: capacity negotiation failed");
+            c->x_cap = hsmall[3] + hsmall[3] / 4 + 1024;
+            continue;
+        }
+        const uint32_t NO = hsmall[2];
+        if (NV) {
+            x_global_ids_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->own_idx.as<uint32_t>(),
+                NV, rank, d_voff, c->x_recv2.as<uint32_t>(), cap, c->x_table.as<uint32_t>(), tsize - 1,
+                c->gid.as<uint32_t>(), d_bad);
+            if (NFV)
+                apply_gids_kernel<<<grid_for(NFV, 256, sm), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
+                    c->gid.as<uint32_t>());
+            const size_t no1 = std::max(NO, 1u);
+            CK(c->o_tet.ensure(no1 * 4));
+            CK(c->o_local.ensure(no1));
+            CK(c->o_size.ensure(no1));
+            CK(c->o_simplex.ensure(no1 * 16));
+            CK(c->o_funcs.ensure(no1 * 16));
+            CK(c->o_xyz.ensure(no1 * 24));
+            CK(c->o_key.ensure(no1 * 16));
+            compact_own_verts_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->own_idx.as<uint32_t>(), NV,
+                c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(),
+                c->v_funcs.as<uint4>(), c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(),
+                c->o_local.as<uint8_t>(), c->o_size.as<uint8_t>(), c->o_simplex.as<uint4>(), c->o_funcs.as<uint4>(),
+                c->o_xyz.as<double>(), c->o_key.as<uint4>());
+            CK(cudaGetLastError());
+        }
+        unsigned bad = 0;
+        CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (bad) return fail(RIN_ERR_STATE, "exchange: " + std::to_string(bad) + " shared vertices have no owner");
+        std::swap(c->v_tet, c->o_tet);
+        std::swap(c->v_local, c->o_local);
+        std::swap(c->v_size, c->o_size);
+        std::swap(c->v_simplex, c->o_simplex);
+        std::swap(c->v_funcs, c->o_funcs);
+        std::swap(c->v_xyz, c->o_xyz);
+        std::swap(c->v_key, c->o_key);
+        c->n_own = NO;
+        c->counts.num_verts = NO;
+        c->marked = c->finalized = true;
+        if (vert_offset) *vert_offset = hsmall[64 + rank];
+        if (n_verts_total) *n_verts_total = hsmall[64 + world];
+        if (face_offset) *face_offset = hsmall[64 + (world + 1) + rank];
+        if (n_faces_total) *n_faces_total = hsmall[64 + (world + 1) + world];
+        return RIN_OK;
+    }
 }
 
 // introspection for tests: host copy of the IA tables

@@ -73,12 +73,23 @@ def lib():
         L.rin_mark_foreign.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.rin_finalize_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
         L.rin_get_vertex_range.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.rin_nccl_unique_id.argtypes = [C.c_void_p]
+        L.rin_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.rin_exchange_nccl.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
         L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Counts)]
         L.rin_get_complexes.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                         C.c_void_p, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def nccl_unique_id():
+    uid = np.zeros(128, np.uint8)
+    rc = lib().rin_nccl_unique_id(uid.ctypes.data)
+    if rc != 0:
+        raise RinError(rc, lib().rin_last_error().decode())
+    return uid
 
 
 def _ptr(a):
@@ -217,6 +228,18 @@ class Context:
         gids = np.ascontiguousarray(gids, np.uint32)
         self._check(lib().rin_finalize_sharded(self._h, offset, keys.ctypes.data if len(keys) else None,
                                                gids.ctypes.data if len(keys) else None, len(keys)))
+
+    def nccl_init(self, unique_id, rank, world):
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        self._check(lib().rin_nccl_init(self._h, uid.ctypes.data, rank, world))
+
+    def exchange_nccl(self):
+        """Device-side slab-boundary exchange (two ncclAllGather calls on the context's stream)."""
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(lib().rin_exchange_nccl(self._h, *[C.byref(x) for x in v]))
+        return {"vert_offset": v[0].value, "n_verts_total": v[1].value, "face_offset": v[2].value,
+                "n_faces_total": v[3].value}
 
     def kernel_times(self):
         e, f, t = C.c_float(), C.c_float(), C.c_float()
