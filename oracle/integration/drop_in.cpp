@@ -1,0 +1,284 @@
+// INTEGRATION DEMONSTRATION (test infrastructure, NOT product code).
+//
+// The reference's entry points implicit_arrangement() / material_interface()
+// (/root/reference/src/implicit_arrangement.h:39-62, src/material_interface.h:38-61) re-implemented
+// as a maintainer would after adopting librin_b200: the hot stages (:53-402 / :53-447) are ONE call
+// into the GPU library through the C++ host layer (robust-implicit-surface-networks_b200/host),
+// the per-tet complexes come from rin_get_complexes, and every host topology stage after
+// "compute xyz" is the reference's OWN code (mesh_connectivity / pair_faces / topo_ray_shooting
+// objects compiled in place from /root/reference/src and linked here).  The reference's csg.cpp is
+// linked unchanged and therefore calls THIS implicit_arrangement: a literal drop-in.
+// The oracle's CPU engine (oracle/sa/*.cpp) is NOT linked into this library.
+#include <simplicial_arrangement/lookup_table.h>
+#include <simplicial_arrangement/simplicial_arrangement.h>
+
+#include "implicit_arrangement.h"
+#include "material_interface.h"
+
+#include "../../robust-implicit-surface-networks_b200/host/rin_host.h"
+
+#include <iostream>
+
+// the tables live inside the GPU library: the switches of the un-vendored library are no-ops here
+namespace simplicial_arrangement {
+bool load_lookup_table(LookupTableType) { return true; }
+void enable_lookup_table() {}
+void disable_lookup_table() {}
+} // namespace simplicial_arrangement
+
+namespace {
+
+using HalfFacePair = std::pair<std::pair<size_t, int>, std::pair<size_t, int>>;
+
+template <typename Complex>
+void to_reference(const rin_host::TetComplex& in, Complex& out);
+
+template <>
+void to_reference(const rin_host::TetComplex& in, simplicial_arrangement::Arrangement<3>& out)
+{
+    out.vertices.resize(in.vertices.size());
+    for (size_t v = 0; v < in.vertices.size(); ++v) out.vertices[v] = {in.vertices[v][0], in.vertices[v][1], in.vertices[v][2]};
+    out.faces.resize(in.faces.size());
+    for (size_t f = 0; f < in.faces.size(); ++f) {
+        out.faces[f].vertices = in.faces[f].vertices;
+        out.faces[f].supporting_plane = in.faces[f].a;
+        out.faces[f].positive_cell = in.faces[f].b;
+        out.faces[f].negative_cell = in.faces[f].c;
+    }
+    out.cells.resize(in.cells.size());
+    for (size_t c = 0; c < in.cells.size(); ++c) out.cells[c].faces = in.cells[c].faces;
+    if (!in.unique_indices.empty()) {
+        out.unique_plane_indices = in.unique_indices;
+        size_t groups = 0;
+        for (size_t g : in.unique_indices) groups = std::max(groups, g + 1);
+        out.unique_planes.assign(groups, {});
+        for (size_t p = 0; p < in.unique_indices.size(); ++p) out.unique_planes[in.unique_indices[p]].push_back(p);
+        out.unique_plane_orientations = in.unique_orientations;
+    }
+}
+
+template <>
+void to_reference(const rin_host::TetComplex& in, simplicial_arrangement::MaterialInterface<3>& out)
+{
+    out.vertices = in.vertices;
+    out.faces.resize(in.faces.size());
+    for (size_t f = 0; f < in.faces.size(); ++f) {
+        out.faces[f].vertices = in.faces[f].vertices;
+        out.faces[f].positive_material_label = in.faces[f].a;
+        out.faces[f].negative_material_label = in.faces[f].b;
+    }
+    out.cells.resize(in.cells.size());
+    for (size_t c = 0; c < in.cells.size(); ++c) {
+        out.cells[c].faces = in.cells[c].faces;
+        out.cells[c].material_label = in.cells[c].material_label;
+    }
+    if (!in.unique_indices.empty()) {
+        out.unique_material_indices = in.unique_indices;
+        size_t groups = 0;
+        for (size_t g : in.unique_indices) groups = std::max(groups, g + 1);
+        out.unique_materials.assign(groups, {});
+        for (size_t p = 0; p < in.unique_indices.size(); ++p) out.unique_materials[in.unique_indices[p]].push_back(p);
+    }
+}
+
+// cut_results / cut_result_index of the reference, filled from the device on demand
+template <typename Complex>
+bool materialise_complexes(int mode, const rin_host::HotPathOutput& hot, size_t n_tets, std::vector<Complex>& cut_results,
+    std::vector<size_t>& cut_result_index)
+{
+    std::vector<size_t> active;
+    cut_result_index.assign(n_tets, Complex::None);
+    for (size_t t = 0; t < n_tets; ++t)
+        if (hot.start_index_of_tet[t + 1] > hot.start_index_of_tet[t]) {
+            cut_result_index[t] = active.size();
+            active.push_back(t);
+        }
+    std::vector<rin_host::TetComplex> raw;
+    std::string err;
+    if (!rin_host::fetch_complexes(mode, active, raw, err)) {
+        std::cout << err << std::endl;
+        return false;
+    }
+    cut_results.resize(raw.size());
+    for (size_t i = 0; i < raw.size(); ++i) to_reference(raw[i], cut_results[i]);
+    return true;
+}
+
+struct Topology
+{
+    std::vector<std::vector<size_t>> edges_of_face;
+    std::vector<size_t> patch_of_face;
+    std::vector<std::vector<HalfFacePair>> half_patch_pairs;
+    std::vector<size_t> shell_of_half_patch, component_of_patch;
+    std::vector<std::vector<size_t>> components;
+};
+
+void push_stat(std::vector<std::string>& l, std::vector<size_t>& s, const char* name, size_t v)
+{
+    l.emplace_back(name);
+    s.push_back(v);
+}
+
+} // namespace
+
+bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_lookup, bool use_topo_ray_shooting,
+    const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<size_t, 4>>& tets,
+    const Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>& funcVals,
+    std::vector<std::array<double, 3>>& iso_pts, std::vector<PolygonFace>& iso_faces,
+    std::vector<std::vector<size_t>>& patches, std::vector<size_t>& patch_function_label, std::vector<Edge>& iso_edges,
+    std::vector<std::vector<size_t>>& chains, std::vector<std::vector<size_t>>& non_manifold_edges_of_vert,
+    std::vector<std::vector<size_t>>& shells, std::vector<std::vector<size_t>>& arrangement_cells,
+    std::vector<std::vector<bool>>& cell_function_label, std::vector<std::string>& timing_labels,
+    std::vector<double>& timings, std::vector<std::string>& stats_labels, std::vector<size_t>& stats)
+{
+    if (robust_test || !use_topo_ray_shooting) {
+        std::cout << "GPU drop-in: robust_test / cell-grouping modes are not served by the device path" << std::endl;
+        return false;
+    }
+    const size_t n_func = funcVals.cols();
+    push_stat(stats_labels, stats, "num_pts", pts.size());
+    push_stat(stats_labels, stats, "num_tets", tets.size());
+    std::vector<IsoVert> iso_verts;
+    rin_host::HotPathOutput hot;
+    if (!rin_host::implicit_arrangement_hot(use_lookup, use_secondary_lookup, pts, tets, funcVals.data(), n_func, false,
+            iso_pts, iso_faces, iso_verts, hot, timing_labels, timings, stats_labels, stats))
+        return false;
+    std::vector<simplicial_arrangement::Arrangement<3>> cut_results;
+    std::vector<size_t> cut_result_index;
+    if (!materialise_complexes(0, hot, tets.size(), cut_results, cut_result_index)) return false;
+
+    // ---- from here on: the reference's own host stages (src/implicit_arrangement.cpp:404-647)
+    Topology T;
+    compute_mesh_edges(iso_faces, T.edges_of_face, iso_edges);
+    push_stat(stats_labels, stats, "num_iso_edges", iso_edges.size());
+    compute_patches(T.edges_of_face, iso_edges, iso_faces, patches, patch_function_label);
+    push_stat(stats_labels, stats, "num_patches", patches.size());
+    T.patch_of_face.resize(iso_faces.size());
+    for (size_t p = 0; p < patches.size(); ++p)
+        for (size_t f : patches[p]) T.patch_of_face[f] = p;
+    non_manifold_edges_of_vert.resize(iso_pts.size());
+    for (size_t e = 0; e < iso_edges.size(); ++e)
+        if (iso_edges[e].face_edge_indices.size() > 2) {
+            non_manifold_edges_of_vert[iso_edges[e].v1].push_back(e);
+            non_manifold_edges_of_vert[iso_edges[e].v2].push_back(e);
+        }
+    compute_chains(iso_edges, non_manifold_edges_of_vert, chains);
+    push_stat(stats_labels, stats, "num_chains", chains.size());
+    absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets;
+    if (hot.num_degenerate_vertex > 0) {
+        std::vector<bool> degenerate(pts.size(), false);
+        for (size_t v = 0; v < pts.size(); ++v)
+            for (size_t f = 0; f < n_func; ++f)
+                if (funcVals(v, f) == 0) degenerate[v] = true;
+        for (size_t t = 0; t < tets.size(); ++t)
+            for (size_t v : tets[t])
+                if (degenerate[v]) incident_tets[v].push_back(t);
+    }
+    T.half_patch_pairs.resize(chains.size());
+    for (size_t c = 0; c < chains.size(); ++c) {
+        std::vector<HalfFacePair> face_pairs;
+        try {
+            compute_face_order(iso_edges[chains[c][0]], tets, iso_verts, iso_faces, cut_results, cut_result_index,
+                hot.func_in_tet, hot.start_index_of_tet, incident_tets, face_pairs);
+        } catch (std::exception& e) {
+            std::cout << "order patches failed: " << e.what() << std::endl;
+            return false;
+        }
+        for (const auto& fp : face_pairs)
+            T.half_patch_pairs[c].push_back({{T.patch_of_face[fp.first.first], fp.first.second},
+                {T.patch_of_face[fp.second.first], fp.second.second}});
+    }
+    compute_shells_and_components(patches.size(), T.half_patch_pairs, shells, T.shell_of_half_patch, T.components,
+        T.component_of_patch);
+    push_stat(stats_labels, stats, "num_shells", shells.size());
+    push_stat(stats_labels, stats, "num_components", T.components.size());
+    if (T.components.size() < 2) {
+        for (size_t s = 0; s < shells.size(); ++s) arrangement_cells.push_back({s});
+    } else {
+        topo_ray_shooting(pts, tets, cut_results, cut_result_index, iso_verts, iso_faces, patches, T.patch_of_face, shells,
+            T.shell_of_half_patch, T.components, T.component_of_patch, arrangement_cells);
+    }
+    push_stat(stats_labels, stats, "num_cells", arrangement_cells.size());
+    std::vector<bool> sample(n_func);
+    for (size_t f = 0; f < n_func; ++f) sample[f] = funcVals(0, f) > 0;
+    cell_function_label =
+        sign_propagation(arrangement_cells, T.shell_of_half_patch, shells, patch_function_label, n_func, sample);
+    return true;
+}
+
+bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lookup, bool use_topo_ray_shooting,
+    const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<size_t, 4>>& tets,
+    const Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>& funcVals,
+    std::vector<std::array<double, 3>>& MI_pts, std::vector<PolygonFace>& MI_faces,
+    std::vector<std::vector<size_t>>& patches, std::vector<std::pair<size_t, size_t>>& patch_function_label,
+    std::vector<Edge>& MI_edges, std::vector<std::vector<size_t>>& chains,
+    std::vector<std::vector<size_t>>& non_manifold_edges_of_vert, std::vector<std::vector<size_t>>& shells,
+    std::vector<std::vector<size_t>>& material_cells, std::vector<size_t>& cell_function_label,
+    std::vector<std::string>& timing_labels, std::vector<double>& timings, std::vector<std::string>& stats_labels,
+    std::vector<size_t>& stats)
+{
+    if (robust_test || !use_topo_ray_shooting) {
+        std::cout << "GPU drop-in: robust_test / cell-grouping modes are not served by the device path" << std::endl;
+        return false;
+    }
+    const size_t n_func = funcVals.cols();
+    push_stat(stats_labels, stats, "num_pts", pts.size());
+    push_stat(stats_labels, stats, "num_tets", tets.size());
+    std::vector<MI_Vert> MI_verts;
+    rin_host::HotPathOutput hot;
+    if (!rin_host::material_interface_hot(use_lookup, use_secondary_lookup, pts, tets, funcVals.data(), n_func, MI_pts,
+            MI_faces, MI_verts, hot, timing_labels, timings, stats_labels, stats))
+        return false;
+    std::vector<simplicial_arrangement::MaterialInterface<3>> cut_results;
+    std::vector<size_t> cut_result_index;
+    if (!materialise_complexes(1, hot, tets.size(), cut_results, cut_result_index)) return false;
+
+    // ---- the reference's own host stages (src/material_interface.cpp:449-695)
+    Topology T;
+    compute_mesh_edges(MI_faces, T.edges_of_face, MI_edges);
+    push_stat(stats_labels, stats, "num_MI_edges", MI_edges.size());
+    compute_patches(T.edges_of_face, MI_edges, MI_faces, patches, patch_function_label);
+    push_stat(stats_labels, stats, "num_patches", patches.size());
+    T.patch_of_face.resize(MI_faces.size());
+    for (size_t p = 0; p < patches.size(); ++p)
+        for (size_t f : patches[p]) T.patch_of_face[f] = p;
+    non_manifold_edges_of_vert.resize(MI_pts.size());
+    for (size_t e = 0; e < MI_edges.size(); ++e)
+        if (MI_edges[e].face_edge_indices.size() > 2) {
+            non_manifold_edges_of_vert[MI_edges[e].v1].push_back(e);
+            non_manifold_edges_of_vert[MI_edges[e].v2].push_back(e);
+        }
+    compute_chains(MI_edges, non_manifold_edges_of_vert, chains);
+    push_stat(stats_labels, stats, "num_chains", chains.size());
+    absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets; // only filled for tied vertices upstream
+    T.half_patch_pairs.resize(chains.size());
+    for (size_t c = 0; c < chains.size(); ++c) {
+        std::vector<HalfFacePair> face_pairs;
+        try {
+            compute_face_order(MI_edges[chains[c][0]], MI_faces, cut_results, cut_result_index, incident_tets, face_pairs);
+        } catch (std::exception& e) {
+            std::cout << "order patches failed: " << e.what() << std::endl;
+            return false;
+        }
+        for (const auto& fp : face_pairs)
+            T.half_patch_pairs[c].push_back({{T.patch_of_face[fp.first.first], fp.first.second},
+                {T.patch_of_face[fp.second.first], fp.second.second}});
+    }
+    compute_shells_and_components(patches.size(), T.half_patch_pairs, shells, T.shell_of_half_patch, T.components,
+        T.component_of_patch);
+    push_stat(stats_labels, stats, "num_shells", shells.size());
+    push_stat(stats_labels, stats, "num_components", T.components.size());
+    if (T.components.size() < 2) {
+        for (size_t s = 0; s < shells.size(); ++s) material_cells.push_back({s});
+        if (material_cells.empty()) material_cells.push_back({Mesh_None}); // no interface at all (:619-623)
+    } else {
+        topo_ray_shooting(pts, tets, cut_results, cut_result_index, MI_verts, MI_faces, patches, T.patch_of_face, shells,
+            T.shell_of_half_patch, T.components, T.component_of_patch, material_cells);
+    }
+    push_stat(stats_labels, stats, "num_cells", material_cells.size());
+    std::vector<double> sample(n_func);
+    for (size_t f = 0; f < n_func; ++f) sample[f] = funcVals(0, f);
+    cell_function_label =
+        sign_propagation_MI(material_cells, T.shell_of_half_patch, shells, patch_function_label, n_func, sample);
+    return true;
+}

@@ -148,20 +148,25 @@ __global__ void __launch_bounds__(256) x_mark_scan_kernel(const uint4* __restric
 }
 
 // offsets[s] = sum of n_own of ranks < s; offsets[world] = total; face offsets likewise
-__global__ void x_offsets_kernel(const uint32_t* __restrict__ all, uint32_t cap, int world, uint32_t* __restrict__ voff,
-    uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
+// `first` is the gathered buffer of the first collective: every rank derives the SAME overflow
+// decision from the same gathered headers (a rank deciding alone would desynchronise the collectives)
+__global__ void x_offsets_kernel(const uint32_t* __restrict__ first, const uint32_t* __restrict__ all, uint32_t cap,
+    int world, uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
 {
     if (threadIdx.x || blockIdx.x) return;
     const size_t stride = xmsg_words(cap);
     uint32_t v = 0, f = 0;
+    unsigned ovf = 0;
     for (int s = 0; s < world; ++s) {
         voff[s] = v;
         foff[s] = f;
         const uint32_t* m = all + s * stride;
         v += m[1];
         f += m[2];
-        if (m[0] > cap) *overflow = max(*overflow, m[0]);
+        if (m[0] > cap) ovf = max(ovf, m[0]);
+        if (first[s * stride] > cap) ovf = max(ovf, first[s * stride]);
     }
+    *overflow = ovf;
     voff[world] = v;
     foff[world] = f;
 }

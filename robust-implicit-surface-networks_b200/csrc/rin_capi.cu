@@ -3,6 +3,7 @@
 // kernels_*.cuh.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "../../include/rin_b200.h"
 #include "kernels_mi.cuh"
+#include "complexes.cuh"
 #include "exchange.cuh"
 
 #include <dlfcn.h>
@@ -151,6 +152,7 @@ struct rin_ctx
     uint32_t x_cap = 0, x_lo = 1, x_hi = 0;
     bool x_window = false;
     DevBuf x_send, x_recv1, x_recv2, x_table, x_small;
+    DevBuf cx_out; // rin_get_complexes output arena
     uint32_t n_local_verts = 0, n_own = 0;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
     uint32_t act_cap = 0;
@@ -236,7 +238,7 @@ void rin_destroy(rin_ctx* c)
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
-        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->f_off, &c->f_verts,
+        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->cx_out, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob,
         &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
@@ -536,10 +538,115 @@ int rin_run_host(rin_ctx* c, int mode, uint32_t flags, const double* pts, uint64
     return RIN_OK;
 }
 
-int rin_get_complexes(rin_ctx*, int, uint32_t, const uint64_t*, uint64_t, uint64_t*, uint32_t*, uint64_t*)
+extern "C++" {
+namespace {
+template <int W>
+int get_complexes_w(rin_ctx* c, int mode, const uint32_t* d_req, uint32_t n, uint32_t* d_out, uint32_t out_cap,
+    uint2* d_span, ComplexCounters* d_cc)
 {
-    return fail(RIN_ERR_STATE, "rin_get_complexes: not built yet");
+    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet;
+    if (mode == RIN_MODE_IA)
+        complexes_ia_kernel<W><<<grid_for(n, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
+            c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
+            c->vals.as<double>(), (uint32_t)c->V, d_req, n, d_out, out_cap, d_span, d_cc);
+    else
+        complexes_mi_kernel<W><<<grid_for(n, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
+            c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
+            c->vals.as<double>(), (uint32_t)c->V, d_req, n, d_out, out_cap, d_span, d_cc);
+    CK(cudaGetLastError());
+    return RIN_OK;
 }
+} // namespace
+} // extern "C++"
+
+// flags are unused: the general algorithm and the tables give identical complexes
+int rin_get_complexes(rin_ctx* c, int mode, uint32_t, const uint64_t* tet_ids, uint64_t n, uint64_t* offsets,
+    uint32_t* words, uint64_t* n_words)
+{
+    if (!c || (n && !tet_ids) || !n_words) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran || c->last_mode != mode) return fail(RIN_ERR_STATE, "rin_get_complexes: no finished run of that mode");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    std::vector<uint32_t> req(n);
+    for (uint64_t i = 0; i < n; ++i) req[i] = (uint32_t)tet_ids[i];
+    DevBuf d_req, d_span, d_cc;
+    auto cleanup = [&]() {
+        d_req.release();
+        d_span.release();
+        d_cc.release();
+    };
+    cudaError_t e;
+    if ((e = d_req.ensure(std::max<uint64_t>(n, 1) * 4)) != cudaSuccess || (e = d_span.ensure(std::max<uint64_t>(n, 1) * 8)) != cudaSuccess ||
+        (e = d_cc.ensure(sizeof(ComplexCounters))) != cudaSuccess) {
+        cleanup();
+        return fail(RIN_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (n) cudaMemcpyAsync(d_req.p, req.data(), n * 4, cudaMemcpyHostToDevice, s);
+    std::vector<uint2> span(n);
+    ComplexCounters hc{};
+    size_t cap_words = std::max<size_t>(c->cx_out.cap / 4, 1 << 18);
+    for (int attempt = 0;; ++attempt) {
+        if ((e = c->cx_out.ensure(cap_words * 4)) != cudaSuccess) {
+            cleanup();
+            return fail(RIN_ERR_CUDA, cudaGetErrorString(e));
+        }
+        cudaMemsetAsync(d_cc.p, 0, sizeof(ComplexCounters), s);
+        int rc = RIN_OK;
+        if (n) {
+            switch (words_for(c->F)) {
+            case 1: rc = get_complexes_w<1>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
+            case 2: rc = get_complexes_w<2>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
+            case 3: rc = get_complexes_w<3>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
+            default: rc = get_complexes_w<4>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
+            }
+        }
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+        cudaMemcpyAsync(&hc, d_cc.p, sizeof(hc), cudaMemcpyDeviceToHost, s);
+        if (n) cudaMemcpyAsync(span.data(), d_span.p, n * 8, cudaMemcpyDeviceToHost, s);
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) {
+            cleanup();
+            return fail(RIN_ERR_CUDA, cudaGetErrorString(e));
+        }
+        if (hc.err) {
+            cleanup();
+            return fail(hc.err, "rin_get_complexes: per-tet computation failed in tet " + std::to_string(hc.err_tet));
+        }
+        if (!hc.overflow) break;
+        if (attempt > 2) {
+            cleanup();
+            return fail(RIN_ERR_STATE, "rin_get_complexes: output overflow");
+        }
+        cap_words = (size_t)hc.top + hc.top / 8 + 1024;
+    }
+    // repack in request order
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) total += span[i].y;
+    *n_words = total;
+    if (offsets) {
+        uint64_t p = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            offsets[i] = p;
+            p += span[i].y;
+        }
+        offsets[n] = p;
+    }
+    if (words && total) {
+        std::vector<uint32_t> all(hc.top);
+        cudaMemcpyAsync(all.data(), c->cx_out.p, (size_t)hc.top * 4, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        uint64_t p = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            memcpy(words + p, all.data() + span[i].x, (size_t)span[i].y * 4);
+            p += span[i].y;
+        }
+    }
+    cleanup();
+    return RIN_OK;
+}
+
 int rin_get_vertex_range(const rin_ctx* c, uint32_t* lo, uint32_t* hi)
 {
     if (!c) return fail(RIN_ERR_ARG, "null ctx");
@@ -790,7 +897,11 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         c->x_hi = any ? wh : 0;
         c->x_window = true;
     }
-    if (c->x_cap == 0) c->x_cap = 4096;
+    if (c->x_cap == 0) {
+        const char* env = getenv("RIN_XCAP"); // test hook: a tiny capacity forces the renegotiation path
+        c->x_cap = env ? (uint32_t)std::max(4, atoi(env)) : 4096;
+    }
+    c->x_cap = (c->x_cap + 3u) & ~3u; // keys are read as uint4: keep every rank's segment 16-byte aligned
     for (int attempt = 0;; ++attempt) {
         const uint32_t cap = c->x_cap;
         const size_t words = xmsg_words(cap);
@@ -836,7 +947,8 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
                 c->x_lo, c->x_hi, c->own_idx.as<uint32_t>(), msg, cap, d_cnt2);
         x_header_kernel<<<1, 1, 0, s>>>(msg, d_cnt2, cap, d_nown, (uint32_t)c->counts.num_faces, d_ovf);
         NK(g_nccl.AllGather(msg, c->x_recv2.p, words, 3, c->nccl_comm, s));
-        x_offsets_kernel<<<1, 1, 0, s>>>(c->x_recv2.as<uint32_t>(), cap, world, d_voff, d_foff, d_ovf);
+        x_offsets_kernel<<<1, 1, 0, s>>>(c->x_recv1.as<uint32_t>(), c->x_recv2.as<uint32_t>(), cap, world, d_voff, d_foff,
+            d_ovf);
         // 4. global ids, rewrite the face vertex lists, keep the owned vertices
         CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
         if (rank > 0)
@@ -847,7 +959,7 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         CK(cudaStreamSynchronize(s));
         if (hsmall[3]) { // a rank's payload outgrew the capacity: every rank sees it, redo larger
             if (attempt > 3) return fail(RIN_ERR_STATE, "exchange: capacity negotiation failed");
-            c->x_cap = hsmall[3] + hsmall[3] / 4 + 1024;
+            c->x_cap = (hsmall[3] + hsmall[3] / 4 + 1024 + 3u) & ~3u;
             continue;
         }
         const uint32_t NO = hsmall[2];

@@ -1,0 +1,66 @@
+// C++ host layer above the C-ABI (include/rin_b200.h): the hot stages of the reference's drivers
+// with the reference's own container types, so that a maintainer can replace
+// src/implicit_arrangement.cpp:53-402 / src/material_interface.cpp:53-447 by one call and keep the
+// host topology stages (:404-647 / :449-695) unchanged.  No CPU fallback: every function returns
+// false with a message when the CUDA library reports an error.
+#pragma once
+#include "mesh_types.h"
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace rin_host {
+
+// Per-tet complex as the reference's host stages read it (fields of simplicial_arrangement::
+// Arrangement<3> / MaterialInterface<3>); None == SIZE_MAX.
+struct TetComplex
+{
+    std::vector<std::array<size_t, 4>> vertices; // IA uses the first three entries
+    struct Face
+    {
+        std::vector<size_t> vertices;
+        size_t a = Mesh_None, b = Mesh_None, c = Mesh_None; // IA: supporting plane, positive cell, negative cell
+                                                            // MI: positive label, negative label, -
+    };
+    std::vector<Face> faces;
+    struct Cell
+    {
+        std::vector<size_t> faces;
+        size_t material_label = Mesh_None;
+    };
+    std::vector<Cell> cells;
+    std::vector<size_t> unique_indices;       // plane / material -> group (empty when all distinct)
+    std::vector<bool> unique_orientations;    // IA only
+};
+
+struct HotPathOutput
+{
+    std::vector<size_t> func_in_tet, start_index_of_tet; // CRS of active functions / materials
+    size_t num_degenerate_vertex = 0;                    // IA: zero (vertex, function) pairs
+    size_t num_intersecting_tet = 0, num_k1 = 0, num_k2 = 0, num_kmore = 0;
+    std::string error;
+};
+
+// funcVals: the reference's row-major V x F matrix (Eigen data()), rows == pts.size().
+// Appends "func signs" .. "compute xyz" to timing_labels/timings and the stats of
+// src/implicit_arrangement.cpp:46-393 to stats_labels/stats, exactly in the reference's order.
+bool implicit_arrangement_hot(bool use_lookup, bool use_secondary_lookup,
+    const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<size_t, 4>>& tets,
+    const double* funcVals, size_t n_func, bool negate, std::vector<std::array<double, 3>>& iso_pts,
+    std::vector<PolygonFace>& iso_faces, std::vector<IsoVert>& iso_verts, HotPathOutput& out,
+    std::vector<std::string>& timing_labels, std::vector<double>& timings, std::vector<std::string>& stats_labels,
+    std::vector<size_t>& stats);
+
+bool material_interface_hot(bool use_lookup, bool use_secondary_lookup,
+    const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<size_t, 4>>& tets,
+    const double* funcVals, size_t n_func, std::vector<std::array<double, 3>>& MI_pts,
+    std::vector<PolygonFace>& MI_faces, std::vector<MI_Vert>& MI_verts, HotPathOutput& out,
+    std::vector<std::string>& timing_labels, std::vector<double>& timings, std::vector<std::string>& stats_labels,
+    std::vector<size_t>& stats);
+
+// Complexes of the given tets of the LAST hot-path call (mode 0 = IA, 1 = MI); inactive tets give
+// an empty complex.  This is the lazy replacement of cut_results[cut_result_index[tet]].
+bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<TetComplex>& out, std::string& error);
+
+} // namespace rin_host

@@ -241,6 +241,18 @@ class Context:
         return {"vert_offset": v[0].value, "n_verts_total": v[1].value, "face_offset": v[2].value,
                 "n_faces_total": v[3].value}
 
+    def get_complexes(self, mode, tet_ids):
+        """Full per-tet complexes (layout in include/rin_b200.h) -> (offsets, words)."""
+        ids = np.ascontiguousarray(tet_ids, np.uint64)
+        n = C.c_uint64()
+        off = np.zeros(len(ids) + 1, np.uint64)
+        self._check(lib().rin_get_complexes(self._h, mode, 0, ids.ctypes.data, len(ids), off.ctypes.data, None,
+                                            C.byref(n)))
+        words = np.zeros(max(n.value, 1), np.uint32)
+        self._check(lib().rin_get_complexes(self._h, mode, 0, ids.ctypes.data, len(ids), off.ctypes.data,
+                                            words.ctypes.data, C.byref(n)))
+        return off, words[:n.value]
+
     def kernel_times(self):
         e, f, t = C.c_float(), C.c_float(), C.c_float()
         self._check(lib().rin_get_kernel_times(self._h, C.byref(e), C.byref(f), C.byref(t)))

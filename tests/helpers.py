@@ -83,6 +83,32 @@ def ref_lib():
     return _ref
 
 
+_dropin = None
+
+
+def dropin_lib():
+    """Reference host stages + csg on top of the GPU library (oracle/_ref/libref_gpu_dropin.so), or None."""
+    global _dropin
+    if _dropin is None:
+        so = os.path.join(ORACLE_DIR, "_ref", "libref_gpu_dropin.so")
+        if not os.path.exists(so):
+            return None
+        lib = C.CDLL(so)
+        for nm in ("ref_ia_run", "ref_mi_run"):
+            fn = getattr(lib, nm)
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]
+        for nm, rt in (("ref_i64", C.POINTER(C.c_int64)), ("ref_f64", C.POINTER(C.c_double))):
+            fn = getattr(lib, nm)
+            fn.restype = rt
+            fn.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64)]
+        lib.ref_error.restype = C.c_char_p
+        lib.ref_error.argtypes = [C.c_void_p]
+        lib.ref_free.argtypes = [C.c_void_p]
+        _dropin = lib
+    return _dropin
+
+
 class Bag:
     """Named result vectors of one oracle / reference run (copied out, handle freed)."""
 
@@ -193,8 +219,8 @@ def orc_run(mode, pts, tets, vals, flags=FLAG_LOOKUP | FLAG_SECONDARY, tet_first
     return Bag(lib, "orc", h, PORT_I64, ["vert_xyz", "timings"])
 
 
-def ref_run(mode, pts, tets, vals, robust=False, lookup=True, secondary=True, ray=True, quiet=True):
-    lib = ref_lib()
+def ref_run(mode, pts, tets, vals, robust=False, lookup=True, secondary=True, ray=True, quiet=True, lib=None):
+    lib = lib or ref_lib()
     assert lib is not None
     pts, tets, vals = _prep(pts, tets, vals)
     flags = (1 if robust else 0) | (2 if lookup else 0) | (4 if secondary else 0) | (8 if ray else 0) | \

@@ -1,0 +1,72 @@
+"""GPU: the reference's known-answer tests (tests/test_implicit_networks.cpp) replayed END TO END
+through the drop-in: hot path on the GPU (librin_b200 via the C++ host layer), per-tet complexes
+from rin_get_complexes, every host topology stage = the reference's own code
+(oracle/_ref/libref_gpu_dropin.so, built where /root/reference is present and shipped prebuilt).
+Expectations are the reference test's own numbers (transcribed in tests/golden/*.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import crs, dropin_lib, load_funcs, orc_eval, orc_grid, ref_run
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(dropin_lib() is None, reason="drop-in library not built (needs /root/reference)")]
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(G, "ia_goldens.json")) as _f:
+    IA_GOLD = json.load(_f)
+with open(os.path.join(G, "mi_goldens.json")) as _f:
+    MI_GOLD = json.load(_f)
+
+
+@pytest.fixture(scope="module")
+def grid101():
+    return orc_grid(101)
+
+
+@pytest.mark.parametrize("name", sorted(IA_GOLD))
+def test_ia_known_answers_through_the_gpu_drop_in(name, grid101):
+    pts, tets = grid101
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", name + ".json")), pts)
+    if name == "3-sphere-5":
+        vals[:, 2] = -vals[:, 2]
+    b = ref_run("ia", pts, tets, vals, lib=dropin_lib())
+    assert b.error == "" and b["success"][0] == 1
+    exp = IA_GOLD[name]["reference_test_expectation"]
+    F = vals.shape[1]
+    assert len(crs(b, "patches")) == exp["patches"]
+    assert len(crs(b, "chains")) == exp["chains"]
+    assert len(crs(b, "cells")) == exp["cells"]
+    assert b["patch_function_label"].tolist() == exp["patch_function_label"]
+    assert b["cell_function_label"].reshape(-1, F).tolist() == exp["cell_function_label"]
+    for k in ("num_iso_verts", "num_iso_faces", "num_iso_edges", "num_patches", "num_chains", "num_shells",
+              "num_components", "num_cells"):
+        assert b.stats[k] == IA_GOLD[name]["stats"][k], k
+
+
+@pytest.mark.parametrize("name", sorted(k for k in MI_GOLD if k != "8-sphere"))
+def test_mi_known_answers_through_the_gpu_drop_in(name, grid101):
+    pts, tets = grid101
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", name + ".json")), pts)
+    b = ref_run("mi", pts, tets, vals, lib=dropin_lib())
+    assert b.error == "" and b["success"][0] == 1
+    exp = MI_GOLD[name]["reference_test_expectation"]
+    assert len(crs(b, "patches")) == exp["patches"]
+    assert len(crs(b, "chains")) == exp["chains"]
+    assert len(crs(b, "cells")) == exp["cells"]
+    assert b["patch_function_label"].reshape(-1, 2).tolist() == exp["patch_function_label"]
+    assert b["cell_function_label"].tolist() == exp["cell_function_label"]
+
+
+def test_c1_example_config_through_the_gpu_drop_in():
+    """examples/implicit_arrangement/config.json (18 spheres on tet5_grid_10k): 1944 patches, 672 cells."""
+    d = np.load(os.path.join(G, "c1_inputs.npz"))
+    with open(os.path.join(G, "c1_golden.json")) as f:
+        gold = json.load(f)
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", "18-sphere.json")), d["pts"])
+    b = ref_run("ia", d["pts"], d["tets"], vals, lib=dropin_lib())
+    assert b.error == "" and b["success"][0] == 1
+    for k, v in gold["stats"].items():
+        assert b.stats[k] == v, k
+    assert b["patch_function_label"].tolist() == gold["patch_function_label"]
