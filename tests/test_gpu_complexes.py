@@ -11,7 +11,7 @@ from helpers import make_funcs, oracle_lib, orc_eval, orc_grid, orc_run, synthet
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode,cfg,R", [("ia", "C2", 14), ("ia", "C4", 12), ("mi", "C3", 14)])
+@pytest.mark.parametrize("mode,cfg,R", [("ia", "C2", 14), ("ia", "C4", 24), ("mi", "C3", 14)])
 def test_complexes_match_oracle(mode, cfg, R):
     import rin_b200 as rin
     funcs = make_funcs(synthetic_functions(cfg))
