@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--resolution", type=int, default=0, help="override the grid resolution (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -173,7 +174,7 @@ def main():
         dist = None
         torch.cuda.set_device(0)
 
-    R = grid_resolution(world)
+    R = args.resolution or grid_resolution(world)
     funcs = make_funcs(synthetic_functions(args.config))
     F = len(funcs)
     ctx = rin.Context(local)

@@ -414,6 +414,8 @@ struct GeneralCounters
 };
 
 constexpr uint32_t REF_GENERAL = 0x80000000u;
+constexpr uint32_t REF_GATED = 0x40000000u; // MI: record also lists the simplex-boundary faces (degenerate ties)
+constexpr uint32_t REF_FLAGS = REF_GENERAL | REF_GATED;
 constexpr uint16_t LUT_MISS = 0xffffu;
 
 struct LutView
@@ -688,7 +690,7 @@ struct ScanTotals
 
 __device__ __forceinline__ const uint8_t* record_ptr(uint32_t ref, const uint8_t* lut_blob, const uint8_t* arena)
 {
-    return (ref & REF_GENERAL) ? arena + (size_t)(ref & ~REF_GENERAL) * 4 : lut_blob + (size_t)ref * 4;
+    return (ref & REF_GENERAL) ? arena + (size_t)(ref & ~REF_FLAGS) * 4 : lut_blob + (size_t)ref * 4;
 }
 
 template <int W>
@@ -956,8 +958,12 @@ __global__ void __launch_bounds__(256) hash_insert_kernel(const uint4* __restric
 
 // rep[c] = first candidate with the same key; single-lane look-back scan of the representative
 // flags gives vid[c] (valid at representatives).
+constexpr uint32_t CAND_DEDUP = 1u << 16, CAND_DEAD = 1u << 17; // bits of cand_pay.y
+constexpr uint32_t FACE_BND = 1u << 24, FACE_INACTIVE = 1u << 25; // bits of face_hdr.y
+
 __global__ void __launch_bounds__(256) rank_reps_kernel(const uint32_t* __restrict__ table,
-    const uint32_t* __restrict__ slot_of, uint32_t n, uint32_t* __restrict__ rep, uint32_t* __restrict__ vid,
+    const uint32_t* __restrict__ slot_of, const uint4* __restrict__ pay /* nullable: marks dead candidates */,
+    uint32_t n, uint32_t* __restrict__ rep, uint32_t* __restrict__ vid,
     volatile unsigned long long* __restrict__ status, unsigned* __restrict__ tile_counter,
     unsigned* __restrict__ n_unique)
 {
@@ -978,6 +984,7 @@ __global__ void __launch_bounds__(256) rank_reps_kernel(const uint32_t* __restri
         if (c < n) {
             const uint32_t s = slot_of[c];
             r[j] = (s == NONE32) ? c : table[s];
+            if (pay && (pay[c].y & CAND_DEAD)) r[j] = NONE32; // reserved slot that was never activated
             cnt += (r[j] == c);
         }
     }
@@ -1108,8 +1115,10 @@ __global__ void __launch_bounds__(256) write_verts_ia_kernel(const uint4* __rest
 __global__ void __launch_bounds__(256) remap_face_verts_kernel(const uint32_t* __restrict__ fv_ref,
     uint32_t n, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ vid, uint32_t* __restrict__ out)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        out[i] = vid[rep[fv_ref[i]]];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t r = rep[fv_ref[i]];
+        out[i] = (r == NONE32) ? NONE32 : vid[r];
+    }
 }
 
 // generic (no iso-face on a tet boundary): one output face per face record
@@ -1256,7 +1265,7 @@ __global__ void __launch_bounds__(256) bface_write_kernel(const uint4* __restric
     const uint32_t* __restrict__ fverts_in, const uint32_t* __restrict__ frep, const uint4* __restrict__ pos,
     uint32_t* __restrict__ cursor, const uint32_t* __restrict__ totals, uint32_t* __restrict__ f_off,
     uint32_t* __restrict__ f_verts, uint32_t* __restrict__ f_toff, uint32_t* __restrict__ f_tets,
-    uint32_t* __restrict__ f_funcs)
+    uint32_t* __restrict__ f_funcs, int mi_labels)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
         if (i == n) {
@@ -1274,9 +1283,15 @@ __global__ void __launch_bounds__(256) bface_write_kernel(const uint4* __restric
             f_toff[p.x] = p.z;
             f_tets[2 * (size_t)p.z] = h.x;
             f_tets[2 * (size_t)p.z + 1] = h.y & 0xffffu;
-            f_funcs[2 * (size_t)p.x] = h.z;
-            f_funcs[2 * (size_t)p.x + 1] = NONE32;
-        } else {
+            if (mi_labels) {
+                const uint32_t a = h.z & 0xffffu, b = h.z >> 16;
+                f_funcs[2 * (size_t)p.x] = (a == 0xffffu) ? NONE32 : a;
+                f_funcs[2 * (size_t)p.x + 1] = b;
+            } else {
+                f_funcs[2 * (size_t)p.x] = h.z;
+                f_funcs[2 * (size_t)p.x + 1] = NONE32;
+            }
+        } else if (r != NONE32) {
             const uint4 p = pos[r];
             const uint32_t slot = p.z + 1 + atomicAdd(&cursor[r], 1u);
             f_tets[2 * (size_t)slot] = h.x;

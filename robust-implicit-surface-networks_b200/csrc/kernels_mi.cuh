@@ -62,7 +62,7 @@ template <int W>
 __global__ void __launch_bounds__(FILT_THREADS) filter_mi_tiles_kernel(const uint4* __restrict__ tets,
     uint32_t t_first, uint32_t t_count, const uint2* __restrict__ vmask, const double* __restrict__ vals,
     uint32_t V, uint32_t F, uint32_t* __restrict__ tl_tet, uint32_t* __restrict__ tl_mask, size_t tl_stride,
-    uint2* __restrict__ tile_cnt, FilterCounters* __restrict__ ctr, unsigned* __restrict__ n_tie_faces)
+    uint2* __restrict__ tile_cnt, FilterCounters* __restrict__ ctr)
 {
     __shared__ unsigned s_cnt[FILT_ITEMS][FILT_THREADS / 32];
     __shared__ unsigned s_kf[FILT_THREADS / 32];
@@ -73,14 +73,13 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_mi_tiles_kernel(const uin
     if (threadIdx.x < 3) s_k[threadIdx.x] = 0;
     uint32_t m[FILT_ITEMS][W];
     unsigned ball[FILT_ITEMS];
-    unsigned k1 = 0, k2 = 0, km = 0, kf = 0, ties = 0;
+    unsigned k1 = 0, k2 = 0, km = 0, kf = 0;
 #pragma unroll
     for (int j = 0; j < FILT_ITEMS; ++j) {
         const uint32_t i = base + j * FILT_THREADS + threadIdx.x;
         const uint4 tv = __ldg(&tets[t_first + min(i, t_count - 1)]);
         const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
         int kq = 0, ns = 0;
-        unsigned tie_cnt = 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) {
             uint32_t s = 0;
@@ -88,7 +87,7 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_mi_tiles_kernel(const uin
             for (int c = 0; c < 4; ++c) {
                 const uint2 g = __ldg(&vmask[(size_t)w * V + vv[c]]);
                 s |= g.x;
-                if (w == 0) tie_cnt += g.y & 1u;
+
             }
             m[j][w] = s;
             ns += __popc(s);
@@ -118,29 +117,6 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_mi_tiles_kernel(const uin
                 }
 #pragma unroll
             for (int w = 0; w < W; ++w) kq += __popc(m[j][w]);
-            if (tie_cnt >= 3) {
-                // exact test: an active material g and any other material coincide at the three
-                // corners of one tet face -> a boundary face piece may be a material interface
-                bool found = false;
-                for (uint32_t g = 0; g < F && !found; ++g) {
-                    bool active = false;
-#pragma unroll
-                    for (int w = 0; w < W; ++w)
-                        if ((g >> 5) == (uint32_t)w) active = (m[j][w] >> (g & 31)) & 1;
-                    if (!active) continue;
-                    double xg[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) xg[c] = __ldg(&vals[(size_t)g * V + vv[c]]);
-                    for (uint32_t f = 0; f < F && !found; ++f) {
-                        if (f == g) continue;
-                        int eq = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) eq += (__ldg(&vals[(size_t)f * V + vv[c]]) == xg[c]);
-                        found = (eq >= 3);
-                    }
-                }
-                ties += found;
-            }
         } else {
 #pragma unroll
             for (int w = 0; w < W; ++w) m[j][w] = 0;
@@ -157,7 +133,6 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_mi_tiles_kernel(const uin
         k2 += __shfl_xor_sync(0xffffffffu, k2, o);
         km += __shfl_xor_sync(0xffffffffu, km, o);
         kf += __shfl_xor_sync(0xffffffffu, kf, o);
-        ties += __shfl_xor_sync(0xffffffffu, ties, o);
     }
     if (lane == 0) s_kf[warp] = kf;
     __syncthreads();
@@ -165,7 +140,6 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_mi_tiles_kernel(const uin
         if (k1) atomicAdd(&s_k[0], k1);
         if (k2) atomicAdd(&s_k[1], k2);
         if (km) atomicAdd(&s_k[2], km);
-        if (ties) atomicAdd(n_tie_faces, ties);
     }
     unsigned my_off[FILT_ITEMS];
     unsigned run = 0;
@@ -221,9 +195,31 @@ struct MIIsoScan
 {
     uint32_t isov[(Caps::MAXV + 31) / 32];
     int nvi, nfi, nfv, nfw;
+    int n_bf, n_extra, bf_words, bf_fv; // gated records: simplex-boundary faces
+    __device__ static bool is_corner(const MIComplex<Caps>& cx, int v) { return cx.vm[v][2] < 4; }
+    __device__ bool is_mi_vert(int v) const { return (isov[v >> 5] >> (v & 31)) & 1; }
+    // boundary faces (positive label <= 3) of a tet whose materials tie on a whole tet face:
+    // the extraction matches them with the neighbouring tet (src/extract_mesh.cpp:833-981)
+    __device__ void run_boundary(const MIComplex<Caps>& cx)
+    {
+        const int B = cx.cur;
+        n_bf = n_extra = bf_words = bf_fv = 0;
+        for (int f = 0; f < cx.nf; ++f)
+            if (!cx.is_mi_face(f)) {
+                const int n = cx.flen[B][f];
+                ++n_bf;
+                bf_words += 2 + n;
+                bf_fv += n;
+                for (int k = 0; k < n; ++k) {
+                    const int v = cx.fv[B][cx.foff[B][f] + k];
+                    if (!is_mi_vert(v)) ++n_extra; // a tet corner not on the interface
+                }
+            }
+    }
     __device__ void run(const MIComplex<Caps>& cx)
     {
         const int B = cx.cur;
+        n_bf = n_extra = bf_words = bf_fv = 0;
         for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) isov[i] = 0;
         nfi = nfv = nfw = 0;
         for (int f = 0; f < cx.nf; ++f)
@@ -247,12 +243,19 @@ struct MIIsoScan
         for (int i = 0; i < (v >> 5); ++i) r += __popc(isov[i]);
         return r;
     }
-    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + 2 * nvi + nfw); }
-    __device__ void write(const MIComplex<Caps>& cx, uint32_t* w) const
+    __device__ uint32_t size_bytes(bool gated) const
+    {
+        return 4u * uint32_t(1 + 2 * nvi + nfw + (gated ? 1 + bf_words : 0));
+    }
+    __device__ void write(const MIComplex<Caps>& cx, uint32_t* w, bool gated) const
     {
         const int B = cx.cur;
         int p = 0;
-        w[p++] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
+        if (gated) {
+            w[p++] = (uint32_t)(nvi + n_extra) | ((uint32_t)(nfi + n_bf) << 8) | ((uint32_t)(nfv + bf_fv) << 16);
+            w[p++] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)n_extra << 16);
+        } else
+            w[p++] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
         for (int v = 0; v < cx.nv; ++v)
             if ((isov[v >> 5] >> (v & 31)) & 1) {
                 w[p++] = (uint32_t)v;
@@ -268,6 +271,27 @@ struct MIIsoScan
                     uint32_t x = 0;
                     for (int k = k0; k < n && k < k0 + 4; ++k)
                         x |= (uint32_t)rank(cx.fv[B][cx.foff[B][f] + k]) << (8 * (k - k0));
+                    w[p++] = x;
+                }
+            }
+        if (!gated) return;
+        for (int f = 0; f < cx.nf; ++f)
+            if (!cx.is_mi_face(f)) {
+                const int n = cx.flen[B][f];
+                w[p++] = (uint32_t)f | ((uint32_t)n << 24);
+                w[p++] = (uint32_t)cx.pos_label(f) | ((uint32_t)cx.neg_label(f) << 8);
+                for (int k = 0; k < n; ++k) {
+                    const int v = cx.fv[B][cx.foff[B][f] + k];
+                    uint32_t x = ((uint32_t)v << 8);
+                    if (is_corner(cx, v)) {
+                        // the corner not among the three boundary pseudo materials
+                        const int corner = 6 - cx.vm[v][0] - cx.vm[v][1] - cx.vm[v][2];
+                        x |= 0x80000000u | ((uint32_t)corner << 16);
+                    }
+                    if (is_mi_vert(v))
+                        x |= (uint32_t)rank(v);
+                    else
+                        x |= 0x40000000u;
                     w[p++] = x;
                 }
             }
@@ -299,10 +323,15 @@ __device__ bool general_mi_one(MIComplex<Caps>& cx, uint32_t a, const uint4* __r
                 cx.insert(pv);
         }
     }
+    const bool gated = (rec_ref[a] & REF_GATED) != 0;
     MIIsoScan<Caps> iso;
     if (!cx.err) {
         iso.run(cx);
-        if (iso.nvi > 255 || iso.nfi > 255 || iso.nfv > 65535) cx.err = 1;
+        if (gated) {
+            iso.run_boundary(cx);
+            if (cx.has_dup) cx.err = 2; // identical materials in a tie tet: label sets are not built
+        }
+        if (iso.nvi + iso.n_extra > 255 || iso.nfi + iso.n_bf > 255 || iso.nfv + iso.bf_fv > 65535) cx.err = 1;
     }
     if (cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
     if (cx.err == 1 && !last_tier) return false;
@@ -312,15 +341,15 @@ __device__ bool general_mi_one(MIComplex<Caps>& cx, uint32_t a, const uint4* __r
         rec_ref[a] = REF_GENERAL;
         return true;
     }
-    const uint32_t szal = iso.size_bytes();
+    const uint32_t szal = iso.size_bytes(gated);
     const uint32_t off = atomicAdd(&gc->arena_top, szal);
     if (off + szal > arena_cap) {
         gc->arena_overflow = 1;
-        rec_ref[a] = REF_GENERAL;
+        rec_ref[a] = REF_GENERAL | (gated ? REF_GATED : 0u); // keep the flag for the retry
         return true;
     }
-    iso.write(cx, reinterpret_cast<uint32_t*>(arena + off));
-    rec_ref[a] = REF_GENERAL | (off >> 2);
+    iso.write(cx, reinterpret_cast<uint32_t*>(arena + off), gated);
+    rec_ref[a] = REF_GENERAL | (gated ? REF_GATED : 0u) | (off >> 2);
     return true;
 }
 
@@ -370,9 +399,10 @@ __global__ void __launch_bounds__(GEN_THREADS) general_mi_big_kernel(const uint4
 template <int W>
 __global__ void __launch_bounds__(256) classify_mi_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
-    uint32_t n_active, const double* __restrict__ vals, uint32_t V, const uint16_t* __restrict__ lut2,
-    int use_lookup, uint32_t* __restrict__ rec_ref, uint32_t* __restrict__ small_list,
-    uint32_t* __restrict__ big_list, GeneralCounters* __restrict__ gc)
+    uint32_t n_active, const double* __restrict__ vals, const uint2* __restrict__ vmask, uint32_t V, uint32_t F,
+    const uint16_t* __restrict__ lut2, int use_lookup, uint32_t* __restrict__ rec_ref,
+    uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list, GeneralCounters* __restrict__ gc,
+    unsigned* __restrict__ n_gated)
 {
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         uint32_t m[W];
@@ -383,9 +413,39 @@ __global__ void __launch_bounds__(256) classify_mi_kernel(const uint4* __restric
             k += __popc(m[w]);
         }
         uint32_t ref = REF_GENERAL;
-        if (use_lookup && k == 2) {
-            const uint4 tv = __ldg(&tets[act_tet[a]]);
-            const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
+        const uint4 tv = __ldg(&tets[act_tet[a]]);
+        const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
+        // tie gate: an active material and any other material coincide exactly at the three corners
+        // of one tet face -> a simplex-boundary face piece may be a material interface
+        bool gated = false;
+        {
+            unsigned tie_cnt = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tie_cnt += __ldg(&vmask[vv[c]]).y & 1u;
+            if (tie_cnt >= 3) {
+                for (uint32_t g = 0; g < F && !gated; ++g) {
+                    bool active = false;
+#pragma unroll
+                    for (int w = 0; w < W; ++w)
+                        if ((g >> 5) == (uint32_t)w) active = (m[w] >> (g & 31)) & 1;
+                    if (!active) continue;
+                    double xg[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) xg[c] = __ldg(&vals[(size_t)g * V + vv[c]]);
+                    for (uint32_t f = 0; f < F && !gated; ++f) {
+                        if (f == g) continue;
+                        int eq = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) eq += (__ldg(&vals[(size_t)f * V + vv[c]]) == xg[c]);
+                        gated = (eq >= 3);
+                    }
+                }
+            }
+        }
+        if (gated) {
+            ref = REF_GENERAL | REF_GATED;
+            atomicAdd(n_gated, 1u);
+        } else if (use_lookup && k == 2) {
             const int f0 = nth_set_bit(m, W, 0), f1 = nth_set_bit(m, W, 1);
             int key = 0;
 #pragma unroll
@@ -417,16 +477,20 @@ __global__ void __launch_bounds__(256) emit_mi_kernel(const uint4* __restrict__ 
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     uint32_t n_active, const uint32_t* __restrict__ rec_ref, const uint4* __restrict__ offs,
     const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena, uint4* __restrict__ cand_key,
-    uint4* __restrict__ cand_pay, uint4* __restrict__ face_hdr, uint32_t* __restrict__ fv_ref)
+    uint4* __restrict__ cand_pay, uint4* __restrict__ face_hdr, uint32_t* __restrict__ fv_ref,
+    unsigned* __restrict__ n_bface_slots)
 {
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         const uint32_t ref = rec_ref[a];
         const uint32_t* r = (ref & REF_GENERAL)
-                                ? reinterpret_cast<const uint32_t*>(arena) + (size_t)(ref & ~REF_GENERAL)
+                                ? reinterpret_cast<const uint32_t*>(arena) + (size_t)(ref & ~REF_FLAGS)
                                 : reinterpret_cast<const uint32_t*>(lut_blob) + ref;
-        const uint32_t hdr = r[0];
+        const bool gated = (ref & REF_GATED) && (ref & ~REF_FLAGS); // offset 0 = empty error record
+        uint32_t hdr = r[0];
+        if ((hdr & 0xffffu) == 0) continue;
+        int n_total_f = (hdr >> 8) & 255;
+        if (gated) hdr = r[1]; // (MI vertices, interface faces, reserved corner slots)
         const int nv = hdr & 255, nf = (hdr >> 8) & 255;
-        if (nv == 0 && nf == 0) continue;
         const uint32_t t = act_tet[a];
         const uint4 tv4 = __ldg(&tets[t]);
         const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
@@ -434,7 +498,7 @@ __global__ void __launch_bounds__(256) emit_mi_kernel(const uint4* __restrict__ 
 #pragma unroll
         for (int w = 0; w < W; ++w) m[w] = act_mask[(size_t)w * cap + a];
         const uint4 o = offs[a];
-        const uint32_t* p = r + 1;
+        const uint32_t* p = r + (gated ? 2 : 1);
         for (int i = 0; i < nv; ++i, p += 2) {
             const int local = p[0] & 0xffff;
             const uint32_t e = p[1];
@@ -495,14 +559,161 @@ __global__ void __launch_bounds__(256) emit_mi_kernel(const uint4* __restrict__ 
             const int n = (e0 >> 24) & 127;
             const uint32_t fpos = (uint32_t)nth_set_bit(m, W, (int)(e1 & 255) - 4);
             const uint32_t fneg = (uint32_t)nth_set_bit(m, W, (int)((e1 >> 8) & 255) - 4);
-            face_hdr[o.y + j] = make_uint4(t, local | ((uint32_t)n << 16), fpos | (fneg << 16), fvo);
+            // gated records list EVERY face of the complex: the slot is the local face id, so that the
+            // output keeps the reference's local face order (interface and boundary faces interleave)
+            face_hdr[o.y + (gated ? local : (uint32_t)j)] =
+                make_uint4(t, local | ((uint32_t)n << 16), fpos | (fneg << 16), fvo);
             for (int k0 = 0; k0 < n; k0 += 4) {
                 const uint32_t x = *p++;
                 for (int k = k0; k < n && k < k0 + 4; ++k) fv_ref[fvo + k] = o.x + ((x >> (8 * (k - k0))) & 255);
             }
             fvo += n;
         }
+        if (!gated) continue;
+        // simplex-boundary faces of a tie tet: reserved (inactive) face slots and, for tet corners
+        // that are not interface vertices, reserved (dead) vertex candidates; both are switched on
+        // by mi_bface_decide_kernel when the neighbouring tet holds a different material
+        uint32_t xe = o.x + nv;
+        const int nbf = n_total_f - nf;
+        for (int j = 0; j < nbf; ++j) {
+            const uint32_t e0 = *p++, e1 = *p++;
+            const uint32_t local = e0 & 0xffffu;
+            const int n = (e0 >> 24) & 127;
+            const uint32_t bface = e1 & 255;
+            const uint32_t inside = (uint32_t)nth_set_bit(m, W, (int)((e1 >> 8) & 255) - 4);
+            face_hdr[o.y + local] =
+                make_uint4(t, local | ((uint32_t)n << 16) | FACE_BND | FACE_INACTIVE, bface | (inside << 16), fvo);
+            for (int k = 0; k < n; ++k) {
+                const uint32_t x = *p++;
+                if (x & 0x40000000u) { // corner that is not an interface vertex
+                    const uint32_t corner = (x >> 16) & 3;
+                    cand_key[xe] = make_uint4(tv[corner], NONE32, NONE32, 0x3fffffffu);
+                    cand_pay[xe] = make_uint4(t, ((x >> 8) & 255) | (1u << 8) | CAND_DEAD, 0xffffffffu, 0xffffffffu);
+                    fv_ref[fvo + k] = xe++;
+                } else
+                    fv_ref[fvo + k] = o.x + (x & 255);
+            }
+            fvo += n;
+        }
+        if (nbf) atomicAdd(n_bface_slots, (unsigned)nbf);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Degenerate ties only: matching of simplex-boundary faces between neighbouring tets
+// (src/extract_mesh.cpp:833-981).  A boundary face is identified by (smallest, second smallest,
+// largest) vertex identity, where tet corners count as corners (the reference's -(id)-1) and
+// every other vertex by its first-occurrence candidate.  The SECOND tet (in tet order) that sees a
+// face whose inside material differs from the first tet's emits it as a material-interface face.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mi_bface_keys_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    const uint32_t* __restrict__ fv_ref, const uint4* __restrict__ cand_key, const uint4* __restrict__ cand_pay,
+    const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ table, uint4* __restrict__ fkeys)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = face_hdr[i];
+        if (!(h.y & FACE_BND)) continue;
+        const int nv = (h.y >> 16) & 255;
+        uint32_t mn = 0, mx = 0, second = 0;
+        int mn_pos = 0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int k = 0; k < nv; ++k) {
+                const uint32_t c = fv_ref[h.w + k];
+                uint32_t id;
+                if (((cand_pay[c].y >> 8) & 255) == 1)
+                    id = 0x80000000u | cand_key[c].x; // on a tet vertex
+                else {
+                    const uint32_t s = slot_of[c];
+                    id = (s == NONE32) ? c : table[s];
+                }
+                if (pass == 0) {
+                    if (k == 0) {
+                        mn = mx = id;
+                        mn_pos = 0;
+                    } else if (id < mn) {
+                        mn = id;
+                        mn_pos = k;
+                    } else if (id > mx)
+                        mx = id;
+                } else {
+                    if (k == 0) second = 0xffffffffu;
+                    if (k != mn_pos && id < second) second = id;
+                }
+            }
+        fkeys[i] = make_uint4(mn, second, mx, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) mi_bface_decide_kernel(uint4* __restrict__ face_hdr, uint32_t n,
+    const uint32_t* __restrict__ frep, const uint32_t* __restrict__ ndup, const uint32_t* __restrict__ fv_ref,
+    uint4* __restrict__ cand_pay, const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask,
+    uint32_t cap, uint32_t n_active, int W, unsigned* __restrict__ n_bad)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint4 h = face_hdr[i];
+        if (!(h.y & FACE_BND)) continue;
+        const uint32_t r = frep[i];
+        if (r == i) continue; // first visitor (or unmatched): stays inactive
+        if (ndup[r] > 1) {
+            atomicAdd(n_bad, 1u); // more than two tets on one face: not a manifold tet mesh
+            continue;
+        }
+        const uint32_t mine = h.z >> 16, other = face_hdr[r].z >> 16;
+        if (mine == other) continue; // same material on both sides
+        // func_index.first = material_in_tet[positive label - 4 + start] with a boundary label (< 4):
+        // QUIRK kept from the reference (:979): an earlier CRS entry
+        uint32_t first = 0xffffu;
+        {
+            uint32_t lo = 0, hi = n_active;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (act_tet[mid] < h.x)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            int back = 4 - (int)(h.z & 255);
+            for (uint32_t ap = lo; ap > 0 && back > 0;) {
+                --ap;
+                int kp = 0;
+                for (int w = 0; w < W; ++w) kp += __popc(act_mask[(size_t)w * cap + ap]);
+                if (back <= kp) {
+                    int want = kp - back; // index among the set bits
+                    for (int w = 0; w < W; ++w) {
+                        const uint32_t mm = act_mask[(size_t)w * cap + ap];
+                        const int c = __popc(mm);
+                        if (want < c) {
+                            first = w * 32 + __fns(mm, 0, want + 1);
+                            break;
+                        }
+                        want -= c;
+                    }
+                    back = 0;
+                } else
+                    back -= kp;
+            }
+        }
+        h.y &= ~FACE_INACTIVE;
+        h.z = first | (mine << 16);
+        face_hdr[i] = h;
+        const int nv = (h.y >> 16) & 255;
+        for (int k = 0; k < nv; ++k) {
+            const uint32_t c = fv_ref[h.w + k];
+            uint4 p = cand_pay[c];
+            if (p.y & CAND_DEAD) {
+                p.y = (p.y & ~CAND_DEAD) | CAND_DEDUP;
+                cand_pay[c] = p;
+            }
+        }
+    }
+}
+
+// keep[i] as a representative array for bface_scan / bface_write: i when the face stays, NONE32 else
+__global__ void __launch_bounds__(256) mi_face_keep_kernel(const uint4* __restrict__ face_hdr, uint32_t n,
+    uint32_t* __restrict__ keep)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        keep[i] = (face_hdr[i].y & FACE_INACTIVE) ? NONE32 : i;
 }
 
 // ---------------------------------------------------------------------------------------------

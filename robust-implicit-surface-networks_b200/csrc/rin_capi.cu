@@ -1217,7 +1217,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         const uint32_t r_tiles = (NC + 1023) / 1024;
         CK(c->status.ensure((size_t)r_tiles * 8 + 64));
         CK(cudaMemsetAsync(c->status.p, 0, (size_t)r_tiles * 8, s));
-        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NC,
+        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), nullptr, NC,
             c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
             &dctr->n_unique);
         CK(cudaGetLastError());
@@ -1290,7 +1290,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         bface_write_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
             c->tmp_fverts.as<uint32_t>(), c->frep.as<uint32_t>(), c->fpos.as<uint4>(), cursor, totals,
             c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(),
-            c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>());
+            c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>(), 0);
         CK(cudaGetLastError());
         uint32_t ht[3];
         CK(cudaMemcpyAsync(ht, totals, 12, cudaMemcpyDeviceToHost, s));
@@ -1376,17 +1376,12 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     (void)last_mask;
     filter_mi_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
         c->vmask.as<uint2>(), c->vals.as<double>(), V, F, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
-        tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt, &dctr->n_tie_faces);
+        tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
     CK(cudaEventRecord(c->kev[3], s));
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (h.n_tie_faces)
-        return fail(RIN_ERR_STATE, "material interface: materials tie exactly on whole tet faces (" +
-                                       std::to_string(h.n_tie_faces) +
-                                       " candidate tets); the degenerate boundary-face matching of "
-                                       "src/extract_mesh.cpp:833-981 is not built on the device yet");
     const uint32_t A = h.filt.n_active;
     c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 16 + 1024);
     CK(c->act_tet.ensure((size_t)c->act_cap * 4));
@@ -1418,9 +1413,9 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
     if (A) {
         classify_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
-            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vals.as<double>(), V,
-            c->lut_mi.lut1.as<uint16_t>(), use_lookup, c->rec_ref.as<uint32_t>(), c->general_list.as<uint32_t>(),
-            c->big_list.as<uint32_t>(), &dctr->gen);
+            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vals.as<double>(),
+            c->vmask.as<uint2>(), V, F, c->lut_mi.lut1.as<uint16_t>(), use_lookup, c->rec_ref.as<uint32_t>(),
+            c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_tie_faces);
         CK(cudaGetLastError());
     }
     (void)use_secondary;
@@ -1491,7 +1486,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         emit_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(), c->act_tet.as<uint32_t>(),
             c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(),
             c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->cand_key.as<uint4>(),
-            c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>());
+            c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>(), &dctr->n_bndry_faces);
         CK(cudaGetLastError());
     }
 
@@ -1508,10 +1503,49 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
         hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
             c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
+        // degenerate ties: reserved boundary-face slots exist -> match them across tets
+        unsigned n_slots = 0;
+        CK(cudaMemcpyAsync(&n_slots, &dctr->n_bndry_faces, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h.n_bndry_faces = n_slots;
+        if (n_slots) {
+            uint32_t t2 = 1024;
+            while (t2 < 2 * NFc) t2 <<= 1;
+            CK(c->ftable.ensure((size_t)t2 * 4));
+            CK(c->bfkeys.ensure((size_t)NFc * 16));
+            CK(c->frep.ensure((size_t)NFc * 4));
+            CK(c->fpos.ensure((size_t)NFc * 16));
+            CK(c->fdup.ensure((size_t)NFc * 8 + 16));
+            CK(c->bids.ensure((size_t)NFc * 4)); // face slot -> table slot
+            uint32_t* ndup = c->fdup.as<uint32_t>();
+            CK(cudaMemsetAsync(c->ftable.p, 0xff, (size_t)t2 * 4, s));
+            CK(cudaMemsetAsync(c->fdup.p, 0, (size_t)NFc * 8 + 16, s));
+            CK(cudaMemsetAsync(&dctr->n_unique, 0, 4, s));
+            const int g = grid_for(NFc, 256, sm, 8);
+            mi_bface_keys_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->fv_ref.as<uint32_t>(),
+                c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->slot_of.as<uint32_t>(), c->table.as<uint32_t>(),
+                c->bfkeys.as<uint4>());
+            bface_insert_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->bfkeys.as<uint4>(),
+                c->ftable.as<uint32_t>(), t2 - 1, c->bids.as<uint32_t>());
+            bface_reps_kernel<<<g, 256, 0, s>>>(c->ftable.as<uint32_t>(), c->bids.as<uint32_t>(), NFc,
+                c->frep.as<uint32_t>(), ndup);
+            mi_bface_decide_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
+                c->fv_ref.as<uint32_t>(), c->cand_pay.as<uint4>(), c->act_tet.as<uint32_t>(),
+                c->act_mask.as<uint32_t>(), c->act_cap, A, W, &dctr->n_unique);
+            // the activated corner candidates join the vertex table
+            hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
+                c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
+            CK(cudaGetLastError());
+            unsigned bad = 0;
+            CK(cudaMemcpyAsync(&bad, &dctr->n_unique, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (bad) return fail(RIN_ERR_STATE, "material interface: a tet face is shared by more than two active tets");
+        }
         const uint32_t r_tiles = (NC + 1023) / 1024;
         CK(c->status.ensure((size_t)r_tiles * 8 + 64));
         CK(cudaMemsetAsync(c->status.p, 0, (size_t)r_tiles * 8, s));
-        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NC,
+        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(),
+            c->cand_pay.as<uint4>(), NC,
             c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
             &dctr->n_unique);
         CK(cudaGetLastError());
@@ -1546,12 +1580,39 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->f_tets.ensure((size_t)std::max(NFc, 1u) * 8));
     CK(c->f_funcs.ensure((size_t)std::max(NFc, 1u) * 8));
     uint32_t NF = NFc, NFVout = NFV, NFT = NFc;
-    if (NFV)
+    if (!h.n_bndry_faces) {
+        if (NFV)
+            remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
+                c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
+        write_faces_mi_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
+            NFV, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(),
+            c->f_funcs.as<uint32_t>());
+        CK(cudaGetLastError());
+    } else {
+        // drop the boundary-face slots that were not switched on
+        CK(c->tmp_fverts.ensure((size_t)std::max(NFV, 1u) * 4));
+        uint32_t* ndup = c->fdup.as<uint32_t>();
+        uint32_t* cursor = ndup + NFc;
+        uint32_t* totals = cursor + NFc;
+        CK(cudaMemsetAsync(c->fdup.p, 0, (size_t)NFc * 8 + 16, s));
         remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
-            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
-    write_faces_mi_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, NFV,
-        c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>());
-    CK(cudaGetLastError());
+            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->tmp_fverts.as<uint32_t>());
+        mi_face_keep_kernel<<<grid_for(NFc, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
+            c->frep.as<uint32_t>());
+        bface_scan_kernel<<<1, 1024, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
+            c->fpos.as<uint4>(), totals);
+        bface_write_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
+            c->tmp_fverts.as<uint32_t>(), c->frep.as<uint32_t>(), c->fpos.as<uint4>(), cursor, totals,
+            c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(),
+            c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>(), 1);
+        CK(cudaGetLastError());
+        uint32_t ht[3];
+        CK(cudaMemcpyAsync(ht, totals, 12, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        NF = ht[0];
+        NFVout = ht[1];
+        NFT = ht[2];
+    }
     CK(cudaEventRecord(c->ev[ST_COUNT], s));
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));

@@ -59,6 +59,20 @@ def test_mi_known_answers_through_the_gpu_drop_in(name, grid101):
     assert b["cell_function_label"].tolist() == exp["cell_function_label"]
 
 
+def test_mi_eight_spheres_through_the_gpu_drop_in():
+    """tests/test_implicit_networks.cpp:685-731 on examples/tests/mesh.json: 8 shells, 8 cells, 6 corners and
+    the 19-pair patch label vector; the symmetric spheres tie on tet faces (degenerate matching path)."""
+    d = np.load(os.path.join(G, "mi_8sphere_inputs.npz"))
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", "8-sphere.json")), d["pts"])
+    b = ref_run("mi", d["pts"], d["tets"], vals, lib=dropin_lib())
+    assert b.error == "" and b["success"][0] == 1
+    exp = MI_GOLD["8-sphere"]["reference_test_expectation"]
+    assert len(crs(b, "shells")) == exp["shells"] and len(crs(b, "cells")) == exp["cells"]
+    assert sum(1 for l in crs(b, "non_manifold_edges_of_vert") if len(l) > 2) == exp["corners"]
+    assert b["patch_function_label"].reshape(-1, 2).tolist() == exp["patch_function_label"]
+    assert b["cell_function_label"].tolist() == exp["cell_function_label"]
+
+
 def test_c1_example_config_through_the_gpu_drop_in():
     """examples/implicit_arrangement/config.json (18 spheres on tet5_grid_10k): 1944 patches, 672 cells."""
     d = np.load(os.path.join(G, "c1_inputs.npz"))

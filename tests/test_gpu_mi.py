@@ -94,9 +94,6 @@ def test_reference_mi_golden_cases(ctx, rin, name):
         assert d[k] == v, k
 
 
-@pytest.mark.xfail(reason="symmetric spheres tie exactly on tet faces of examples/tests/mesh.json: needs the "
-                          "degenerate boundary-face matching (src/extract_mesh.cpp:833-981) on the device",
-                   strict=False)
 def test_reference_mi_eight_spheres_unstructured(ctx, rin):
     """tests/test_implicit_networks.cpp:685-731: 8 spheres on examples/tests/mesh.json."""
     d = np.load(os.path.join(G, "mi_8sphere_inputs.npz"))
@@ -112,14 +109,29 @@ def test_reference_mi_eight_spheres_unstructured(ctx, rin):
     compare_mi(ctx, mesh, orc_run("mi", d["pts"], d["tets"], vals), cnt)
 
 
-def test_materials_tying_on_a_tet_face_fail_loudly(ctx, rin):
-    """x and -x tie on the plane x = 0 through grid vertices: the degenerate boundary-face matching
-    (src/extract_mesh.cpp:833-981) is not built on the device; the call must say so, not guess."""
-    pts, tets = orc_grid(8)
-    funcs = make_funcs([{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
-                        {"type": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]}])
+DEGENERATE = {
+    # x and -x tie on the plane x = 0 through grid vertices: the whole interface lies on tet faces
+    "x_vs_negx": [{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
+                  {"type": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]}],
+    # spheres mirrored about grid planes: parts of the interface lie on tet faces
+    "sym_spheres": [{"type": "sphere", "center": [-0.5, 0, 0], "radius": 0.7},
+                    {"type": "sphere", "center": [0.5, 0, 0], "radius": 0.7},
+                    {"type": "sphere", "center": [0, 0.5, 0], "radius": 0.6},
+                    {"type": "sphere", "center": [0, -0.5, 0], "radius": 0.6}],
+}
+
+
+@pytest.mark.parametrize("name", sorted(DEGENERATE))
+@pytest.mark.parametrize("R", [8, 20])
+def test_materials_tying_on_tet_faces(ctx, rin, name, R):
+    """Degenerate boundary-face matching of extract_MI_mesh (src/extract_mesh.cpp:833-981): the
+    second tet that sees a tet face whose two sides hold different materials emits it."""
+    pts, tets = orc_grid(R)
+    funcs = make_funcs(DEGENERATE[name])
+    vals = orc_eval(funcs, pts)
+    port = orc_run("mi", pts, tets, vals)
+    assert port.error == ""
     ctx.set_mesh(pts, tets)
     ctx.set_functions(funcs)
-    with pytest.raises(rin.RinError) as e:
-        ctx.run(rin.MODE_MI, FLAG_LOOKUP)
-    assert "tie" in str(e.value)
+    cnt = ctx.run(rin.MODE_MI, FLAG_LOOKUP | FLAG_SECONDARY)
+    compare_mi(ctx, ctx.download_mesh(), port, cnt)
