@@ -153,6 +153,7 @@ struct rin_ctx
     bool x_window = false;
     DevBuf x_send, x_recv1, x_recv2, x_table, x_small;
     DevBuf cx_out; // rin_get_complexes output arena
+    void* h_pinned = nullptr; // pinned host mirror of the device counters (cheap read-back)
     uint32_t n_local_verts = 0, n_own = 0;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
     uint32_t act_cap = 0;
@@ -224,6 +225,7 @@ int rin_create(int device, rin_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& e : c->kev) CK(cudaEventCreate(&e));
+    CK(cudaHostAlloc(&c->h_pinned, sizeof(Counters), cudaHostAllocDefault));
     *out = c;
     return RIN_OK;
 }
@@ -246,6 +248,7 @@ void rin_destroy(rin_ctx* c)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1083,8 +1086,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventRecord(c->kev[3], s));
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    Counters* hp = static_cast<Counters*>(c->h_pinned);
+    CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    h = *hp;
     const uint32_t A = h.filt.n_active;
     c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 16 + 1024);
     CK(c->act_tet.ensure((size_t)c->act_cap * 4));
@@ -1126,8 +1131,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         CK(cudaGetLastError());
     }
 
-    // ---- K4: general kernels (arena grows on overflow)
+    // ---- K4: general kernels (arena grows on overflow) + K5a: counts and offsets
     CK(cudaEventRecord(c->ev[ST_GENERAL], s));
+    const uint32_t a_tiles = (A + 255) / 256;
     if (A) {
         const uint32_t est =
             use_lookup ? (use_secondary ? h.filt.n_kmore : h.filt.n_kmore + h.filt.n_k2) : A;
@@ -1150,8 +1156,21 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
                 c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
                 c->rec_ref.as<uint32_t>(), &dctr->gen);
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(&h.gen, &dctr->gen, sizeof(GeneralCounters), cudaMemcpyDeviceToHost, s));
+            // counts + offsets right behind the general kernels: ONE read-back serves both
+            // (an arena overflow leaves empty records, the scan is then simply repeated)
+            CK(cudaEventRecord(c->ev[ST_SCAN], s));
+            CK(c->status.ensure((size_t)a_tiles * 16 + 64));
+            CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
+            CK(cudaMemsetAsync(&dctr->scan, 0, sizeof(ScanTotals), s));
+            count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
+                c->act_cap, A, c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
+                c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
+            h.gen = hp->gen;
+            h.scan = hp->scan;
+            h.n_exact_classify = hp->n_exact_classify;
             if (h.gen.err)
                 return fail(h.gen.err, "per-tet arrangement failed in tet " + std::to_string(h.gen.err_tet) +
                                            (h.gen.err == RIN_ERR_CAPACITY ? " (complex exceeds kernel capacity)"
@@ -1165,22 +1184,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             z.n_big = h.gen.n_big;
             CK(cudaMemcpyAsync(&dctr->gen, &z, sizeof(GeneralCounters), cudaMemcpyHostToDevice, s));
         }
+    } else {
+        CK(cudaEventRecord(c->ev[ST_SCAN], s));
     }
     n.num_general_tets = h.gen.n_general;
-
-    // ---- K5a: counts + offsets
-    CK(cudaEventRecord(c->ev[ST_SCAN], s));
-    const uint32_t a_tiles = (A + 255) / 256;
-    if (A) {
-        CK(c->status.ensure((size_t)a_tiles * 16 + 64));
-        CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
-        count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
-            c->act_cap, A, c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
-            c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h.scan, &dctr->scan, sizeof(ScanTotals), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-    }
     const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
 
     // ---- K5b: emit
@@ -1221,20 +1228,19 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
             &dctr->n_unique);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        NV = h.n_unique;
     }
+    // the number of unique vertices is read back with the final synchronisation; NC bounds it
+    const uint32_t NVcap = NC;
 
     // ---- K7: unique vertices + xyz
     CK(cudaEventRecord(c->ev[ST_VERTS], s));
-    CK(c->v_tet.ensure((size_t)std::max(NV, 1u) * 4));
-    CK(c->v_local.ensure(std::max(NV, 1u)));
-    CK(c->v_size.ensure(std::max(NV, 1u)));
-    CK(c->v_simplex.ensure((size_t)std::max(NV, 1u) * 16));
-    CK(c->v_funcs.ensure((size_t)std::max(NV, 1u) * 16));
-    CK(c->v_xyz.ensure((size_t)std::max(NV, 1u) * 24));
-    CK(c->v_key.ensure((size_t)std::max(NV, 1u) * 16));
+    CK(c->v_tet.ensure((size_t)std::max(NVcap, 1u) * 4));
+    CK(c->v_local.ensure(std::max(NVcap, 1u)));
+    CK(c->v_size.ensure(std::max(NVcap, 1u)));
+    CK(c->v_simplex.ensure((size_t)std::max(NVcap, 1u) * 16));
+    CK(c->v_funcs.ensure((size_t)std::max(NVcap, 1u) * 16));
+    CK(c->v_xyz.ensure((size_t)std::max(NVcap, 1u) * 24));
+    CK(c->v_key.ensure((size_t)std::max(NVcap, 1u) * 16));
     if (NC) {
         write_verts_ia_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
             c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
@@ -1252,7 +1258,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(c->f_tets.ensure((size_t)std::max(NFc, 1u) * 8));
     CK(c->f_funcs.ensure((size_t)std::max(NFc, 1u) * 8));
     uint32_t NF = NFc, NFVout = NFV, NFT = NFc;
-    if (!h.n_bndry_faces) {
+    {
         if (NFV)
             remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
                 c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
@@ -1260,7 +1266,15 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             NFV, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(),
             c->f_funcs.as<uint32_t>());
         CK(cudaGetLastError());
-    } else {
+    }
+    // final read-back: unique vertex count, boundary-face count
+    CK(cudaEventRecord(c->ev[ST_COUNT], s));
+    CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h.n_unique = hp->n_unique;
+    h.n_bndry_faces = hp->n_bndry_faces;
+    NV = NC ? h.n_unique : 0;
+    if (h.n_bndry_faces) {
         // degenerate input: iso-faces on tet boundaries are shared between two tets
         uint32_t tsize = 1024;
         while (tsize < 2 * NFc) tsize <<= 1;
@@ -1301,9 +1315,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         bface_sort_pairs_kernel<<<grid_for(NF, 256, sm, 8), 256, 0, s>>>(NF, c->f_toff.as<uint32_t>(),
             c->f_tets.as<uint32_t>());
         CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev[ST_COUNT], s));
+        CK(cudaStreamSynchronize(s));
     }
-    CK(cudaEventRecord(c->ev[ST_COUNT], s));
-    CK(cudaStreamSynchronize(s));
     for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
     CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
     CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
