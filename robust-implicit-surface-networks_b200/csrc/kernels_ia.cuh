@@ -436,6 +436,31 @@ __device__ __forceinline__ int nth_set_bit(const uint32_t* m, int W, int n)
     return -1;
 }
 
+// key of a 2-plane arrangement: vertex signs (8 bits) | order of the two crossing points on every
+// simplex edge crossed by both planes (6 bits, << 8); -1 when a value is zero or two crossings coincide
+__device__ __forceinline__ int ia2_key(const double p0[4], const double p1[4], unsigned* exact)
+{
+    int s0 = 0, s1 = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (p0[c] == 0.0 || p1[c] == 0.0) return -1;
+        s0 |= (p0[c] > 0 ? 1 : 0) << c;
+        s1 |= (p1[c] > 0 ? 1 : 0) << c;
+    }
+    int key = s0 | (s1 << 4);
+    int e = 0;
+    for (int x = 0; x < 4; ++x)
+        for (int y = x + 1; y < 4; ++y, ++e) {
+            bool c0 = ((s0 >> x) & 1) != ((s0 >> y) & 1);
+            bool c1 = ((s1 >> x) & 1) != ((s1 >> y) & 1);
+            if (!(c0 && c1)) continue;
+            int s = det2_sign(p0[x], p0[y], p1[x], p1[y], exact);
+            if (s == 0) return -1;
+            if (s > 0) key |= 1 << (8 + e);
+        }
+    return key;
+}
+
 template <int W>
 __global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
@@ -485,27 +510,13 @@ __global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restric
                     key = s0;
                     ref = s_lut1[s0];
                 } else {
-                    key = s0 | (s1 << 4);
                     double p0[4], p1[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         p0[c] = __ldg(&vals[(size_t)f0 * V + vv[c]]);
                         p1[c] = __ldg(&vals[(size_t)f1 * V + vv[c]]);
                     }
-                    int e = 0;
-                    for (int x = 0; x < 4 && key >= 0; ++x)
-                        for (int y = x + 1; y < 4; ++y, ++e) {
-                            bool c0 = ((s0 >> x) & 1) != ((s0 >> y) & 1);
-                            bool c1 = ((s1 >> x) & 1) != ((s1 >> y) & 1);
-                            if (!(c0 && c1)) continue;
-                            // order of the two crossing points on edge (x,y)
-                            int s = det2_sign(p0[x], p0[y], p1[x], p1[y], &exact);
-                            if (s == 0) {
-                                key = -1;
-                                break;
-                            }
-                            if (s > 0) key |= 1 << (8 + e);
-                        }
+                    key = ia2_key(p0, p1, &exact);
                     if (key >= 0 && use_secondary) {
                         uint16_t off = s_lut2[key];
                         ref = (off == LUT_MISS) ? REF_GENERAL : off;
@@ -592,15 +603,18 @@ template <class Caps, int W>
 __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int skip = 0)
 {
+    // skip > 0: the complex already holds the arrangement of the first `skip` active functions
     const uint4 tv = __ldg(&tets[act_tet[a]]);
-    cx.init();
+    if (!skip) cx.init();
+    int seen = 0;
     for (int w = 0; w < W; ++w) {
         uint32_t mm = act_mask[(size_t)w * cap + a];
         while (mm) {
             int f = w * 32 + __ffs(mm) - 1;
             mm &= mm - 1;
+            if (seen++ < skip) continue;
             double pv[4];
             pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
             pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
@@ -637,31 +651,104 @@ __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __r
 // Small tier: complexes in shared memory, `lanes` active lanes per warp (few lanes = little
 // divergence when there are only a handful of general tets, the usual case).
 constexpr int GEN_SMALL_WARPS = 4;
+constexpr int GEN_THREADS = 64;
+// cx2 / lut2cx (nullable): complete 2-plane complexes per key.  A tet with >= 3 functions whose first
+// two functions have a tabulated key starts from that complex (copied by the whole warp) and only
+// inserts the remaining planes: every branch of the insertion depends on the vertex signs alone,
+// which the key determines, so the state equals what two insertions would have produced.
 template <int W>
 __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_ia_small_kernel(
     const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet,
     const uint32_t* __restrict__ act_mask, uint32_t cap, const uint32_t* __restrict__ small_list,
-    uint32_t* __restrict__ ovf_list, int lanes, const double* __restrict__ vals, uint32_t V,
+    uint32_t* __restrict__ ovf_list, const IAComplex<IACapsSmall>* __restrict__ cx2,
+    const uint16_t* __restrict__ lut2cx, const double* __restrict__ vals, uint32_t V,
     uint8_t* __restrict__ arena, uint32_t arena_cap, uint32_t* __restrict__ rec_ref,
     GeneralCounters* __restrict__ gc)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
     IAComplex<IACapsSmall>* s_cx = reinterpret_cast<IAComplex<IACapsSmall>*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane >= lanes) return;
     const uint32_t n = gc->n_small;
-    const uint32_t slots = gridDim.x * GEN_SMALL_WARPS * lanes;
-    IAComplex<IACapsSmall>& cx = s_cx[warp * lanes + lane];
-    for (uint32_t g = (blockIdx.x * GEN_SMALL_WARPS + warp) * lanes + lane; g < n; g += slots) {
+    IAComplex<IACapsSmall>& cx = s_cx[warp];
+    for (uint32_t g = blockIdx.x * GEN_SMALL_WARPS + warp; g < n; g += gridDim.x * GEN_SMALL_WARPS) {
         const uint32_t a = small_list[g];
-        if (!general_ia_one<IACapsSmall, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap,
-                rec_ref, gc, false))
-            ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
+        int skip = 0;
+        if (cx2) {
+            // lane 0 derives the key of the first two active functions
+            int entry = -1;
+            double p0[4], p1[4];
+            if (lane == 0) {
+                uint32_t m[W];
+                int kk = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    m[w] = act_mask[(size_t)w * cap + a];
+                    kk += __popc(m[w]);
+                }
+                if (kk >= 3) {
+                    const uint4 tv = __ldg(&tets[act_tet[a]]);
+                    const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
+                    const int f0 = nth_set_bit(m, W, 0), f1 = nth_set_bit(m, W, 1);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        p0[c] = __ldg(&vals[(size_t)f0 * V + vv[c]]);
+                        p1[c] = __ldg(&vals[(size_t)f1 * V + vv[c]]);
+                    }
+                    unsigned ex = 0;
+                    const int key = ia2_key(p0, p1, &ex);
+                    if (ex) atomicAdd(&gc->n_exact, ex);
+                    if (key >= 0 && lut2cx[key] != LUT_MISS) entry = lut2cx[key];
+                }
+            }
+            entry = __shfl_sync(0xffffffffu, entry, 0);
+            if (entry >= 0) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(cx2 + entry);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&cx);
+                for (int i = lane; i < (int)(sizeof(IAComplex<IACapsSmall>) / 4); i += 32) dst[i] = src[i];
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        cx.plv[0][c] = p0[c];
+                        cx.plv[1][c] = p1[c];
+                    }
+                    cx.n_exact = 0;
+                    cx.err = 0;
+                }
+                skip = 2;
+            }
+        }
+        if (lane == 0) {
+            if (!general_ia_one<IACapsSmall, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap,
+                    rec_ref, gc, false, skip))
+                ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
+        }
+        __syncwarp();
+    }
+}
+
+// dumps the complete 2-plane complexes of the chosen witnesses (table generation)
+__global__ void __launch_bounds__(GEN_THREADS) dump_ia2_kernel(const uint32_t* __restrict__ witness, uint32_t n,
+    const double* __restrict__ vals, uint32_t V, IAComplex<IACapsSmall>* __restrict__ out, int* __restrict__ err)
+{
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const uint32_t w = witness[g]; // witness tet w owns vertices 4w..4w+3
+        IAComplex<IACapsSmall> cx;
+        cx.init();
+        for (int f = 0; f < 2; ++f) {
+            double pv[4];
+            for (int c = 0; c < 4; ++c) pv[c] = vals[(size_t)f * V + 4 * w + c];
+            cx.insert(pv);
+        }
+        if (cx.err) *err = cx.err;
+        cx.n_exact = 0;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&cx);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + g);
+        for (int i = 0; i < (int)(sizeof(IAComplex<IACapsSmall>) / 4); ++i) dst[i] = src[i];
     }
 }
 
 // Big tier: complexes in per-thread local memory.
-constexpr int GEN_THREADS = 64;
 template <int W>
 __global__ void __launch_bounds__(GEN_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,

@@ -97,6 +97,7 @@ NcclApi g_nccl;
 struct Lut
 {
     DevBuf lut1, lut2, blob;
+    DevBuf cx2, lut2cx; // complete 2-plane complexes (start state of the general kernel) + key -> entry
     uint32_t blob_bytes = 0;
     bool built = false;
     // host copies (tests / introspection)
@@ -241,7 +242,7 @@ void rin_destroy(rin_ctx* c)
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
         &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->cx_out, &c->f_off, &c->f_verts,
-        &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob,
+        &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob, &c->lut_ia.cx2, &c->lut_ia.lut2cx,
         &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
     for (auto& e : c->ev)
@@ -1149,8 +1150,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             // small tier: one tet per warp, complex in shared memory; capacity overflow -> ovf list
             general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
                 c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
-                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A, 1, c->vals.as<double>(), V,
-                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
+                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A,
+                c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr,
+                c->lut_ia.lut2cx.as<uint16_t>(), c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
+                c->rec_ref.as<uint32_t>(), &dctr->gen);
             general_ia_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
                 c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
                 c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
@@ -1813,6 +1816,33 @@ int build_ia_tables(rin_ctx* c)
             L.h_lut2[kv.first & 0xfffff] = (uint16_t)off;
         else
             L.h_lut1[kv.first] = (uint16_t)off;
+    }
+    // complete 2-plane complexes, one per 2-plane key, in key order
+    {
+        std::vector<uint32_t> w2;
+        std::vector<uint16_t> idx(256 * 64, LUT_MISS);
+        for (auto& kv : order)
+            if (kv.first & (1 << 20)) {
+                idx[kv.first & 0xfffff] = (uint16_t)w2.size();
+                w2.push_back(kv.second);
+            }
+        CKC(L.cx2.ensure(std::max<size_t>(w2.size(), 1) * sizeof(IAComplex<IACapsSmall>)));
+        CKC(L.lut2cx.ensure(256 * 64 * 2));
+        CKC(cudaMemcpyAsync(d_gl.p, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice, s));
+        int* d_err = reinterpret_cast<int*>(&dctr->gen.err);
+        CKC(cudaMemsetAsync(d_err, 0, 4, s));
+        if (!w2.empty())
+            dump_ia2_kernel<<<sm, GEN_THREADS, 0, s>>>(d_gl.as<uint32_t>(), (uint32_t)w2.size(), d_vals.as<double>(),
+                Vw, L.cx2.as<IAComplex<IACapsSmall>>(), d_err);
+        CKC(cudaGetLastError());
+        int herr = 0;
+        CKC(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, s));
+        CKC(cudaMemcpyAsync(L.lut2cx.p, idx.data(), 256 * 64 * 2, cudaMemcpyHostToDevice, s));
+        CKC(cudaStreamSynchronize(s));
+        if (herr) {
+            cleanup();
+            return fail(RIN_ERR_STATE, "table generation failed (2-plane complexes)");
+        }
     }
     L.blob_bytes = (uint32_t)L.h_blob.size();
     CKC(L.lut1.ensure(32));
