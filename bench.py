@@ -257,11 +257,12 @@ def main():
     # function value once (8F per vertex); this implementation reads 8 B of sign masks per vertex
     # instead of the values, so the bytes it can possibly move are the smaller figure below.
     alg_survey = 20.0 * t_count + 8.0 * F * V_rank
-    alg_masks = 16.0 * t_count + 8.0 * V_rank * ((F + 31) // 32) + 8.0 * cnt.num_intersecting_tet
+    mask_bytes = 4.0 if F <= 16 else 8.0 * ((F + 31) // 32)  # packed P|N word when F <= 16
+    alg_masks = 16.0 * t_count + mask_bytes * V_rank + 8.0 * cnt.num_intersecting_tet
     filt = float(np.mean(filt_ms))
     evl = float(np.mean(eval_ms))
     achieved = min(alg_survey, alg_masks) / (filt * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "filter_ia_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "filter_tiles_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": min(alg_survey, alg_masks),
                 "algorithmic_bytes_survey_formula": alg_survey, "kernel_ms": filt,

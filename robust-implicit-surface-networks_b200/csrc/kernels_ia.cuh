@@ -122,9 +122,11 @@ __device__ __forceinline__ double eval_func(const rin_func_desc& f, double x, do
 
 __global__ void __launch_bounds__(256) eval_functions_kernel(const double* __restrict__ pts,
     uint32_t v_first, uint32_t v_count, uint32_t V, const rin_func_desc* __restrict__ funcs, uint32_t F,
-    int negate, double* __restrict__ vals, uint2* __restrict__ vmask,
+    int negate, double* __restrict__ vals, uint2* __restrict__ vmask, uint32_t* __restrict__ vmask16,
     unsigned long long* __restrict__ n_zero)
 {
+    // vmask16 (nullable, F <= 16): P | N << 16 in ONE word per vertex: halves the sectors the filter's
+    // four mask gathers touch
     extern __shared__ rin_func_desc s_funcs[];
     for (uint32_t i = threadIdx.x; i < F * (sizeof(rin_func_desc) / 8); i += blockDim.x)
         reinterpret_cast<double*>(s_funcs)[i] = reinterpret_cast<const double*>(funcs)[i];
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) eval_functions_kernel(const double* __res
                 Nn |= (val < 0 ? 1u : 0u) << (f & 31);
             }
             vmask[(size_t)w * V + v] = make_uint2(P, Nn);
+            if (vmask16) vmask16[v] = P | (Nn << 16);
             zeros += (fe - w * 32) - __popc(P | Nn);
         }
     }
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(256) eval_functions_kernel(const double* __res
 // build the sign masks (the "func signs" loop).
 __global__ void __launch_bounds__(256) ingest_values_kernel(const double* __restrict__ rowmajor,
     uint32_t v_first, uint32_t v_count, uint32_t V, uint32_t F, int negate, double* __restrict__ vals,
-    uint2* __restrict__ vmask, unsigned long long* __restrict__ n_zero)
+    uint2* __restrict__ vmask, uint32_t* __restrict__ vmask16, unsigned long long* __restrict__ n_zero)
 {
     unsigned zeros = 0;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < v_count;
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(256) ingest_values_kernel(const double* __rest
                 Nn |= (val < 0 ? 1u : 0u) << (f & 31);
             }
             vmask[(size_t)w * V + v] = make_uint2(P, Nn);
+            if (vmask16) vmask16[v] = P | (Nn << 16);
             zeros += (fe - w * 32) - __popc(P | Nn);
         }
     }
@@ -205,9 +209,10 @@ struct FilterCounters
 
 // Pass 1 (streams the index records): per-tile compaction into tile-local slots
 // tl_tet / tl_mask [tile * FILT_TILE + rank] and per-tile totals.  No inter-block dependency.
-template <int W>
+template <int W, bool PACK>
 __global__ void __launch_bounds__(FILT_THREADS) filter_tiles_kernel(const uint4* __restrict__ tets,
-    uint32_t t_first, uint32_t t_count, const uint2* __restrict__ vmask, uint32_t V, uint32_t last_mask,
+    uint32_t t_first, uint32_t t_count, const uint2* __restrict__ vmask, const uint32_t* __restrict__ vmask16,
+    uint32_t V, uint32_t last_mask,
     uint32_t* __restrict__ tl_tet, uint32_t* __restrict__ tl_mask, size_t tl_stride,
     uint2* __restrict__ tile_cnt, FilterCounters* __restrict__ ctr)
 {
@@ -234,6 +239,27 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_tiles_kernel(const uint4*
         int kk[FILT_BATCH];
 #pragma unroll
         for (int j = 0; j < FILT_BATCH; ++j) kk[j] = 0;
+        if (PACK) {
+            // one 32-bit word per vertex: the AND of the four words holds "positive everywhere" in
+            // the low half and "negative everywhere" in the high half
+            uint32_t g[FILT_BATCH][4];
+#pragma unroll
+            for (int j = 0; j < FILT_BATCH; ++j) {
+                g[j][0] = __ldg(&vmask16[tv[j].x]);
+                g[j][1] = __ldg(&vmask16[tv[j].y]);
+                g[j][2] = __ldg(&vmask16[tv[j].z]);
+                g[j][3] = __ldg(&vmask16[tv[j].w]);
+            }
+#pragma unroll
+            for (int j = 0; j < FILT_BATCH; ++j) {
+                const uint32_t x = g[j][0] & g[j][1] & g[j][2] & g[j][3];
+                uint32_t mm = ~((x & 0xffffu) | (x >> 16)) & last_mask;
+                const uint32_t i = base + (j0 + j) * FILT_THREADS + threadIdx.x;
+                if (i >= t_count) mm = 0;
+                m[j0 + j][0] = mm;
+                kk[j] += __popc(mm);
+            }
+        } else {
 #pragma unroll
         for (int w = 0; w < W; ++w) {
             uint2 g[FILT_BATCH][4];
@@ -254,6 +280,7 @@ __global__ void __launch_bounds__(FILT_THREADS) filter_tiles_kernel(const uint4*
                 m[j0 + j][w] = mm;
                 kk[j] += __popc(mm);
             }
+        }
         }
 #pragma unroll
         for (int j = 0; j < FILT_BATCH; ++j) {

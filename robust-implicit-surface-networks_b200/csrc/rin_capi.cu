@@ -132,7 +132,7 @@ struct rin_ctx
     DevBuf funcs;
     bool have_funcs = false, have_values = false;
     DevBuf rowmajor; // caller-provided values (device copy)
-    DevBuf vals, vmask;
+    DevBuf vals, vmask, vmask16;
     // work buffers
     DevBuf counters; // small zeroed block: FilterCounters | GeneralCounters | ScanTotals | misc
     DevBuf status;   // look-back status words
@@ -236,7 +236,7 @@ void rin_destroy(rin_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->counters,
+    DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->vmask16, &c->counters,
         &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
@@ -1054,6 +1054,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     // only for generated grids by the caller (rin_set_tet_range keeps all V by default).
     CK(c->vals.ensure((size_t)V * F * 8));
     CK(c->vmask.ensure((size_t)V * W * 8));
+    const bool pack = (F <= 16);
+    if (pack) CK(c->vmask16.ensure((size_t)V * 4));
+    uint32_t* vm16 = pack ? c->vmask16.as<uint32_t>() : nullptr;
     CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
     CK(cudaEventRecord(c->ev[ST_EVAL], s));
     const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
@@ -1063,10 +1066,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_functions_kernel<<<grid_for(vc, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), vf, vc, V,
-            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16, &dctr->n_zero);
     } else {
         ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
-            negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+            negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16, &dctr->n_zero);
     }
     CK(cudaEventRecord(c->kev[1], s));
     CK(cudaGetLastError());
@@ -1081,9 +1084,14 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(c->tile_cnt.ensure((size_t)n_tiles * 8));
     CK(c->tile_off.ensure((size_t)(n_tiles + 1) * 8));
     CK(cudaEventRecord(c->kev[2], s));
-    filter_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
-        c->vmask.as<uint2>(), V, last_mask, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(), tl_stride,
-        c->tile_cnt.as<uint2>(), &dctr->filt);
+    if (pack && W == 1)
+        filter_tiles_kernel<1, true><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
+            c->vmask.as<uint2>(), vm16, V, last_mask, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(), tl_stride,
+            c->tile_cnt.as<uint2>(), &dctr->filt);
+    else
+        filter_tiles_kernel<W, false><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
+            c->vmask.as<uint2>(), nullptr, V, last_mask, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
+            tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
     CK(cudaEventRecord(c->kev[3], s));
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
@@ -1368,10 +1376,10 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_functions_kernel<<<grid_for(vc, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), vf, vc, V,
-            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr, &dctr->n_zero);
     } else {
         ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
-            negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+            negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr, &dctr->n_zero);
     }
     // "highest func": masks of the maximal materials replace the sign masks
     CK(cudaMemsetAsync(&dctr->n_zero, 0, 8, s));
