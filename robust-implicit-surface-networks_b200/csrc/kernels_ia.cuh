@@ -807,6 +807,9 @@ __device__ __forceinline__ const uint8_t* record_ptr(uint32_t ref, const uint8_t
     return (ref & REF_GENERAL) ? arena + (size_t)(ref & ~REF_FLAGS) * 4 : lut_blob + (size_t)ref * 4;
 }
 
+constexpr int CS_ITEMS = 4;
+constexpr int CS_TILE = 256 * CS_ITEMS;
+
 template <int W>
 __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restrict__ rec_ref,
     const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active,
@@ -820,16 +823,26 @@ __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restr
     if (threadIdx.x == 0) s_tile = atomicAdd(&tot->tile_counter, 1u);
     __syncthreads();
     const unsigned tile = s_tile;
-    const uint32_t a = tile * 256 + threadIdx.x;
+    const uint32_t a0 = tile * CS_TILE + threadIdx.x * CS_ITEMS; // CS_ITEMS consecutive active tets per thread
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 ci[CS_ITEMS];
     uint4 c = make_uint4(0, 0, 0, 0);
-    if (a < n_active) {
-        const uint8_t* r = record_ptr(rec_ref[a], lut_blob, arena);
-        const uint32_t h = *reinterpret_cast<const uint32_t*>(r);
-        c.x = h & 255;
-        c.y = (h >> 8) & 255;
-        c.z = h >> 16;
-        for (int w = 0; w < W; ++w) c.w += __popc(act_mask[(size_t)w * cap + a]);
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j) {
+        const uint32_t a = a0 + j;
+        ci[j] = make_uint4(0, 0, 0, 0);
+        if (a < n_active) {
+            const uint8_t* r = record_ptr(rec_ref[a], lut_blob, arena);
+            const uint32_t h = *reinterpret_cast<const uint32_t*>(r);
+            ci[j].x = h & 255;
+            ci[j].y = (h >> 8) & 255;
+            ci[j].z = h >> 16;
+            for (int w = 0; w < W; ++w) ci[j].w += __popc(act_mask[(size_t)w * cap + a]);
+        }
+        c.x += ci[j].x;
+        c.y += ci[j].y;
+        c.z += ci[j].z;
+        c.w += ci[j].w;
     }
     uint4 x = c;
     for (int o = 1; o < 32; o <<= 1) {
@@ -874,7 +887,7 @@ __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restr
         tile_lookback_warp(statusB, (int)tile, run.z, run.w, e2, e3);
         if (lane == 0) {
             s_base = make_uint4(e0, e1, e2, e3);
-            if (tile == (n_active + 255) / 256 - 1) {
+            if (tile == (n_active + CS_TILE - 1) / CS_TILE - 1) {
                 tot->n_cand = e0 + run.x;
                 tot->n_faces = e1 + run.y;
                 tot->n_fv = e2 + run.z;
@@ -883,10 +896,18 @@ __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restr
         }
     }
     __syncthreads();
-    if (a < n_active) {
+    {
         const uint4 b = s_base, wv = s_warp[warp];
-        offs[a] = make_uint4(b.x + wv.x + x.x - c.x, b.y + wv.y + x.y - c.y, b.z + wv.z + x.z - c.z,
+        uint4 run = make_uint4(b.x + wv.x + x.x - c.x, b.y + wv.y + x.y - c.y, b.z + wv.z + x.z - c.z,
             b.w + wv.w + x.w - c.w);
+#pragma unroll
+        for (int j = 0; j < CS_ITEMS; ++j) {
+            if (a0 + j < n_active) offs[a0 + j] = run;
+            run.x += ci[j].x;
+            run.y += ci[j].y;
+            run.z += ci[j].z;
+            run.w += ci[j].w;
+        }
     }
 }
 
@@ -900,7 +921,7 @@ __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restr
 // cand_pay  = (tet, local | simplex_size<<8 | dedup<<16, f0 | f1<<16, f2)
 // face_hdr  = (tet, local face | n<<16 | boundary<<24, function id, face-vertex offset)
 // ---------------------------------------------------------------------------------------------
-template <int W>
+template <int W, bool SMEM_BLOB>
 __global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     uint32_t n_active, const uint32_t* __restrict__ rec_ref, const uint4* __restrict__ offs,
@@ -909,14 +930,18 @@ __global__ void __launch_bounds__(256) emit_ia_kernel(const uint4* __restrict__ 
     uint32_t* __restrict__ fv_ref, unsigned* __restrict__ n_bndry_faces)
 {
     extern __shared__ __align__(16) uint8_t s_blob[];
-    for (uint32_t i = threadIdx.x; i < lut_bytes / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(s_blob)[i] = reinterpret_cast<const uint32_t*>(lut_blob)[i];
-    __syncthreads();
+    if (SMEM_BLOB) {
+        for (uint32_t i = threadIdx.x; i < lut_bytes / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(s_blob)[i] = reinterpret_cast<const uint32_t*>(lut_blob)[i];
+        __syncthreads();
+    }
+    const uint32_t* table = SMEM_BLOB ? reinterpret_cast<const uint32_t*>(s_blob)
+                                      : reinterpret_cast<const uint32_t*>(lut_blob);
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         const uint32_t ref = rec_ref[a];
         const uint32_t* r = (ref & REF_GENERAL)
                                 ? reinterpret_cast<const uint32_t*>(arena) + (size_t)(ref & ~REF_GENERAL)
-                                : reinterpret_cast<const uint32_t*>(s_blob) + ref;
+                                : table + ref;
         const uint32_t hdr = r[0];
         const int nv = hdr & 255, nf = (hdr >> 8) & 255;
         if (nv == 0 && nf == 0) continue;

@@ -1142,7 +1142,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
 
     // ---- K4: general kernels (arena grows on overflow) + K5a: counts and offsets
     CK(cudaEventRecord(c->ev[ST_GENERAL], s));
-    const uint32_t a_tiles = (A + 255) / 256;
+    const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
     if (A) {
         const uint32_t est =
             use_lookup ? (use_secondary ? h.filt.n_kmore : h.filt.n_kmore + h.filt.n_k2) : A;
@@ -1209,13 +1209,26 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(c->fv_ref.ensure((size_t)std::max(NFV, 1u) * 4));
     if (A) {
         const size_t smem = (c->lut_ia.blob_bytes + 3) & ~3u;
-        if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(emit_ia_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        emit_ia_kernel<W><<<grid_for(A, 256, sm, 4), 256, smem, s>>>(c->tets.as<uint4>(),
-            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(),
-            c->offs.as<uint4>(), c->lut_ia.blob.as<uint8_t>(), (uint32_t)smem, c->arena.as<uint8_t>(),
-            c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>(),
-            &dctr->n_bndry_faces);
+        static const bool smem_blob = []() {
+            const char* e = getenv("RIN_EMIT_SMEM"); // 1: stage the record table in shared memory
+            return e ? atoi(e) != 0 : false;
+        }();
+        if (smem_blob) {
+            if (smem > 48 * 1024)
+                CK(cudaFuncSetAttribute(emit_ia_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emit_ia_kernel<W, true><<<grid_for(A, 256, sm, 4), 256, smem, s>>>(c->tets.as<uint4>(),
+                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(),
+                c->offs.as<uint4>(), c->lut_ia.blob.as<uint8_t>(), (uint32_t)smem, c->arena.as<uint8_t>(),
+                c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(),
+                c->fv_ref.as<uint32_t>(), &dctr->n_bndry_faces);
+        } else {
+            // the 63 KB record table stays L1/L2 resident; no per-block staging, full occupancy
+            emit_ia_kernel<W, false><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tets.as<uint4>(),
+                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(),
+                c->offs.as<uint4>(), c->lut_ia.blob.as<uint8_t>(), (uint32_t)smem, c->arena.as<uint8_t>(),
+                c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(),
+                c->fv_ref.as<uint32_t>(), &dctr->n_bndry_faces);
+        }
         CK(cudaGetLastError());
     }
 
@@ -1488,7 +1501,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
 
     // ---- K5a: counts + offsets
     CK(cudaEventRecord(c->ev[ST_SCAN], s));
-    const uint32_t a_tiles = (A + 255) / 256;
+    const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
     if (A) {
         CK(c->status.ensure((size_t)a_tiles * 16 + 64));
         CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
