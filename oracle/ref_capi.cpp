@@ -16,6 +16,7 @@
 
 #include "result_bag.h"
 
+#include <functional>
 #include <iostream>
 
 namespace {
@@ -208,6 +209,63 @@ void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
     }
     auto& cl = bag->i64["cell_function_label"];
     for (auto x : cell_label) cl.push_back(x == Mesh_None ? -1 : int64_t(x));
+    return bag;
+}
+
+// csg() (src/csg.h:46-72) with one of the boolean expressions of the reference's CSG tests
+// (tests/test_implicit_networks.cpp:865,910,955,1000): expr 0: f0 & !f0, 1: f0 | (f1 & f2),
+// 2: f0 & !(f1 & f2), 3: f1 | f2.
+void* ref_csg_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint64_t T, const double* vals,
+    uint32_t F, uint32_t flags, int expr, int positive_inside)
+{
+    auto* bag = new ResultBag;
+    CoutMute mute(flags & 16);
+    std::vector<std::array<double, 3>> pts(V);
+    for (uint64_t i = 0; i < V; ++i) pts[i] = {pts_in[3 * i], pts_in[3 * i + 1], pts_in[3 * i + 2]};
+    std::vector<std::array<size_t, 4>> tets(T);
+    for (uint64_t i = 0; i < T; ++i)
+        tets[i] = {tets_in[4 * i], tets_in[4 * i + 1], tets_in[4 * i + 2], tets_in[4 * i + 3]};
+    Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> fv(V, F);
+    std::copy(vals, vals + V * F, fv.data());
+    bool use_lookup = flags & 2;
+    if (use_lookup) {
+        simplicial_arrangement::load_lookup_table(simplicial_arrangement::ARRANGEMENT);
+        simplicial_arrangement::enable_lookup_table();
+    } else
+        simplicial_arrangement::disable_lookup_table();
+    std::function<bool(std::vector<bool>)> lambda;
+    switch (expr) {
+    case 0: lambda = [](std::vector<bool> c) { return c[0] && !c[0]; }; break;
+    case 1: lambda = [](std::vector<bool> c) { return c[0] || (c[1] && c[2]); }; break;
+    case 2: lambda = [](std::vector<bool> c) { return c[0] && !(c[1] && c[2]); }; break;
+    default: lambda = [](std::vector<bool> c) { return c[1] || c[2]; }; break;
+    }
+    std::vector<std::array<double, 3>> iso_pts;
+    std::vector<PolygonFace> iso_faces;
+    std::vector<std::vector<size_t>> patches, chains, nme, shells, cells;
+    std::vector<size_t> patch_label;
+    std::vector<bool> patch_sign;
+    std::vector<Edge> edges;
+    std::vector<std::vector<bool>> cell_label;
+    std::vector<std::string> tl, sl;
+    std::vector<double> tm;
+    std::vector<size_t> st;
+    bool ok = false;
+    try {
+        ok = csg(flags & 1, use_lookup, flags & 4, flags & 8, positive_inside != 0, pts, tets, fv, lambda, iso_pts,
+            iso_faces, patches, patch_label, patch_sign, edges, chains, nme, shells, cells, cell_label, tl, tm, sl, st);
+    } catch (std::exception& e) {
+        bag->i64["threw"] = {1};
+        bag->error = e.what();
+        return bag;
+    }
+    bag->i64["success"] = {ok ? 1 : 0};
+    pack_mesh(bag, iso_pts, iso_faces);
+    pack_crs(bag, "patches", patches);
+    pack_crs(bag, "chains", chains);
+    pack_crs(bag, "non_manifold_edges_of_vert", nme);
+    auto& ps = bag->i64["patch_sign_label"];
+    for (bool b : patch_sign) ps.push_back(b ? 1 : 0);
     return bag;
 }
 

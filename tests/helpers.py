@@ -234,6 +234,20 @@ def ref_run(mode, pts, tets, vals, robust=False, lookup=True, secondary=True, ra
     return b
 
 
+def ref_csg(pts, tets, vals, expr, positive_inside=True, lib=None):
+    """csg() of the reference with one of its test expressions (see oracle/ref_capi.cpp)."""
+    lib = lib or ref_lib()
+    pts, tets, vals = _prep(pts, tets, vals)
+    lib.ref_csg_run.restype = C.c_void_p
+    lib.ref_csg_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32,
+                                C.c_int, C.c_int]
+    h = lib.ref_csg_run(pts.ctypes.data, len(pts), tets.ctypes.data, len(tets), vals.ctypes.data, vals.shape[1],
+                        2 | 4 | 8 | 16, expr, int(positive_inside))
+    return Bag(lib, "ref", h, ["success", "threw", "patches", "patches_offsets", "chains", "chains_offsets",
+                               "non_manifold_edges_of_vert", "non_manifold_edges_of_vert_offsets",
+                               "patch_sign_label"], [])
+
+
 def crs(bag, name):
     off = bag[name + "_offsets"]
     dat = bag[name]

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import crs, dropin_lib, load_funcs, orc_eval, orc_grid, ref_run
+from helpers import crs, dropin_lib, load_funcs, make_funcs, orc_eval, orc_grid, ref_csg, ref_run
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(dropin_lib() is None, reason="drop-in library not built (needs /root/reference)")]
@@ -84,3 +84,26 @@ def test_c1_example_config_through_the_gpu_drop_in():
     for k, v in gold["stats"].items():
         assert b.stats[k] == v, k
     assert b["patch_function_label"].tolist() == gold["patch_function_label"]
+
+
+# tests/test_implicit_networks.cpp:853-1033: (functions, expression, patches, chains, corners, patch_sign_label)
+CSG_GOLD = {
+    "sphere_and_not_sphere": ("1-sphere", 0, 0, 0, 0, []),
+    "three_spheres_2": ("3-sphere-2", 1, 4, 2, 0, [1, 1, 1, 1]),
+    "three_spheres_3": ("3-sphere-3", 2, 5, 5, 2, [1, 1, 0, 0, 1]),
+    "plane_two_spheres": ("3-planesphere", 3, 4, 2, 0, [1, 1, 1, 1]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CSG_GOLD))
+def test_csg_known_answers_through_the_gpu_drop_in(name, grid101):
+    """The reference's csg.cpp, linked unchanged, calls the GPU-backed implicit_arrangement."""
+    fn, expr, npatch, nchain, ncorner, sign = CSG_GOLD[name]
+    pts, tets = grid101
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", fn + ".json")), pts)
+    b = ref_csg(pts, tets, vals, expr, lib=dropin_lib())
+    assert b.error == "" and b["success"][0] == 1
+    assert len(crs(b, "patches")) == npatch
+    assert len(crs(b, "chains")) == nchain
+    assert sum(1 for l in crs(b, "non_manifold_edges_of_vert") if len(l) > 2) == ncorner
+    assert b["patch_sign_label"].tolist() == sign

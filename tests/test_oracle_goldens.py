@@ -107,3 +107,27 @@ def test_port_equals_reference_code(cfg, R):
     assert p["stats"].tolist()[2:] == [r.stats[k] for k in ("num_degenerate_vertex", "num_intersecting_tet",
                                                             "num_1_func", "num_2_func", "num_more_func",
                                                             "num_iso_verts", "num_iso_faces")]
+
+
+# tests/test_implicit_networks.cpp:853-1033: (functions, expression, patches, chains, corners, patch_sign_label)
+CSG_GOLD = {
+    "sphere_and_not_sphere": ("1-sphere", 0, 0, 0, 0, []),
+    "three_spheres_2": ("3-sphere-2", 1, 4, 2, 0, [1, 1, 1, 1]),
+    "three_spheres_3": ("3-sphere-3", 2, 5, 5, 2, [1, 1, 0, 0, 1]),
+    "plane_two_spheres": ("3-planesphere", 3, 4, 2, 0, [1, 1, 1, 1]),
+}
+
+
+@pytest.mark.skipif(ref_lib() is None, reason="hybrid reference not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(CSG_GOLD))
+def test_reference_csg_known_answers_on_the_restated_engine(name, grid101):
+    """The reference's csg() + host stages on the restated per-tet engine reproduce its CSG tests."""
+    from helpers import crs, ref_csg
+    fn, expr, npatch, nchain, ncorner, sign = CSG_GOLD[name]
+    pts, tets = grid101
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", fn + ".json")), pts)
+    b = ref_csg(pts, tets, vals, expr)
+    assert b.error == "" and b["success"][0] == 1
+    assert (len(crs(b, "patches")), len(crs(b, "chains"))) == (npatch, nchain)
+    assert sum(1 for l in crs(b, "non_manifold_edges_of_vert") if len(l) > 2) == ncorner
+    assert b["patch_sign_label"].tolist() == sign
