@@ -197,6 +197,14 @@ struct MIIsoScan
     int nvi, nfi, nfv, nfw;
     int n_bf, n_extra, bf_words, bf_fv; // gated records: simplex-boundary faces
     __device__ static bool is_corner(const MIComplex<Caps>& cx, int v) { return cx.vm[v][2] < 4; }
+    // number of materials identical to material m inside this tet (unique_materials group)
+    __device__ static int group_size(const MIComplex<Caps>& cx, int m)
+    {
+        if (!cx.has_dup) return 1;
+        int g = 0;
+        for (int p = 4; p < cx.nm; ++p) g += (cx.umi[p] == cx.umi[m]);
+        return g;
+    }
     __device__ bool is_mi_vert(int v) const { return (isov[v >> 5] >> (v & 31)) & 1; }
     // boundary faces (positive label <= 3) of a tet whose materials tie on a whole tet face:
     // the extraction matches them with the neighbouring tet (src/extract_mesh.cpp:833-981)
@@ -210,6 +218,8 @@ struct MIIsoScan
                 ++n_bf;
                 bf_words += 2 + n;
                 bf_fv += n;
+                const int g = group_size(cx, cx.neg_label(f));
+                if (g > 1) bf_words += (g + 3) / 4; // the inside cell carries several identical materials
                 for (int k = 0; k < n; ++k) {
                     const int v = cx.fv[B][cx.foff[B][f] + k];
                     if (!is_mi_vert(v)) ++n_extra; // a tet corner not on the interface
@@ -278,8 +288,10 @@ struct MIIsoScan
         for (int f = 0; f < cx.nf; ++f)
             if (!cx.is_mi_face(f)) {
                 const int n = cx.flen[B][f];
+                const int inside = cx.neg_label(f);
+                const int g = group_size(cx, inside);
                 w[p++] = (uint32_t)f | ((uint32_t)n << 24);
-                w[p++] = (uint32_t)cx.pos_label(f) | ((uint32_t)cx.neg_label(f) << 8);
+                w[p++] = (uint32_t)cx.pos_label(f) | ((uint32_t)inside << 8) | ((uint32_t)g << 16);
                 for (int k = 0; k < n; ++k) {
                     const int v = cx.fv[B][cx.foff[B][f] + k];
                     uint32_t x = ((uint32_t)v << 8);
@@ -293,6 +305,19 @@ struct MIIsoScan
                     else
                         x |= 0x40000000u;
                     w[p++] = x;
+                }
+                if (g > 1) { // members of the inside cell's material group, four ids per word
+                    uint32_t x = 0;
+                    int cnt = 0;
+                    for (int q = 4; q < cx.nm; ++q) {
+                        if (cx.umi[q] != cx.umi[inside]) continue;
+                        x |= (uint32_t)q << (8 * (cnt & 3));
+                        if ((++cnt & 3) == 0) {
+                            w[p++] = x;
+                            x = 0;
+                        }
+                    }
+                    if (cnt & 3) w[p++] = x;
                 }
             }
     }
@@ -329,7 +354,6 @@ __device__ bool general_mi_one(MIComplex<Caps>& cx, uint32_t a, const uint4* __r
         iso.run(cx);
         if (gated) {
             iso.run_boundary(cx);
-            if (cx.has_dup) cx.err = 2; // identical materials in a tie tet: label sets are not built
         }
         if (iso.nvi + iso.n_extra > 255 || iso.nfi + iso.n_bf > 255 || iso.nfv + iso.bf_fv > 65535) cx.err = 1;
     }
@@ -478,6 +502,7 @@ __global__ void __launch_bounds__(256) emit_mi_kernel(const uint4* __restrict__ 
     uint32_t n_active, const uint32_t* __restrict__ rec_ref, const uint4* __restrict__ offs,
     const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena, uint4* __restrict__ cand_key,
     uint4* __restrict__ cand_pay, uint4* __restrict__ face_hdr, uint32_t* __restrict__ fv_ref,
+    uint32_t* __restrict__ bf_mask /* [face slot][W] material sets of boundary faces; null without tie tets */,
     unsigned* __restrict__ n_bface_slots)
 {
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
@@ -581,6 +606,7 @@ __global__ void __launch_bounds__(256) emit_mi_kernel(const uint4* __restrict__ 
             const int n = (e0 >> 24) & 127;
             const uint32_t bface = e1 & 255;
             const uint32_t inside = (uint32_t)nth_set_bit(m, W, (int)((e1 >> 8) & 255) - 4);
+            const int grp = (e1 >> 16) & 255;
             face_hdr[o.y + local] =
                 make_uint4(t, local | ((uint32_t)n << 16) | FACE_BND | FACE_INACTIVE, bface | (inside << 16), fvo);
             for (int k = 0; k < n; ++k) {
@@ -593,6 +619,28 @@ __global__ void __launch_bounds__(256) emit_mi_kernel(const uint4* __restrict__ 
                 } else
                     fv_ref[fvo + k] = o.x + (x & 255);
             }
+            // the set of materials the inside cell stands for (several when materials coincide)
+            uint32_t lm[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) lm[w] = 0;
+            if (grp > 1) {
+                for (int q0 = 0; q0 < grp; q0 += 4) {
+                    const uint32_t x = *p++;
+                    for (int q = q0; q < grp && q < q0 + 4; ++q) {
+                        const uint32_t gm = (uint32_t)nth_set_bit(m, W, (int)((x >> (8 * (q - q0))) & 255) - 4);
+#pragma unroll
+                        for (int w = 0; w < W; ++w)
+                            if ((gm >> 5) == (uint32_t)w) lm[w] |= 1u << (gm & 31);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                    if ((inside >> 5) == (uint32_t)w) lm[w] |= 1u << (inside & 31);
+            }
+            if (bf_mask)
+#pragma unroll
+                for (int w = 0; w < W; ++w) bf_mask[(size_t)(o.y + local) * W + w] = lm[w];
             fvo += n;
         }
         if (nbf) atomicAdd(n_bface_slots, (unsigned)nbf);
@@ -646,8 +694,8 @@ __global__ void __launch_bounds__(256) mi_bface_keys_kernel(const uint4* __restr
 
 __global__ void __launch_bounds__(256) mi_bface_decide_kernel(uint4* __restrict__ face_hdr, uint32_t n,
     const uint32_t* __restrict__ frep, const uint32_t* __restrict__ ndup, const uint32_t* __restrict__ fv_ref,
-    uint4* __restrict__ cand_pay, const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask,
-    uint32_t cap, uint32_t n_active, int W, unsigned* __restrict__ n_bad)
+    uint4* __restrict__ cand_pay, const uint32_t* __restrict__ bf_mask, const uint32_t* __restrict__ act_tet,
+    const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active, int W, unsigned* __restrict__ n_bad)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint4 h = face_hdr[i];
@@ -658,8 +706,10 @@ __global__ void __launch_bounds__(256) mi_bface_decide_kernel(uint4* __restrict_
             atomicAdd(n_bad, 1u); // more than two tets on one face: not a manifold tet mesh
             continue;
         }
-        const uint32_t mine = h.z >> 16, other = face_hdr[r].z >> 16;
-        if (mine == other) continue; // same material on both sides
+        const uint32_t mine = h.z >> 16;
+        uint32_t common = 0; // a material present on both sides: not an interface (:870-950)
+        for (int w = 0; w < W; ++w) common |= bf_mask[(size_t)i * W + w] & bf_mask[(size_t)r * W + w];
+        if (common) continue;
         // func_index.first = material_in_tet[positive label - 4 + start] with a boundary label (< 4):
         // QUIRK kept from the reference (:979): an earlier CRS entry
         uint32_t first = 0xffffu;

@@ -140,7 +140,7 @@ struct rin_ctx
     DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
-    DevBuf tmp_fverts, bfkeys, frep, fdup, fpos; // degenerate boundary-face dedup
+    DevBuf tmp_fverts, bfkeys, frep, fdup, fpos, bf_mask; // degenerate boundary-face dedup
     // outputs
     DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz, v_key;
     // sharded runs
@@ -238,7 +238,7 @@ void rin_destroy(rin_ctx* c)
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->vmask16, &c->counters,
         &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
-        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos,
+        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
         &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->cx_out, &c->f_off, &c->f_verts,
@@ -1520,11 +1520,23 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->cand_pay.ensure((size_t)std::max(NC, 1u) * 16));
     CK(c->face_hdr.ensure((size_t)std::max(NFc, 1u) * 16));
     CK(c->fv_ref.ensure((size_t)std::max(NFV, 1u) * 4));
+    // tie tets exist: boundary faces carry the material set of their inside cell
+    uint32_t* bf_mask = nullptr;
+    {
+        unsigned n_gated = 0;
+        CK(cudaMemcpyAsync(&n_gated, &dctr->n_tie_faces, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (n_gated) {
+            CK(c->bf_mask.ensure((size_t)std::max(NFc, 1u) * W * 4));
+            bf_mask = c->bf_mask.as<uint32_t>();
+        }
+    }
     if (A) {
         emit_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(), c->act_tet.as<uint32_t>(),
             c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(),
             c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->cand_key.as<uint4>(),
-            c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>(), &dctr->n_bndry_faces);
+            c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>(), bf_mask,
+            &dctr->n_bndry_faces);
         CK(cudaGetLastError());
     }
 
@@ -1568,7 +1580,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             bface_reps_kernel<<<g, 256, 0, s>>>(c->ftable.as<uint32_t>(), c->bids.as<uint32_t>(), NFc,
                 c->frep.as<uint32_t>(), ndup);
             mi_bface_decide_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
-                c->fv_ref.as<uint32_t>(), c->cand_pay.as<uint4>(), c->act_tet.as<uint32_t>(),
+                c->fv_ref.as<uint32_t>(), c->cand_pay.as<uint4>(), bf_mask, c->act_tet.as<uint32_t>(),
                 c->act_mask.as<uint32_t>(), c->act_cap, A, W, &dctr->n_unique);
             // the activated corner candidates join the vertex table
             hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
