@@ -152,6 +152,11 @@ int rin_num_stages(void);
 int rin_get_complexes(rin_ctx*, int mode, uint32_t flags, const uint64_t* tet_ids, uint64_t n,
                       uint64_t* offsets, uint32_t* words, uint64_t* n_words);
 
+/* robust_test (-R) of the reference (src/implicit_arrangement.cpp:137-243): every active tet of the
+ * last run is computed with its functions in forward and in reversed order.
+ * out = {type 1 (inconsistent counts), type 2 (forward run failed), type 3 (reversed run failed), tets tested} */
+int rin_robust_test(rin_ctx*, int mode, uint32_t out[4]);
+
 /* ---- one-shot host entry (what the C++ drop-in drivers call) ---------------------------- */
 int rin_run_host(rin_ctx*, int mode, uint32_t flags, const double* pts, uint64_t n_pts,
                  const void* tets, uint64_t n_tets, int index_bytes,

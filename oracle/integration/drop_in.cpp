@@ -131,8 +131,8 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     std::vector<std::vector<bool>>& cell_function_label, std::vector<std::string>& timing_labels,
     std::vector<double>& timings, std::vector<std::string>& stats_labels, std::vector<size_t>& stats)
 {
-    if (robust_test || !use_topo_ray_shooting) {
-        std::cout << "GPU drop-in: robust_test / cell-grouping modes are not served by the device path" << std::endl;
+    if (!robust_test && !use_topo_ray_shooting) {
+        std::cout << "GPU drop-in: the cell-grouping mode is not served by the device path" << std::endl;
         return false;
     }
     const size_t n_func = funcVals.cols();
@@ -143,6 +143,12 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     if (!rin_host::implicit_arrangement_hot(use_lookup, use_secondary_lookup, pts, tets, funcVals.data(), n_func, false,
             iso_pts, iso_faces, iso_verts, hot, timing_labels, timings, stats_labels, stats))
         return false;
+    if (robust_test) { // -R: verdict only, no mesh outputs (src/implicit_arrangement.cpp:329-343)
+        iso_pts.clear();
+        iso_faces.clear();
+        std::string err;
+        return rin_host::robust_test_verdict(0, err);
+    }
     std::vector<simplicial_arrangement::Arrangement<3>> cut_results;
     std::vector<size_t> cut_result_index;
     if (!materialise_complexes(0, hot, tets.size(), cut_results, cut_result_index)) return false;
@@ -217,8 +223,8 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     std::vector<std::string>& timing_labels, std::vector<double>& timings, std::vector<std::string>& stats_labels,
     std::vector<size_t>& stats)
 {
-    if (robust_test || !use_topo_ray_shooting) {
-        std::cout << "GPU drop-in: robust_test / cell-grouping modes are not served by the device path" << std::endl;
+    if (!robust_test && !use_topo_ray_shooting) {
+        std::cout << "GPU drop-in: the cell-grouping mode is not served by the device path" << std::endl;
         return false;
     }
     const size_t n_func = funcVals.cols();
@@ -229,6 +235,12 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     if (!rin_host::material_interface_hot(use_lookup, use_secondary_lookup, pts, tets, funcVals.data(), n_func, MI_pts,
             MI_faces, MI_verts, hot, timing_labels, timings, stats_labels, stats))
         return false;
+    if (robust_test) {
+        MI_pts.clear();
+        MI_faces.clear();
+        std::string err;
+        return rin_host::robust_test_verdict(1, err);
+    }
     std::vector<simplicial_arrangement::MaterialInterface<3>> cut_results;
     std::vector<size_t> cut_result_index;
     if (!materialise_complexes(1, hot, tets.size(), cut_results, cut_result_index)) return false;

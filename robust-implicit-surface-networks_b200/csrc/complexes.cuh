@@ -6,6 +6,8 @@
 #pragma once
 #include "kernels_mi.cuh"
 
+#include <type_traits>
+
 namespace rin {
 
 struct ComplexCounters
@@ -182,6 +184,66 @@ __global__ void __launch_bounds__(GEN_THREADS) complexes_mi_kernel(const uint4* 
             *w++ = cx.nm;
             for (int p = 0; p < cx.nm; ++p) *w++ = cx.umi[p];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// robust_test (-R) of the reference (src/implicit_arrangement.cpp:137-243,
+// src/material_interface.cpp:167-288): every active tet is computed twice, with the functions in
+// forward and in reversed order; a failure of the first run is "type 2", of the second "type 3",
+// different vertex / face / cell counts "type 1".
+// ---------------------------------------------------------------------------------------------
+struct RobustCounters
+{
+    unsigned type1, type2, type3, tested;
+};
+
+template <int W, bool MI>
+__global__ void __launch_bounds__(GEN_THREADS) robust_test_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active,
+    const double* __restrict__ vals, uint32_t V, RobustCounters* __restrict__ rc)
+{
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        const uint4 tv = __ldg(&tets[act_tet[a]]);
+        uint32_t m[W];
+        int k = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            m[w] = act_mask[(size_t)w * cap + a];
+            k += __popc(m[w]);
+        }
+        int cnt[2][3];
+        int err[2];
+        for (int pass = 0; pass < 2; ++pass) {
+            typename std::conditional<MI, MIComplex<MICaps>, IAComplex<IACaps>>::type cx;
+            bool first = true;
+            if (!MI) reinterpret_cast<IAComplex<IACaps>*>(&cx)->init();
+            for (int j = 0; j < k; ++j) {
+                const int f = nth_set_bit(m, W, pass ? k - 1 - j : j);
+                double pv[4] = {__ldg(&vals[(size_t)f * V + tv.x]), __ldg(&vals[(size_t)f * V + tv.y]),
+                    __ldg(&vals[(size_t)f * V + tv.z]), __ldg(&vals[(size_t)f * V + tv.w])};
+                if (MI) {
+                    MIComplex<MICaps>* c = reinterpret_cast<MIComplex<MICaps>*>(&cx);
+                    if (first)
+                        c->init(pv);
+                    else
+                        c->insert(pv);
+                    first = false;
+                } else
+                    reinterpret_cast<IAComplex<IACaps>*>(&cx)->insert(pv);
+            }
+            err[pass] = cx.err;
+            cnt[pass][0] = cx.nv;
+            cnt[pass][1] = cx.nf;
+            cnt[pass][2] = cx.nc;
+        }
+        atomicAdd(&rc->tested, 1u);
+        if (err[0])
+            atomicAdd(&rc->type2, 1u);
+        else if (err[1])
+            atomicAdd(&rc->type3, 1u);
+        else if (cnt[0][0] != cnt[1][0] || cnt[0][1] != cnt[1][1] || cnt[0][2] != cnt[1][2])
+            atomicAdd(&rc->type1, 1u);
     }
 }
 

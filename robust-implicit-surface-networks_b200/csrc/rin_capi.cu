@@ -651,6 +651,51 @@ int rin_get_complexes(rin_ctx* c, int mode, uint32_t, const uint64_t* tet_ids, u
     return RIN_OK;
 }
 
+extern "C++" {
+namespace {
+template <int W>
+int robust_w(rin_ctx* c, int mode, RobustCounters* d_rc)
+{
+    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet;
+    if (!A) return RIN_OK;
+    if (mode == RIN_MODE_IA)
+        robust_test_kernel<W, false><<<grid_for(A, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
+            c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
+            c->vals.as<double>(), (uint32_t)c->V, d_rc);
+    else
+        robust_test_kernel<W, true><<<grid_for(A, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
+            c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
+            c->vals.as<double>(), (uint32_t)c->V, d_rc);
+    CK(cudaGetLastError());
+    return RIN_OK;
+}
+} // namespace
+} // extern "C++"
+
+// robust_test of the last run's active tets; out = {type1, type2, type3, tested}
+int rin_robust_test(rin_ctx* c, int mode, uint32_t out[4])
+{
+    if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran || c->last_mode != mode) return fail(RIN_ERR_STATE, "rin_robust_test: no finished run of that mode");
+    CK(cudaSetDevice(c->device));
+    DevBuf d;
+    CK(d.ensure(sizeof(RobustCounters)));
+    cudaMemsetAsync(d.p, 0, sizeof(RobustCounters), c->stream);
+    int rc;
+    switch (words_for(c->F)) {
+    case 1: rc = robust_w<1>(c, mode, d.as<RobustCounters>()); break;
+    case 2: rc = robust_w<2>(c, mode, d.as<RobustCounters>()); break;
+    case 3: rc = robust_w<3>(c, mode, d.as<RobustCounters>()); break;
+    default: rc = robust_w<4>(c, mode, d.as<RobustCounters>()); break;
+    }
+    if (rc == RIN_OK) {
+        cudaMemcpyAsync(out, d.p, 16, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(RIN_ERR_CUDA, "rin_robust_test: kernel failed");
+    }
+    d.release();
+    return rc;
+}
+
 int rin_get_vertex_range(const rin_ctx* c, uint32_t* lo, uint32_t* hi)
 {
     if (!c) return fail(RIN_ERR_ARG, "null ctx");

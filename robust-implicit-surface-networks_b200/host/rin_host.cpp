@@ -196,6 +196,34 @@ bool material_interface_hot(bool use_lookup, bool use_secondary_lookup,
     return true;
 }
 
+bool robust_test_verdict(int mode, std::string& error)
+{
+    if (!g_ctx) {
+        error = "no hot-path run";
+        return false;
+    }
+    uint32_t r[4] = {0, 0, 0, 0};
+    if (rin_robust_test(g_ctx, mode, r) != RIN_OK) {
+        error = rin_last_error();
+        std::cout << error << std::endl;
+        return false;
+    }
+    if (r[1]) {
+        std::cout << "type 2 failure (crash in the normal order)." << std::endl;
+        return false;
+    }
+    if (r[2]) {
+        std::cout << "type 3 failure (crash in the reverse order)." << std::endl;
+        return false;
+    }
+    if (r[0]) {
+        std::cout << "type 1 failure (inconsistency)." << std::endl;
+        return false;
+    }
+    std::cout << "success." << std::endl;
+    return true;
+}
+
 bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<TetComplex>& out, std::string& error)
 {
     if (!g_ctx) {

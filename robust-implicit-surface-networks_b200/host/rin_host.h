@@ -59,6 +59,11 @@ bool material_interface_hot(bool use_lookup, bool use_secondary_lookup,
     std::vector<std::string>& timing_labels, std::vector<double>& timings, std::vector<std::string>& stats_labels,
     std::vector<size_t>& stats);
 
+// robust_test (-R): forward / reversed insertion order on every active tet of the LAST hot-path call.
+// Prints the reference's verdict line ("success." / "type N failure ...") and returns its value
+// (src/implicit_arrangement.cpp:329-343).
+bool robust_test_verdict(int mode, std::string& error);
+
 // Complexes of the given tets of the LAST hot-path call (mode 0 = IA, 1 = MI); inactive tets give
 // an empty complex.  This is the lazy replacement of cut_results[cut_result_index[tet]].
 bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<TetComplex>& out, std::string& error);

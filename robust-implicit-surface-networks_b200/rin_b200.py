@@ -76,6 +76,7 @@ def lib():
         L.rin_nccl_unique_id.argtypes = [C.c_void_p]
         L.rin_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rin_exchange_nccl.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+        L.rin_robust_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Counts)]
         L.rin_get_complexes.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -252,6 +253,11 @@ class Context:
         self._check(lib().rin_get_complexes(self._h, mode, 0, ids.ctypes.data, len(ids), off.ctypes.data,
                                             words.ctypes.data, C.byref(n)))
         return off, words[:n.value]
+
+    def robust_test(self, mode):
+        out = np.zeros(4, np.uint32)
+        self._check(lib().rin_robust_test(self._h, mode, out.ctypes.data))
+        return {"type1": int(out[0]), "type2": int(out[1]), "type3": int(out[2]), "tested": int(out[3])}
 
     def kernel_times(self):
         e, f, t = C.c_float(), C.c_float(), C.c_float()

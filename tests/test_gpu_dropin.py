@@ -107,3 +107,12 @@ def test_csg_known_answers_through_the_gpu_drop_in(name, grid101):
     assert len(crs(b, "chains")) == nchain
     assert sum(1 for l in crs(b, "non_manifold_edges_of_vert") if len(l) > 2) == ncorner
     assert b["patch_sign_label"].tolist() == sign
+
+
+def test_robust_test_mode_through_the_gpu_drop_in(grid101):
+    """-R (src/implicit_arrangement.cpp:137-243, 329-343): returns true ("success.") and no mesh."""
+    pts, tets = grid101
+    vals = orc_eval(load_funcs(os.path.join(G, "functions", "3-sphere-3.json")), pts)
+    b = ref_run("ia", pts, tets, vals, robust=True, lib=dropin_lib())
+    assert b.error == "" and b["success"][0] == 1
+    assert len(b["face_offsets"]) <= 1

@@ -33,8 +33,10 @@ def test_ia_near_coincident_spheres(eps):
     ctx.set_mesh(pts, tets)
     ctx.set_functions(funcs)
     cnt = ctx.run(rin.MODE_IA)
-    assert cnt.num_kmore > 0
     compare_ia(ctx, ctx.download_mesh(), port, cnt)
+    # the reference's -R self-test on the device: forward vs reversed insertion order
+    r = ctx.robust_test(rin.MODE_IA)
+    assert r == {"type1": 0, "type2": 0, "type3": 0, "tested": cnt.num_intersecting_tet}
     ctx.close()
 
 
@@ -51,6 +53,8 @@ def test_mi_near_coincident_spheres(eps):
     ctx.set_functions(funcs)
     cnt = ctx.run(rin.MODE_MI)
     compare_mi(ctx, ctx.download_mesh(), port, cnt)
+    r = ctx.robust_test(rin.MODE_MI)
+    assert r == {"type1": 0, "type2": 0, "type3": 0, "tested": cnt.num_intersecting_tet}
     ctx.close()
 
 
