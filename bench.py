@@ -184,7 +184,8 @@ def main():
     if world > 1:
         ctx.set_tet_range(t_first, t_count)
     T_total = 5 * R ** 3
-    mode, flags = rin.MODE_IA, rin.FLAG_LOOKUP | rin.FLAG_SECONDARY
+    mode = rin.MODE_MI if args.config == "C3" else rin.MODE_IA  # C3 is the material-interface configuration
+    flags = rin.FLAG_LOOKUP | rin.FLAG_SECONDARY
 
     def barrier():
         if dist is not None:
@@ -262,8 +263,13 @@ def main():
     filt = float(np.mean(filt_ms))
     evl = float(np.mean(eval_ms))
     achieved = min(alg_survey, alg_masks) / (filt * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp) and world == 1 and args.config == "C2" and not args.resolution:
+        with open(tp) as f:
+            traffic = json.load(f).get("filter_tiles_kernel", {}).get("dram_bytes")
     roofline = {"bound": "hbm", "kernel": "filter_tiles_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": min(alg_survey, alg_masks),
                 "algorithmic_bytes_survey_formula": alg_survey, "kernel_ms": filt,
                 "eval_kernel": {"ms": evl, "bytes": (24.0 + 8.0 * F + 8.0) * V_rank,
@@ -276,7 +282,7 @@ def main():
 
     # ---- e2e: legacy host-array entry point, pinned host buffers, copies inside the timed region --
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if world == 1 and not args.no_e2e and mode == rin.MODE_IA:
         V = (R + 1) ** 3
         pts_h = torch.empty((V, 3), dtype=torch.float64, pin_memory=True).numpy()
         tets_h = torch.empty((T_total, 4), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
@@ -324,7 +330,7 @@ def main():
 
     # ---- CPU baseline on the host cores of this box (rank 0, N=1 only) ---------------------------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.config == "C2":
         try:
             cpu = cpu_reference_run(args.config)
         except Exception as ex:  # the baseline is reported, never required
@@ -337,9 +343,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "implicit arrangement, generated tet5 grid %d^3 (%d tets), %d random "
-                                       "spheres+planes (seed 1), lookup tables on" % (R, T_total, F),
-                           "baseline_config": "C2" if world == 1 else ("C5" if world == 8 else "C2-weak"),
+                "config": {"workload": "%s, generated tet5 grid %d^3 (%d tets), %d synthetic functions of BASELINE "
+                                       "config %s (SURVEY 8(d) generator), lookup tables on" % (
+                                           "material interface" if mode == rin.MODE_MI else "implicit arrangement",
+                                           R, T_total, F, args.config),
+                           "baseline_config": args.config if world == 1 else ("C5" if world == 8 else "C2-weak"),
                            "sharding": "x-slabs, one contiguous tet range per GPU" if world > 1 else "none",
                            "cache": "inputs (%.0f MB) + intermediates exceed the 126 MB L2" %
                                     ((16.0 * T_total + 88.0 * (R + 1) ** 3) / 1e6)},
