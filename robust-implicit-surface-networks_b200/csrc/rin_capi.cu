@@ -1984,6 +1984,7 @@ int build_mi_tables(rin_ctx* c)
     CKC(cudaMemcpyAsync(d_gl.p, gl.data(), NW * 4, cudaMemcpyHostToDevice, s));
     CKC(cudaMemsetAsync(d_ctr.p, 0, sizeof(Counters), s));
     CKC(cudaMemsetAsync(d_arena.p, 0, 4, s));
+    CKC(cudaMemsetAsync(d_ref.p, 0, NW * 4, s)); // the general kernel reads the tie-gate flag from here
     Counters* dctr = d_ctr.as<Counters>();
     GeneralCounters g0{};
     g0.n_general = g0.n_big = NW;
@@ -2008,7 +2009,11 @@ int build_mi_tables(rin_ctx* c)
     L.h_lut1.assign(16, 0);
     L.h_blob.assign(4, 0);
     for (uint32_t w = 0; w < NW; ++w) {
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(arena.data() + (size_t)(refs[w] & ~REF_GENERAL) * 4);
+        if ((refs[w] & REF_FLAGS) != REF_GENERAL || (size_t)(refs[w] & ~REF_FLAGS) * 4 + 4 > arena.size()) {
+            cleanup();
+            return fail(RIN_ERR_STATE, "MI table generation: witness without a plain record");
+        }
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(arena.data() + (size_t)(refs[w] & ~REF_FLAGS) * 4);
         const int nv = rw[0] & 255, nf = (rw[0] >> 8) & 255;
         uint32_t words = 1 + 2 * nv;
         for (int f = 0; f < nf; ++f) words += 1 + rec_face_words((rw[words] >> 24) & 127);
