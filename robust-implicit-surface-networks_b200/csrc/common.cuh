@@ -2,26 +2,11 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "record_words.cuh"
 
 namespace rin {
 
 constexpr uint32_t NONE32 = 0xffffffffu;
-
-// ---------------------------------------------------------------------------------------------
-// Iso record: the part of a per-tet complex that the mesh extraction consumes
-// (/root/reference/src/extract_mesh.cpp:60-261 reads only iso vertices and iso faces).
-// A sequence of 32-bit words (records are 4-byte aligned so that one load fetches one entry):
-//   word 0                 n_iso_verts | n_iso_faces << 8 | n_face_vertex_entries << 16
-//   n_iso_verts words      local vertex id | plane0 << 8 | plane1 << 16 | plane2 << 24  (ascending)
-//   per iso face           local face id (16) | supporting plane << 16 | n << 24 | boundary << 31
-//                          followed by ceil(n/4) words of iso-vertex ranks, one byte each
-// boundary: the face lies on the tet boundary (negative_cell == None).
-// Plane ids: 0..3 simplex faces, 4+j the j-th active function of the tet.
-// ---------------------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t rec_face_words(int n)
-{
-    return 1u + uint32_t(n + 3) / 4u;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Decoupled look-back over tiles for a PAIR of 31-bit partial sums packed with a 2-bit flag in

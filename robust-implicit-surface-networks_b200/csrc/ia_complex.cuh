@@ -120,7 +120,8 @@ struct IAComplex
 
     // exact sign of plane q at the point where the three planes of vertex v meet:
     // q(X) = det[impl; q] / det[impl; 1] restricted to the corners not fixed by boundary planes
-    __device__ int orient_vertex(int v, const double* q)
+    // nex / bad: exact-fallback counter and degeneracy flag of the caller (per lane in the warp version)
+    __device__ int orient_vertex(int v, const double* q, unsigned& nex, int& bad)
     {
         const double* impl[3];
         int ni = 0;
@@ -142,7 +143,7 @@ struct IAComplex
         int sq, sd;
         if (n == 2) {
             const double a = impl[0][idx[0]], b = impl[0][idx[1]];
-            sq = det2_sign(a, b, q[idx[0]], q[idx[1]], &n_exact);
+            sq = det2_sign(a, b, q[idx[0]], q[idx[1]], &nex);
             if (sq == 0) return 0;
             sd = (a > b) - (a < b); // det[[a,b],[1,1]]
         } else if (n == 3) {
@@ -153,10 +154,10 @@ struct IAComplex
                 m[3 + c] = impl[1][idx[c]];
                 m[6 + c] = q[idx[c]];
             }
-            sq = det3_sign(m, &n_exact);
+            sq = det3_sign(m, &nex);
             if (sq == 0) return 0;
             m[6] = m[7] = m[8] = 1.0;
-            sd = det3_sign(m, &n_exact);
+            sd = det3_sign(m, &nex);
         } else {
             double m[16];
 #pragma unroll
@@ -166,12 +167,12 @@ struct IAComplex
                 m[8 + c] = impl[2][c];
                 m[12 + c] = q[c];
             }
-            sq = det4_sign(m, &n_exact);
+            sq = det4_sign(m, &nex);
             if (sq == 0) return 0;
             m[12] = m[13] = m[14] = m[15] = 1.0;
-            sd = det4_sign(m, &n_exact);
+            sd = det4_sign(m, &nex);
         }
-        if (sd == 0) err = 2;
+        if (sd == 0) bad = 2;
         return sq * sd;
     }
 
@@ -190,7 +191,7 @@ struct IAComplex
         // ---- 1. vertices
         bool any = false;
         for (int v = 0; v < nv; ++v) {
-            vo[v] = (int8_t)orient_vertex(v, q);
+            vo[v] = (int8_t)orient_vertex(v, q, n_exact, err);
             any |= (vo[v] != 0);
         }
         if (!any) {

@@ -5,6 +5,7 @@
 #include "../../include/rin_b200.h"
 #include "common.cuh"
 #include "ia_complex.cuh"
+#include "iso_record.cuh"
 
 namespace rin {
 
@@ -568,62 +569,6 @@ __global__ void __launch_bounds__(256) classify_ia_kernel(const uint4* __restric
 // K4: general arrangement kernel: one thread per tet, complex in local memory, iso record out.
 // ---------------------------------------------------------------------------------------------
 
-// iso part of a finished complex: counts, then serialisation straight into the arena
-template <class Caps>
-struct IsoScan
-{
-    uint32_t isov[(Caps::MAXV + 31) / 32];
-    int nvi, nfi, nfv, nfw; // nfw: words used by the face entries
-    __device__ void run(const IAComplex<Caps>& cx)
-    {
-        for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) isov[i] = 0;
-        nfi = 0;
-        nfv = 0;
-        nfw = 0;
-        for (int f = 0; f < cx.nf; ++f)
-            if (cx.is_iso_face(f)) {
-                ++nfi;
-                nfv += cx.flen[f];
-                if (cx.flen[f] > 127) nfv = 1 << 20; // loop too long for the record format -> capacity error
-                nfw += rec_face_words(cx.flen[f]);
-                for (int k = 0; k < cx.flen[f]; ++k) {
-                    int v = cx.fv[cx.foff[f] + k];
-                    isov[v >> 5] |= 1u << (v & 31);
-                }
-            }
-        nvi = 0;
-        for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) nvi += __popc(isov[i]);
-    }
-    __device__ int rank(int v) const
-    {
-        int r = __popc(isov[v >> 5] & ((1u << (v & 31)) - 1u));
-        for (int i = 0; i < (v >> 5); ++i) r += __popc(isov[i]);
-        return r;
-    }
-    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + nvi + nfw); }
-    __device__ void write(const IAComplex<Caps>& cx, uint32_t* w) const
-    {
-        int p = 0;
-        w[p++] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
-        for (int v = 0; v < cx.nv; ++v)
-            if ((isov[v >> 5] >> (v & 31)) & 1)
-                w[p++] = (uint32_t)v | ((uint32_t)cx.vp[v][0] << 8) | ((uint32_t)cx.vp[v][1] << 16) |
-                         ((uint32_t)cx.vp[v][2] << 24);
-        for (int f = 0; f < cx.nf; ++f)
-            if (cx.is_iso_face(f)) {
-                const int n = cx.flen[f];
-                w[p++] = (uint32_t)f | ((uint32_t)cx.fplane[f] << 16) | ((uint32_t)n << 24) |
-                         ((cx.fneg[f] == N8) ? 0x80000000u : 0u);
-                for (int k0 = 0; k0 < n; k0 += 4) {
-                    uint32_t x = 0;
-                    for (int k = k0; k < n && k < k0 + 4; ++k)
-                        x |= (uint32_t)rank(cx.fv[cx.foff[f] + k]) << (8 * (k - k0));
-                    w[p++] = x;
-                }
-            }
-    }
-};
-
 // One general tet: gather the active functions' values, build the complex, publish the record.
 // Returns false when the complex did not fit this tier (caller re-queues it for the big tier).
 template <class Caps, int W>
@@ -675,10 +620,77 @@ __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __r
     return true;
 }
 
-// Small tier: complexes in shared memory, `lanes` active lanes per warp (few lanes = little
-// divergence when there are only a handful of general tets, the usual case).
+// Warp-cooperative version of general_ia_one (small tier): all 32 lanes call it with the same arguments.
+template <class Caps, int W>
+__device__ bool general_ia_one_warp(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc, uint32_t a,
+    const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask,
+    uint32_t cap, const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int skip, int lane)
+{
+    const uint4 tv = __ldg(&tets[act_tet[a]]);
+    if (!skip) {
+        if (lane == 0) cx.init();
+        __syncwarp();
+    }
+    int seen = 0;
+    for (int w = 0; w < W; ++w) {
+        uint32_t mm = act_mask[(size_t)w * cap + a];
+        while (mm) {
+            const int f = w * 32 + __ffs(mm) - 1;
+            mm &= mm - 1;
+            if (seen++ < skip) continue;
+            double pv[4];
+            pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
+            pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
+            pv[2] = __ldg(&vals[(size_t)f * V + tv.z]);
+            pv[3] = __ldg(&vals[(size_t)f * V + tv.w]);
+            warp_insert(cx, sc, pv, lane);
+        }
+    }
+    __syncwarp();
+    int err = cx.err;
+    WarpIso<Caps> iso;
+    if (!err) {
+        iso.run(cx, lane);
+        if (iso.nvi > 255 || iso.nfi > 255 || iso.nfv > 65535 || cx.nf > 65535) err = 1;
+    }
+    if (lane == 0 && cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
+    if (err == 1 && !last_tier) return false;
+    if (err) {
+        if (lane == 0) {
+            if (atomicCAS(&gc->err, 0, err == 1 ? RIN_ERR_CAPACITY : RIN_ERR_ARRANGEMENT) == 0)
+                gc->err_tet = act_tet[a];
+            rec_ref[a] = REF_GENERAL; // offset 0: the arena starts with an empty record
+        }
+        return true;
+    }
+    const uint32_t szal = iso.size_bytes();
+    uint32_t off = 0;
+    if (lane == 0) off = atomicAdd(&gc->arena_top, szal);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + szal > arena_cap) {
+        if (lane == 0) {
+            gc->arena_overflow = 1;
+            rec_ref[a] = REF_GENERAL;
+        }
+        return true;
+    }
+    iso.write(cx, reinterpret_cast<uint32_t*>(arena + off), lane);
+    if (lane == 0) rec_ref[a] = REF_GENERAL | (off >> 2);
+    return true;
+}
+
+// Small tier: one tet per warp, complex in shared memory, warp-cooperative insertion
+// (ia_complex_warp.cuh): the stage is latency-bound (a few hundred general tets), so the serial
+// dependency chain per tet is what sets its duration.
 constexpr int GEN_SMALL_WARPS = 4;
 constexpr int GEN_THREADS = 64;
+// shared memory of one warp of the small tier: the complex and the re-packing scratch
+struct alignas(16) SmallSlot
+{
+    IAComplex<IACapsSmall> cx;
+    IAWarpScratch<IACapsSmall> sc;
+};
 // cx2 / lut2cx (nullable): complete 2-plane complexes per key.  A tet with >= 3 functions whose first
 // two functions have a tabulated key starts from that complex (copied by the whole warp) and only
 // inserts the remaining planes: every branch of the insertion depends on the vertex signs alone,
@@ -693,10 +705,11 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_ia_small_kernel(
     GeneralCounters* __restrict__ gc)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
-    IAComplex<IACapsSmall>* s_cx = reinterpret_cast<IAComplex<IACapsSmall>*>(s_raw);
+    SmallSlot* s_slot = reinterpret_cast<SmallSlot*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = gc->n_small;
-    IAComplex<IACapsSmall>& cx = s_cx[warp];
+    IAComplex<IACapsSmall>& cx = s_slot[warp].cx;
+    IAWarpScratch<IACapsSmall>& sc = s_slot[warp].sc;
     for (uint32_t g = blockIdx.x * GEN_SMALL_WARPS + warp; g < n; g += gridDim.x * GEN_SMALL_WARPS) {
         const uint32_t a = small_list[g];
         int skip = 0;
@@ -745,10 +758,10 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_ia_small_kernel(
                 skip = 2;
             }
         }
-        if (lane == 0) {
-            if (!general_ia_one<IACapsSmall, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap,
-                    rec_ref, gc, false, skip))
-                ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
+        __syncwarp();
+        if (!general_ia_one_warp<IACapsSmall, W>(cx, sc, a, tets, act_tet, act_mask, cap, vals, V, arena,
+                arena_cap, rec_ref, gc, false, skip, lane)) {
+            if (lane == 0) ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
         }
         __syncwarp();
     }
