@@ -9,6 +9,10 @@
 #pragma once
 #include "predicates.cuh"
 
+#ifndef RIN_TRACK_PEAK
+#define RIN_TRACK_PEAK(nv, ne, nf, nc, nfe, ncf) // sizing instrumentation hook (scripts/size_caps.cpp)
+#endif
+
 namespace rin {
 
 // Big tier: per-thread local memory, 16-bit indices.
@@ -37,6 +41,22 @@ struct IACapsSmall
     static constexpr int MAXFE = 384;
     static constexpr int MAXCF = 160;
     static constexpr int MAXLOOP = 12;
+};
+
+// Mid tier (5..20 functions, or a small-tier overflow): 8-bit indices, ~9 KB, shared memory, one tet per
+// warp.  Sized from the peak transient counts of the 32-function stress configuration (scripts/size_caps.cpp:
+// ne <= 239, nf <= 195, nfe <= 779 at k = 20); anything larger falls through to the big tier.
+struct IACapsMid
+{
+    using idx = uint8_t;
+    static constexpr int MAXK = 20;
+    static constexpr int MAXV = 128;
+    static constexpr int MAXE = 254;
+    static constexpr int MAXF = 224;
+    static constexpr int MAXC = 64;
+    static constexpr int MAXFE = 1024;
+    static constexpr int MAXCF = 384;
+    static constexpr int MAXLOOP = 24;
 };
 
 constexpr uint8_t N8 = 0xff;
@@ -478,6 +498,7 @@ struct IAComplex
             }
         }
         // ---- 5. consolidate in place (survivors keep their order)
+        RIN_TRACK_PEAK(nv, ne, nf, nc, nfe, ncf);
         {
             int k = 0;
             for (int e = 0; e < ne; ++e) {

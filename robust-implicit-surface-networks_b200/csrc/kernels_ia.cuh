@@ -439,6 +439,7 @@ struct GeneralCounters
     int err;            // first error code (RIN_ERR_*)
     unsigned err_tet;
     unsigned arena_overflow;
+    unsigned n_ovf2;    // mid-tier capacity overflows (IA), re-queued for the per-thread big tier
 };
 
 constexpr uint32_t REF_GENERAL = 0x80000000u;
@@ -788,20 +789,49 @@ __global__ void __launch_bounds__(GEN_THREADS) dump_ia2_kernel(const uint32_t* _
     }
 }
 
-// Big tier: complexes in per-thread local memory.
+// Mid tier: the big list (more functions than the small tier takes) and the small tier's overflows, one tet
+// per warp, complex in shared memory, warp-cooperative insertion.  Capacity overflow -> ovf2 list.
+constexpr int GEN_MID_WARPS = 4;
+struct alignas(16) MidSlot
+{
+    IAComplex<IACapsMid> cx;
+    IAWarpScratch<IACapsMid> sc;
+};
 template <int W>
-__global__ void __launch_bounds__(GEN_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
+__global__ void __launch_bounds__(GEN_MID_WARPS * 32) general_ia_mid_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
-    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ ovf_list,
+    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ ovf_list, uint32_t* __restrict__ ovf2_list,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
     uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc)
 {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    MidSlot* s_slot = reinterpret_cast<MidSlot*>(s_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nb = gc->n_big, n = nb + gc->n_ovf;
+    for (uint32_t g = blockIdx.x * GEN_MID_WARPS + warp; g < n; g += gridDim.x * GEN_MID_WARPS) {
+        const uint32_t a = g < nb ? big_list[g] : ovf_list[g - nb];
+        __syncwarp();
+        if (!general_ia_one_warp<IACapsMid, W>(s_slot[warp].cx, s_slot[warp].sc, a, tets, act_tet, act_mask, cap,
+                vals, V, arena, arena_cap, rec_ref, gc, false, 0, lane)) {
+            if (lane == 0) ovf2_list[atomicAdd(&gc->n_ovf2, 1u)] = a;
+        }
+        __syncwarp();
+    }
+}
+
+// Big tier: complexes in per-thread local memory (what neither shared-memory tier could hold).
+template <int W>
+__global__ void __launch_bounds__(GEN_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    const uint32_t* __restrict__ list, const unsigned* __restrict__ n_list,
+    const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc)
+{
+    const uint32_t n = *n_list;
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
         IAComplex<IACaps> cx;
-        const uint32_t a = g < nb ? big_list[g] : ovf_list[g - nb];
-        general_ia_one<IACaps, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref, gc,
-            true);
+        general_ia_one<IACaps, W>(cx, list[g], tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref,
+            gc, true);
     }
 }
 

@@ -123,6 +123,7 @@ struct rin_ctx
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    size_t smem_per_sm = 227 * 1024;
     // mesh
     uint64_t V = 0, T = 0;
     DevBuf pts, tets;
@@ -224,6 +225,7 @@ int rin_create(int device, rin_ctx** out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->smem_per_sm = prop.sharedMemPerMultiprocessor;
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     for (auto& e : c->kev) CK(cudaEventCreate(&e));
     CK(cudaHostAlloc(&c->h_pinned, sizeof(Counters), cudaHostAllocDefault));
@@ -1171,7 +1173,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
     CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
     CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
-    CK(c->big_list.ensure((size_t)std::max(A, 1u) * 8)); // [big | small-tier overflow]
+    CK(c->big_list.ensure((size_t)std::max(A, 1u) * 12)); // [big | small-tier overflow | mid-tier overflow]
     CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
     LutView lv{c->lut_ia.lut1.as<uint16_t>(), c->lut_ia.lut2.as<uint16_t>(), c->lut_ia.blob.as<uint8_t>(),
         c->lut_ia.blob_bytes};
@@ -1194,6 +1196,14 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         const int small_blocks = (int)std::max<uint32_t>(
             1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
         const size_t small_smem = GEN_SMALL_WARPS * sizeof(SmallSlot);
+        const size_t mid_smem = GEN_MID_WARPS * sizeof(MidSlot);
+        const int mid_per_sm = (int)std::max<size_t>(1, c->smem_per_sm / (mid_smem + 1024));
+        const int mid_blocks = (int)std::max<uint32_t>(
+            1, std::min<uint32_t>((est + 64 + GEN_MID_WARPS - 1) / GEN_MID_WARPS, (uint32_t)(sm * mid_per_sm)));
+        if (mid_smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
+        CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            (int)cudaSharedmemCarveoutMaxShared));
         for (int attempt = 0;; ++attempt) {
             if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
             const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
@@ -1207,10 +1217,16 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
                 c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr,
                 c->lut_ia.lut2cx.as<uint16_t>(), c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
                 c->rec_ref.as<uint32_t>(), &dctr->gen);
-            general_ia_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
+            // mid tier: big list + small-tier overflows, one tet per warp; overflow -> third list
+            general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(),
                 c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
-                c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
-                c->rec_ref.as<uint32_t>(), &dctr->gen);
+                c->big_list.as<uint32_t>() + A, c->big_list.as<uint32_t>() + 2 * (size_t)A, c->vals.as<double>(), V,
+                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
+            // big tier: what is left (per-thread local memory)
+            general_ia_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
+                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
+                c->big_list.as<uint32_t>() + 2 * (size_t)A, &dctr->gen.n_ovf2, c->vals.as<double>(), V,
+                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
             CK(cudaGetLastError());
             // counts + offsets right behind the general kernels: ONE read-back serves both
             // (an arena overflow leaves empty records, the scan is then simply repeated)
@@ -1854,7 +1870,7 @@ int build_ia_tables(rin_ctx* c)
     CKC(d_arena.ensure((size_t)NCH * 256 + 4096));
     CKC(cudaMemsetAsync(d_arena.p, 0, 4, s));
     general_ia_big_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
-        d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), d_gl.as<uint32_t>(), d_vals.as<double>(), Vw,
+        d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), &dctr->gen.n_big, d_vals.as<double>(), Vw,
         d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
     CKC(cudaGetLastError());
     GeneralCounters g1;

@@ -28,7 +28,7 @@ def test_warp_insertion_equals_serial(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     out = subprocess.run([exe, "400", "21"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]
-    assert out.stdout.count("mismatches 0") == 2, out.stdout
+    assert out.stdout.count("mismatches 0") == 3, out.stdout
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
