@@ -4,6 +4,7 @@
 #pragma once
 #include "kernels_ia.cuh"
 #include "mi_complex.cuh"
+#include "mi_complex_warp.cuh"
 
 namespace rin {
 
@@ -377,6 +378,74 @@ __device__ bool general_mi_one(MIComplex<Caps>& cx, uint32_t a, const uint4* __r
     return true;
 }
 
+// Warp-cooperative version (small tier): the insertions run on all 32 lanes (mi_complex_warp.cuh), lane 0
+// serialises the record.  All lanes call it with the same arguments.
+template <class Caps, int W>
+__device__ bool general_mi_one_warp(MIComplex<Caps>& cx, MIWarpScratch<Caps>& sc, uint32_t a,
+    const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask,
+    uint32_t cap, const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int lane)
+{
+    const uint4 tv = __ldg(&tets[act_tet[a]]);
+    bool first = true;
+    for (int w = 0; w < W; ++w) {
+        uint32_t mm = act_mask[(size_t)w * cap + a];
+        while (mm) {
+            const int f = w * 32 + __ffs(mm) - 1;
+            mm &= mm - 1;
+            double pv[4];
+            pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
+            pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
+            pv[2] = __ldg(&vals[(size_t)f * V + tv.z]);
+            pv[3] = __ldg(&vals[(size_t)f * V + tv.w]);
+            if (first) {
+                if (lane == 0) cx.init(pv);
+                __syncwarp();
+                first = false;
+            } else
+                warp_insert_material(cx, sc, pv, lane);
+        }
+    }
+    __syncwarp();
+    int done = 1;
+    if (lane == 0) {
+        const bool gated = (rec_ref[a] & REF_GATED) != 0;
+        MIIsoScan<Caps> iso;
+        if (!cx.err) {
+            iso.run(cx);
+            if (gated) iso.run_boundary(cx);
+            if (iso.nvi + iso.n_extra > 255 || iso.nfi + iso.n_bf > 255 || iso.nfv + iso.bf_fv > 65535) cx.err = 1;
+        }
+        if (cx.n_exact) atomicAdd(&gc->n_exact, cx.n_exact);
+        if (cx.err == 1 && !last_tier)
+            done = 0;
+        else if (cx.err) {
+            if (atomicCAS(&gc->err, 0, cx.err == 1 ? RIN_ERR_CAPACITY : RIN_ERR_ARRANGEMENT) == 0)
+                gc->err_tet = act_tet[a];
+            rec_ref[a] = REF_GENERAL;
+        } else {
+            const uint32_t szal = iso.size_bytes(gated);
+            const uint32_t off = atomicAdd(&gc->arena_top, szal);
+            if (off + szal > arena_cap) {
+                gc->arena_overflow = 1;
+                rec_ref[a] = REF_GENERAL | (gated ? REF_GATED : 0u); // keep the flag for the retry
+            } else {
+                iso.write(cx, reinterpret_cast<uint32_t*>(arena + off), gated);
+                rec_ref[a] = REF_GENERAL | (gated ? REF_GATED : 0u) | (off >> 2);
+            }
+        }
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    __syncwarp();
+    return done != 0;
+}
+
+struct alignas(16) MISmallSlot
+{
+    MIComplex<MICapsSmall> cx;
+    MIWarpScratch<MICapsSmall> sc;
+};
+
 template <int W>
 __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_mi_small_kernel(
     const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet,
@@ -386,16 +455,17 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_mi_small_kernel(
     GeneralCounters* __restrict__ gc)
 {
     extern __shared__ __align__(16) uint8_t s_raw_mi[];
-    MIComplex<MICapsSmall>* s_cx = reinterpret_cast<MIComplex<MICapsSmall>*>(s_raw_mi);
+    MISmallSlot* s_slot = reinterpret_cast<MISmallSlot*>(s_raw_mi);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane != 0) return;
     const uint32_t n = gc->n_small;
-    MIComplex<MICapsSmall>& cx = s_cx[warp];
     for (uint32_t g = blockIdx.x * GEN_SMALL_WARPS + warp; g < n; g += gridDim.x * GEN_SMALL_WARPS) {
         const uint32_t a = small_list[g];
-        if (!general_mi_one<MICapsSmall, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap,
-                rec_ref, gc, false))
-            ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
+        __syncwarp();
+        if (!general_mi_one_warp<MICapsSmall, W>(s_slot[warp].cx, s_slot[warp].sc, a, tets, act_tet, act_mask, cap,
+                vals, V, arena, arena_cap, rec_ref, gc, false, lane)) {
+            if (lane == 0) ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
+        }
+        __syncwarp();
     }
 }
 

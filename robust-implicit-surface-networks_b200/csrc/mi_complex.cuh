@@ -183,7 +183,8 @@ struct MIComplex
     }
 
     // exact sign of (M - current maximum) at vertex v
-    __device__ int orient_vertex(int v, const double* M)
+    // nex / bad: exact-fallback counter and degeneracy flag of the caller (per lane in the warp version)
+    __device__ int orient_vertex(int v, const double* M, unsigned& nex, int& bad)
     {
         const double* real[4];
         int k = 0;
@@ -214,10 +215,10 @@ struct MIComplex
             da[(k - 1) * n + c] = 1.0;
             db[(k - 1) * n + c] = 0.0;
         }
-        int sq = detn_diff_sign(n, qa, qb, &n_exact);
+        int sq = detn_diff_sign(n, qa, qb, &nex);
         if (sq == 0) return 0;
-        int sd = detn_diff_sign(n, da, db, &n_exact);
-        if (sd == 0) err = 2;
+        int sd = detn_diff_sign(n, da, db, &nex);
+        if (sd == 0) bad = 2;
         return sq * sd;
     }
 
@@ -232,7 +233,7 @@ struct MIComplex
     {
         const double* M = mval[mid - 4];
         const int B = cur, B2 = cur ^ 1;
-        for (int v = 0; v < nv; ++v) vo[v] = (int8_t)orient_vertex(v, M);
+        for (int v = 0; v < nv; ++v) vo[v] = (int8_t)orient_vertex(v, M, n_exact, err);
         if (err) return -1;
         // ---- edges
         const int nE = ne;

@@ -1525,7 +1525,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         const uint32_t est = use_lookup ? (h.filt.n_kmore + h.filt.n_k2) : A;
         const int small_blocks = (int)std::max<uint32_t>(
             1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
-        const size_t small_smem = GEN_SMALL_WARPS * sizeof(MIComplex<MICapsSmall>);
+        const size_t small_smem = GEN_SMALL_WARPS * sizeof(MISmallSlot);
         for (int attempt = 0;; ++attempt) {
             if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
             const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
