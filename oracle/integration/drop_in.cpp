@@ -131,10 +131,6 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     std::vector<std::vector<bool>>& cell_function_label, std::vector<std::string>& timing_labels,
     std::vector<double>& timings, std::vector<std::string>& stats_labels, std::vector<size_t>& stats)
 {
-    if (!robust_test && !use_topo_ray_shooting) {
-        std::cout << "GPU drop-in: the cell-grouping mode is not served by the device path" << std::endl;
-        return false;
-    }
     const size_t n_func = funcVals.cols();
     push_stat(stats_labels, stats, "num_pts", pts.size());
     push_stat(stats_labels, stats, "num_tets", tets.size());
@@ -200,9 +196,28 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     push_stat(stats_labels, stats, "num_components", T.components.size());
     if (T.components.size() < 2) {
         for (size_t s = 0; s < shells.size(); ++s) arrangement_cells.push_back({s});
-    } else {
+    } else if (use_topo_ray_shooting) {
         topo_ray_shooting(pts, tets, cut_results, cut_result_index, iso_verts, iso_faces, patches, T.patch_of_face, shells,
             T.shell_of_half_patch, T.components, T.component_of_patch, arrangement_cells);
+    } else {
+        // cell grouping (src/implicit_arrangement.cpp:590-622): the maps of the second extract_iso_mesh overload
+        // come from the device (rin_tet_maps), the grouping itself is the reference's own code
+        std::vector<long long> global_vId_of_tet_vert;
+        std::vector<size_t> global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet;
+        std::string err;
+        if (!rin_host::fetch_tet_maps(tets.size(), global_vId_of_tet_vert, global_vId_start_index_of_tet,
+                iso_fId_of_tet_face, iso_fId_start_index_of_tet, err)) {
+            std::cout << err << std::endl;
+            return false;
+        }
+        std::vector<std::pair<size_t, size_t>> tet_cell_of_simp_cell;
+        std::vector<long long> simp_half_face_info;
+        std::vector<size_t> simp_hFace_start_index;
+        build_simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
+            global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet, T.patch_of_face,
+            T.shell_of_half_patch, tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
+        compute_simplicial_cell_connected_components(tet_cell_of_simp_cell, simp_half_face_info,
+            simp_hFace_start_index, arrangement_cells);
     }
     push_stat(stats_labels, stats, "num_cells", arrangement_cells.size());
     std::vector<bool> sample(n_func);

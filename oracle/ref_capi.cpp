@@ -11,6 +11,7 @@
 #include <simplicial_arrangement/simplicial_arrangement.h>
 
 #include "csg.h"
+#include "extract_mesh.h"
 #include "implicit_arrangement.h"
 #include "material_interface.h"
 
@@ -150,6 +151,67 @@ void* ref_ia_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
         for (bool b : row) cl.push_back(b ? 1 : 0);
     return bag;
 }
+
+#ifndef RIN_GPU_DROPIN // the drop-in library does not link the reference's extraction
+// The reference's cell-grouping extraction (second extract_iso_mesh overload, src/extract_mesh.cpp:268-566)
+// called directly: its inputs are produced here the way implicit_arrangement() produces them (active
+// function lists per tet, one arrangement per active tet), its maps are returned for the parity test of
+// rin_tet_maps.
+void* ref_ia_cellgroup_maps(const uint64_t* tets_in, uint64_t T, uint64_t V, const double* vals, uint32_t F)
+{
+    auto* bag = new ResultBag;
+    using simplicial_arrangement::Arrangement;
+    std::vector<std::array<size_t, 4>> tets(T);
+    for (uint64_t i = 0; i < T; ++i)
+        tets[i] = {tets_in[4 * i], tets_in[4 * i + 1], tets_in[4 * i + 2], tets_in[4 * i + 3]};
+    simplicial_arrangement::disable_lookup_table();
+    std::vector<size_t> func_in_tet, start_index_of_tet(1, 0), cut_result_index(T, Arrangement<3>::None);
+    std::vector<Arrangement<3>> cut_results;
+    size_t n1 = 0, n2 = 0, nm = 0;
+    try {
+        for (uint64_t i = 0; i < T; ++i) {
+            std::vector<simplicial_arrangement::Plane<double, 3>> planes;
+            for (uint32_t f = 0; f < F; ++f) {
+                int pos = 0, neg = 0;
+                for (int c = 0; c < 4; ++c) {
+                    const double x = vals[tets[i][c] * F + f];
+                    pos += x > 0;
+                    neg += x < 0;
+                }
+                if (pos == 4 || neg == 4) continue;
+                func_in_tet.push_back(f);
+                planes.push_back({vals[tets[i][0] * F + f], vals[tets[i][1] * F + f], vals[tets[i][2] * F + f],
+                    vals[tets[i][3] * F + f]});
+            }
+            start_index_of_tet.push_back(func_in_tet.size());
+            if (planes.empty()) continue;
+            cut_result_index[i] = cut_results.size();
+            cut_results.emplace_back(simplicial_arrangement::compute_arrangement(planes));
+            (planes.size() == 1 ? n1 : planes.size() == 2 ? n2 : nm)++;
+        }
+        std::vector<IsoVert> iso_verts;
+        std::vector<PolygonFace> iso_faces;
+        std::vector<long long> gv;
+        std::vector<size_t> gv_start, ff, ff_start;
+        extract_iso_mesh(n1, n2, nm, cut_results, cut_result_index, func_in_tet, start_index_of_tet, tets, iso_verts,
+            iso_faces, gv, gv_start, ff, ff_start);
+        auto& a = bag->i64["global_vId_of_tet_vert"];
+        for (auto x : gv) a.push_back(int64_t(x));
+        auto& b = bag->i64["global_vId_start_index_of_tet"];
+        for (auto x : gv_start) b.push_back(int64_t(x));
+        auto& c = bag->i64["iso_fId_of_tet_face"];
+        for (auto x : ff) c.push_back(x == Arrangement<3>::None ? -1 : int64_t(x));
+        auto& d = bag->i64["iso_fId_start_index_of_tet"];
+        for (auto x : ff_start) d.push_back(int64_t(x));
+        bag->i64["counts"] = {int64_t(iso_verts.size()), int64_t(iso_faces.size())};
+    } catch (std::exception& e) {
+        bag->error = e.what();
+    }
+    (void)V;
+    return bag;
+}
+
+#endif
 
 void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint64_t T,
     const double* vals, uint32_t F, uint32_t flags)

@@ -38,9 +38,10 @@ struct IsoScan
         for (int i = 0; i < (v >> 5); ++i) r += __popc(isov[i]);
         return r;
     }
-    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + nvi + nfw); }
+    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + nvi + nfw + 1); }
     __device__ void write(const IAComplex<Caps>& cx, uint32_t* w) const
     {
+        w[1 + nvi + nfw] = (uint32_t)cx.nf; // trailing word: faces of the whole complex (record_words.cuh)
         int p = 0;
         w[p++] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
         for (int v = 0; v < cx.nv; ++v)
@@ -113,10 +114,13 @@ struct WarpIso
         for (int i = 0; i < (v >> 5); ++i) r += __popc(isov[i]);
         return r;
     }
-    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + nvi + nfw); }
+    __device__ uint32_t size_bytes() const { return 4u * uint32_t(1 + nvi + nfw + 1); }
     __device__ void write(const IAComplex<Caps>& cx, uint32_t* w, int lane) const
     {
-        if (lane == 0) w[0] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
+        if (lane == 0) {
+            w[0] = (uint32_t)nvi | ((uint32_t)nfi << 8) | ((uint32_t)nfv << 16);
+            w[1 + nvi + nfw] = (uint32_t)cx.nf; // trailing word: faces of the whole complex
+        }
         for (int v = lane; v < cx.nv; v += 32)
             if ((isov[v >> 5] >> (v & 31)) & 1)
                 w[1 + rank(v)] = (uint32_t)v | ((uint32_t)cx.vp[v][0] << 8) | ((uint32_t)cx.vp[v][1] << 16) |

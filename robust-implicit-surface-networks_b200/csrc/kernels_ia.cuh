@@ -1325,6 +1325,101 @@ __global__ void __launch_bounds__(256) write_faces_kernel(const uint4* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cell-grouping maps (the second extract_iso_mesh overload, src/extract_mesh.cpp:268-566): for every
+// active tet, the global id of every local vertex of its complex (global_vId_of_tet_vert: iso-vertex id,
+// tet corners encoded -(grid vertex id)-1, :402,518) and the iso-face id of every local face
+// (iso_fId_of_tet_face, None when the face is not on an iso-surface, :529-556).
+// Local vertices 0..3 of a complex are the tet corners and never move; every other vertex was created
+// by an input plane and is an iso-vertex, so the record lists it.  The number of local faces is the
+// record's trailing word.  Pass 1 counts, a one-block scan makes the CRS offsets, pass 2 writes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tetmap_count_kernel(const uint32_t* __restrict__ rec_ref,
+    uint32_t n_active, const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena,
+    uint2* __restrict__ cnt)
+{
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(record_ptr(rec_ref[a], lut_blob, arena));
+        const int nv = r[0] & 255, nf = (r[0] >> 8) & 255;
+        int top = 4;
+        for (int i = 0; i < nv; ++i) top = max(top, (int)(r[1 + i] & 255) + 1);
+        const uint32_t* p = r + 1 + nv;
+        for (int q = 0; q < nf; ++q) p += rec_face_words((p[0] >> 24) & 127);
+        cnt[a] = make_uint2((uint32_t)top, p[0]);
+    }
+}
+
+// single-block exclusive scan of pairs; off has n + 1 entries
+__global__ void __launch_bounds__(1024) scan_pairs_kernel(const uint2* __restrict__ cnt, uint32_t n,
+    uint2* __restrict__ off)
+{
+    __shared__ uint32_t s_w[32][2];
+    __shared__ uint32_t s_run[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2) s_run[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint2 c = i < n ? cnt[i] : make_uint2(0, 0);
+        uint32_t x[2] = {c.x, c.y};
+        for (int o = 1; o < 32; o <<= 1)
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x[q], o);
+                if (lane >= o) x[q] += y;
+            }
+        if (lane == 31)
+            for (int q = 0; q < 2; ++q) s_w[warp][q] = x[q];
+        __syncthreads();
+        if (warp == 0)
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t t = s_w[lane][q];
+                uint32_t y = t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t z = __shfl_up_sync(0xffffffffu, y, o);
+                    if (lane >= o) y += z;
+                }
+                s_w[lane][q] = y - t;
+            }
+        __syncthreads();
+        if (i < n) off[i] = make_uint2(s_run[0] + s_w[warp][0] + x[0] - c.x, s_run[1] + s_w[warp][1] + x[1] - c.y);
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            for (int q = 0; q < 2; ++q) s_run[q] += s_w[31][q] + x[q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n] = make_uint2(s_run[0], s_run[1]);
+}
+
+// frep / fpos: face slot -> representative slot -> final face id (degenerate runs only, else nullptr)
+__global__ void __launch_bounds__(256) tetmap_write_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, uint32_t n_active, const uint32_t* __restrict__ rec_ref,
+    const uint4* __restrict__ offs, const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena,
+    const uint32_t* __restrict__ rep, const uint32_t* __restrict__ vid, const uint32_t* __restrict__ frep,
+    const uint4* __restrict__ fpos, const uint2* __restrict__ off, long long* __restrict__ vmap,
+    uint32_t* __restrict__ fmap)
+{
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(record_ptr(rec_ref[a], lut_blob, arena));
+        const int nv = r[0] & 255, nf = (r[0] >> 8) & 255;
+        const uint4 tv4 = __ldg(&tets[act_tet[a]]);
+        const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
+        const uint4 o = offs[a];
+        const uint2 b = off[a], e = off[a + 1];
+        for (int j = 0; j < 4; ++j) vmap[b.x + j] = -(long long)tv[j] - 1;
+        for (int i = 0; i < nv; ++i) {
+            const int local = r[1 + i] & 255;
+            if (local >= 4) vmap[b.x + local] = (long long)vid[rep[o.x + i]];
+        }
+        for (uint32_t f = b.y; f < e.y; ++f) fmap[f] = NONE32;
+        const uint32_t* p = r + 1 + nv;
+        for (int q = 0; q < nf; ++q) {
+            const uint32_t slot = o.y + q;
+            fmap[b.y + (p[0] & 0xffffu)] = frep ? fpos[frep[slot]].x : slot;
+            p += rec_face_words((p[0] >> 24) & 127);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Degenerate inputs only: iso-faces lying on a tet boundary are shared by two tets and are
 // deduplicated by (smallest, second smallest, largest) vertex id; the first tet keeps the face and
 // collects the (tet, local face) pairs of the others (src/extract_mesh.cpp:240-253,

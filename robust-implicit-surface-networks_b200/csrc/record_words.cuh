@@ -12,6 +12,8 @@ namespace rin {
 //   n_iso_verts words      local vertex id | plane0 << 8 | plane1 << 16 | plane2 << 24  (ascending)
 //   per iso face           local face id (16) | supporting plane << 16 | n << 24 | boundary << 31
 //                          followed by ceil(n/4) words of iso-vertex ranks, one byte each
+//   trailing word          number of faces of the WHOLE complex (read only by the cell-grouping maps,
+//                          src/extract_mesh.cpp:268-566; the extraction kernels stop before it)
 // boundary: the face lies on the tet boundary (negative_cell == None).
 // Plane ids: 0..3 simplex faces, 4+j the j-th active function of the tet.
 // ---------------------------------------------------------------------------------------------

@@ -142,6 +142,10 @@ struct rin_ctx
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
     DevBuf tmp_fverts, bfkeys, frep, fdup, fpos, bf_mask; // degenerate boundary-face dedup
+    DevBuf m_cnt, m_off, m_vmap, m_fmap;                  // cell-grouping maps (rin_tet_maps)
+    bool ia_bndry_faces = false;                          // last IA run took the boundary-face path
+    uint64_t m_nv = 0, m_nf = 0;
+    bool maps_ready = false;
     // outputs
     DevBuf v_tet, v_local, v_size, v_simplex, v_funcs, v_xyz, v_key;
     // sharded runs
@@ -239,7 +243,7 @@ void rin_destroy(rin_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->vmask16, &c->counters,
-        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs,
+        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs, &c->m_cnt, &c->m_off, &c->m_vmap, &c->m_fmap,
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
@@ -675,6 +679,73 @@ int robust_w(rin_ctx* c, int mode, RobustCounters* d_rc)
 } // extern "C++"
 
 // robust_test of the last run's active tets; out = {type1, type2, type3, tested}
+int rin_tet_maps(rin_ctx* c, uint64_t* n_active, uint64_t* n_vert_entries, uint64_t* n_face_entries)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->ran || c->last_mode != RIN_MODE_IA)
+        return fail(RIN_ERR_STATE, "rin_tet_maps: no finished implicit-arrangement run");
+    if (c->marked || c->finalized) return fail(RIN_ERR_STATE, "rin_tet_maps: not available after a sharded exchange");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet;
+    if (!c->maps_ready) {
+        CK(c->m_cnt.ensure((size_t)std::max(A, 1u) * 8));
+        CK(c->m_off.ensure((size_t)(A + 1) * 8));
+        uint2 tot = make_uint2(0, 0);
+        if (A) {
+            tetmap_count_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->rec_ref.as<uint32_t>(), A,
+                c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->m_cnt.as<uint2>());
+            scan_pairs_kernel<<<1, 1024, 0, s>>>(c->m_cnt.as<uint2>(), A, c->m_off.as<uint2>());
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&tot, c->m_off.as<uint2>() + A, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        } else
+            CK(cudaMemsetAsync(c->m_off.p, 0, 8, s));
+        c->m_nv = tot.x;
+        c->m_nf = tot.y;
+        CK(c->m_vmap.ensure(std::max<size_t>(tot.x, 1) * 8));
+        CK(c->m_fmap.ensure(std::max<size_t>(tot.y, 1) * 4));
+        if (A) {
+            tetmap_write_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->tets.as<uint4>(),
+                c->act_tet.as<uint32_t>(), A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(),
+                c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(),
+                c->ia_bndry_faces ? c->frep.as<uint32_t>() : nullptr, c->ia_bndry_faces ? c->fpos.as<uint4>() : nullptr,
+                c->m_off.as<uint2>(), c->m_vmap.as<long long>(), c->m_fmap.as<uint32_t>());
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(s));
+        }
+        c->maps_ready = true;
+    }
+    if (n_active) *n_active = A;
+    if (n_vert_entries) *n_vert_entries = c->m_nv;
+    if (n_face_entries) *n_face_entries = c->m_nf;
+    return RIN_OK;
+}
+
+int rin_download_tet_maps(rin_ctx* c, uint32_t* active_tets, uint32_t* vert_offsets, int64_t* vert_ids,
+    uint32_t* face_offsets, uint32_t* face_ids)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->maps_ready) return fail(RIN_ERR_STATE, "rin_download_tet_maps: call rin_tet_maps first");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet;
+    if (active_tets && A) CK(cudaMemcpyAsync(active_tets, c->act_tet.p, (size_t)A * 4, cudaMemcpyDeviceToHost, s));
+    if (vert_offsets || face_offsets) {
+        std::vector<uint2> off(A + 1);
+        CK(cudaMemcpyAsync(off.data(), c->m_off.p, (size_t)(A + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint32_t a = 0; a <= A; ++a) {
+            if (vert_offsets) vert_offsets[a] = off[a].x;
+            if (face_offsets) face_offsets[a] = off[a].y;
+        }
+    }
+    if (vert_ids && c->m_nv) CK(cudaMemcpyAsync(vert_ids, c->m_vmap.p, c->m_nv * 8, cudaMemcpyDeviceToHost, s));
+    if (face_ids && c->m_nf) CK(cudaMemcpyAsync(face_ids, c->m_fmap.p, c->m_nf * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return RIN_OK;
+}
+
 int rin_robust_test(rin_ctx* c, int mode, uint32_t out[4])
 {
     if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
@@ -1207,8 +1278,8 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         for (int attempt = 0;; ++attempt) {
             if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
             const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
-            const unsigned top0 = 4;
-            CK(cudaMemsetAsync(c->arena.p, 0, 4, s));
+            const unsigned top0 = 8; // the arena starts with an empty record (header + trailing word)
+            CK(cudaMemsetAsync(c->arena.p, 0, 8, s));
             CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
             // small tier: one tet per warp, complex in shared memory; capacity overflow -> ovf list
             general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
@@ -1409,6 +1480,8 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
     c->marked = c->finalized = false;
+    c->ia_bndry_faces = h.n_bndry_faces != 0;
+    c->maps_ready = false;
     c->n_local_verts = NV;
     c->n_own = NV;
     n.num_verts = NV;
@@ -1732,6 +1805,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
     c->marked = c->finalized = false;
+    c->maps_ready = false;
     c->n_local_verts = NV;
     c->n_own = NV;
     n.num_verts = NV;
@@ -1865,10 +1939,10 @@ int build_ia_tables(rin_ctx* c)
     GeneralCounters g0{};
     g0.n_general = NCH;
     g0.n_big = NCH;
-    g0.arena_top = 4;
+    g0.arena_top = 8;
     CKC(cudaMemcpyAsync(&dctr->gen, &g0, sizeof(g0), cudaMemcpyHostToDevice, s));
     CKC(d_arena.ensure((size_t)NCH * 256 + 4096));
-    CKC(cudaMemsetAsync(d_arena.p, 0, 4, s));
+    CKC(cudaMemsetAsync(d_arena.p, 0, 8, s));
     general_ia_big_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
         d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), &dctr->gen.n_big, d_vals.as<double>(), Vw,
         d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
@@ -1888,7 +1962,7 @@ int build_ia_tables(rin_ctx* c)
     // pack: blob = [empty record][records in (table, key) order]
     L.h_lut1.assign(16, LUT_MISS);
     L.h_lut2.assign(256 * 64, LUT_MISS);
-    L.h_blob.assign(4, 0);
+    L.h_blob.assign(8, 0); // empty record: header + trailing word
     std::map<int, uint32_t> order; // key (with table tag) -> witness
     for (uint32_t i = 0; i < NCH; ++i) order[chosen_key[i]] = chosen[i];
     for (auto& kv : order) {
@@ -1898,6 +1972,7 @@ int build_ia_tables(rin_ctx* c)
         const int nv = rw[0] & 255, nf = (rw[0] >> 8) & 255;
         uint32_t words = 1 + nv;
         for (int f = 0; f < nf; ++f) words += rec_face_words((rw[words] >> 24) & 127);
+        words += 1; // trailing word: faces of the whole complex
         const uint32_t sz = 4 * words;
         const uint32_t off = (uint32_t)L.h_blob.size() / 4;
         if (off >= LUT_MISS) {

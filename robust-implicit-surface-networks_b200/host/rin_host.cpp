@@ -284,4 +284,39 @@ bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<T
     return true;
 }
 
+bool fetch_tet_maps(size_t n_tets, std::vector<long long>& global_vId_of_tet_vert,
+    std::vector<size_t>& global_vId_start_index_of_tet, std::vector<size_t>& iso_fId_of_tet_face,
+    std::vector<size_t>& iso_fId_start_index_of_tet, std::string& error)
+{
+    if (!g_ctx) {
+        error = "no hot-path run";
+        return false;
+    }
+    uint64_t na = 0, nv = 0, nf = 0;
+    if (rin_tet_maps(g_ctx, &na, &nv, &nf) != RIN_OK) {
+        error = rin_last_error();
+        return false;
+    }
+    std::vector<uint32_t> act(na), voff(na + 1), foff(na + 1), fid(nf);
+    std::vector<int64_t> vidv(nv);
+    if (rin_download_tet_maps(g_ctx, act.data(), voff.data(), vidv.data(), foff.data(), fid.data()) != RIN_OK) {
+        error = rin_last_error();
+        return false;
+    }
+    global_vId_of_tet_vert.assign(vidv.begin(), vidv.end());
+    iso_fId_of_tet_face.resize(nf);
+    for (uint64_t i = 0; i < nf; ++i) iso_fId_of_tet_face[i] = widen(fid[i]);
+    // inactive tets have empty ranges (src/extract_mesh.cpp:329-330); active tets are in tet order
+    global_vId_start_index_of_tet.assign(n_tets + 1, 0);
+    iso_fId_start_index_of_tet.assign(n_tets + 1, 0);
+    uint64_t a = 0;
+    for (size_t t = 0; t < n_tets; ++t) {
+        const bool active = a < na && act[a] == t;
+        global_vId_start_index_of_tet[t + 1] = global_vId_start_index_of_tet[t] + (active ? voff[a + 1] - voff[a] : 0);
+        iso_fId_start_index_of_tet[t + 1] = iso_fId_start_index_of_tet[t] + (active ? foff[a + 1] - foff[a] : 0);
+        if (active) ++a;
+    }
+    return true;
+}
+
 } // namespace rin_host

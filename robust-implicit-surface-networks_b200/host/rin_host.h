@@ -68,4 +68,11 @@ bool robust_test_verdict(int mode, std::string& error);
 // an empty complex.  This is the lazy replacement of cut_results[cut_result_index[tet]].
 bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<TetComplex>& out, std::string& error);
 
+// Cell-grouping maps of the LAST implicit-arrangement call, in the shape the reference's second
+// extract_iso_mesh overload returns them (src/extract_mesh.cpp:268-566) and build_simplicial_cell_adjacency
+// consumes them (src/cell_connectivity.h:13-26): start arrays have n_tets + 1 entries.
+bool fetch_tet_maps(size_t n_tets, std::vector<long long>& global_vId_of_tet_vert,
+    std::vector<size_t>& global_vId_start_index_of_tet, std::vector<size_t>& iso_fId_of_tet_face,
+    std::vector<size_t>& iso_fId_start_index_of_tet, std::string& error);
+
 } // namespace rin_host

@@ -61,6 +61,8 @@ def lib():
         L.rin_set_values_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         L.rin_run.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
         L.rin_get_counts.argtypes = [C.c_void_p, C.POINTER(Counts)]
+        L.rin_tet_maps.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.rin_download_tet_maps.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.rin_download_mesh.argtypes = [C.c_void_p, C.POINTER(MeshOut)]
         L.rin_download_active.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rin_download_values.argtypes = [C.c_void_p, C.c_void_p]
@@ -253,6 +255,18 @@ class Context:
         self._check(lib().rin_get_complexes(self._h, mode, 0, ids.ctypes.data, len(ids), off.ctypes.data,
                                             words.ctypes.data, C.byref(n)))
         return off, words[:n.value]
+
+    def tet_maps(self):
+        """Cell-grouping maps of the last IA run (second extract_iso_mesh overload, src/extract_mesh.cpp:268-566)."""
+        na, nv, nf = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(lib().rin_tet_maps(self._h, C.byref(na), C.byref(nv), C.byref(nf)))
+        out = {"active_tets": np.zeros(na.value, np.uint32), "vert_offsets": np.zeros(na.value + 1, np.uint32),
+               "vert_ids": np.zeros(nv.value, np.int64), "face_offsets": np.zeros(na.value + 1, np.uint32),
+               "face_ids": np.zeros(nf.value, np.uint32)}
+        self._check(lib().rin_download_tet_maps(self._h, out["active_tets"].ctypes.data,
+                                                out["vert_offsets"].ctypes.data, out["vert_ids"].ctypes.data,
+                                                out["face_offsets"].ctypes.data, out["face_ids"].ctypes.data))
+        return out
 
     def robust_test(self, mode):
         out = np.zeros(4, np.uint32)

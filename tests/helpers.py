@@ -234,6 +234,18 @@ def ref_run(mode, pts, tets, vals, robust=False, lookup=True, secondary=True, ra
     return b
 
 
+def ref_cellgroup_maps(tets, vals, n_pts):
+    """The reference's own second extract_iso_mesh overload (src/extract_mesh.cpp:268-566) on these inputs."""
+    lib = ref_lib()
+    tets = np.ascontiguousarray(tets, np.uint64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    lib.ref_ia_cellgroup_maps.restype = C.c_void_p
+    lib.ref_ia_cellgroup_maps.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32]
+    h = lib.ref_ia_cellgroup_maps(tets.ctypes.data, len(tets), n_pts, vals.ctypes.data, vals.shape[1])
+    return Bag(lib, "ref", h, ["global_vId_of_tet_vert", "global_vId_start_index_of_tet", "iso_fId_of_tet_face",
+                               "iso_fId_start_index_of_tet", "counts"], [])
+
+
 def ref_csg(pts, tets, vals, expr, positive_inside=True, lib=None):
     """csg() of the reference with one of its test expressions (see oracle/ref_capi.cpp)."""
     lib = lib or ref_lib()

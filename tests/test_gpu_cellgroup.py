@@ -1,0 +1,83 @@
+"""rin_tet_maps vs the reference's own cell-grouping extraction (second extract_iso_mesh overload,
+src/extract_mesh.cpp:268-566), called directly in the hybrid reference library."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (load_funcs, make_funcs, orc_eval, orc_grid, ref_cellgroup_maps, ref_lib, synthetic_functions)
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_lib() is None, reason="hybrid reference not built")]
+
+
+@pytest.fixture()
+def ctx():
+    import rin_b200 as rin
+    c = rin.Context(0)
+    yield c
+    c.close()
+
+
+def expand(maps, T):
+    """active-tet CRS -> the reference's T+1-entry start arrays (inactive tets have empty ranges, :329-330)."""
+    out = {}
+    for kind in ("vert", "face"):
+        off = maps[kind + "_offsets"].astype(np.int64)
+        sizes = np.zeros(T, np.int64)
+        sizes[maps["active_tets"]] = off[1:] - off[:-1]
+        start = np.zeros(T + 1, np.int64)
+        np.cumsum(sizes, out=start[1:])
+        out[kind + "_start"] = start
+    ff = maps["face_ids"].astype(np.int64)
+    ff[ff == 0xFFFFFFFF] = -1
+    out["face_ids"] = ff
+    out["vert_ids"] = maps["vert_ids"]
+    return out
+
+
+def check(ctx, pts, tets, vals, **run_kw):
+    ctx.set_mesh(pts, tets)
+    ctx.set_values(vals)
+    cnt = ctx.run(**run_kw)
+    got = expand(ctx.tet_maps(), len(tets))
+    ref = ref_cellgroup_maps(tets, vals, len(pts))
+    assert ref.error == "", ref.error
+    assert ref["counts"].tolist() == [cnt.num_verts, cnt.num_faces]
+    assert np.array_equal(got["vert_start"], ref["global_vId_start_index_of_tet"])
+    assert np.array_equal(got["vert_ids"], ref["global_vId_of_tet_vert"])
+    assert np.array_equal(got["face_start"], ref["iso_fId_start_index_of_tet"])
+    assert np.array_equal(got["face_ids"], ref["iso_fId_of_tet_face"])
+    return cnt
+
+
+@pytest.mark.parametrize("cfg,R", [("C2", 16), ("C4", 24)])
+def test_maps_on_synthetic_configs(ctx, cfg, R):
+    pts, tets = orc_grid(R)
+    vals = orc_eval(make_funcs(synthetic_functions(cfg)), pts)
+    cnt = check(ctx, pts, tets, vals)
+    assert cnt.num_kmore > 0
+
+
+def test_maps_without_lookup_tables(ctx):
+    import rin_b200 as rin
+    pts, tets = orc_grid(10)
+    vals = orc_eval(make_funcs(synthetic_functions("C2")), pts)
+    check(ctx, pts, tets, vals, mode=rin.MODE_IA, flags=0)
+
+
+def test_maps_with_iso_faces_on_tet_boundaries(ctx):
+    """A plane through grid vertices: iso-vertices on tet corners (encoded -(id)-1, :518) and iso-faces shared by
+    two tets (deduplicated ids, :536-551)."""
+    pts, tets = orc_grid(8)
+    specs = [{"type": "plane", "point": [0.0, 0.0, 0.0], "normal": [1.0, 0.0, 0.0]},
+             {"type": "sphere", "center": [0.1, 0.05, -0.02], "radius": 0.6, "squared": True}]
+    vals = orc_eval(make_funcs(specs), pts)
+    cnt = check(ctx, pts, tets, vals)
+    assert cnt.num_degenerate_vertex > 0 and cnt.num_face_tets > cnt.num_faces
+
+
+def test_maps_on_reference_fixture(ctx):
+    funcs = load_funcs(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "functions", "3-sphere-1.json"))
+    pts, tets = orc_grid(12)
+    vals = orc_eval(funcs, pts)
+    check(ctx, pts, tets, vals)

@@ -116,3 +116,30 @@ def test_robust_test_mode_through_the_gpu_drop_in(grid101):
     b = ref_run("ia", pts, tets, vals, robust=True, lib=dropin_lib())
     assert b.error == "" and b["success"][0] == 1
     assert len(b["face_offsets"]) <= 1
+
+
+def nested_components_case():
+    """Four components (two disjoint spheres, a sphere nested inside one of them, a plane above): the cells cannot be
+    found from the shells alone, the nesting order has to be resolved (src/implicit_arrangement.cpp:573-622)."""
+    pts, tets = orc_grid(24)
+    specs = [{"type": "sphere", "center": [-0.45, 0.0, 0.0], "radius": 0.3, "squared": True},
+             {"type": "sphere", "center": [0.45, 0.1, 0.0], "radius": 0.32, "squared": True},
+             {"type": "sphere", "center": [0.5, 0.1, 0.05], "radius": 0.12, "squared": True},
+             {"type": "plane", "point": [0.0, 0.0, 0.6], "normal": [0.1, 0.0, 1.0]}]
+    return pts, tets, orc_eval(make_funcs(specs), pts)
+
+
+def test_cell_grouping_mode_through_the_gpu_drop_in():
+    """useTopoRayShooting = false: maps of the second extract_iso_mesh overload from the device
+    (rin_tet_maps), simplicial-cell grouping by the reference's own code; equal to the CPU reference in the same
+    mode, and the same number of cells as ray shooting (the reference's Fig. 14 differential check)."""
+    pts, tets, vals = nested_components_case()
+    gpu = ref_run("ia", pts, tets, vals, ray=False, lib=dropin_lib())
+    assert gpu.error == "" and gpu["success"][0] == 1
+    cpu = ref_run("ia", pts, tets, vals, ray=False)
+    assert gpu.stats["num_components"] == cpu.stats["num_components"] == 4
+    assert crs(gpu, "cells") == crs(cpu, "cells")
+    assert np.array_equal(gpu["cell_function_label"], cpu["cell_function_label"])
+    shot = ref_run("ia", pts, tets, vals, ray=True, lib=dropin_lib())
+    assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 5
+    assert sorted(map(sorted, crs(shot, "cells"))) == sorted(map(sorted, crs(gpu, "cells")))

@@ -224,3 +224,24 @@ def test_c4_dense_functions(ctx):
     cnt = ctx.run()
     assert cnt.num_kmore > cnt.num_k1
     compare_ia(ctx, ctx.download_mesh(), orc_run("ia", pts, tets, vals), cnt)
+
+
+def many_sheet_functions(n=24):
+    """n nearly parallel, closely spaced planes: every tet they cross sees all of them (k = n > the 20 functions
+    the shared-memory tiers hold) while the complexes stay small (the sheets do not meet inside a tet)."""
+    return [{"type": "plane", "point": [0.31 + 0.004 * j, 0.0, 0.0], "normal": [1.0, 0.013 * (j % 5), 0.007 * (j % 3)]}
+            for j in range(n)]
+
+
+def test_more_functions_than_the_shared_memory_tiers_hold(ctx):
+    """k = 24 active functions per tet: small tier (<= 4) and mid tier (<= 20) pass, the per-thread big tier runs."""
+    R = 4
+    funcs = make_funcs(many_sheet_functions(24))
+    pts, tets = orc_grid(R)
+    vals = orc_eval(funcs, pts)
+    port = orc_run("ia", pts, tets, vals)
+    ctx.generate_grid(R)
+    ctx.set_functions(funcs)
+    cnt = ctx.run()
+    assert cnt.num_kmore > 0 and cnt.num_active_funcs >= 24 * cnt.num_kmore // 2
+    compare_ia(ctx, ctx.download_mesh(), port, cnt)
