@@ -21,8 +21,9 @@
  *                              "extract mesh", "compute xyz" src/material_interface.cpp:53-447
  *                              + extract_MI_mesh()         src/extract_mesh.cpp:569-986
  *                              + compute_MI_vert_xyz()     src/extract_mesh.cpp:1541-1637
- *   rin_tet_maps               extract_iso_mesh(), cell-grouping overload: global_vId_of_tet_vert,
- *                              iso_fId_of_tet_face         src/extract_mesh.cpp:268-566
+ *   rin_tet_maps               extract_iso_mesh() / extract_MI_mesh(), cell-grouping overloads:
+ *                              global_vId_of_tet_vert, iso_fId_of_tet_face / MI_fId_of_tet_face
+ *                                                          src/extract_mesh.cpp:268-566, :988-1443
  *   rin_get_complexes          cut_results[cut_result_index[tet]] as consumed by
  *                              src/pair_faces.cpp:138-238, src/topo_ray_shooting.cpp:56-57
  */
@@ -154,12 +155,14 @@ int rin_num_stages(void);
 int rin_get_complexes(rin_ctx*, int mode, uint32_t flags, const uint64_t* tet_ids, uint64_t n,
                       uint64_t* offsets, uint32_t* words, uint64_t* n_words);
 
-/* ---- cell-grouping maps: the second extract_iso_mesh overload (src/extract_mesh.cpp:268-566) ----
- * For the last IA run, per ACTIVE tet a (in tet order; active_tets[a] is its tet id):
+/* ---- cell-grouping maps: the second extract_iso_mesh / extract_MI_mesh overloads
+ *      (src/extract_mesh.cpp:268-566, :988-1443) ----
+ * For the last run (either mode), per ACTIVE tet a (in tet order; active_tets[a] is its tet id):
  *   vert_ids[vert_offsets[a] + j]  = global_vId_of_tet_vert of local vertex j of the tet's complex: the
  *                                    iso-vertex id, or -(grid vertex id)-1 for a tet corner (:402,518)
  *   face_ids[face_offsets[a] + j]  = iso_fId_of_tet_face of local face j, UINT32_MAX when the face is not on
- *                                    an iso-surface (:529-556)
+ *                                    an iso-surface (:529-556); MI: MI_fId_of_tet_face, a boundary face that is a
+ *                                    material interface between two tie tets has the same id in both (:1391-1392)
  * (The reference's T+1-entry start arrays follow by giving inactive tets empty ranges, :329-330.)
  * rin_tet_maps computes them on the device and returns the sizes; rin_download_tet_maps copies them
  * (offset arrays have n_active + 1 entries; any pointer may be NULL).  Single-process runs only. */

@@ -238,10 +238,6 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     std::vector<std::string>& timing_labels, std::vector<double>& timings, std::vector<std::string>& stats_labels,
     std::vector<size_t>& stats)
 {
-    if (!robust_test && !use_topo_ray_shooting) {
-        std::cout << "GPU drop-in: the cell-grouping mode is not served by the device path" << std::endl;
-        return false;
-    }
     const size_t n_func = funcVals.cols();
     push_stat(stats_labels, stats, "num_pts", pts.size());
     push_stat(stats_labels, stats, "num_tets", tets.size());
@@ -298,9 +294,28 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     if (T.components.size() < 2) {
         for (size_t s = 0; s < shells.size(); ++s) material_cells.push_back({s});
         if (material_cells.empty()) material_cells.push_back({Mesh_None}); // no interface at all (:619-623)
-    } else {
+    } else if (use_topo_ray_shooting) {
         topo_ray_shooting(pts, tets, cut_results, cut_result_index, MI_verts, MI_faces, patches, T.patch_of_face, shells,
             T.shell_of_half_patch, T.components, T.component_of_patch, material_cells);
+    } else {
+        // cell grouping (src/material_interface.cpp:640-672): maps of the second extract_MI_mesh overload from
+        // the device (rin_tet_maps), the grouping itself is the reference's own code
+        std::vector<long long> global_vId_of_tet_vert;
+        std::vector<size_t> global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet;
+        std::string err;
+        if (!rin_host::fetch_tet_maps(tets.size(), global_vId_of_tet_vert, global_vId_start_index_of_tet,
+                MI_fId_of_tet_face, MI_fId_start_index_of_tet, err)) {
+            std::cout << err << std::endl;
+            return false;
+        }
+        std::vector<std::pair<size_t, size_t>> tet_cell_of_simp_cell;
+        std::vector<long long> simp_half_face_info;
+        std::vector<size_t> simp_hFace_start_index;
+        build_simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
+            global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet, T.patch_of_face,
+            T.shell_of_half_patch, tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
+        compute_simplicial_cell_connected_components(tet_cell_of_simp_cell, simp_half_face_info,
+            simp_hFace_start_index, material_cells);
     }
     push_stat(stats_labels, stats, "num_cells", material_cells.size());
     std::vector<double> sample(n_func);

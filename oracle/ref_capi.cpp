@@ -211,6 +211,55 @@ void* ref_ia_cellgroup_maps(const uint64_t* tets_in, uint64_t T, uint64_t V, con
     return bag;
 }
 
+// Material-interface analogue (second extract_MI_mesh overload, src/extract_mesh.cpp:988-1443); the active
+// material lists (material_in_tet / start_index_of_tet, src/material_interface.cpp:99-152) are passed in.
+void* ref_mi_cellgroup_maps(const uint64_t* tets_in, uint64_t T, const double* vals, uint32_t F,
+    const int64_t* material_in_tet_in, uint64_t n_mit, const int64_t* start_in)
+{
+    auto* bag = new ResultBag;
+    using simplicial_arrangement::MaterialInterface;
+    std::vector<std::array<size_t, 4>> tets(T);
+    for (uint64_t i = 0; i < T; ++i)
+        tets[i] = {tets_in[4 * i], tets_in[4 * i + 1], tets_in[4 * i + 2], tets_in[4 * i + 3]};
+    simplicial_arrangement::disable_lookup_table();
+    std::vector<size_t> material_in_tet(material_in_tet_in, material_in_tet_in + n_mit),
+        start_index_of_tet(start_in, start_in + T + 1), cut_result_index(T, MaterialInterface<3>::None);
+    std::vector<MaterialInterface<3>> cut_results;
+    size_t n2 = 0, n3 = 0, nm = 0;
+    try {
+        for (uint64_t i = 0; i < T; ++i) {
+            const size_t k = start_index_of_tet[i + 1] - start_index_of_tet[i];
+            if (k == 0) continue;
+            std::vector<simplicial_arrangement::Material<double, 3>> mats;
+            for (size_t j = 0; j < k; ++j) {
+                const size_t f = material_in_tet[start_index_of_tet[i] + j];
+                mats.push_back({vals[tets[i][0] * F + f], vals[tets[i][1] * F + f], vals[tets[i][2] * F + f],
+                    vals[tets[i][3] * F + f]});
+            }
+            cut_result_index[i] = cut_results.size();
+            cut_results.emplace_back(simplicial_arrangement::compute_material_interface(mats));
+            (k == 2 ? n2 : k == 3 ? n3 : nm)++;
+        }
+        std::vector<MI_Vert> verts;
+        std::vector<PolygonFace> faces;
+        std::vector<long long> gv;
+        std::vector<size_t> gv_start, ff, ff_start;
+        extract_MI_mesh(n2, n3, nm, cut_results, cut_result_index, material_in_tet, start_index_of_tet, tets, verts,
+            faces, gv, gv_start, ff, ff_start);
+        auto& a = bag->i64["global_vId_of_tet_vert"];
+        for (auto x : gv) a.push_back(int64_t(x));
+        auto& b = bag->i64["global_vId_start_index_of_tet"];
+        for (auto x : gv_start) b.push_back(int64_t(x));
+        auto& c = bag->i64["iso_fId_of_tet_face"];
+        for (auto x : ff) c.push_back(x == MaterialInterface<3>::None ? -1 : int64_t(x));
+        auto& d = bag->i64["iso_fId_start_index_of_tet"];
+        for (auto x : ff_start) d.push_back(int64_t(x));
+        bag->i64["counts"] = {int64_t(verts.size()), int64_t(faces.size())};
+    } catch (std::exception& e) {
+        bag->error = e.what();
+    }
+    return bag;
+}
 #endif
 
 void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint64_t T,

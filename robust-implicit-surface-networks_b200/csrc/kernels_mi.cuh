@@ -256,7 +256,8 @@ struct MIIsoScan
     }
     __device__ uint32_t size_bytes(bool gated) const
     {
-        return 4u * uint32_t(1 + 2 * nvi + nfw + (gated ? 1 + bf_words : 0));
+        // non-gated records end with the face count of the whole complex (gated ones list every face)
+        return 4u * uint32_t(1 + 2 * nvi + nfw + (gated ? 1 + bf_words : 1));
     }
     __device__ void write(const MIComplex<Caps>& cx, uint32_t* w, bool gated) const
     {
@@ -285,7 +286,10 @@ struct MIIsoScan
                     w[p++] = x;
                 }
             }
-        if (!gated) return;
+        if (!gated) {
+            w[p++] = (uint32_t)cx.nf; // trailing word (read by the cell-grouping maps only)
+            return;
+        }
         for (int f = 0; f < cx.nf; ++f)
             if (!cx.is_mi_face(f)) {
                 const int n = cx.flen[B][f];
@@ -765,7 +769,8 @@ __global__ void __launch_bounds__(256) mi_bface_keys_kernel(const uint4* __restr
 __global__ void __launch_bounds__(256) mi_bface_decide_kernel(uint4* __restrict__ face_hdr, uint32_t n,
     const uint32_t* __restrict__ frep, const uint32_t* __restrict__ ndup, const uint32_t* __restrict__ fv_ref,
     uint4* __restrict__ cand_pay, const uint32_t* __restrict__ bf_mask, const uint32_t* __restrict__ act_tet,
-    const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active, int W, unsigned* __restrict__ n_bad)
+    const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active, int W, unsigned* __restrict__ n_bad,
+    uint32_t* __restrict__ partner /* first visitor's slot -> the slot that carries the face */)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint4 h = face_hdr[i];
@@ -816,6 +821,7 @@ __global__ void __launch_bounds__(256) mi_bface_decide_kernel(uint4* __restrict_
         h.y &= ~FACE_INACTIVE;
         h.z = first | (mine << 16);
         face_hdr[i] = h;
+        partner[r] = i;
         const int nv = (h.y >> 16) & 255;
         for (int k = 0; k < nv; ++k) {
             const uint32_t c = fv_ref[h.w + k];
@@ -834,6 +840,97 @@ __global__ void __launch_bounds__(256) mi_face_keep_kernel(const uint4* __restri
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         keep[i] = (face_hdr[i].y & FACE_INACTIVE) ? NONE32 : i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cell-grouping maps, material-interface version (second extract_MI_mesh overload,
+// src/extract_mesh.cpp:988-1443): global_vId_of_tet_vert as for the arrangement (corners -(id)-1,
+// :1130,1259) and MI_fId_of_tet_face; a simplex-boundary face that became an interface between two tie
+// tets carries the same face id in BOTH tets (:1391-1392).
+// ---------------------------------------------------------------------------------------------
+struct MIRecView
+{
+    const uint32_t* verts; // nvi entries of 2 words
+    const uint32_t* faces; // interface faces
+    int nvi, nfi, n_bf, nf_total;
+    bool gated;
+};
+__device__ __forceinline__ MIRecView mi_rec_view(uint32_t ref, const uint8_t* lut_blob, const uint8_t* arena)
+{
+    const uint32_t* r = (ref & REF_GENERAL) ? reinterpret_cast<const uint32_t*>(arena) + (size_t)(ref & ~REF_FLAGS)
+                                            : reinterpret_cast<const uint32_t*>(lut_blob) + ref;
+    MIRecView v;
+    v.gated = (ref & REF_GATED) && (ref & ~REF_FLAGS);
+    const uint32_t hdr = v.gated ? r[1] : r[0];
+    v.nvi = hdr & 255;
+    v.nfi = (hdr >> 8) & 255;
+    v.verts = r + (v.gated ? 2 : 1);
+    v.faces = v.verts + 2 * v.nvi;
+    v.n_bf = v.gated ? (int)((r[0] >> 8) & 255) - v.nfi : 0;
+    v.nf_total = 0;
+    return v;
+}
+// end of the interface-face entries
+__device__ __forceinline__ const uint32_t* mi_rec_skip_faces(const MIRecView& v)
+{
+    const uint32_t* p = v.faces;
+    for (int q = 0; q < v.nfi; ++q) p += 1 + rec_face_words((p[0] >> 24) & 127);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) tetmap_mi_count_kernel(const uint32_t* __restrict__ rec_ref,
+    uint32_t n_active, const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena,
+    uint2* __restrict__ cnt)
+{
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        const MIRecView v = mi_rec_view(rec_ref[a], lut_blob, arena);
+        int top = 4;
+        for (int i = 0; i < v.nvi; ++i) top = max(top, (int)(v.verts[2 * i] & 255) + 1);
+        const uint32_t* p = mi_rec_skip_faces(v);
+        cnt[a] = make_uint2((uint32_t)top, v.gated ? (uint32_t)(v.nfi + v.n_bf) : p[0]);
+    }
+}
+
+// degenerate runs (frep != nullptr): frep[slot] = slot when the face was kept, fpos = its final position,
+// partner[slot] = the slot of the neighbouring tet that carries the shared boundary face
+__global__ void __launch_bounds__(256) tetmap_mi_write_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, uint32_t n_active, const uint32_t* __restrict__ rec_ref,
+    const uint4* __restrict__ offs, const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena,
+    const uint32_t* __restrict__ rep, const uint32_t* __restrict__ vid, const uint32_t* __restrict__ frep,
+    const uint4* __restrict__ fpos, const uint32_t* __restrict__ partner, const uint2* __restrict__ off,
+    long long* __restrict__ vmap, uint32_t* __restrict__ fmap)
+{
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
+        const MIRecView v = mi_rec_view(rec_ref[a], lut_blob, arena);
+        const uint4 tv4 = __ldg(&tets[act_tet[a]]);
+        const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
+        const uint4 o = offs[a];
+        const uint2 b = off[a], e = off[a + 1];
+        for (int j = 0; j < 4; ++j) vmap[b.x + j] = -(long long)tv[j] - 1;
+        for (int i = 0; i < v.nvi; ++i) {
+            const int local = v.verts[2 * i] & 255;
+            if (local >= 4) vmap[b.x + local] = (long long)vid[rep[o.x + i]];
+        }
+        for (uint32_t f = b.y; f < e.y; ++f) fmap[f] = NONE32;
+        auto final_id = [&](uint32_t slot) -> uint32_t {
+            if (!frep) return slot;
+            if (frep[slot] == slot) return fpos[slot].x;
+            const uint32_t q = partner[slot];
+            return (q != NONE32 && frep[q] == q) ? fpos[q].x : NONE32;
+        };
+        const uint32_t* p = v.faces;
+        for (int q = 0; q < v.nfi; ++q) {
+            const uint32_t local = p[0] & 0xffffu;
+            fmap[b.y + local] = final_id(o.y + (v.gated ? local : (uint32_t)q));
+            p += 1 + rec_face_words((p[0] >> 24) & 127);
+        }
+        for (int q = 0; q < v.n_bf; ++q) { // gated records: every simplex-boundary face has a slot
+            const uint32_t local = p[0] & 0xffffu;
+            const int n = (p[0] >> 24) & 127, g = (p[1] >> 16) & 255;
+            fmap[b.y + local] = final_id(o.y + local);
+            p += 2 + n + (g > 1 ? (g + 3) / 4 : 0);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -142,8 +142,8 @@ struct rin_ctx
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
     DevBuf tmp_fverts, bfkeys, frep, fdup, fpos, bf_mask; // degenerate boundary-face dedup
-    DevBuf m_cnt, m_off, m_vmap, m_fmap;                  // cell-grouping maps (rin_tet_maps)
-    bool ia_bndry_faces = false;                          // last IA run took the boundary-face path
+    DevBuf m_cnt, m_off, m_vmap, m_fmap, fpartner;        // cell-grouping maps (rin_tet_maps)
+    bool ia_bndry_faces = false;                          // last run took the boundary-face path
     uint64_t m_nv = 0, m_nf = 0;
     bool maps_ready = false;
     // outputs
@@ -243,7 +243,7 @@ void rin_destroy(rin_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->vmask16, &c->counters,
-        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs, &c->m_cnt, &c->m_off, &c->m_vmap, &c->m_fmap,
+        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs, &c->m_cnt, &c->m_off, &c->m_vmap, &c->m_fmap, &c->fpartner,
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
@@ -682,8 +682,9 @@ int robust_w(rin_ctx* c, int mode, RobustCounters* d_rc)
 int rin_tet_maps(rin_ctx* c, uint64_t* n_active, uint64_t* n_vert_entries, uint64_t* n_face_entries)
 {
     if (!c) return fail(RIN_ERR_ARG, "null ctx");
-    if (!c->ran || c->last_mode != RIN_MODE_IA)
-        return fail(RIN_ERR_STATE, "rin_tet_maps: no finished implicit-arrangement run");
+    if (!c->ran) return fail(RIN_ERR_STATE, "rin_tet_maps: no finished run");
+    const bool mi = c->last_mode == RIN_MODE_MI;
+    const uint8_t* blob = mi ? c->lut_mi.blob.as<uint8_t>() : c->lut_ia.blob.as<uint8_t>();
     if (c->marked || c->finalized) return fail(RIN_ERR_STATE, "rin_tet_maps: not available after a sharded exchange");
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
@@ -693,8 +694,12 @@ int rin_tet_maps(rin_ctx* c, uint64_t* n_active, uint64_t* n_vert_entries, uint6
         CK(c->m_off.ensure((size_t)(A + 1) * 8));
         uint2 tot = make_uint2(0, 0);
         if (A) {
-            tetmap_count_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->rec_ref.as<uint32_t>(), A,
-                c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->m_cnt.as<uint2>());
+            if (mi)
+                tetmap_mi_count_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->rec_ref.as<uint32_t>(), A,
+                    blob, c->arena.as<uint8_t>(), c->m_cnt.as<uint2>());
+            else
+                tetmap_count_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->rec_ref.as<uint32_t>(), A,
+                    blob, c->arena.as<uint8_t>(), c->m_cnt.as<uint2>());
             scan_pairs_kernel<<<1, 1024, 0, s>>>(c->m_cnt.as<uint2>(), A, c->m_off.as<uint2>());
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(&tot, c->m_off.as<uint2>() + A, 8, cudaMemcpyDeviceToHost, s));
@@ -706,11 +711,19 @@ int rin_tet_maps(rin_ctx* c, uint64_t* n_active, uint64_t* n_vert_entries, uint6
         CK(c->m_vmap.ensure(std::max<size_t>(tot.x, 1) * 8));
         CK(c->m_fmap.ensure(std::max<size_t>(tot.y, 1) * 4));
         if (A) {
-            tetmap_write_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->tets.as<uint4>(),
-                c->act_tet.as<uint32_t>(), A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(),
-                c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(),
-                c->ia_bndry_faces ? c->frep.as<uint32_t>() : nullptr, c->ia_bndry_faces ? c->fpos.as<uint4>() : nullptr,
-                c->m_off.as<uint2>(), c->m_vmap.as<long long>(), c->m_fmap.as<uint32_t>());
+            const uint32_t* frep = c->ia_bndry_faces ? c->frep.as<uint32_t>() : nullptr;
+            const uint4* fpos = c->ia_bndry_faces ? c->fpos.as<uint4>() : nullptr;
+            if (mi)
+                tetmap_mi_write_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->tets.as<uint4>(),
+                    c->act_tet.as<uint32_t>(), A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(), blob,
+                    c->arena.as<uint8_t>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), frep, fpos,
+                    c->fpartner.as<uint32_t>(), c->m_off.as<uint2>(), c->m_vmap.as<long long>(),
+                    c->m_fmap.as<uint32_t>());
+            else
+                tetmap_write_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->tets.as<uint4>(),
+                    c->act_tet.as<uint32_t>(), A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(), blob,
+                    c->arena.as<uint8_t>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), frep, fpos,
+                    c->m_off.as<uint2>(), c->m_vmap.as<long long>(), c->m_fmap.as<uint32_t>());
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(s));
         }
@@ -1713,9 +1726,11 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
                 c->ftable.as<uint32_t>(), t2 - 1, c->bids.as<uint32_t>());
             bface_reps_kernel<<<g, 256, 0, s>>>(c->ftable.as<uint32_t>(), c->bids.as<uint32_t>(), NFc,
                 c->frep.as<uint32_t>(), ndup);
+            CK(c->fpartner.ensure((size_t)NFc * 4));
+            CK(cudaMemsetAsync(c->fpartner.p, 0xff, (size_t)NFc * 4, s));
             mi_bface_decide_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
                 c->fv_ref.as<uint32_t>(), c->cand_pay.as<uint4>(), bf_mask, c->act_tet.as<uint32_t>(),
-                c->act_mask.as<uint32_t>(), c->act_cap, A, W, &dctr->n_unique);
+                c->act_mask.as<uint32_t>(), c->act_cap, A, W, &dctr->n_unique, c->fpartner.as<uint32_t>());
             // the activated corner candidates join the vertex table
             hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
                 c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
@@ -1805,6 +1820,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
     c->marked = c->finalized = false;
+    c->ia_bndry_faces = h.n_bndry_faces != 0;
     c->maps_ready = false;
     c->n_local_verts = NV;
     c->n_own = NV;
@@ -2108,6 +2124,7 @@ int build_mi_tables(rin_ctx* c)
         const int nv = rw[0] & 255, nf = (rw[0] >> 8) & 255;
         uint32_t words = 1 + 2 * nv;
         for (int f = 0; f < nf; ++f) words += 1 + rec_face_words((rw[words] >> 24) & 127);
+        words += 1; // trailing word: faces of the whole complex
         L.h_lut1[w] = (uint16_t)(L.h_blob.size() / 4);
         const uint8_t* r = reinterpret_cast<const uint8_t*>(rw);
         L.h_blob.insert(L.h_blob.end(), r, r + 4 * words);

@@ -246,6 +246,22 @@ def ref_cellgroup_maps(tets, vals, n_pts):
                                "iso_fId_start_index_of_tet", "counts"], [])
 
 
+def ref_mi_cellgroup_maps(tets, vals, material_in_tet, start_index_of_tet):
+    """The reference's own second extract_MI_mesh overload (src/extract_mesh.cpp:988-1443)."""
+    lib = ref_lib()
+    tets = np.ascontiguousarray(tets, np.uint64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    mit = np.ascontiguousarray(material_in_tet, np.int64)
+    st = np.ascontiguousarray(start_index_of_tet, np.int64)
+    lib.ref_mi_cellgroup_maps.restype = C.c_void_p
+    lib.ref_mi_cellgroup_maps.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                          C.c_void_p]
+    h = lib.ref_mi_cellgroup_maps(tets.ctypes.data, len(tets), vals.ctypes.data, vals.shape[1], mit.ctypes.data,
+                                  len(mit), st.ctypes.data)
+    return Bag(lib, "ref", h, ["global_vId_of_tet_vert", "global_vId_start_index_of_tet", "iso_fId_of_tet_face",
+                               "iso_fId_start_index_of_tet", "counts"], [])
+
+
 def ref_csg(pts, tets, vals, expr, positive_inside=True, lib=None):
     """csg() of the reference with one of its test expressions (see oracle/ref_capi.cpp)."""
     lib = lib or ref_lib()

@@ -81,3 +81,48 @@ def test_maps_on_reference_fixture(ctx):
     pts, tets = orc_grid(12)
     vals = orc_eval(funcs, pts)
     check(ctx, pts, tets, vals)
+
+
+# ---- material interface (second extract_MI_mesh overload, src/extract_mesh.cpp:988-1443) ----------------------
+
+def check_mi(ctx, pts, tets, vals):
+    import rin_b200 as rin
+    from helpers import orc_run, ref_mi_cellgroup_maps
+    port = orc_run("mi", pts, tets, vals)
+    assert port.error == ""
+    ctx.set_mesh(pts, tets)
+    ctx.set_values(vals)
+    cnt = ctx.run(rin.MODE_MI)
+    got = expand(ctx.tet_maps(), len(tets))
+    ref = ref_mi_cellgroup_maps(tets, vals, port["func_in_tet"], port["start_index_of_tet"])
+    assert ref.error == "", ref.error
+    assert ref["counts"].tolist() == [cnt.num_verts, cnt.num_faces]
+    assert np.array_equal(got["vert_start"], ref["global_vId_start_index_of_tet"])
+    assert np.array_equal(got["vert_ids"], ref["global_vId_of_tet_vert"])
+    assert np.array_equal(got["face_start"], ref["iso_fId_start_index_of_tet"])
+    assert np.array_equal(got["face_ids"], ref["iso_fId_of_tet_face"])
+    return cnt
+
+
+def test_mi_maps_on_c3(ctx):
+    pts, tets = orc_grid(16)
+    vals = orc_eval(make_funcs(synthetic_functions("C3")), pts)
+    cnt = check_mi(ctx, pts, tets, vals)
+    assert cnt.num_k2 > 0  # three-material tets: general kernel records
+
+
+@pytest.mark.parametrize("name", ["x_vs_negx", "sym_spheres"])
+def test_mi_maps_with_materials_tying_on_tet_faces(ctx, name):
+    """Boundary faces that are material interfaces carry the same face id in both tets (:1391-1392)."""
+    from test_gpu_mi import DEGENERATE
+    pts, tets = orc_grid(8)
+    vals = orc_eval(make_funcs(DEGENERATE[name]), pts)
+    check_mi(ctx, pts, tets, vals)
+
+
+def test_mi_maps_with_duplicate_materials(ctx):
+    pts, tets = orc_grid(10)
+    specs = synthetic_functions("C3")[:4]
+    specs.append(dict(specs[1]))  # an identical copy of a material
+    vals = orc_eval(make_funcs(specs), pts)
+    check_mi(ctx, pts, tets, vals)

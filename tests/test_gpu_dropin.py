@@ -143,3 +143,22 @@ def test_cell_grouping_mode_through_the_gpu_drop_in():
     shot = ref_run("ia", pts, tets, vals, ray=True, lib=dropin_lib())
     assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 5
     assert sorted(map(sorted, crs(shot, "cells"))) == sorted(map(sorted, crs(gpu, "cells")))
+
+
+def test_mi_cell_grouping_mode_through_the_gpu_drop_in():
+    """Material-interface analogue (src/material_interface.cpp:625-672): two components (a lone ball and two
+    overlapping balls in a zero background material)."""
+    pts, tets = orc_grid(20)
+    specs = [{"type": "zero"},
+             {"type": "sphere", "center": [-0.45, 0.03, 0.02], "radius": 0.3},
+             {"type": "sphere", "center": [0.45, 0.1, 0.0], "radius": 0.32},
+             {"type": "sphere", "center": [0.62, 0.1, 0.05], "radius": 0.3}]
+    vals = orc_eval(make_funcs(specs), pts)
+    gpu = ref_run("mi", pts, tets, vals, ray=False, lib=dropin_lib())
+    assert gpu.error == "" and gpu["success"][0] == 1
+    cpu = ref_run("mi", pts, tets, vals, ray=False)
+    assert gpu.stats["num_components"] == cpu.stats["num_components"] == 2
+    assert crs(gpu, "cells") == crs(cpu, "cells")
+    assert np.array_equal(gpu["cell_function_label"], cpu["cell_function_label"])
+    shot = ref_run("mi", pts, tets, vals, ray=True, lib=dropin_lib())
+    assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 4
