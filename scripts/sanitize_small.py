@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import rin_b200 as rin
 from helpers import make_funcs, synthetic_functions
 
-for cfg, mode, R in (("C2", rin.MODE_IA, 12), ("C3", rin.MODE_MI, 12), ("C4", rin.MODE_IA, 16)):
+for cfg, mode, R in (("C2", rin.MODE_IA, 12), ("C3", rin.MODE_MI, 12), ("C4", rin.MODE_IA, 20)):
     ctx = rin.Context(0)
     ctx.generate_grid(R)
     ctx.set_functions(make_funcs(synthetic_functions(cfg)))
