@@ -17,11 +17,6 @@ namespace rin {
 
 constexpr unsigned WFULL = 0xffffffffu;
 
-#ifndef RIN_RACY_LD
-// Byte fields two lanes touch at different indices of the same word / with benign overlap.
-#define RIN_RACY_LD(x) (x)
-#define RIN_RACY_ST(x, v) ((x) = (v))
-#endif
 
 __device__ __forceinline__ int warp_excl_scan(int x, int lane, int& total)
 {
@@ -295,7 +290,7 @@ __device__ int warp_add_plane(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc, int 
                 };
                 for (int k = 0; k < cl; ++k) {
                     const int f = cx.cf[co + k];
-                    const bool inward = (RIN_RACY_LD(cx.fpos[f]) == c);
+                    const bool inward = (cx.fpos[f] == c);
                     if (cx.fc_split[f]) {
                         const int ce = cx.fc_cut[f];
                         add_cut_edge(ce, cx.ev0[ce], cx.ev1[ce], inward, true);
@@ -382,23 +377,30 @@ __device__ int warp_add_plane(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc, int 
                 }
                 if (cur != first_a) chain_bad = 1;
             }
-            // the sub-cells' faces now border cp / cn instead of c (each face has c on one side only)
-            for (int k = 0; k < cx.clen[cp] - 1; ++k) {
-                const int f = cx.cf[cx.coff[cp] + k];
-                if (RIN_RACY_LD(cx.fpos[f]) == c)
-                    RIN_RACY_ST(cx.fpos[f], (uint8_t)cp);
-                else
-                    RIN_RACY_ST(cx.fneg[f], (uint8_t)cp);
-            }
-            for (int k = 0; k < cx.clen[cn] - 1; ++k) {
-                const int f = cx.cf[cx.coff[cn] + k];
-                if (RIN_RACY_LD(cx.fpos[f]) == c)
-                    RIN_RACY_ST(cx.fpos[f], (uint8_t)cn);
-                else
-                    RIN_RACY_ST(cx.fneg[f], (uint8_t)cn);
+            // which side of each sub-cell face is c: noted now (scratch pool, same positions as cf), written
+            // after the barrier, because a face shared with another split cell is updated by that lane too
+            for (int k = cx.coff[cp]; k < w; ++k) {
+                const int f = cx.cf[k];
+                sc.cf2[k] = (f != G && cx.fpos[f] == c) ? 1 : 0;
             }
         }
         if (__ballot_sync(WFULL, chain_bad != 0)) return warp_fail(cx, 2, lane);
+        __syncwarp();
+        if (split) {
+            // the sub-cells' faces now border cp / cn instead of c (each face has c on one side only)
+            const int r = __popc(ms & lt);
+            const int cp = nc + 2 * r, cn = cp + 1;
+            for (int half = 0; half < 2; ++half) {
+                const int d = half ? cn : cp;
+                for (int k = 0; k < cx.clen[d] - 1; ++k) {
+                    const int pos = cx.coff[d] + k, f = cx.cf[pos];
+                    if (sc.cf2[pos])
+                        cx.fpos[f] = (uint8_t)d;
+                    else
+                        cx.fneg[f] = (uint8_t)d;
+                }
+            }
+        }
         nc += 2 * cnt;
         nf += cnt;
         ncf += tot_cf;
@@ -528,13 +530,13 @@ template <class Caps>
 __device__ void warp_insert(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc, const double v[4], int lane)
 {
     __syncwarp();
-    if (cx.err) return;
-    const int pid = cx.np;
+    const int err0 = cx.err, pid = cx.np;
+    __syncwarp(); // every lane has read the state before lane 0 may change it
+    if (err0) return;
     if (pid >= Caps::MAXK + 4) {
         warp_fail(cx, 1, lane);
         return;
     }
-    __syncwarp();
     if (lane < 4) cx.plv[pid - 4][lane] = v[lane];
     if (lane == 0) cx.np = pid + 1;
     __syncwarp();

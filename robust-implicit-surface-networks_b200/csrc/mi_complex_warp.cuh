@@ -664,13 +664,13 @@ template <class Caps>
 __device__ void warp_insert_material(MIComplex<Caps>& cx, MIWarpScratch<Caps>& sc, const double v[4], int lane)
 {
     __syncwarp();
-    if (cx.err) return;
-    const int mid = cx.nm;
+    const int err0 = cx.err, mid = cx.nm;
+    __syncwarp(); // every lane has read the state before lane 0 may change it
+    if (err0) return;
     if (mid >= Caps::MAXK + 4) {
         mi_warp_fail(cx, 1, lane);
         return;
     }
-    __syncwarp();
     if (lane < 4) cx.mval[mid - 4][lane] = v[lane];
     if (lane == 0) cx.nm = mid + 1;
     __syncwarp();

@@ -170,7 +170,7 @@ int main(int argc, char** argv)
     const int n = argc > 1 ? std::atoi(argv[1]) : 2000;
     const unsigned seed = argc > 2 ? (unsigned)std::atoi(argv[2]) : 1u;
     int bad = 0;
-    bad += run<IACapsSmall>(n, seed, 4, "small tier caps (k<=4)");
+    bad += run<IACapsSmall>(n, seed, 6, "small tier caps (k<=6: more than the tier holds -> capacity path)");
     bad += run<IACapsMid>(n / 4 + 1, seed + 3, 10, "mid tier caps (k<=10)");
     bad += run<IACaps>(n / 4 + 1, seed + 7, 8, "big tier caps (k<=8)");
     return bad ? 1 : 0;

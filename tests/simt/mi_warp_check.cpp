@@ -145,7 +145,7 @@ int main(int argc, char** argv)
     const int n = argc > 1 ? std::atoi(argv[1]) : 2000;
     const unsigned seed = argc > 2 ? (unsigned)std::atoi(argv[2]) : 1u;
     int bad = 0;
-    bad += run<MICapsSmall>(n, seed, 5, "small tier caps (k<=5)");
+    bad += run<MICapsSmall>(n, seed, 7, "small tier caps (k<=7: more than the tier holds -> capacity path)");
     bad += run<MICaps>(n / 4 + 1, seed + 7, 9, "big tier caps (k<=9)");
     return bad ? 1 : 0;
 }

@@ -85,7 +85,3 @@ template <class T>
 inline T __shfl_up_sync(unsigned, T v, int d) { return simt_exchange(v, simt::t_lane - d); }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int d) { return simt_exchange(v, simt::t_lane ^ d); }
-
-// lane-disjoint byte fields that two lanes may touch concurrently (see ia_complex_warp.cuh)
-#define RIN_RACY_LD(x) __atomic_load_n(&(x), __ATOMIC_RELAXED)
-#define RIN_RACY_ST(x, v) __atomic_store_n(&(x), (v), __ATOMIC_RELAXED)
