@@ -135,8 +135,12 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(vals) / len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "implicit arrangement, tet5 grid 128^3 (bounded sample), 8 random "
-                                   "spheres+planes (seed 1)", "sample": last["sample"]},
+            "config": {"workload": "implicit arrangement, generated tet5 grid 128^3 (10485760 tets), 8 synthetic functions "
+                                   "of BASELINE config C2 (SURVEY 8(d) generator), lookup tables on",
+                       "baseline_config": "C2",
+                       "sample": last["sample"] + ("" if args.gpus == 1 else
+                                                   "; bounded sample of the %d-GPU weak-scaling workload (grid %d^3): its "
+                                                   "single-GPU instance" % (args.gpus, grid_resolution(args.gpus)))},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
