@@ -289,6 +289,7 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
     c->v_first = c->v_count = 0;
     c->have_values = false;
     c->ran = false;
+    c->maps_ready = false;
     return RIN_OK;
 }
 
@@ -312,6 +313,7 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     c->v_first = c->v_count = 0;
     c->have_values = false;
     c->ran = false;
+    c->maps_ready = false;
     return RIN_OK;
 }
 
