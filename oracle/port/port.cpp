@@ -277,8 +277,20 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
     };
     std::vector<size_t> gid;
     std::vector<char> is_iso_v, is_iso_f;
+    // maps of the cell-grouping overload (src/extract_mesh.cpp:268-566): same extraction, plus per tet the global
+    // id of every local vertex (tet corners as -(id)-1, :402,518) and the iso-face id of every local face (:529-556)
+    auto& tet_vmap = bag->i64["global_vId_of_tet_vert"];
+    auto& tet_vstart = bag->i64["global_vId_start_index_of_tet"];
+    auto& tet_fmap = bag->i64["iso_fId_of_tet_face"];
+    auto& tet_fstart = bag->i64["iso_fId_start_index_of_tet"];
+    tet_vstart.push_back(0);
+    tet_fstart.push_back(0);
     for (uint64_t t = 0; t < T; ++t) {
-        if (cut_index[t] == NONE64) continue;
+        if (cut_index[t] == NONE64) {
+            tet_vstart.push_back(int64_t(tet_vmap.size()));
+            tet_fstart.push_back(int64_t(tet_fmap.size()));
+            continue;
+        }
         const auto& ar = cuts[cut_index[t]];
         const uint64_t* tv = tets + 4 * t;
         const int64_t s0 = start[t];
@@ -304,7 +316,6 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
         // iso-vertices (:93-230)
         gid.assign(ar.vertices.size(), size_t(-1));
         for (size_t j = 0; j < ar.vertices.size(); ++j) {
-            if (!is_iso_v[j]) continue;
             std::array<int64_t, 3> fi = {NONE64, NONE64, NONE64};
             bool on_bndry[4] = {false, false, false, false};
             int nb = 0, ni = 0;
@@ -316,6 +327,12 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
                     ++nb;
                 }
             }
+            if (!is_iso_v[j] || nb == 3) { // a tet corner: the one not on the three boundary planes (:389-402,:518)
+                int corner = 0;
+                while (on_bndry[corner]) ++corner;
+                tet_vmap.push_back(-int64_t(tv[corner]) - 1);
+            }
+            if (!is_iso_v[j]) continue;
             // the minimal simplex containing the point = tet corners NOT on its boundary planes
             std::vector<uint64_t> corners;
             for (int c = 0; c < 4; ++c)
@@ -323,6 +340,7 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
             if (nb == 0) { // interior: never shared (:185-195), corners in tet order
                 gid[j] = new_vert(t + tet_first, j, 4,
                     {int64_t(tv[0]), int64_t(tv[1]), int64_t(tv[2]), int64_t(tv[3])}, fi);
+                tet_vmap.push_back(int64_t(gid[j]));
                 continue;
             }
             std::sort(corners.begin(), corners.end());
@@ -341,9 +359,12 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
                 new_vert(t + tet_first, j, int(corners.size()), sv, fstore);
             }
             gid[j] = ins.first->second;
+            if (nb != 3) tet_vmap.push_back(int64_t(gid[j]));
         }
+        tet_vstart.push_back(int64_t(tet_vmap.size()));
         // iso-faces (:232-261)
         for (size_t f = 0; f < ar.faces.size(); ++f) {
+            tet_fmap.push_back(NONE64);
             if (!is_iso_f[f]) continue;
             std::vector<int64_t> fv;
             for (size_t v : ar.faces[f].vertices) fv.push_back(int64_t(gid[v]));
@@ -363,14 +384,17 @@ void* orc_ia_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
                 if (!ins.second) {
                     face_tlist[ins.first->second].push_back(int64_t(t + tet_first));
                     face_tlist[ins.first->second].push_back(int64_t(f));
+                    tet_fmap.back() = int64_t(ins.first->second);
                     continue;
                 }
             }
+            tet_fmap.back() = int64_t(face_vlist.size());
             face_vlist.push_back(fv);
             face_tlist.push_back({int64_t(t + tet_first), int64_t(f)});
             ffunc.push_back(fn);
             ffunc.push_back(NONE64);
         }
+        tet_fstart.push_back(int64_t(tet_fmap.size()));
     }
     foff.push_back(0);
     ftoff.push_back(0);
@@ -588,10 +612,24 @@ void* orc_mi_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
     };
     // boundary-face matching state (:603-605): face key -> material label(s) of the first side
     std::map<std::array<int64_t, 3>, std::vector<int64_t>> open_bfaces;
+    std::map<std::array<int64_t, 3>, size_t> open_bface_slot; // ... and where its MI_fId_of_tet_face entry is
     std::vector<int64_t> lid;
     std::vector<char> is_mi_v, is_mi_f;
+    // maps of the cell-grouping overload (src/extract_mesh.cpp:988-1443): per tet the global id of every local
+    // vertex (tet corners as -(id)-1, :1130,1259) and the MI-face id of every local face; a boundary face that is
+    // an interface between two tets gets the id in both (:1391-1392)
+    auto& tet_vmap = bag->i64["global_vId_of_tet_vert"];
+    auto& tet_vstart = bag->i64["global_vId_start_index_of_tet"];
+    auto& tet_fmap = bag->i64["iso_fId_of_tet_face"];
+    auto& tet_fstart = bag->i64["iso_fId_start_index_of_tet"];
+    tet_vstart.push_back(0);
+    tet_fstart.push_back(0);
     for (uint64_t t = 0; t < T; ++t) {
-        if (cut_index[t] == NONE64) continue;
+        if (cut_index[t] == NONE64) {
+            tet_vstart.push_back(int64_t(tet_vmap.size()));
+            tet_fstart.push_back(int64_t(tet_fmap.size()));
+            continue;
+        }
         const auto& mi = cuts[cut_index[t]];
         const uint64_t* tv = tets + 4 * t;
         const int64_t s0 = start[t];
@@ -646,11 +684,16 @@ void* orc_mi_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
             }
             lid[j] = int64_t(ins.first->second);
         }
+        for (size_t j = 0; j < mi.vertices.size(); ++j)
+            tet_vmap.push_back((lid[j] >= 0 && vsize[lid[j]] == 1) ? -vsimplex0[lid[j]] - 1 : lid[j]);
+        tet_vstart.push_back(int64_t(tet_vmap.size()));
         for (size_t f = 0; f < mi.faces.size(); ++f) {
             const auto& face = mi.faces[f];
+            tet_fmap.push_back(NONE64);
             if (is_mi_f[f]) { // :823-832
                 std::vector<int64_t> fv;
                 for (size_t v : face.vertices) fv.push_back(lid[v]);
+                tet_fmap.back() = int64_t(face_vlist.size());
                 face_vlist.push_back(fv);
                 face_tlist.push_back({int64_t(tg), int64_t(f)});
                 ffunc.push_back(mat_in_tet[s0 + int64_t(face.positive_material_label) - 4]);
@@ -676,6 +719,7 @@ void* orc_mi_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
             auto it = open_bfaces.find(key);
             if (it == open_bfaces.end()) {
                 open_bfaces.emplace(key, labels);
+                open_bface_slot[key] = tet_fmap.size() - 1;
                 continue;
             }
             bool common = false;
@@ -685,6 +729,8 @@ void* orc_mi_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
                 open_bfaces.erase(it); // same material on both sides: not an interface
                 continue;
             }
+            tet_fmap.back() = int64_t(face_vlist.size());
+            tet_fmap[open_bface_slot[key]] = int64_t(face_vlist.size());
             // different materials on the two sides: the second tet emits the face (:952-981)
             std::vector<int64_t> fv;
             for (size_t k = 0; k < face.vertices.size(); ++k) {
@@ -709,6 +755,7 @@ void* orc_mi_run(const double* pts, uint64_t V, const uint64_t* tets_all, uint64
             ffunc.push_back(fidx >= 0 ? mat_in_tet[fidx] : NONE64);
             ffunc.push_back(mat_in_tet[s0 + int64_t(nl) - 4]);
         }
+        tet_fstart.push_back(int64_t(tet_fmap.size()));
     }
     auto& foff = bag->i64["face_offsets"];
     auto& fverts = bag->i64["face_verts"];

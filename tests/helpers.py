@@ -137,7 +137,9 @@ class Bag:
 
 
 MESH_I64 = ["stats", "face_offsets", "face_verts", "face_tet_offsets", "face_tets", "face_funcs"]
-PORT_I64 = MESH_I64 + ["func_in_tet", "start_index_of_tet", "vert_rec", "engine"]
+MAP_I64 = ["global_vId_of_tet_vert", "global_vId_start_index_of_tet", "iso_fId_of_tet_face",
+           "iso_fId_start_index_of_tet"]
+PORT_I64 = MESH_I64 + ["func_in_tet", "start_index_of_tet", "vert_rec", "engine"] + MAP_I64
 REF_I64 = MESH_I64 + ["success", "threw", "patches", "patches_offsets", "chains", "chains_offsets",
                       "shells", "shells_offsets", "cells", "cells_offsets", "patch_function_label",
                       "cell_function_label", "edges", "timing_label_bytes", "stats_label_bytes",

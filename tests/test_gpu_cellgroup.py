@@ -1,13 +1,15 @@
-"""rin_tet_maps vs the reference's own cell-grouping extraction (second extract_iso_mesh overload,
-src/extract_mesh.cpp:268-566), called directly in the hybrid reference library."""
+"""rin_tet_maps vs the oracle's restatement of the cell-grouping extraction (oracle/port/port.cpp; second
+extract_iso_mesh / extract_MI_mesh overloads, src/extract_mesh.cpp:268-566 and :988-1443) and,
+where the hybrid reference library is present, vs the reference's own functions called directly."""
 import os
 
 import numpy as np
 import pytest
 
-from helpers import (load_funcs, make_funcs, orc_eval, orc_grid, ref_cellgroup_maps, ref_lib, synthetic_functions)
+from helpers import (MAP_I64, load_funcs, make_funcs, orc_eval, orc_grid, orc_run, ref_cellgroup_maps, ref_lib,
+                     synthetic_functions)
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_lib() is None, reason="hybrid reference not built")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture()
@@ -35,18 +37,27 @@ def expand(maps, T):
     return out
 
 
+def compare_maps(got, bag):
+    """got: expand()-ed device maps; bag: oracle port run or reference function result (same four arrays)."""
+    assert bag.error == "", bag.error
+    assert np.array_equal(got["vert_start"], bag["global_vId_start_index_of_tet"])
+    assert np.array_equal(got["vert_ids"], bag["global_vId_of_tet_vert"])
+    assert np.array_equal(got["face_start"], bag["iso_fId_start_index_of_tet"])
+    assert np.array_equal(got["face_ids"], bag["iso_fId_of_tet_face"])
+
+
 def check(ctx, pts, tets, vals, **run_kw):
     ctx.set_mesh(pts, tets)
     ctx.set_values(vals)
     cnt = ctx.run(**run_kw)
     got = expand(ctx.tet_maps(), len(tets))
-    ref = ref_cellgroup_maps(tets, vals, len(pts))
-    assert ref.error == "", ref.error
-    assert ref["counts"].tolist() == [cnt.num_verts, cnt.num_faces]
-    assert np.array_equal(got["vert_start"], ref["global_vId_start_index_of_tet"])
-    assert np.array_equal(got["vert_ids"], ref["global_vId_of_tet_vert"])
-    assert np.array_equal(got["face_start"], ref["iso_fId_start_index_of_tet"])
-    assert np.array_equal(got["face_ids"], ref["iso_fId_of_tet_face"])
+    port = orc_run("ia", pts, tets, vals)
+    assert port["stats"][-2:].tolist() == [cnt.num_verts, cnt.num_faces]
+    compare_maps(got, port)
+    if ref_lib() is not None:
+        ref = ref_cellgroup_maps(tets, vals, len(pts))
+        assert ref["counts"].tolist() == [cnt.num_verts, cnt.num_faces]
+        compare_maps(got, ref)
     return cnt
 
 
@@ -94,13 +105,12 @@ def check_mi(ctx, pts, tets, vals):
     ctx.set_values(vals)
     cnt = ctx.run(rin.MODE_MI)
     got = expand(ctx.tet_maps(), len(tets))
-    ref = ref_mi_cellgroup_maps(tets, vals, port["func_in_tet"], port["start_index_of_tet"])
-    assert ref.error == "", ref.error
-    assert ref["counts"].tolist() == [cnt.num_verts, cnt.num_faces]
-    assert np.array_equal(got["vert_start"], ref["global_vId_start_index_of_tet"])
-    assert np.array_equal(got["vert_ids"], ref["global_vId_of_tet_vert"])
-    assert np.array_equal(got["face_start"], ref["iso_fId_start_index_of_tet"])
-    assert np.array_equal(got["face_ids"], ref["iso_fId_of_tet_face"])
+    assert port["stats"][-2:].tolist() == [cnt.num_verts, cnt.num_faces]
+    compare_maps(got, port)
+    if ref_lib() is not None:
+        ref = ref_mi_cellgroup_maps(tets, vals, port["func_in_tet"], port["start_index_of_tet"])
+        assert ref["counts"].tolist() == [cnt.num_verts, cnt.num_faces]
+        compare_maps(got, ref)
     return cnt
 
 
