@@ -327,6 +327,39 @@ def synthetic_functions(config):
             c = [0.1 * next(g) - 0.05 for _ in range(3)]
             r = 0.45 + 0.1 * next(g)
             specs.append({"type": "sphere", "center": c, "radius": r, "squared": True})
+    elif config == "C2cyl":
+        # SURVEY 8(d) cylinder swap: C2 with the spheres 0 and 4 replaced by cylinders (seed 11)
+        specs = synthetic_functions("C2")
+        g = splitmix64(11)
+        for f in (0, 4):
+            ap = [next(g) - 0.5 for _ in range(3)]
+            while True:
+                n = [2 * next(g) - 1 for _ in range(3)]
+                l2 = sum(x * x for x in n)
+                if 1e-6 < l2 <= 1.0:
+                    break
+            l = l2 ** 0.5
+            specs[f] = {"type": "cylinder", "axis_point": ap, "axis_vector": [x / l for x in n],
+                        "radius": 0.1 + 0.3 * next(g)}
+    elif config == "TOR":
+        # cylinders, tori, a plane and a sphere (every parametric type of the device evaluator; seed 12)
+        g = splitmix64(12)
+
+        def unit():
+            while True:
+                n = [2 * next(g) - 1 for _ in range(3)]
+                l2 = sum(x * x for x in n)
+                if 1e-6 < l2 <= 1.0:
+                    l = l2 ** 0.5
+                    return [x / l for x in n]
+        for f in range(3):
+            specs.append({"type": "torus", "center": [0.6 * next(g) - 0.3 for _ in range(3)], "axis_vector": unit(),
+                          "major_radius": 0.3 + 0.3 * next(g), "minor_radius": 0.08 + 0.1 * next(g)})
+        for f in range(2):
+            specs.append({"type": "cylinder", "axis_point": [next(g) - 0.5 for _ in range(3)], "axis_vector": unit(),
+                          "radius": 0.1 + 0.3 * next(g), "is_flipped": bool(f)})
+        specs.append({"type": "plane", "point": [0.1, -0.2, 0.05], "normal": unit()})
+        specs.append({"type": "sphere", "center": [0.0, 0.1, -0.1], "radius": 0.7, "squared": False})
     else:
         raise ValueError(config)
     return specs
