@@ -67,6 +67,7 @@ typedef struct rin_func_desc {
 } rin_func_desc;
 
 enum { RIN_MODE_IA = 0, RIN_MODE_MI = 1 };
+#define RIN_MAX_FUNCS 128 /* functions / materials per run (four 32-bit mask words per tet) */
 enum {
     RIN_FLAG_USE_LOOKUP = 1,           /* use_lookup            (src/implicit_arrangement.cpp:15) */
     RIN_FLAG_USE_SECONDARY_LOOKUP = 2, /* use_secondary_lookup  (:16, :38-40)                     */
@@ -119,7 +120,9 @@ int rin_set_mesh_host(rin_ctx*, const double* pts, uint64_t n_pts, const void* t
                       uint64_t n_tets, int index_bytes /* 4 or 8 */);
 /* generate_tet_mesh() on the device (same vertex and tet order as src/io.cpp:95-152) */
 int rin_generate_grid(rin_ctx*, uint32_t resolution, const double bbox_min[3], const double bbox_max[3]);
-/* restrict the run to tets [first, first+count) (slab sharding); count==0 means all */
+/* restrict the run to tets [first, first+count) (slab sharding).  count == RIN_TET_RANGE_ALL: up to the last
+ * tet; count == 0: an empty range (rin_run then returns an empty result); out-of-range -> RIN_ERR_ARG */
+#define RIN_TET_RANGE_ALL UINT64_MAX
 int rin_set_tet_range(rin_ctx*, uint64_t first, uint64_t count);
 
 /* function values: either parametric (evaluated on the device) ... */

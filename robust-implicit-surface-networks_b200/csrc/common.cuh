@@ -8,6 +8,13 @@ namespace rin {
 
 constexpr uint32_t NONE32 = 0xffffffffu;
 
+// per-tile totals / exclusive prefixes of the streaming filter (32 bytes): active tets, active functions
+// (CRS length), vertex candidates, faces, face-vertex entries
+struct TileTot
+{
+    unsigned act, funcs, cand, face, fv, pad0, pad1, pad2;
+};
+
 // ---------------------------------------------------------------------------------------------
 // Decoupled look-back over tiles for a PAIR of 31-bit partial sums packed with a 2-bit flag in
 // one 64-bit word, so that flag and value are published atomically.
@@ -88,6 +95,16 @@ __device__ __forceinline__ uint32_t hash4(uint4 k)
     h *= 0x2C1B3C6Du;
     h ^= h >> 12;
     return h;
+}
+
+// After the ranking pass of the implicit-arrangement pipeline a candidate's slot_of entry, or the table entry
+// of its slot, holds VID_FLAG | final vertex id.
+constexpr uint32_t VID_FLAG = 0x80000000u;
+__device__ __forceinline__ uint32_t final_vid(uint32_t c, const uint32_t* __restrict__ slot_of,
+    const uint32_t* __restrict__ table)
+{
+    const uint32_t s = slot_of[c];
+    return ((s & VID_FLAG) ? s : table[s]) & ~VID_FLAG;
 }
 
 __device__ __forceinline__ bool key_eq(uint4 a, uint4 b)

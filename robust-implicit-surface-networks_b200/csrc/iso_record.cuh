@@ -12,15 +12,18 @@ struct IsoScan
 {
     uint32_t isov[(Caps::MAXV + 31) / 32];
     int nvi, nfi, nfv, nfw; // nfw: words used by the face entries
+    int nbnd;               // iso faces on the tet boundary (negative_cell == None)
     __device__ void run(const IAComplex<Caps>& cx)
     {
         for (int i = 0; i < (Caps::MAXV + 31) / 32; ++i) isov[i] = 0;
         nfi = 0;
         nfv = 0;
         nfw = 0;
+        nbnd = 0;
         for (int f = 0; f < cx.nf; ++f)
             if (cx.is_iso_face(f)) {
                 ++nfi;
+                nbnd += (cx.fneg[f] == N8);
                 nfv += cx.flen[f];
                 if (cx.flen[f] > 127) nfv = 1 << 20; // loop too long for the record format -> capacity error
                 nfw += rec_face_words(cx.flen[f]);
@@ -73,18 +76,19 @@ struct WarpIso
 {
     static constexpr int NW = (Caps::MAXV + 31) / 32;
     uint32_t isov[NW]; // identical in all lanes after run()
-    int nvi, nfi, nfv, nfw;
+    int nvi, nfi, nfv, nfw, nbnd;
 
     __device__ void run(const IAComplex<Caps>& cx, int lane)
     {
 #pragma unroll
         for (int i = 0; i < NW; ++i) isov[i] = 0;
-        int lfi = 0, lfv = 0, lfw = 0;
+        int lfi = 0, lfv = 0, lfw = 0, lbnd = 0;
         bool toolong = false;
         for (int f = lane; f < cx.nf; f += 32)
             if (cx.is_iso_face(f)) {
                 const int n = cx.flen[f], off = cx.foff[f];
                 ++lfi;
+                lbnd += (cx.fneg[f] == N8);
                 lfv += n;
                 toolong |= n > 127;
                 lfw += (int)rec_face_words(n);
@@ -98,10 +102,12 @@ struct WarpIso
             lfi += __shfl_xor_sync(WFULL, lfi, d);
             lfv += __shfl_xor_sync(WFULL, lfv, d);
             lfw += __shfl_xor_sync(WFULL, lfw, d);
+            lbnd += __shfl_xor_sync(WFULL, lbnd, d);
 #pragma unroll
             for (int i = 0; i < NW; ++i) isov[i] |= __shfl_xor_sync(WFULL, isov[i], d);
         }
         nfi = lfi;
+        nbnd = lbnd;
         nfv = __ballot_sync(WFULL, toolong) ? (1 << 20) : lfv; // loop too long for the record format
         nfw = lfw;
         nvi = 0;

@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(256) eval_functions_kernel(const double* __res
                 P |= (val > 0 ? 1u : 0u) << (f & 31);
                 Nn |= (val < 0 ? 1u : 0u) << (f & 31);
             }
-            vmask[(size_t)w * V + v] = make_uint2(P, Nn);
-            if (vmask16) vmask16[v] = P | (Nn << 16);
+            if (vmask16)
+                vmask16[v] = P | (Nn << 16);
+            else
+                vmask[(size_t)w * V + v] = make_uint2(P, Nn);
             zeros += (fe - w * 32) - __popc(P | Nn);
         }
     }
@@ -177,8 +179,10 @@ __global__ void __launch_bounds__(256) ingest_values_kernel(const double* __rest
                 P |= (val > 0 ? 1u : 0u) << (f & 31);
                 Nn |= (val < 0 ? 1u : 0u) << (f & 31);
             }
-            vmask[(size_t)w * V + v] = make_uint2(P, Nn);
-            if (vmask16) vmask16[v] = P | (Nn << 16);
+            if (vmask16)
+                vmask16[v] = P | (Nn << 16);
+            else
+                vmask[(size_t)w * V + v] = make_uint2(P, Nn);
             zeros += (fe - w * 32) - __popc(P | Nn);
         }
     }
@@ -440,6 +444,8 @@ struct GeneralCounters
     unsigned err_tet;
     unsigned arena_overflow;
     unsigned n_ovf2;    // mid-tier capacity overflows (IA), re-queued for the per-thread big tier
+    unsigned n_bnd_faces; // iso faces on a tet boundary among the general records (degenerate inputs)
+    unsigned done_blocks; // last-block ticket of the big tier (tile scan in its tail)
 };
 
 constexpr uint32_t REF_GENERAL = 0x80000000u;
@@ -576,9 +582,11 @@ template <class Caps, int W>
 __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int skip = 0)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int skip = 0,
+    TileTot* __restrict__ tile_tot = nullptr, uint32_t tile_slots = 1)
 {
     // skip > 0: the complex already holds the arrangement of the first `skip` active functions
+    // tile_tot (nullable): per-tile output totals of the streaming filter; `a` is then a tile-local slot
     const uint4 tv = __ldg(&tets[act_tet[a]]);
     if (!skip) cx.init();
     int seen = 0;
@@ -618,6 +626,13 @@ __device__ bool general_ia_one(IAComplex<Caps>& cx, uint32_t a, const uint4* __r
     }
     iso.write(cx, reinterpret_cast<uint32_t*>(arena + off));
     rec_ref[a] = REF_GENERAL | (off >> 2);
+    if (tile_tot) {
+        TileTot* tt = tile_tot + a / tile_slots;
+        if (iso.nvi) atomicAdd(&tt->cand, (unsigned)iso.nvi);
+        if (iso.nfi) atomicAdd(&tt->face, (unsigned)iso.nfi);
+        if (iso.nfv) atomicAdd(&tt->fv, (unsigned)iso.nfv);
+        if (iso.nbnd) atomicAdd(&gc->n_bnd_faces, (unsigned)iso.nbnd);
+    }
     return true;
 }
 
@@ -626,7 +641,8 @@ template <class Caps, int W>
 __device__ bool general_ia_one_warp(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc, uint32_t a,
     const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask,
     uint32_t cap, const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int skip, int lane)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int skip, int lane,
+    TileTot* __restrict__ tile_tot = nullptr, uint32_t tile_slots = 1)
 {
     const uint4 tv = __ldg(&tets[act_tet[a]]);
     if (!skip) {
@@ -677,7 +693,16 @@ __device__ bool general_ia_one_warp(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc
         return true;
     }
     iso.write(cx, reinterpret_cast<uint32_t*>(arena + off), lane);
-    if (lane == 0) rec_ref[a] = REF_GENERAL | (off >> 2);
+    if (lane == 0) {
+        rec_ref[a] = REF_GENERAL | (off >> 2);
+        if (tile_tot) {
+            TileTot* tt = tile_tot + a / tile_slots;
+            if (iso.nvi) atomicAdd(&tt->cand, (unsigned)iso.nvi);
+            if (iso.nfi) atomicAdd(&tt->face, (unsigned)iso.nfi);
+            if (iso.nfv) atomicAdd(&tt->fv, (unsigned)iso.nfv);
+            if (iso.nbnd) atomicAdd(&gc->n_bnd_faces, (unsigned)iso.nbnd);
+        }
+    }
     return true;
 }
 
@@ -686,6 +711,7 @@ __device__ bool general_ia_one_warp(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc
 // dependency chain per tet is what sets its duration.
 constexpr int GEN_SMALL_WARPS = 4;
 constexpr int GEN_THREADS = 64;
+constexpr int GEN_BIG_THREADS = 128;
 // shared memory of one warp of the small tier: the complex and the re-packing scratch
 struct alignas(16) SmallSlot
 {
@@ -703,12 +729,13 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_ia_small_kernel(
     uint32_t* __restrict__ ovf_list, const IAComplex<IACapsSmall>* __restrict__ cx2,
     const uint16_t* __restrict__ lut2cx, const double* __restrict__ vals, uint32_t V,
     uint8_t* __restrict__ arena, uint32_t arena_cap, uint32_t* __restrict__ rec_ref,
-    GeneralCounters* __restrict__ gc)
+    GeneralCounters* __restrict__ gc, TileTot* __restrict__ tile_tot = nullptr, uint32_t tile_slots = 1,
+    uint32_t list_cap = 0xffffffffu)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
     SmallSlot* s_slot = reinterpret_cast<SmallSlot*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t n = gc->n_small;
+    const uint32_t n = min(gc->n_small, list_cap); // a list that outgrew its capacity is cut (the pass is repeated)
     IAComplex<IACapsSmall>& cx = s_slot[warp].cx;
     IAWarpScratch<IACapsSmall>& sc = s_slot[warp].sc;
     for (uint32_t g = blockIdx.x * GEN_SMALL_WARPS + warp; g < n; g += gridDim.x * GEN_SMALL_WARPS) {
@@ -761,7 +788,7 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_ia_small_kernel(
         }
         __syncwarp();
         if (!general_ia_one_warp<IACapsSmall, W>(cx, sc, a, tets, act_tet, act_mask, cap, vals, V, arena,
-                arena_cap, rec_ref, gc, false, skip, lane)) {
+                arena_cap, rec_ref, gc, false, skip, lane, tile_tot, tile_slots)) {
             if (lane == 0) ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
         }
         __syncwarp();
@@ -802,36 +829,160 @@ __global__ void __launch_bounds__(GEN_MID_WARPS * 32) general_ia_mid_kernel(cons
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ ovf_list, uint32_t* __restrict__ ovf2_list,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, TileTot* __restrict__ tile_tot = nullptr,
+    uint32_t tile_slots = 1, uint32_t list_cap = 0xffffffffu)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
     MidSlot* s_slot = reinterpret_cast<MidSlot*>(s_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nb = gc->n_big, n = nb + gc->n_ovf;
+    const uint32_t nb = min(gc->n_big, list_cap), n = nb + min(gc->n_ovf, list_cap);
     for (uint32_t g = blockIdx.x * GEN_MID_WARPS + warp; g < n; g += gridDim.x * GEN_MID_WARPS) {
         const uint32_t a = g < nb ? big_list[g] : ovf_list[g - nb];
         __syncwarp();
         if (!general_ia_one_warp<IACapsMid, W>(s_slot[warp].cx, s_slot[warp].sc, a, tets, act_tet, act_mask, cap,
-                vals, V, arena, arena_cap, rec_ref, gc, false, 0, lane)) {
+                vals, V, arena, arena_cap, rec_ref, gc, false, 0, lane, tile_tot, tile_slots)) {
             if (lane == 0) ovf2_list[atomicAdd(&gc->n_ovf2, 1u)] = a;
         }
         __syncwarp();
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan of the per-tile totals by ONE block (any multiple of 32 threads): every thread owns a run
+// of consecutive tiles.  Grand totals -> *totals; capacities are checked here so that the kernels behind
+// never write out of bounds: on overflow they do nothing and the host repeats the pass with larger buffers.
+// ---------------------------------------------------------------------------------------------
+struct PassTotals
+{
+    unsigned n_active, n_funcs, n_cand, n_faces, n_fv;
+};
+enum : unsigned {
+    OVF_LIST = 1u, // a general work list outgrew its capacity
+    OVF_ACT = 2u,  // active tets
+    OVF_CAND = 4u, // vertex candidates
+    OVF_FACE = 8u, // faces
+    OVF_FV = 16u,  // face-vertex entries
+};
+struct TileScanArgs
+{
+    const TileTot* tot;
+    uint32_t n_tiles;
+    TileTot* off; // n_tiles + 1 entries
+    PassTotals* totals;
+    uint32_t act_cap, cand_cap, face_cap, fv_cap;
+    unsigned* overflow;
+};
+
+__device__ void tile_scan_block(const TileScanArgs& S)
+{
+    __shared__ unsigned s_w[32][5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t per = (S.n_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(S.n_tiles, threadIdx.x * per), e = min(S.n_tiles, b + per);
+    unsigned c[5] = {0, 0, 0, 0, 0};
+    for (uint32_t t = b; t < e; ++t) {
+        const uint4 a = __ldcg(reinterpret_cast<const uint4*>(S.tot + t));
+        c[0] += a.x;
+        c[1] += a.y;
+        c[2] += a.z;
+        c[3] += a.w;
+        c[4] += __ldcg(&S.tot[t].fv);
+    }
+    unsigned x[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        x[q] = c[q];
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x[q], o);
+            if (lane >= o) x[q] += y;
+        }
+        if (lane == 31) s_w[warp][q] = x[q];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const unsigned t = lane < nwarps ? s_w[lane][q] : 0u;
+            unsigned y = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned z = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= o) y += z;
+            }
+            if (lane < nwarps) s_w[lane][q] = y - t;
+            if (lane == 31) {
+                unsigned o = 0;
+                if (q == 0) {
+                    S.totals->n_active = y;
+                    if (y > S.act_cap) o = OVF_ACT;
+                } else if (q == 1)
+                    S.totals->n_funcs = y;
+                else if (q == 2) {
+                    S.totals->n_cand = y;
+                    if (y > S.cand_cap) o = OVF_CAND;
+                } else if (q == 3) {
+                    S.totals->n_faces = y;
+                    if (y > S.face_cap) o = OVF_FACE;
+                } else {
+                    S.totals->n_fv = y;
+                    if (y > S.fv_cap) o = OVF_FV;
+                }
+                if (o) atomicOr(S.overflow, o);
+            }
+        }
+    }
+    __syncthreads();
+    unsigned run[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) run[q] = s_w[warp][q] + x[q] - c[q];
+    for (uint32_t t = b; t < e; ++t) {
+        uint4* o4 = reinterpret_cast<uint4*>(S.off + t);
+        o4[0] = make_uint4(run[0], run[1], run[2], run[3]);
+        o4[1] = make_uint4(run[4], 0, 0, 0);
+        const uint4 a = __ldcg(reinterpret_cast<const uint4*>(S.tot + t));
+        run[0] += a.x;
+        run[1] += a.y;
+        run[2] += a.z;
+        run[3] += a.w;
+        run[4] += __ldcg(&S.tot[t].fv);
+    }
+    if (threadIdx.x == blockDim.x - 1) { // owns the tail (possibly empty): run = grand totals
+        uint4* o4 = reinterpret_cast<uint4*>(S.off + S.n_tiles);
+        o4[0] = make_uint4(run[0], run[1], run[2], run[3]);
+        o4[1] = make_uint4(run[4], 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_tiles5_kernel(const TileScanArgs S)
+{
+    tile_scan_block(S);
+}
+
 // Big tier: complexes in per-thread local memory (what neither shared-memory tier could hold).
+// The last block to finish also runs the tile scan (S.tot non-null): all general records exist by then.
 template <int W>
-__global__ void __launch_bounds__(GEN_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
+__global__ void __launch_bounds__(GEN_BIG_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     const uint32_t* __restrict__ list, const unsigned* __restrict__ n_list,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, TileTot* __restrict__ tile_tot,
+    uint32_t tile_slots, const TileScanArgs S, uint32_t list_cap = 0xffffffffu)
 {
-    const uint32_t n = *n_list;
+    const uint32_t n = min(*n_list, list_cap);
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
         IAComplex<IACaps> cx;
         general_ia_one<IACaps, W>(cx, list[g], tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref,
-            gc, true);
+            gc, true, 0, tile_tot, tile_slots);
+    }
+    if (S.tot) {
+        __shared__ bool s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&gc->done_blocks, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            tile_scan_block(S);
+        }
     }
 }
 
@@ -1393,7 +1544,7 @@ __global__ void __launch_bounds__(1024) scan_pairs_kernel(const uint2* __restric
 __global__ void __launch_bounds__(256) tetmap_write_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, uint32_t n_active, const uint32_t* __restrict__ rec_ref,
     const uint4* __restrict__ offs, const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena,
-    const uint32_t* __restrict__ rep, const uint32_t* __restrict__ vid, const uint32_t* __restrict__ frep,
+    const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ table, const uint32_t* __restrict__ frep,
     const uint4* __restrict__ fpos, const uint2* __restrict__ off, long long* __restrict__ vmap,
     uint32_t* __restrict__ fmap)
 {
@@ -1407,7 +1558,7 @@ __global__ void __launch_bounds__(256) tetmap_write_kernel(const uint4* __restri
         for (int j = 0; j < 4; ++j) vmap[b.x + j] = -(long long)tv[j] - 1;
         for (int i = 0; i < nv; ++i) {
             const int local = r[1 + i] & 255;
-            if (local >= 4) vmap[b.x + local] = (long long)vid[rep[o.x + i]];
+            if (local >= 4) vmap[b.x + local] = (long long)final_vid(o.x + i, slot_of, table);
         }
         for (uint32_t f = b.y; f < e.y; ++f) fmap[f] = NONE32;
         const uint32_t* p = r + 1 + nv;

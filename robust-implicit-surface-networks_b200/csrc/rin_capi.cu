@@ -3,6 +3,7 @@
 // kernels_*.cuh.  There is no CPU fallback: without a CUDA device every entry point fails.
 #include "../../include/rin_b200.h"
 #include "kernels_mi.cuh"
+#include "pipeline_ia.cuh"
 #include "complexes.cuh"
 #include "exchange.cuh"
 
@@ -114,6 +115,8 @@ struct Counters
     GeneralCounters gen;
     ScanTotals scan;
     unsigned rank_tile, n_unique, n_bndry_faces, n_exact_classify, n_tie_faces;
+    unsigned overflow; // OVF_* bits of the implicit-arrangement pass
+    PassTotals tot;    // totals of the tile scan
     unsigned long long n_zero;
 };
 } // namespace
@@ -126,7 +129,9 @@ struct rin_ctx
     size_t smem_per_sm = 227 * 1024;
     // mesh
     uint64_t V = 0, T = 0;
-    DevBuf pts, tets;
+    uint32_t VS = 0;      // row stride of vals / vmask: V rounded up to 16 entries (128-byte rows)
+    uint32_t grid_R = 0;  // != 0: the mesh is generate_tet_mesh(grid_R) (structured filter, axis tables)
+    DevBuf pts, tets, axes;
     uint64_t t_first = 0, t_count = 0;
     // functions / values
     uint32_t F = 0;
@@ -138,6 +143,10 @@ struct rin_ctx
     DevBuf counters; // small zeroed block: FilterCounters | GeneralCounters | ScanTotals | misc
     DevBuf status;   // look-back status words
     DevBuf tl_tet, tl_mask, tile_cnt, tile_off; // tile-local filter output
+    DevBuf tl_ref, tile_tot, tile_pre;          // implicit-arrangement pass: record refs, tile totals / prefixes
+    // sizes learnt from the previous pass (0 = unknown: the next pass sizes its buffers after the tile scan)
+    uint32_t h_act = 0, h_list = 0, h_cand = 0, h_face = 0, h_fv = 0;
+    uint32_t table_size = 0; // vertex hash table slots of the last IA pass
     DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
     DevBuf cand_key, cand_pay, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
@@ -174,10 +183,23 @@ struct rin_ctx
     float total_ms = 0;
     uint32_t v_first = 0, v_count = 0; // vertex range touched by the tet range
     bool ran = false;
+    // snapshot of the inputs of the last successful run (what the download / introspection calls refer to)
+    uint32_t run_F = 0, run_VS = 0;
+    uint64_t run_V = 0, run_t_first = 0, run_t_count = 0;
+    int launches = 0; // kernels launched by the last rin_run
 };
 
 namespace {
 
+
+// every change of the inputs invalidates the results of the previous run (downloads then fail with
+// RIN_ERR_STATE instead of reading buffers sized for other inputs)
+void invalidate(rin_ctx* c)
+{
+    c->ran = false;
+    c->maps_ready = false;
+    c->marked = c->finalized = false;
+}
 
 int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8)
 {
@@ -225,14 +247,20 @@ int rin_create(int device, rin_ctx** out)
     CK(cudaSetDevice(device));
     auto* c = new rin_ctx;
     c->device = device;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    for (auto& ev : c->ev)
+        if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    for (auto& ev : c->kev)
+        if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaHostAlloc(&c->h_pinned, sizeof(Counters), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        rin_destroy(c); // frees whatever was created
+        return fail(RIN_ERR_CUDA, std::string("rin_create: ") + cudaGetErrorString(e));
+    }
     c->sm_count = prop.multiProcessorCount;
     c->smem_per_sm = prop.sharedMemPerMultiprocessor;
-    for (auto& e : c->ev) CK(cudaEventCreate(&e));
-    for (auto& e : c->kev) CK(cudaEventCreate(&e));
-    CK(cudaHostAlloc(&c->h_pinned, sizeof(Counters), cudaHostAllocDefault));
     *out = c;
     return RIN_OK;
 }
@@ -241,9 +269,9 @@ void rin_destroy(rin_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->vmask16, &c->counters,
-        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs, &c->m_cnt, &c->m_off, &c->m_vmap, &c->m_fmap, &c->fpartner,
+        &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->tl_ref, &c->tile_tot, &c->tile_pre, &c->axes, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs, &c->m_cnt, &c->m_off, &c->m_vmap, &c->m_fmap, &c->fpartner,
         &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
@@ -257,7 +285,7 @@ void rin_destroy(rin_ctx* c)
         if (e) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -283,13 +311,15 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
         CK(cudaGetLastError());
     }
     c->V = n_pts;
+    c->VS = (uint32_t)((n_pts + 15) & ~15ull);
+    c->grid_R = 0;
     c->T = n_tets;
     c->t_first = 0;
     c->t_count = n_tets;
     c->v_first = c->v_count = 0;
     c->have_values = false;
-    c->ran = false;
-    c->maps_ready = false;
+    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = 0;
+    invalidate(c);
     return RIN_OK;
 }
 
@@ -305,29 +335,38 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     grid_points_kernel<<<grid_for(V, 256, c->sm_count), 256, 0, c->stream>>>((uint32_t)N,
         make_double3(bmin[0], bmin[1], bmin[2]), make_double3(bmax[0], bmax[1], bmax[2]), c->pts.as<double>());
     grid_tets_kernel<<<grid_for(T, 256, c->sm_count), 256, 0, c->stream>>>(R, c->tets.as<uint4>());
+    // axis tables: the evaluation kernel of a generated grid reads these instead of the points
+    CK(c->axes.ensure(3 * N * 8));
+    grid_axes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>((uint32_t)N,
+        make_double3(bmin[0], bmin[1], bmin[2]), make_double3(bmax[0], bmax[1], bmax[2]), c->axes.as<double>());
     CK(cudaGetLastError());
     c->V = V;
+    c->VS = (uint32_t)((V + 15) & ~15ull);
+    c->grid_R = R;
     c->T = T;
     c->t_first = 0;
     c->t_count = T;
     c->v_first = c->v_count = 0;
     c->have_values = false;
-    c->ran = false;
-    c->maps_ready = false;
+    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = 0;
+    invalidate(c);
     return RIN_OK;
 }
 
 int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
 {
     if (!c) return fail(RIN_ERR_ARG, "null ctx");
-    if (count == 0) count = c->T - first;
-    if (first + count > c->T) return fail(RIN_ERR_ARG, "tet range out of bounds");
+    if (first > c->T) return fail(RIN_ERR_ARG, "tet range out of bounds");
+    if (count == RIN_TET_RANGE_ALL) count = c->T - first;
+    if (count > c->T - first) return fail(RIN_ERR_ARG, "tet range out of bounds");
     c->t_first = first;
-    c->t_count = count;
+    c->t_count = count; // 0: an empty range, rin_run then returns an empty result
     c->v_first = 0;
     c->v_count = 0;
     c->x_window = false;
-    if (first != 0 || count != c->T) {
+    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = 0;
+    invalidate(c);
+    if (count != 0 && (first != 0 || count != c->T)) {
         // vertex id range referenced by the tet range: only these vertices are evaluated
         CK(cudaSetDevice(c->device));
         CK(c->counters.ensure(sizeof(Counters)));
@@ -348,13 +387,14 @@ int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
 int rin_set_functions(rin_ctx* c, const rin_func_desc* funcs, uint32_t F)
 {
     if (!c || !funcs || F == 0) return fail(RIN_ERR_ARG, "rin_set_functions: bad argument");
-    if (F > 65534) return fail(RIN_ERR_ARG, "too many functions");
+    if (F > RIN_MAX_FUNCS) return fail(RIN_ERR_ARG, "more than 128 functions are not supported by this build");
     CK(cudaSetDevice(c->device));
     CK(c->funcs.ensure(F * sizeof(rin_func_desc)));
     CK(cudaMemcpyAsync(c->funcs.p, funcs, F * sizeof(rin_func_desc), cudaMemcpyHostToDevice, c->stream));
     c->F = F;
     c->have_funcs = true;
     c->have_values = false;
+    invalidate(c);
     return RIN_OK;
 }
 
@@ -362,13 +402,14 @@ int rin_set_values_host(rin_ctx* c, const double* vals, uint64_t n_pts, uint32_t
 {
     if (!c || !vals || F == 0) return fail(RIN_ERR_ARG, "rin_set_values_host: bad argument");
     if (n_pts != c->V) return fail(RIN_ERR_ARG, "rin_set_values_host: row count != number of points");
-    if (F > 65534) return fail(RIN_ERR_ARG, "too many functions");
+    if (F > RIN_MAX_FUNCS) return fail(RIN_ERR_ARG, "more than 128 functions are not supported by this build");
     CK(cudaSetDevice(c->device));
     CK(c->rowmajor.ensure(n_pts * F * 8));
     CK(cudaMemcpyAsync(c->rowmajor.p, vals, n_pts * F * 8, cudaMemcpyHostToDevice, c->stream));
     c->F = F;
     c->have_values = true;
     c->have_funcs = false;
+    invalidate(c);
     return RIN_OK;
 }
 
@@ -378,6 +419,17 @@ int rin_run(rin_ctx* c, int mode, uint32_t flags)
     if (c->T == 0 || c->V == 0) return fail(RIN_ERR_STATE, "rin_run: no mesh");
     if (!c->have_funcs && !c->have_values) return fail(RIN_ERR_STATE, "rin_run: no functions / values");
     CK(cudaSetDevice(c->device));
+    invalidate(c); // a failed run must not leave the previous run's results readable
+    auto snapshot = [&]() {
+        c->last_mode = mode;
+        c->last_flags = flags;
+        c->run_F = c->F;
+        c->run_V = c->V;
+        c->run_VS = c->VS;
+        c->run_t_first = c->t_first;
+        c->run_t_count = c->t_count;
+        c->ran = true;
+    };
     if (!(flags & RIN_FLAG_USE_LOOKUP)) flags &= ~RIN_FLAG_USE_SECONDARY_LOOKUP; // :38-40
     if (mode == RIN_MODE_IA) {
         if ((flags & RIN_FLAG_USE_LOOKUP) && !c->lut_ia.built) {
@@ -392,15 +444,10 @@ int rin_run(rin_ctx* c, int mode, uint32_t flags)
         case 4: rc = run_ia_w<4>(c, flags); break;
         default: return fail(RIN_ERR_ARG, "more than 128 functions are not supported by this build");
         }
-        if (rc == RIN_OK) {
-            c->last_mode = mode;
-            c->last_flags = flags;
-            c->ran = true;
-        }
+        if (rc == RIN_OK) snapshot();
         return rc;
     }
     if (mode == RIN_MODE_MI) {
-        if (c->F > 1023) return fail(RIN_ERR_ARG, "material interface: more than 1023 materials");
         if ((flags & RIN_FLAG_USE_LOOKUP) && !c->lut_mi.built) {
             int rc = build_mi_tables(c);
             if (rc) return rc;
@@ -413,11 +460,7 @@ int rin_run(rin_ctx* c, int mode, uint32_t flags)
         case 4: rc = run_mi_w<4>(c, flags); break;
         default: return fail(RIN_ERR_ARG, "more than 128 materials are not supported by this build");
         }
-        if (rc == RIN_OK) {
-            c->last_mode = mode;
-            c->last_flags = flags;
-            c->ran = true;
-        }
+        if (rc == RIN_OK) snapshot();
         return rc;
     }
     return fail(RIN_ERR_ARG, "rin_run: unknown mode");
@@ -461,7 +504,7 @@ int rin_download_active(rin_ctx* c, uint32_t* func_in_tet, uint64_t* start)
     if (!c) return fail(RIN_ERR_ARG, "null ctx");
     if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
     CK(cudaSetDevice(c->device));
-    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet, W = words_for(c->F);
+    const uint32_t A = (uint32_t)c->counts.num_intersecting_tet, W = words_for(c->run_F);
     std::vector<uint32_t> at(A), am((size_t)A * W);
     if (A) {
         CK(cudaMemcpyAsync(at.data(), c->act_tet.p, (size_t)A * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -472,9 +515,9 @@ int rin_download_active(rin_ctx* c, uint32_t* func_in_tet, uint64_t* start)
     CK(cudaStreamSynchronize(c->stream));
     // format conversion only: expand the compact (tet, mask) list into the reference's CRS arrays
     uint64_t pos = 0, a = 0;
-    for (uint64_t t = 0; t < c->t_count; ++t) {
+    for (uint64_t t = 0; t < c->run_t_count; ++t) {
         if (start) start[t] = pos;
-        if (a < A && at[a] == c->t_first + t) {
+        if (a < A && at[a] == c->run_t_first + t) {
             for (uint32_t w = 0; w < W; ++w) {
                 uint32_t m = am[(size_t)w * A + a];
                 while (m) {
@@ -487,7 +530,7 @@ int rin_download_active(rin_ctx* c, uint32_t* func_in_tet, uint64_t* start)
             ++a;
         }
     }
-    if (start) start[c->t_count] = pos;
+    if (start) start[c->run_t_count] = pos;
     return RIN_OK;
 }
 
@@ -496,11 +539,13 @@ int rin_download_values(rin_ctx* c, double* out)
     if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
     if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
     CK(cudaSetDevice(c->device));
-    std::vector<double> soa((size_t)c->V * c->F);
+    const uint64_t V = c->run_V, VS = c->run_VS;
+    const uint32_t F = c->run_F;
+    std::vector<double> soa((size_t)VS * F);
     CK(cudaMemcpyAsync(soa.data(), c->vals.p, soa.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (uint64_t v = 0; v < c->V; ++v)
-        for (uint32_t f = 0; f < c->F; ++f) out[v * c->F + f] = soa[(size_t)f * c->V + v];
+    for (uint64_t v = 0; v < V; ++v)
+        for (uint32_t f = 0; f < F; ++f) out[v * F + f] = soa[(size_t)f * VS + v];
     return RIN_OK;
 }
 
@@ -560,11 +605,11 @@ int get_complexes_w(rin_ctx* c, int mode, const uint32_t* d_req, uint32_t n, uin
     if (mode == RIN_MODE_IA)
         complexes_ia_kernel<W><<<grid_for(n, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
             c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
-            c->vals.as<double>(), (uint32_t)c->V, d_req, n, d_out, out_cap, d_span, d_cc);
+            c->vals.as<double>(), c->run_VS, d_req, n, d_out, out_cap, d_span, d_cc);
     else
         complexes_mi_kernel<W><<<grid_for(n, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
             c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
-            c->vals.as<double>(), (uint32_t)c->V, d_req, n, d_out, out_cap, d_span, d_cc);
+            c->vals.as<double>(), c->run_VS, d_req, n, d_out, out_cap, d_span, d_cc);
     CK(cudaGetLastError());
     return RIN_OK;
 }
@@ -580,7 +625,10 @@ int rin_get_complexes(rin_ctx* c, int mode, uint32_t, const uint64_t* tet_ids, u
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     std::vector<uint32_t> req(n);
-    for (uint64_t i = 0; i < n; ++i) req[i] = (uint32_t)tet_ids[i];
+    for (uint64_t i = 0; i < n; ++i) {
+        if (tet_ids[i] >= c->T) return fail(RIN_ERR_ARG, "rin_get_complexes: tet id out of range");
+        req[i] = (uint32_t)tet_ids[i];
+    }
     DevBuf d_req, d_span, d_cc;
     auto cleanup = [&]() {
         d_req.release();
@@ -605,7 +653,7 @@ int rin_get_complexes(rin_ctx* c, int mode, uint32_t, const uint64_t* tet_ids, u
         cudaMemsetAsync(d_cc.p, 0, sizeof(ComplexCounters), s);
         int rc = RIN_OK;
         if (n) {
-            switch (words_for(c->F)) {
+            switch (words_for(c->run_F)) {
             case 1: rc = get_complexes_w<1>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
             case 2: rc = get_complexes_w<2>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
             case 3: rc = get_complexes_w<3>(c, mode, d_req.as<uint32_t>(), (uint32_t)n, c->cx_out.as<uint32_t>(), (uint32_t)std::min<size_t>(cap_words, 0xffffffffu), d_span.as<uint2>(), d_cc.as<ComplexCounters>()); break;
@@ -669,11 +717,11 @@ int robust_w(rin_ctx* c, int mode, RobustCounters* d_rc)
     if (mode == RIN_MODE_IA)
         robust_test_kernel<W, false><<<grid_for(A, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
             c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
-            c->vals.as<double>(), (uint32_t)c->V, d_rc);
+            c->vals.as<double>(), c->run_VS, d_rc);
     else
         robust_test_kernel<W, true><<<grid_for(A, GEN_THREADS, c->sm_count, 4), GEN_THREADS, 0, c->stream>>>(
             c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A,
-            c->vals.as<double>(), (uint32_t)c->V, d_rc);
+            c->vals.as<double>(), c->run_VS, d_rc);
     CK(cudaGetLastError());
     return RIN_OK;
 }
@@ -724,7 +772,7 @@ int rin_tet_maps(rin_ctx* c, uint64_t* n_active, uint64_t* n_vert_entries, uint6
             else
                 tetmap_write_kernel<<<grid_for(A, 256, c->sm_count), 256, 0, s>>>(c->tets.as<uint4>(),
                     c->act_tet.as<uint32_t>(), A, c->rec_ref.as<uint32_t>(), c->offs.as<uint4>(), blob,
-                    c->arena.as<uint8_t>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), frep, fpos,
+                    c->arena.as<uint8_t>(), c->slot_of.as<uint32_t>(), c->table.as<uint32_t>(), frep, fpos,
                     c->m_off.as<uint2>(), c->m_vmap.as<long long>(), c->m_fmap.as<uint32_t>());
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(s));
@@ -770,7 +818,7 @@ int rin_robust_test(rin_ctx* c, int mode, uint32_t out[4])
     CK(d.ensure(sizeof(RobustCounters)));
     cudaMemsetAsync(d.p, 0, sizeof(RobustCounters), c->stream);
     int rc;
-    switch (words_for(c->F)) {
+    switch (words_for(c->run_F)) {
     case 1: rc = robust_w<1>(c, mode, d.as<RobustCounters>()); break;
     case 2: rc = robust_w<2>(c, mode, d.as<RobustCounters>()); break;
     case 3: rc = robust_w<3>(c, mode, d.as<RobustCounters>()); break;
@@ -1166,345 +1214,453 @@ int rin_debug_ia_tables(rin_ctx* c, const uint16_t** lut1, const uint16_t** lut2
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// One implicit-arrangement pass over tets [t_first, t_first + t_count).
+// One implicit-arrangement pass over tets [t_first, t_first + t_count): eight kernel launches
+// (pipeline_ia.cuh) and ONE host synchronisation when the buffer sizes are known from the previous
+// pass; the first pass over new inputs synchronises once more after the tile scan to size them.
 // ------------------------------------------------------------------------------------------------
 template <int W>
 int run_ia_w(rin_ctx* c, uint32_t flags)
 {
-    const uint32_t V = (uint32_t)c->V, F = c->F;
+    const uint32_t V = (uint32_t)c->V, VS = c->VS, F = c->F;
     const uint32_t T = (uint32_t)c->t_count, t_first = (uint32_t)c->t_first;
     const int use_lookup = (flags & RIN_FLAG_USE_LOOKUP) ? 1 : 0;
     const int use_secondary = (flags & RIN_FLAG_USE_SECONDARY_LOOKUP) ? 1 : 0;
     const int negate = (flags & RIN_FLAG_NEGATE) ? 1 : 0;
     cudaStream_t s = c->stream;
     const int sm = c->sm_count;
+    const bool grid = c->grid_R != 0;
+    const bool pack = (F <= 16);
+    c->launches = 0;
 
     CK(c->counters.ensure(sizeof(Counters)));
     Counters* dctr = c->counters.as<Counters>();
-    Counters h{};
-
-    // ---- K1: values + sign masks.  The vertex range is restricted to what the tet range can touch
-    // only for generated grids by the caller (rin_set_tet_range keeps all V by default).
-    CK(c->vals.ensure((size_t)V * F * 8));
-    CK(c->vmask.ensure((size_t)V * W * 8));
-    const bool pack = (F <= 16);
-    if (pack) CK(c->vmask16.ensure((size_t)V * 4));
-    uint32_t* vm16 = pack ? c->vmask16.as<uint32_t>() : nullptr;
-    CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
-    CK(cudaEventRecord(c->ev[ST_EVAL], s));
-    const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
-    CK(cudaEventRecord(c->kev[0], s));
-    if (c->have_funcs) {
-        size_t smem = F * sizeof(rin_func_desc);
-        if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eval_functions_kernel<<<grid_for(vc, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), vf, vc, V,
-            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16, &dctr->n_zero);
-    } else {
-        ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
-            negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16, &dctr->n_zero);
-    }
-    CK(cudaEventRecord(c->kev[1], s));
-    CK(cudaGetLastError());
-
-    // ---- K2: filter (tile-local compaction) + tile scan + ordered gather
-    CK(cudaEventRecord(c->ev[ST_FILTER], s));
-    const uint32_t n_tiles = (T + FILT_TILE - 1) / FILT_TILE;
-    const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
-    const size_t tl_stride = (size_t)n_tiles * FILT_TILE;
-    CK(c->tl_tet.ensure(tl_stride * 4));
-    CK(c->tl_mask.ensure(tl_stride * 4 * W));
-    CK(c->tile_cnt.ensure((size_t)n_tiles * 8));
-    CK(c->tile_off.ensure((size_t)(n_tiles + 1) * 8));
-    CK(cudaEventRecord(c->kev[2], s));
-    if (pack && W == 1)
-        filter_tiles_kernel<1, true><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
-            c->vmask.as<uint2>(), vm16, V, last_mask, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(), tl_stride,
-            c->tile_cnt.as<uint2>(), &dctr->filt);
-    else
-        filter_tiles_kernel<W, false><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
-            c->vmask.as<uint2>(), nullptr, V, last_mask, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
-            tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
-    CK(cudaEventRecord(c->kev[3], s));
-    scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
-    CK(cudaGetLastError());
     Counters* hp = static_cast<Counters*>(c->h_pinned);
-    CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    h = *hp;
-    const uint32_t A = h.filt.n_active;
-    c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 16 + 1024);
-    CK(c->act_tet.ensure((size_t)c->act_cap * 4));
-    CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
-    if (A) {
-        compact_active_kernel<W><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tl_tet.as<uint32_t>(),
-            c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, A, c->act_tet.as<uint32_t>(),
-            c->act_mask.as<uint32_t>(), c->act_cap);
-        CK(cudaGetLastError());
-    }
 
     rin_counts& n = c->counts;
     n = rin_counts{};
     n.num_pts = c->V;
     n.num_tets = c->t_count;
     n.num_funcs = F;
-    n.num_degenerate_vertex = h.n_zero;
-    n.num_intersecting_tet = A;
-    n.num_k1 = h.filt.n_k1;
-    n.num_k2 = h.filt.n_k2;
-    n.num_kmore = h.filt.n_kmore;
-    n.num_active_funcs = h.filt.n_funcs;
-
-    // ---- K3: classify
-    CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
-    CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
-    CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
-    CK(c->big_list.ensure((size_t)std::max(A, 1u) * 12)); // [big | small-tier overflow | mid-tier overflow]
-    CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
-    LutView lv{c->lut_ia.lut1.as<uint16_t>(), c->lut_ia.lut2.as<uint16_t>(), c->lut_ia.blob.as<uint8_t>(),
-        c->lut_ia.blob_bytes};
-    // without tables the blob is a single empty record so that offsets stay valid
-    if (A) {
-        classify_ia_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
-            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vmask.as<uint2>(),
-            c->vals.as<double>(), V, lv, use_lookup, use_secondary, c->rec_ref.as<uint32_t>(),
-            c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_exact_classify,
-            nullptr);
-        CK(cudaGetLastError());
+    c->ia_bndry_faces = false;
+    c->n_local_verts = c->n_own = 0;
+    if (T == 0) { // empty tet range: a valid empty result
+        CK(c->f_off.ensure(4));
+        CK(c->f_toff.ensure(4));
+        CK(cudaMemsetAsync(c->f_off.p, 0, 4, s));
+        CK(cudaMemsetAsync(c->f_toff.p, 0, 4, s));
+        CK(cudaStreamSynchronize(s));
+        for (auto& x : c->stage_ms) x = 0;
+        c->kernel_ms[0] = c->kernel_ms[1] = c->total_ms = 0;
+        return RIN_OK;
     }
 
-    // ---- K4: general kernels (arena grows on overflow) + K5a: counts and offsets
-    CK(cudaEventRecord(c->ev[ST_GENERAL], s));
-    const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
-    if (A) {
-        const uint32_t est =
-            use_lookup ? (use_secondary ? h.filt.n_kmore : h.filt.n_kmore + h.filt.n_k2) : A;
+    // ---- buffers whose size depends on the inputs only
+    CK(c->vals.ensure((size_t)VS * F * 8));
+    if (pack)
+        CK(c->vmask16.ensure((size_t)V * 4));
+    else
+        CK(c->vmask.ensure((size_t)VS * W * 8));
+    uint32_t* vm16 = pack ? c->vmask16.as<uint32_t>() : nullptr;
+    const uint32_t tile_slots = (uint32_t)filter_tile_slots(W, grid);
+    const uint32_t tile_units = (uint32_t)filter_rounds(W, grid) * 256u;
+    const uint32_t c_first = grid ? t_first / 5 : 0;
+    const uint32_t n_units = grid ? ((t_first + T - 1) / 5 - c_first + 1) : T;
+    const uint32_t n_tiles = (n_units + tile_units - 1) / tile_units;
+    const size_t tl_stride = (size_t)n_tiles * tile_slots;
+    CK(c->tl_tet.ensure(tl_stride * 4));
+    CK(c->tl_mask.ensure(tl_stride * 4 * W));
+    CK(c->tl_ref.ensure(tl_stride * 4));
+    CK(c->tile_tot.ensure((size_t)n_tiles * sizeof(TileTot)));
+    CK(c->tile_pre.ensure((size_t)(n_tiles + 1) * sizeof(TileTot)));
+    const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
+    const size_t small_smem = GEN_SMALL_WARPS * sizeof(SmallSlot);
+    const size_t mid_smem = GEN_MID_WARPS * sizeof(MidSlot);
+    const int mid_per_sm = (int)std::max<size_t>(1, c->smem_per_sm / (mid_smem + 1024));
+    if (mid_smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
+    CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        (int)cudaSharedmemCarveoutMaxShared));
+    if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
+
+    Counters h{};
+    bool evaluated = false;
+    unsigned long long n_zero = 0; // counted by the evaluation kernel, which runs in the first attempt only
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 5) return fail(RIN_ERR_STATE, "implicit arrangement: buffer sizing did not converge");
+        const bool sizing = (c->h_act == 0); // sizes unknown: one extra synchronisation after the tile scan
+        const uint32_t list_cap = std::max<uint32_t>(c->h_list, 4096);
+        CK(c->general_list.ensure((size_t)list_cap * 4));
+        CK(c->big_list.ensure((size_t)list_cap * 12)); // [big | small-tier overflow | mid-tier overflow]
+        uint32_t act_cap = 0, cand_cap = 0, face_cap = 0, fv_cap = 0, tsize = 0;
+        auto size_outputs = [&]() -> int {
+            act_cap = c->h_act;
+            cand_cap = c->h_cand;
+            face_cap = c->h_face;
+            fv_cap = c->h_fv;
+            c->act_cap = std::max(c->act_cap, act_cap);
+            CK(c->act_tet.ensure((size_t)c->act_cap * 4));
+            CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
+            CK(c->rec_ref.ensure((size_t)c->act_cap * 4));
+            CK(c->offs.ensure((size_t)c->act_cap * 16));
+            CK(c->status.ensure(((size_t)act_cap / RV_TILE + 2) * 8 + 64));
+            CK(c->cand_key.ensure((size_t)cand_cap * 16));
+            CK(c->slot_of.ensure((size_t)cand_cap * 4));
+            tsize = 1024;
+            while (tsize < 2ull * cand_cap) tsize <<= 1;
+            CK(c->table.ensure((size_t)tsize * 4));
+            CK(c->v_tet.ensure((size_t)cand_cap * 4));
+            CK(c->v_local.ensure(cand_cap));
+            CK(c->v_size.ensure(cand_cap));
+            CK(c->v_simplex.ensure((size_t)cand_cap * 16));
+            CK(c->v_funcs.ensure((size_t)cand_cap * 16));
+            CK(c->v_xyz.ensure((size_t)cand_cap * 24));
+            CK(c->v_key.ensure((size_t)cand_cap * 16));
+            CK(c->f_off.ensure((size_t)(face_cap + 1) * 4));
+            CK(c->f_toff.ensure((size_t)(face_cap + 1) * 4));
+            CK(c->f_tets.ensure((size_t)face_cap * 8));
+            CK(c->f_funcs.ensure((size_t)face_cap * 8));
+            CK(c->f_verts.ensure((size_t)fv_cap * 4));
+            return RIN_OK;
+        };
+        if (!sizing) {
+            int rc = size_outputs();
+            if (rc) return rc;
+        }
+
+        CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
+        const unsigned top0 = 8; // the arena starts with an empty record (header + trailing word)
+        CK(cudaMemsetAsync(c->arena.p, 0, 8, s));
+        CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
+
+        // ---- K1: values + sign masks (only the vertex range the tet range touches)
+        CK(cudaEventRecord(c->ev[ST_EVAL], s));
+        CK(cudaEventRecord(c->kev[0], s));
+        if (!evaluated) {
+            const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
+            if (c->have_funcs) {
+                const size_t smem = F * sizeof(rin_func_desc);
+                const int g = grid_for((vc + EV_VPT - 1) / EV_VPT, 256, sm, 8);
+                if (grid)
+                    eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1, vf, vc, VS,
+                        c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16,
+                        &dctr->n_zero);
+                else
+                    eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, vf, vc, VS,
+                        c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16,
+                        &dctr->n_zero);
+            } else {
+                ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, VS, F,
+                    negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16, &dctr->n_zero);
+            }
+            CK(cudaGetLastError());
+            ++c->launches;
+        }
+        CK(cudaEventRecord(c->kev[1], s));
+
+        // ---- K2: filter + dispatch
+        CK(cudaEventRecord(c->ev[ST_FILTER], s));
+        FilterArgs fa{};
+        fa.tets = grid ? nullptr : c->tets.as<uint4>();
+        fa.R = c->grid_R;
+        fa.t_first = t_first;
+        fa.t_count = T;
+        fa.c_first = c_first;
+        fa.n_units = n_units;
+        fa.vmask = c->vmask.as<uint2>();
+        fa.vmask16 = vm16;
+        fa.VS = VS;
+        fa.last_mask = last_mask;
+        fa.vals = c->vals.as<double>();
+        fa.lut1 = c->lut_ia.lut1.as<uint16_t>();
+        fa.lut2 = c->lut_ia.lut2.as<uint16_t>();
+        fa.blob32 = c->lut_ia.blob.as<uint32_t>();
+        fa.use_lookup = use_lookup;
+        fa.use_secondary = use_secondary;
+        fa.tl_tet = c->tl_tet.as<uint32_t>();
+        fa.tl_mask = c->tl_mask.as<uint32_t>();
+        fa.tl_ref = c->tl_ref.as<uint32_t>();
+        fa.tl_stride = tl_stride;
+        fa.tile_tot = c->tile_tot.as<TileTot>();
+        fa.small_list = c->general_list.as<uint32_t>();
+        fa.big_list = c->big_list.as<uint32_t>();
+        fa.list_cap = list_cap;
+        fa.fc = &dctr->filt;
+        fa.gc = &dctr->gen;
+        fa.n_exact = &dctr->n_exact_classify;
+        fa.overflow = &dctr->overflow;
+        CK(cudaEventRecord(c->kev[2], s));
+        if (grid) {
+            if (pack && W == 1)
+                filter_classify_kernel<1, true, true><<<n_tiles, 256, 0, s>>>(fa);
+            else
+                filter_classify_kernel<W, false, true><<<n_tiles, 256, 0, s>>>(fa);
+        } else {
+            if (pack && W == 1)
+                filter_classify_kernel<1, true, false><<<n_tiles, 256, 0, s>>>(fa);
+            else
+                filter_classify_kernel<W, false, false><<<n_tiles, 256, 0, s>>>(fa);
+        }
+        CK(cudaEventRecord(c->kev[3], s));
+        CK(cudaGetLastError());
+        ++c->launches;
+
+        // ---- K4: general tiers; the last block of the big tier scans the tile totals
+        CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
+        CK(cudaEventRecord(c->ev[ST_GENERAL], s));
+        const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
+        const uint32_t est = std::min<uint32_t>(list_cap, c->h_list ? c->h_list : list_cap);
         const int small_blocks = (int)std::max<uint32_t>(
-            1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
-        const size_t small_smem = GEN_SMALL_WARPS * sizeof(SmallSlot);
-        const size_t mid_smem = GEN_MID_WARPS * sizeof(MidSlot);
-        const int mid_per_sm = (int)std::max<size_t>(1, c->smem_per_sm / (mid_smem + 1024));
+            1, std::min<uint32_t>((est + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
         const int mid_blocks = (int)std::max<uint32_t>(
-            1, std::min<uint32_t>((est + 64 + GEN_MID_WARPS - 1) / GEN_MID_WARPS, (uint32_t)(sm * mid_per_sm)));
-        if (mid_smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
-        CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout,
-            (int)cudaSharedmemCarveoutMaxShared));
-        for (int attempt = 0;; ++attempt) {
-            if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
-            const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
-            const unsigned top0 = 8; // the arena starts with an empty record (header + trailing word)
-            CK(cudaMemsetAsync(c->arena.p, 0, 8, s));
-            CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
-            // small tier: one tet per warp, complex in shared memory; capacity overflow -> ovf list
-            general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
-                c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
-                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A,
-                c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr,
-                c->lut_ia.lut2cx.as<uint16_t>(), c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
-                c->rec_ref.as<uint32_t>(), &dctr->gen);
-            // mid tier: big list + small-tier overflows, one tet per warp; overflow -> third list
-            general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(),
-                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
-                c->big_list.as<uint32_t>() + A, c->big_list.as<uint32_t>() + 2 * (size_t)A, c->vals.as<double>(), V,
-                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
-            // big tier: what is left (per-thread local memory)
-            general_ia_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
-                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
-                c->big_list.as<uint32_t>() + 2 * (size_t)A, &dctr->gen.n_ovf2, c->vals.as<double>(), V,
-                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
-            CK(cudaGetLastError());
-            // counts + offsets right behind the general kernels: ONE read-back serves both
-            // (an arena overflow leaves empty records, the scan is then simply repeated)
-            CK(cudaEventRecord(c->ev[ST_SCAN], s));
-            CK(c->status.ensure((size_t)a_tiles * 16 + 64));
-            CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
-            CK(cudaMemsetAsync(&dctr->scan, 0, sizeof(ScanTotals), s));
-            count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
-                c->act_cap, A, c->lut_ia.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
-                c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
-            CK(cudaGetLastError());
+            1, std::min<uint32_t>((est + GEN_MID_WARPS - 1) / GEN_MID_WARPS, (uint32_t)(sm * mid_per_sm)));
+        uint32_t* lists = c->big_list.as<uint32_t>();
+        general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet,
+            fa.tl_mask, (uint32_t)tl_stride, fa.small_list, lists + list_cap,
+            c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr, c->lut_ia.lut2cx.as<uint16_t>(),
+            fa.vals, VS, c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
+        general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
+            (uint32_t)tl_stride, lists, lists + list_cap, lists + 2 * (size_t)list_cap, fa.vals, VS,
+            c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
+        TileScanArgs sa{};
+        sa.tot = fa.tile_tot;
+        sa.n_tiles = n_tiles;
+        sa.off = c->tile_pre.as<TileTot>();
+        sa.totals = &dctr->tot;
+        sa.act_cap = sizing ? 0xffffffffu : act_cap;
+        sa.cand_cap = sizing ? 0xffffffffu : cand_cap;
+        sa.face_cap = sizing ? 0xffffffffu : face_cap;
+        sa.fv_cap = sizing ? 0xffffffffu : fv_cap;
+        sa.overflow = &dctr->overflow;
+        general_ia_big_kernel<W><<<sm * 2, GEN_BIG_THREADS, 0, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
+            (uint32_t)tl_stride, lists + 2 * (size_t)list_cap, &dctr->gen.n_ovf2, fa.vals, VS, c->arena.as<uint8_t>(),
+            acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, sa, list_cap);
+        CK(cudaGetLastError());
+        c->launches += 3;
+        CK(cudaEventRecord(c->ev[ST_SCAN], s));
+
+        auto check_general = [&](const Counters& hc, bool& again) -> int {
+            again = false;
+            if (hc.gen.err)
+                return fail(hc.gen.err, "per-tet arrangement failed in tet " + std::to_string(hc.gen.err_tet) +
+                                            (hc.gen.err == RIN_ERR_CAPACITY ? " (complex exceeds kernel capacity)"
+                                                                           : " (degenerate input plane)"));
+            if (hc.gen.arena_overflow) {
+                CK(c->arena.ensure((size_t)hc.gen.arena_top + hc.gen.arena_top / 8 + 4096));
+                again = true;
+            }
+            if (hc.overflow & OVF_LIST) {
+                const uint32_t need = std::max({hc.gen.n_small, hc.gen.n_big, hc.gen.n_ovf, hc.gen.n_ovf2});
+                c->h_list = need + need / 8 + 1024;
+                again = true;
+            }
+            return RIN_OK;
+        };
+        if (sizing) {
             CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            h.gen = hp->gen;
-            h.scan = hp->scan;
-            h.n_exact_classify = hp->n_exact_classify;
-            if (h.gen.err)
-                return fail(h.gen.err, "per-tet arrangement failed in tet " + std::to_string(h.gen.err_tet) +
-                                           (h.gen.err == RIN_ERR_CAPACITY ? " (complex exceeds kernel capacity)"
-                                                                         : " (degenerate input plane)"));
-            if (!h.gen.arena_overflow) break;
-            if (attempt > 2) return fail(RIN_ERR_STATE, "general kernel: arena overflow after regrow");
-            CK(c->arena.ensure((size_t)h.gen.arena_top + h.gen.arena_top / 8 + 4096));
-            GeneralCounters z{};
-            z.n_general = h.gen.n_general;
-            z.n_small = h.gen.n_small;
-            z.n_big = h.gen.n_big;
-            CK(cudaMemcpyAsync(&dctr->gen, &z, sizeof(GeneralCounters), cudaMemcpyHostToDevice, s));
+            h = *hp;
+            if (!evaluated) n_zero = h.n_zero;
+            evaluated = true;
+            bool again;
+            int rc = check_general(h, again);
+            if (rc) return rc;
+            if (again) continue;
+            c->h_act = h.tot.n_active + h.tot.n_active / 8 + 1024;
+            c->h_cand = h.tot.n_cand + h.tot.n_cand / 8 + 1024;
+            c->h_face = h.tot.n_faces + h.tot.n_faces / 8 + 1024;
+            c->h_fv = h.tot.n_fv + h.tot.n_fv / 8 + 1024;
+            rc = size_outputs();
+            if (rc) return rc;
         }
-    } else {
-        CK(cudaEventRecord(c->ev[ST_SCAN], s));
-    }
-    n.num_general_tets = h.gen.n_general;
-    const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
 
-    // ---- K5b: emit
-    CK(cudaEventRecord(c->ev[ST_EMIT], s));
-    CK(c->cand_key.ensure((size_t)std::max(NC, 1u) * 16));
-    CK(c->cand_pay.ensure((size_t)std::max(NC, 1u) * 16));
-    CK(c->face_hdr.ensure((size_t)std::max(NFc, 1u) * 16));
-    CK(c->fv_ref.ensure((size_t)std::max(NFV, 1u) * 4));
-    if (A) {
-        const size_t smem = (c->lut_ia.blob_bytes + 3) & ~3u;
-        static const bool smem_blob = []() {
-            const char* e = getenv("RIN_EMIT_SMEM"); // 1: stage the record table in shared memory
-            return e ? atoi(e) != 0 : false;
-        }();
-        if (smem_blob) {
-            if (smem > 48 * 1024)
-                CK(cudaFuncSetAttribute(emit_ia_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            emit_ia_kernel<W, true><<<grid_for(A, 256, sm, 4), 256, smem, s>>>(c->tets.as<uint4>(),
-                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(),
-                c->offs.as<uint4>(), c->lut_ia.blob.as<uint8_t>(), (uint32_t)smem, c->arena.as<uint8_t>(),
-                c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(),
-                c->fv_ref.as<uint32_t>(), &dctr->n_bndry_faces);
-        } else {
-            // the 63 KB record table stays L1/L2 resident; no per-block staging, full occupancy
-            emit_ia_kernel<W, false><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tets.as<uint4>(),
-                c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->rec_ref.as<uint32_t>(),
-                c->offs.as<uint4>(), c->lut_ia.blob.as<uint8_t>(), (uint32_t)smem, c->arena.as<uint8_t>(),
-                c->cand_key.as<uint4>(), c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(),
-                c->fv_ref.as<uint32_t>(), &dctr->n_bndry_faces);
-        }
-        CK(cudaGetLastError());
-    }
-
-    // ---- K6: dedup (hash-min + rank)
-    CK(cudaEventRecord(c->ev[ST_DEDUP], s));
-    uint32_t NV = 0;
-    if (NC) {
-        uint32_t tsize = 1024;
-        while (tsize < 2 * NC) tsize <<= 1;
-        CK(c->table.ensure((size_t)tsize * 4));
-        CK(c->slot_of.ensure((size_t)NC * 4));
-        CK(c->rep.ensure((size_t)NC * 4));
-        CK(c->vid.ensure((size_t)NC * 4));
+        // ---- K5 + K6: ordered active list, candidates, hash-min insertion
+        CK(cudaEventRecord(c->ev[ST_EMIT], s));
         CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
-        hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
-            c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
-        const uint32_t r_tiles = (NC + 1023) / 1024;
-        CK(c->status.ensure((size_t)r_tiles * 8 + 64));
-        CK(cudaMemsetAsync(c->status.p, 0, (size_t)r_tiles * 8, s));
-        rank_reps_kernel<<<r_tiles, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), nullptr, NC,
-            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
-            &dctr->n_unique);
+        CK(cudaMemsetAsync(c->status.p, 0, ((size_t)act_cap / RV_TILE + 2) * 8, s));
+        EmitArgs ea{};
+        ea.tets = c->tets.as<uint4>();
+        ea.tl_tet = fa.tl_tet;
+        ea.tl_mask = fa.tl_mask;
+        ea.tl_ref = fa.tl_ref;
+        ea.tl_stride = tl_stride;
+        ea.tile_slots = tile_slots;
+        ea.tile_tot = fa.tile_tot;
+        ea.tile_off = c->tile_pre.as<TileTot>();
+        ea.n_tiles = n_tiles;
+        ea.blob32 = fa.blob32;
+        ea.arena32 = c->arena.as<uint32_t>();
+        ea.act_tet = c->act_tet.as<uint32_t>();
+        ea.act_mask = c->act_mask.as<uint32_t>();
+        ea.act_cap = c->act_cap;
+        ea.rec_ref = c->rec_ref.as<uint32_t>();
+        ea.offs = c->offs.as<uint4>();
+        ea.cand_key = c->cand_key.as<uint4>();
+        ea.table = c->table.as<uint32_t>();
+        ea.table_mask = tsize - 1;
+        ea.slot_of = c->slot_of.as<uint32_t>();
+        ea.overflow = &dctr->overflow;
+        emit_insert_kernel<W><<<(int)std::min<uint32_t>(n_tiles, (uint32_t)sm * 8), 256, 0, s>>>(ea);
         CK(cudaGetLastError());
-    }
-    // the number of unique vertices is read back with the final synchronisation; NC bounds it
-    const uint32_t NVcap = NC;
+        ++c->launches;
 
-    // ---- K7: unique vertices + xyz
-    CK(cudaEventRecord(c->ev[ST_VERTS], s));
-    CK(c->v_tet.ensure((size_t)std::max(NVcap, 1u) * 4));
-    CK(c->v_local.ensure(std::max(NVcap, 1u)));
-    CK(c->v_size.ensure(std::max(NVcap, 1u)));
-    CK(c->v_simplex.ensure((size_t)std::max(NVcap, 1u) * 16));
-    CK(c->v_funcs.ensure((size_t)std::max(NVcap, 1u) * 16));
-    CK(c->v_xyz.ensure((size_t)std::max(NVcap, 1u) * 24));
-    CK(c->v_key.ensure((size_t)std::max(NVcap, 1u) * 16));
-    if (NC) {
-        write_verts_ia_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
-            c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
-            c->vals.as<double>(), V, c->pts.as<double>(), c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(),
-            c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>(),
-            c->v_key.as<uint4>());
+        // ---- K6 + K7: ranking, vertex records, coordinates
+        CK(cudaEventRecord(c->ev[ST_DEDUP], s));
+        CK(cudaEventRecord(c->ev[ST_VERTS], s));
+        RankArgs ra{};
+        ra.tets = ea.tets;
+        ra.act_tet = ea.act_tet;
+        ra.act_mask = ea.act_mask;
+        ra.act_cap = c->act_cap;
+        ra.rec_ref = ea.rec_ref;
+        ra.offs = ea.offs;
+        ra.blob32 = ea.blob32;
+        ra.arena32 = ea.arena32;
+        ra.totals = &dctr->tot;
+        ra.table = ea.table;
+        ra.slot_of = ea.slot_of;
+        ra.vals = fa.vals;
+        ra.VS = VS;
+        ra.pts = c->pts.as<double>();
+        ra.v_tet = c->v_tet.as<uint32_t>();
+        ra.v_local = c->v_local.as<uint8_t>();
+        ra.v_size = c->v_size.as<uint8_t>();
+        ra.v_simplex = c->v_simplex.as<uint4>();
+        ra.v_funcs = c->v_funcs.as<uint4>();
+        ra.v_xyz = c->v_xyz.as<double>();
+        ra.v_key = c->v_key.as<uint4>();
+        ra.status = c->status.as<unsigned long long>();
+        ra.tile_counter = &dctr->rank_tile;
+        ra.n_unique = &dctr->n_unique;
+        ra.overflow = &dctr->overflow;
+        const uint32_t a_est = sizing ? h.tot.n_active : act_cap;
+        rank_verts_kernel<W><<<(int)std::max<uint32_t>(1, std::min<uint32_t>((a_est + RV_TILE - 1) / RV_TILE,
+                                   (uint32_t)sm * 8)), 256, 0, s>>>(ra);
         CK(cudaGetLastError());
-    }
+        ++c->launches;
 
-    // ---- faces
-    CK(cudaEventRecord(c->ev[ST_FACES], s));
-    CK(c->f_off.ensure((size_t)(NFc + 1) * 4));
-    CK(c->f_verts.ensure((size_t)std::max(NFV, 1u) * 4));
-    CK(c->f_toff.ensure((size_t)(NFc + 1) * 4));
-    CK(c->f_tets.ensure((size_t)std::max(NFc, 1u) * 8));
-    CK(c->f_funcs.ensure((size_t)std::max(NFc, 1u) * 8));
-    uint32_t NF = NFc, NFVout = NFV, NFT = NFc;
-    {
-        if (NFV)
-            remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
-                c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->f_verts.as<uint32_t>());
-        write_faces_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
-            NFV, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(),
-            c->f_funcs.as<uint32_t>());
+        // ---- faces
+        CK(cudaEventRecord(c->ev[ST_FACES], s));
+        FaceArgs fg{};
+        fg.act_tet = ea.act_tet;
+        fg.act_mask = ea.act_mask;
+        fg.act_cap = c->act_cap;
+        fg.rec_ref = ea.rec_ref;
+        fg.offs = ea.offs;
+        fg.blob32 = ea.blob32;
+        fg.arena32 = ea.arena32;
+        fg.totals = &dctr->tot;
+        fg.table = ea.table;
+        fg.slot_of = ea.slot_of;
+        fg.f_off = c->f_off.as<uint32_t>();
+        fg.f_verts = c->f_verts.as<uint32_t>();
+        fg.f_toff = c->f_toff.as<uint32_t>();
+        fg.f_tets = c->f_tets.as<uint32_t>();
+        fg.f_funcs = c->f_funcs.as<uint32_t>();
+        fg.overflow = &dctr->overflow;
+        const int face_grid = grid_for(a_est, 256, sm, 8);
+        faces_kernel<W, false><<<face_grid, 256, 0, s>>>(fg);
         CK(cudaGetLastError());
-    }
-    // final read-back: unique vertex count, boundary-face count
-    CK(cudaEventRecord(c->ev[ST_COUNT], s));
-    CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    h.n_unique = hp->n_unique;
-    h.n_bndry_faces = hp->n_bndry_faces;
-    NV = NC ? h.n_unique : 0;
-    if (h.n_bndry_faces) {
-        // degenerate input: iso-faces on tet boundaries are shared between two tets
-        uint32_t tsize = 1024;
-        while (tsize < 2 * NFc) tsize <<= 1;
-        CK(c->table.ensure((size_t)tsize * 4));
-        CK(c->slot_of.ensure((size_t)NFc * 4));
-        CK(c->tmp_fverts.ensure((size_t)NFV * 4));
-        CK(c->bfkeys.ensure((size_t)NFc * 16));
-        CK(c->frep.ensure((size_t)NFc * 4));
-        CK(c->fdup.ensure((size_t)NFc * 8 + 16)); // ndup | cursor | totals
-        CK(c->fpos.ensure((size_t)NFc * 16));
-        uint32_t* ndup = c->fdup.as<uint32_t>();
-        uint32_t* cursor = ndup + NFc;
-        uint32_t* totals = cursor + NFc;
-        CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
-        CK(cudaMemsetAsync(c->fdup.p, 0, (size_t)NFc * 8 + 16, s));
-        const int g = grid_for(NFc, 256, sm, 8);
-        remap_face_verts_kernel<<<grid_for(NFV, 256, sm, 8), 256, 0, s>>>(c->fv_ref.as<uint32_t>(), NFV,
-            c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->tmp_fverts.as<uint32_t>());
-        bface_keys_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->tmp_fverts.as<uint32_t>(),
-            c->bfkeys.as<uint4>());
-        bface_insert_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->bfkeys.as<uint4>(),
-            c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
-        bface_reps_kernel<<<g, 256, 0, s>>>(c->table.as<uint32_t>(), c->slot_of.as<uint32_t>(), NFc,
-            c->frep.as<uint32_t>(), ndup);
-        bface_scan_kernel<<<1, 1024, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
-            c->fpos.as<uint4>(), totals);
-        bface_write_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
-            c->tmp_fverts.as<uint32_t>(), c->frep.as<uint32_t>(), c->fpos.as<uint4>(), cursor, totals,
-            c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(),
-            c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>(), 0);
-        CK(cudaGetLastError());
-        uint32_t ht[3];
-        CK(cudaMemcpyAsync(ht, totals, 12, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        NF = ht[0];
-        NFVout = ht[1];
-        NFT = ht[2];
-        bface_sort_pairs_kernel<<<grid_for(NF, 256, sm, 8), 256, 0, s>>>(NF, c->f_toff.as<uint32_t>(),
-            c->f_tets.as<uint32_t>());
-        CK(cudaGetLastError());
+        ++c->launches;
         CK(cudaEventRecord(c->ev[ST_COUNT], s));
-        CK(cudaStreamSynchronize(s));
-    }
-    for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
-    CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
-    CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
-    CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
-    c->marked = c->finalized = false;
-    c->ia_bndry_faces = h.n_bndry_faces != 0;
-    c->maps_ready = false;
-    c->n_local_verts = NV;
-    c->n_own = NV;
-    n.num_verts = NV;
-    n.num_faces = NF;
-    n.num_face_verts = NFVout;
-    n.num_face_tets = NFT;
-    n.num_exact_fallbacks = (uint64_t)h.gen.n_exact + h.n_exact_classify;
-    return RIN_OK;
+        // ---- the one read-back
+        CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h = *hp;
+        if (!evaluated) n_zero = h.n_zero;
+        evaluated = true;
+        bool again;
+        int rc = check_general(h, again);
+        if (rc) return rc;
+        if (again || h.overflow) {
+            c->h_act = 0; // size the next attempt exactly
+            continue;
+        }
+
+        uint32_t NF = h.tot.n_faces, NFVout = h.tot.n_fv, NFT = h.tot.n_faces;
+        if (h.gen.n_bnd_faces) {
+            // degenerate input: iso-faces on tet boundaries are shared between two tets
+            // (src/extract_mesh.cpp:240-253); the vertex table stays untouched (rin_tet_maps reads it)
+            const uint32_t NFc = h.tot.n_faces, NFV = h.tot.n_fv;
+            uint32_t t2 = 1024;
+            while (t2 < 2 * NFc) t2 <<= 1;
+            CK(c->ftable.ensure((size_t)t2 * 4));
+            CK(c->bids.ensure((size_t)NFc * 4));
+            CK(c->face_hdr.ensure((size_t)NFc * 16));
+            CK(c->tmp_fverts.ensure((size_t)std::max(NFV, 1u) * 4));
+            CK(c->bfkeys.ensure((size_t)NFc * 16));
+            CK(c->frep.ensure((size_t)NFc * 4));
+            CK(c->fdup.ensure((size_t)NFc * 8 + 16)); // ndup | cursor | totals
+            CK(c->fpos.ensure((size_t)NFc * 16));
+            uint32_t* ndup = c->fdup.as<uint32_t>();
+            uint32_t* cursor = ndup + NFc;
+            uint32_t* totals = cursor + NFc;
+            CK(cudaMemsetAsync(c->ftable.p, 0xff, (size_t)t2 * 4, s));
+            CK(cudaMemsetAsync(c->fdup.p, 0, (size_t)NFc * 8 + 16, s));
+            FaceArgs fh = fg;
+            fh.f_verts = c->tmp_fverts.as<uint32_t>();
+            fh.face_hdr = c->face_hdr.as<uint4>();
+            faces_kernel<W, true><<<face_grid, 256, 0, s>>>(fh);
+            const int g = grid_for(NFc, 256, sm, 8);
+            bface_keys_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->tmp_fverts.as<uint32_t>(),
+                c->bfkeys.as<uint4>());
+            bface_insert_kernel<<<g, 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->bfkeys.as<uint4>(),
+                c->ftable.as<uint32_t>(), t2 - 1, c->bids.as<uint32_t>());
+            bface_reps_kernel<<<g, 256, 0, s>>>(c->ftable.as<uint32_t>(), c->bids.as<uint32_t>(), NFc,
+                c->frep.as<uint32_t>(), ndup);
+            bface_scan_kernel<<<1, 1024, 0, s>>>(c->face_hdr.as<uint4>(), NFc, c->frep.as<uint32_t>(), ndup,
+                c->fpos.as<uint4>(), totals);
+            bface_write_kernel<<<grid_for((uint64_t)NFc + 1, 256, sm, 8), 256, 0, s>>>(c->face_hdr.as<uint4>(), NFc,
+                c->tmp_fverts.as<uint32_t>(), c->frep.as<uint32_t>(), c->fpos.as<uint4>(), cursor, totals,
+                c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(),
+                c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>(), 0);
+            CK(cudaGetLastError());
+            uint32_t ht[3];
+            CK(cudaMemcpyAsync(ht, totals, 12, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            NF = ht[0];
+            NFVout = ht[1];
+            NFT = ht[2];
+            bface_sort_pairs_kernel<<<grid_for(NF, 256, sm, 8), 256, 0, s>>>(NF, c->f_toff.as<uint32_t>(),
+                c->f_tets.as<uint32_t>());
+            CK(cudaGetLastError());
+            c->launches += 7;
+            CK(cudaEventRecord(c->ev[ST_COUNT], s));
+            CK(cudaStreamSynchronize(s));
+        }
+        for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+        CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
+        CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+        CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
+
+        // learnt sizes for the next pass over these inputs
+        c->h_act = h.tot.n_active + h.tot.n_active / 8 + 1024;
+        c->h_cand = h.tot.n_cand + h.tot.n_cand / 8 + 1024;
+        c->h_face = h.tot.n_faces + h.tot.n_faces / 8 + 1024;
+        c->h_fv = h.tot.n_fv + h.tot.n_fv / 8 + 1024;
+        {
+            const uint32_t need = std::max({h.gen.n_small, h.gen.n_big, h.gen.n_ovf, h.gen.n_ovf2});
+            c->h_list = need + need / 8 + 1024;
+        }
+        c->table_size = tsize;
+        c->ia_bndry_faces = h.gen.n_bnd_faces != 0;
+        const uint32_t NV = h.tot.n_cand ? h.n_unique : 0;
+        c->n_local_verts = NV;
+        c->n_own = NV;
+        n.num_degenerate_vertex = n_zero;
+        n.num_intersecting_tet = h.tot.n_active;
+        n.num_k1 = h.filt.n_k1;
+        n.num_k2 = h.filt.n_k2;
+        n.num_kmore = h.filt.n_kmore;
+        n.num_active_funcs = h.tot.n_funcs;
+        n.num_general_tets = (uint64_t)h.gen.n_small + h.gen.n_big;
+        n.num_verts = NV;
+        n.num_faces = NF;
+        n.num_face_verts = NFVout;
+        n.num_face_tets = NFT;
+        n.num_exact_fallbacks = (uint64_t)h.gen.n_exact + h.n_exact_classify;
+        return RIN_OK;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1513,7 +1669,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
 template <int W>
 int run_mi_w(rin_ctx* c, uint32_t flags)
 {
-    const uint32_t V = (uint32_t)c->V, F = c->F;
+    const uint32_t V = c->VS, F = c->F; // V: row stride of vals / vmask
     const uint32_t T = (uint32_t)c->t_count, t_first = (uint32_t)c->t_first;
     const int use_lookup = (flags & RIN_FLAG_USE_LOOKUP) ? 1 : 0;
     const int use_secondary = (flags & RIN_FLAG_USE_SECONDARY_LOOKUP) ? 1 : 0;
@@ -1531,14 +1687,19 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->vmask.ensure((size_t)V * W * 8));
     CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
     CK(cudaEventRecord(c->ev[ST_EVAL], s));
-    const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
+    const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : (uint32_t)c->V;
     CK(cudaEventRecord(c->kev[0], s));
     if (c->have_funcs) {
-        size_t smem = F * sizeof(rin_func_desc);
-        if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(eval_functions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eval_functions_kernel<<<grid_for(vc, 256, sm, 8), 256, smem, s>>>(c->pts.as<double>(), vf, vc, V,
-            c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr, &dctr->n_zero);
+        const size_t smem = F * sizeof(rin_func_desc);
+        const int g = grid_for((vc + EV_VPT - 1) / EV_VPT, 256, sm, 8);
+        if (c->grid_R)
+            eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1, vf, vc, V,
+                c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
+                &dctr->n_zero);
+        else
+            eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, vf, vc, V,
+                c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
+                &dctr->n_zero);
     } else {
         ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
             negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr, &dctr->n_zero);
@@ -1963,7 +2124,7 @@ int build_ia_tables(rin_ctx* c)
     CKC(cudaMemsetAsync(d_arena.p, 0, 8, s));
     general_ia_big_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
         d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), &dctr->gen.n_big, d_vals.as<double>(), Vw,
-        d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
+        d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen, nullptr, 1, TileScanArgs{});
     CKC(cudaGetLastError());
     GeneralCounters g1;
     CKC(cudaMemcpyAsync(&g1, &dctr->gen, sizeof(g1), cudaMemcpyDeviceToHost, s));
