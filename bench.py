@@ -214,6 +214,7 @@ def main():
         return c
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------
+    ctx.set_stage_timing(False)  # the timed region records two events per pass, not a dozen
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
@@ -223,15 +224,24 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cnt = step()
-        kt = ctx.kernel_times()
-        dev_ms.append(kt["total_ms"])
-        eval_ms.append(kt["eval_ms"])
-        filt_ms.append(kt["filter_ms"])
+        dev_ms.append(ctx.kernel_times()["total_ms"])
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    stage = ctx.stage_times()
+    launches_per_step = ctx.launch_count()
+    # separate profiled passes (per-stage events on) for the stage table and the kernel brackets
+    ctx.set_stage_timing(True)
+    stage_acc = None
+    for _ in range(5):
+        step()
+        kt = ctx.kernel_times()
+        eval_ms.append(kt["eval_ms"])
+        filt_ms.append(kt["filter_ms"])
+        st = ctx.stage_times()
+        stage_acc = st if stage_acc is None else {k: stage_acc[k] + v for k, v in st.items()}
+    stage = {k: v / 5 for k, v in stage_acc.items()}
+    ctx.set_stage_timing(False)
     wall_t = torch.tensor([wall], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
@@ -375,8 +385,8 @@ def main():
                            "cache": "inputs (%.0f MB) + intermediates exceed the 126 MB L2" %
                                     ((16.0 * T_total + 88.0 * (R + 1) ** 3) / 1e6)},
                 "device_ms_per_step": float(np.mean(dev_ms)), "stage_ms": stage,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (15 + (13 if world > 1 else 0)) * args.steps,  # kernels per rin_run + exchange
-               
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (launches_per_step + (13 if world > 1 else 0)) * args.steps,
+                "launches_per_step": launches_per_step,
                 "clocks": sampler.summary(), "counts": cnt.as_dict(),
                 "exchange": None if dist is None else {
                     "what": "slab-boundary vertex keys, 2 ncclAllGather per step (device-side, rin_exchange_nccl)",

@@ -142,6 +142,11 @@ int rin_download_values(rin_ctx*, double* vals_rowmajor);
 int rin_download_grid(rin_ctx*, double* pts, uint32_t* tets);
 /* per-stage device times of the last run in milliseconds (CUDA events); names via rin_stage_name */
 int rin_get_stage_times(const rin_ctx*, float* ms, int capacity);
+/* per-stage CUDA events are recorded while this is on (default); off: only the whole pass is timed
+ * (a dozen event records per pass cost more host time than some of the kernels take) */
+int rin_set_stage_timing(rin_ctx*, int on);
+/* kernels launched by the last rin_run (counted at the launch sites) */
+int rin_get_launch_count(const rin_ctx*);
 const char* rin_stage_name(int i);
 /* CUDA-event durations of the last run: the eval and filter kernels alone, and the whole pass */
 int rin_get_kernel_times(const rin_ctx*, float* eval_ms, float* filter_ms, float* total_ms);

@@ -97,6 +97,43 @@ __device__ __forceinline__ uint32_t hash4(uint4 k)
     return h;
 }
 
+// Division by a run-time constant without the XU pipe (I2F / MUFU.RCP / F2I): multiply-high by a magic
+// number (the branch-free scheme of Granlund & Montgomery as popularised by libdivide).
+struct FastDiv
+{
+    uint32_t m, s, d;
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) {
+        f.m = 0;
+        f.s = 0xffffffffu;
+        return f;
+    }
+    const uint32_t l = 31u - (uint32_t)__builtin_clz(d);
+    if ((d & (d - 1)) == 0) {
+        f.m = 0;
+        f.s = l - 1;
+        return f;
+    }
+    const uint64_t num = 1ull << (32 + l);
+    uint64_t pm = num / d;
+    const uint64_t rem = num % d;
+    pm += pm;
+    if (rem + rem >= d) pm += 1;
+    f.m = (uint32_t)(pm + 1);
+    f.s = l;
+    return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv f)
+{
+    if (f.s == 0xffffffffu) return n;
+    const uint32_t q = __umulhi(n, f.m);
+    return (((n - q) >> 1) + q) >> f.s;
+}
+
 // After the ranking pass of the implicit-arrangement pipeline a candidate's slot_of entry, or the table entry
 // of its slot, holds VID_FLAG | final vertex id.
 constexpr uint32_t VID_FLAG = 0x80000000u;

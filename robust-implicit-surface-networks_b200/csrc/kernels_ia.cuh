@@ -445,7 +445,7 @@ struct GeneralCounters
     unsigned arena_overflow;
     unsigned n_ovf2;    // mid-tier capacity overflows (IA), re-queued for the per-thread big tier
     unsigned n_bnd_faces; // iso faces on a tet boundary among the general records (degenerate inputs)
-    unsigned done_blocks; // last-block ticket of the big tier (tile scan in its tail)
+    unsigned done_blocks; // last-block ticket of the mid tier (tile scan in its tail)
 };
 
 constexpr uint32_t REF_GENERAL = 0x80000000u;
@@ -711,7 +711,6 @@ __device__ bool general_ia_one_warp(IAComplex<Caps>& cx, IAWarpScratch<Caps>& sc
 // dependency chain per tet is what sets its duration.
 constexpr int GEN_SMALL_WARPS = 4;
 constexpr int GEN_THREADS = 64;
-constexpr int GEN_BIG_THREADS = 128;
 // shared memory of one warp of the small tier: the complex and the re-packing scratch
 struct alignas(16) SmallSlot
 {
@@ -816,35 +815,17 @@ __global__ void __launch_bounds__(GEN_THREADS) dump_ia2_kernel(const uint32_t* _
     }
 }
 
-// Mid tier: the big list (more functions than the small tier takes) and the small tier's overflows, one tet
-// per warp, complex in shared memory, warp-cooperative insertion.  Capacity overflow -> ovf2 list.
-constexpr int GEN_MID_WARPS = 4;
-struct alignas(16) MidSlot
-{
-    IAComplex<IACapsMid> cx;
-    IAWarpScratch<IACapsMid> sc;
-};
+// one tet through the serial big tier (complex in the calling thread's local memory)
 template <int W>
-__global__ void __launch_bounds__(GEN_MID_WARPS * 32) general_ia_mid_kernel(const uint4* __restrict__ tets,
+__device__ __noinline__ void general_ia_big_one(uint32_t a, const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
-    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ ovf_list, uint32_t* __restrict__ ovf2_list,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, TileTot* __restrict__ tile_tot = nullptr,
-    uint32_t tile_slots = 1, uint32_t list_cap = 0xffffffffu)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, TileTot* __restrict__ tile_tot,
+    uint32_t tile_slots)
 {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    MidSlot* s_slot = reinterpret_cast<MidSlot*>(s_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nb = min(gc->n_big, list_cap), n = nb + min(gc->n_ovf, list_cap);
-    for (uint32_t g = blockIdx.x * GEN_MID_WARPS + warp; g < n; g += gridDim.x * GEN_MID_WARPS) {
-        const uint32_t a = g < nb ? big_list[g] : ovf_list[g - nb];
-        __syncwarp();
-        if (!general_ia_one_warp<IACapsMid, W>(s_slot[warp].cx, s_slot[warp].sc, a, tets, act_tet, act_mask, cap,
-                vals, V, arena, arena_cap, rec_ref, gc, false, 0, lane, tile_tot, tile_slots)) {
-            if (lane == 0) ovf2_list[atomicAdd(&gc->n_ovf2, 1u)] = a;
-        }
-        __syncwarp();
-    }
+    IAComplex<IACaps> cx;
+    general_ia_one<IACaps, W>(cx, a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref, gc, true, 0,
+        tile_tot, tile_slots);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -862,6 +843,7 @@ enum : unsigned {
     OVF_CAND = 4u, // vertex candidates
     OVF_FACE = 8u, // faces
     OVF_FV = 16u,  // face-vertex entries
+    OVF_TABLE = 32u, // vertex hash table full
 };
 struct TileScanArgs
 {
@@ -880,13 +862,23 @@ __device__ void tile_scan_block(const TileScanArgs& S)
     const uint32_t per = (S.n_tiles + blockDim.x - 1) / blockDim.x;
     const uint32_t b = min(S.n_tiles, threadIdx.x * per), e = min(S.n_tiles, b + per);
     unsigned c[5] = {0, 0, 0, 0, 0};
-    for (uint32_t t = b; t < e; ++t) {
-        const uint4 a = __ldcg(reinterpret_cast<const uint4*>(S.tot + t));
-        c[0] += a.x;
-        c[1] += a.y;
-        c[2] += a.z;
-        c[3] += a.w;
-        c[4] += __ldcg(&S.tot[t].fv);
+    for (uint32_t t0 = b; t0 < e; t0 += 8) { // eight tiles' loads in flight
+        uint4 a[8];
+        unsigned f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const bool in = t0 + q < e;
+            a[q] = in ? __ldcg(reinterpret_cast<const uint4*>(S.tot + t0 + q)) : make_uint4(0, 0, 0, 0);
+            f[q] = in ? __ldcg(&S.tot[t0 + q].fv) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            c[0] += a[q].x;
+            c[1] += a[q].y;
+            c[2] += a[q].z;
+            c[3] += a[q].w;
+            c[4] += f[q];
+        }
     }
     unsigned x[5];
 #pragma unroll
@@ -934,16 +926,27 @@ __device__ void tile_scan_block(const TileScanArgs& S)
     unsigned run[5];
 #pragma unroll
     for (int q = 0; q < 5; ++q) run[q] = s_w[warp][q] + x[q] - c[q];
-    for (uint32_t t = b; t < e; ++t) {
-        uint4* o4 = reinterpret_cast<uint4*>(S.off + t);
-        o4[0] = make_uint4(run[0], run[1], run[2], run[3]);
-        o4[1] = make_uint4(run[4], 0, 0, 0);
-        const uint4 a = __ldcg(reinterpret_cast<const uint4*>(S.tot + t));
-        run[0] += a.x;
-        run[1] += a.y;
-        run[2] += a.z;
-        run[3] += a.w;
-        run[4] += __ldcg(&S.tot[t].fv);
+    for (uint32_t t0 = b; t0 < e; t0 += 8) {
+        uint4 a[8];
+        unsigned f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const bool in = t0 + q < e;
+            a[q] = in ? __ldcg(reinterpret_cast<const uint4*>(S.tot + t0 + q)) : make_uint4(0, 0, 0, 0);
+            f[q] = in ? __ldcg(&S.tot[t0 + q].fv) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (t0 + q < e) {
+                uint4* o4 = reinterpret_cast<uint4*>(S.off + t0 + q);
+                o4[0] = make_uint4(run[0], run[1], run[2], run[3]);
+                o4[1] = make_uint4(run[4], 0, 0, 0);
+                run[0] += a[q].x;
+                run[1] += a[q].y;
+                run[2] += a[q].z;
+                run[3] += a[q].w;
+                run[4] += f[q];
+            }
     }
     if (threadIdx.x == blockDim.x - 1) { // owns the tail (possibly empty): run = grand totals
         uint4* o4 = reinterpret_cast<uint4*>(S.off + S.n_tiles);
@@ -957,33 +960,69 @@ __global__ void __launch_bounds__(1024) scan_tiles5_kernel(const TileScanArgs S)
     tile_scan_block(S);
 }
 
-// Big tier: complexes in per-thread local memory (what neither shared-memory tier could hold).
-// The last block to finish also runs the tile scan (S.tot non-null): all general records exist by then.
+// Mid tier: the big list (more functions than the small tier takes) and the small tier's overflows, one tet
+// per warp, complex in shared memory, warp-cooperative insertion.  Capacity overflow -> ovf2 list.
+constexpr int GEN_MID_WARPS = 4;
+struct alignas(16) MidSlot
+{
+    IAComplex<IACapsMid> cx;
+    IAWarpScratch<IACapsMid> sc;
+};
 template <int W>
-__global__ void __launch_bounds__(GEN_BIG_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
+__global__ void __launch_bounds__(GEN_MID_WARPS * 32) general_ia_mid_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
-    const uint32_t* __restrict__ list, const unsigned* __restrict__ n_list,
+    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ ovf_list, uint32_t* __restrict__ ovf2_list,
     const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
     uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, TileTot* __restrict__ tile_tot,
-    uint32_t tile_slots, const TileScanArgs S, uint32_t list_cap = 0xffffffffu)
+    uint32_t tile_slots, uint32_t list_cap, const TileScanArgs S)
 {
-    const uint32_t n = min(*n_list, list_cap);
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
-        IAComplex<IACaps> cx;
-        general_ia_one<IACaps, W>(cx, list[g], tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref,
-            gc, true, 0, tile_tot, tile_slots);
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    MidSlot* s_slot = reinterpret_cast<MidSlot*>(s_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nb = min(gc->n_big, list_cap), n = nb + min(gc->n_ovf, list_cap);
+    bool worked = false;
+    for (uint32_t g = blockIdx.x * GEN_MID_WARPS + warp; g < n; g += gridDim.x * GEN_MID_WARPS) {
+        const uint32_t a = g < nb ? big_list[g] : ovf_list[g - nb];
+        worked = true;
+        __syncwarp();
+        if (!general_ia_one_warp<IACapsMid, W>(s_slot[warp].cx, s_slot[warp].sc, a, tets, act_tet, act_mask, cap,
+                vals, V, arena, arena_cap, rec_ref, gc, false, 0, lane, tile_tot, tile_slots)) {
+            if (ovf2_list) {
+                if (lane == 0) ovf2_list[atomicAdd(&gc->n_ovf2, 1u)] = a;
+            } else if (lane == 0) {
+                // what this tier cannot hold (rare): lane 0 runs the serial big tier in local memory
+                general_ia_big_one<W>(a, tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref, gc,
+                    tile_tot, tile_slots);
+            }
+        }
+        __syncwarp();
     }
+    // The last block to finish scans the tile totals: all general records exist by then.  Only blocks that
+    // produced records need the fence before they sign off.
     if (S.tot) {
-        __shared__ bool s_last;
-        __threadfence();
+        __shared__ bool s_scan;
+        if (worked) __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&gc->done_blocks, 1u) == gridDim.x - 1;
+        if (threadIdx.x == 0) s_scan = atomicAdd(&gc->done_blocks, 1u) == gridDim.x - 1;
         __syncthreads();
-        if (s_last) {
+        if (s_scan) {
             __threadfence();
             tile_scan_block(S);
         }
     }
+}
+
+// Big tier as a kernel of its own (table generation): complexes in per-thread local memory.
+template <int W>
+__global__ void __launch_bounds__(GEN_THREADS) general_ia_big_kernel(const uint4* __restrict__ tets,
+    const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
+    const uint32_t* __restrict__ list, const unsigned* __restrict__ n_list,
+    const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc)
+{
+    const uint32_t n = *n_list;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
+        general_ia_big_one<W>(list[g], tets, act_tet, act_mask, cap, vals, V, arena, arena_cap, rec_ref, gc, nullptr, 1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -3,9 +3,10 @@
 //   eval_*_kernel            K1  function values (SoA) + per-vertex sign masks
 //   filter_classify_kernel   K2  active-function filter + table dispatch, tile-local ordered compaction
 //   general_ia_small_kernel  K4  general per-tet arrangement, <= 4 functions (kernels_ia.cuh)
-//   general_ia_mid_kernel    K4  5..20 functions / small-tier overflows (kernels_ia.cuh)
-//   general_ia_big_kernel    K4  what is left + exclusive scan of the per-tile totals in its last block
-//   emit_insert_kernel       K5+K6  ordered active list, canonical vertex keys, hash-min insertion
+//   general_ia_mid_kernel    K4  more functions / overflows (kernels_ia.cuh) + exclusive scan of the per-tile
+//                                totals in its last block
+//   emit_kernel              K5  ordered active list, canonical vertex keys
+//   insert_kernel            K6  hash-min insertion of the shareable candidates
 //   rank_verts_kernel        K6+K7  first-occurrence ranking, IsoVert records, coordinates
 //   faces_kernel             K5  PolygonFace arrays with final vertex ids
 //
@@ -32,12 +33,12 @@ __global__ void grid_axes_kernel(uint32_t N, double3 bmin, double3 bmax, double*
     axes[2 * N + i] = (double(i) / d) * (bmax.z - bmin.z) + bmin.z;
 }
 
-// vertex ids of tet t of generate_tet_mesh(R) (src/io.cpp:122-147)
-__device__ __forceinline__ uint4 grid_tet(uint32_t R, uint32_t t)
+// vertex ids of tet t of generate_tet_mesh(R) (src/io.cpp:122-147); d5 / dR divide by 5 / R
+__device__ __forceinline__ uint4 grid_tet(uint32_t R, const FastDiv dR, uint32_t t)
 {
     const uint32_t N = R + 1;
     const uint32_t cube = t / 5, s = t - 5 * cube;
-    const uint32_t k = cube % R, ij = cube / R, j = ij % R, i = ij / R;
+    const uint32_t ij = fd_div(cube, dR), k = cube - ij * R, i = fd_div(ij, dR), j = ij - i * R;
     const uint8_t* tab = ((i + j + k) & 1) ? c_grid_odd[s] : c_grid_even[s];
     uint32_t v[4];
 #pragma unroll
@@ -50,18 +51,81 @@ __device__ __forceinline__ uint4 grid_tet(uint32_t R, uint32_t t)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: evaluation + sign masks, four vertices per thread and iteration (one descriptor fetch serves
-// four evaluations).  GRID: coordinates come from the three axis tables, nothing else is read.
+// K1: evaluation + sign masks, EV_VPT vertices per thread and iteration: the function kind is branched
+// on once per function (warp-uniform), one descriptor fetch serves all the thread's vertices.
+// GRID: coordinates come from the three axis tables, nothing else is read.
 // PACK (F <= 16): only the packed word P | N << 16 is written, else the (P, N) pairs per 32 functions.
 // VS = row stride of vals / vmask (V rounded up so that every row starts on a 128-byte boundary).
+// The arithmetic is that of eval_func (kernels_ia.cuh), operation for operation.
 // ---------------------------------------------------------------------------------------------
 constexpr int EV_VPT = 4;
 
+__device__ __forceinline__ void eval_func_n(const rin_func_desc& f, const double* x, const double* y,
+    const double* z, double* v)
+{
+    switch (f.type) {
+    case RIN_FN_PLANE: {
+        const double p0 = f.p[0], p1 = f.p[1], p2 = f.p[2], n0 = f.p[3], n1 = f.p[4], n2 = f.p[5];
+#pragma unroll
+        for (int j = 0; j < EV_VPT; ++j) {
+            const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
+            v[j] = (n0 * dx + n1 * dy) + n2 * dz;
+        }
+        break;
+    }
+    case RIN_FN_SPHERE: {
+        const double p0 = f.p[0], p1 = f.p[1], p2 = f.p[2], r = f.p[3];
+        if (f.p[4] != 0.0) { // squared
+            const double r2 = r * r;
+#pragma unroll
+            for (int j = 0; j < EV_VPT; ++j) {
+                const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
+                v[j] = r2 - ((dx * dx + dy * dy) + dz * dz);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EV_VPT; ++j) {
+                const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
+                v[j] = r - sqrt((dx * dx + dy * dy) + dz * dz);
+            }
+        }
+        break;
+    }
+    case RIN_FN_CYLINDER:
+    case RIN_FN_TORUS: {
+        const double p0 = f.p[0], p1 = f.p[1], p2 = f.p[2], a0 = f.p[3], a1 = f.p[4], a2 = f.p[5], r = f.p[6];
+        const bool torus = f.type == RIN_FN_TORUS;
+        const double r2 = f.p[7];
+#pragma unroll
+        for (int j = 0; j < EV_VPT; ++j) {
+            const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
+            const double t = (a0 * dx + a1 * dy) + a2 * dz;
+            const double px = dx - t * a0, py = dy - t * a1, pz = dz - t * a2;
+            const double d = sqrt((px * px + py * py) + pz * pz);
+            if (torus) {
+                const double rho = d - r;
+                v[j] = r2 - sqrt(rho * rho + t * t);
+            } else
+                v[j] = r - d;
+        }
+        break;
+    }
+    default:
+#pragma unroll
+        for (int j = 0; j < EV_VPT; ++j) v[j] = 0.0;
+        break;
+    }
+    if (f.flip) {
+#pragma unroll
+        for (int j = 0; j < EV_VPT; ++j) v[j] = -v[j];
+    }
+}
+
 template <bool GRID>
 __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ pts, const double* __restrict__ axes,
-    uint32_t N, uint32_t v_first, uint32_t v_count, uint32_t VS, const rin_func_desc* __restrict__ funcs, uint32_t F,
-    int negate, double* __restrict__ vals, uint2* __restrict__ vmask, uint32_t* __restrict__ vmask16,
-    unsigned long long* __restrict__ n_zero)
+    uint32_t N, const FastDiv dN, uint32_t v_first, uint32_t v_count, uint32_t VS,
+    const rin_func_desc* __restrict__ funcs, uint32_t F, int negate, double* __restrict__ vals,
+    uint2* __restrict__ vmask, uint32_t* __restrict__ vmask16, unsigned long long* __restrict__ n_zero)
 {
     extern __shared__ rin_func_desc s_funcs[];
     for (uint32_t i = threadIdx.x; i < F * (sizeof(rin_func_desc) / 8); i += blockDim.x)
@@ -79,7 +143,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ pt
             ok[j] = idx < v_count;
             v[j] = v_first + (ok[j] ? idx : 0u);
             if (GRID) {
-                const uint32_t k = v[j] % N, ij = v[j] / N, jj = ij % N, ii = ij / N;
+                const uint32_t ij = fd_div(v[j], dN), k = v[j] - ij * N, ii = fd_div(ij, dN), jj = ij - ii * N;
                 x[j] = __ldg(&axes[ii]);
                 y[j] = __ldg(&axes[N + jj]);
                 z[j] = __ldg(&axes[2 * N + k]);
@@ -95,14 +159,16 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ pt
             for (int j = 0; j < EV_VPT; ++j) P[j] = Nn[j] = 0;
             const uint32_t fe = min(F, w * 32 + 32);
             for (uint32_t f = w * 32; f < fe; ++f) {
-                const rin_func_desc& fd = s_funcs[f];
+                double val[EV_VPT];
+                eval_func_n(s_funcs[f], x, y, z, val);
+                double* __restrict__ row = vals + (size_t)f * VS;
+                const uint32_t bit = 1u << (f & 31);
 #pragma unroll
                 for (int j = 0; j < EV_VPT; ++j) {
-                    double val = eval_func(fd, x[j], y[j], z[j]);
-                    if (negate) val = val * -1; // csg(): funcVals * -1 (src/csg.cpp:37)
-                    if (ok[j]) vals[(size_t)f * VS + v[j]] = val;
-                    P[j] |= (val > 0 ? 1u : 0u) << (f & 31);
-                    Nn[j] |= (val < 0 ? 1u : 0u) << (f & 31);
+                    if (negate) val[j] = val[j] * -1; // csg(): funcVals * -1 (src/csg.cpp:37)
+                    if (ok[j]) row[v[j]] = val[j];
+                    if (val[j] > 0) P[j] |= bit;
+                    if (val[j] < 0) Nn[j] |= bit;
                 }
             }
 #pragma unroll
@@ -138,6 +204,7 @@ struct FilterArgs
 {
     const uint4* tets; // explicit index records (null for GRID)
     uint32_t R;        // GRID: resolution
+    FastDiv dR;        // division by R
     uint32_t t_first, t_count;
     uint32_t c_first, n_units; // GRID: first cube / number of cubes; else n_units = t_count
     const uint2* vmask;
@@ -148,6 +215,7 @@ struct FilterArgs
     const uint16_t* lut1;
     const uint16_t* lut2;
     const uint32_t* blob32;
+    uint32_t* arena32;
     int use_lookup, use_secondary;
     uint32_t* tl_tet;
     uint32_t* tl_mask;
@@ -243,6 +311,12 @@ __global__ void __launch_bounds__(256) filter_classify_kernel(const FilterArgs A
     const unsigned tile = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 8) s_tot[threadIdx.x] = 0;
+    if (tile == 0 && threadIdx.x == 0) {
+        // the arena of general records starts with an empty record (header + trailing word)
+        A.arena32[0] = 0;
+        A.arena32[1] = 0;
+        A.gc->arena_top = 8;
+    }
     const uint32_t t_end = A.t_first + A.t_count;
     const uint32_t N = A.R + 1;
 
@@ -254,7 +328,7 @@ __global__ void __launch_bounds__(256) filter_classify_kernel(const FilterArgs A
         const bool in = u < A.n_units;
         if constexpr (GRID) {
             const uint32_t cube = A.c_first + (in ? u : 0u);
-            const uint32_t k = cube % A.R, ij = cube / A.R, j = ij % A.R, i = ij / A.R;
+            const uint32_t ij = fd_div(cube, A.dR), k = cube - ij * A.R, i = fd_div(ij, A.dR), j = ij - i * A.R;
             const uint32_t base = (i * N + j) * N + k;
             const bool odd = (i + j + k) & 1;
             // corner q of the cube, numbered like v0..v7 at src/io.cpp:126-133
@@ -383,51 +457,66 @@ __global__ void __launch_bounds__(256) filter_classify_kernel(const FilterArgs A
         run += __shfl_sync(0xffffffffu, x, 31);
     }
 
-    // ---- dispatch + tile-local slots
+    // ---- tile-local slots (tet id, masks) in tet order; most warps have nothing to write
     const size_t tbase = (size_t)tile * TS;
-    unsigned k1 = 0, k2 = 0, km = 0, kf = 0, nc = 0, nfa = 0, nfv = 0, exact = 0;
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
+        if (s_cnt[r * 8 + warp] == 0) continue;
         unsigned rank = 0;
 #pragma unroll
         for (int s = 0; s < PER; ++s) {
-            int k = 0;
+            uint32_t any = 0;
 #pragma unroll
-            for (int w = 0; w < W; ++w) k += __popc(m[r][s][w]);
-            if (k == 0) continue;
-            const uint32_t u = tile * UNITS + r * 256 + threadIdx.x;
-            const uint32_t t = GRID ? 5 * (A.c_first + u) + s : A.t_first + u;
-            const size_t pos = tbase + my_off[r] + pr[r] + rank++;
-            k1 += (k == 1);
-            k2 += (k == 2);
-            km += (k > 2);
-            kf += k;
-            const uint4 tv = GRID ? grid_tet(A.R, t) : __ldg(&A.tets[t]);
-            const uint32_t ref = classify_ia_tet<W, PACK>(A, tv, m[r][s], k, exact);
-            A.tl_tet[pos] = t;
+            for (int w = 0; w < W; ++w) any |= m[r][s][w];
+            if (any) {
+                const uint32_t u = tile * UNITS + r * 256 + threadIdx.x;
+                const size_t pos = tbase + my_off[r] + pr[r] + rank++;
+                A.tl_tet[pos] = GRID ? 5 * (A.c_first + u) + s : A.t_first + u;
 #pragma unroll
-            for (int w = 0; w < W; ++w) A.tl_mask[(size_t)w * A.tl_stride + pos] = m[r][s][w];
-            A.tl_ref[pos] = ref;
-            if (ref & REF_GENERAL) {
-                if (k <= IACapsSmall::MAXK) {
-                    const unsigned i = agg_inc(&A.gc->n_small);
-                    if (i < A.list_cap)
-                        A.small_list[i] = (uint32_t)pos;
-                    else
-                        *A.overflow = OVF_LIST;
-                } else {
-                    const unsigned i = agg_inc(&A.gc->n_big);
-                    if (i < A.list_cap)
-                        A.big_list[i] = (uint32_t)pos;
-                    else
-                        *A.overflow = OVF_LIST;
-                }
-            } else {
-                const uint32_t h = __ldg(&A.blob32[ref]);
-                nc += h & 255;
-                nfa += (h >> 8) & 255;
-                nfv += h >> 16;
+                for (int w = 0; w < W; ++w) A.tl_mask[(size_t)w * A.tl_stride + pos] = m[r][s][w];
             }
+        }
+    }
+    __syncthreads(); // the block's own global writes are visible to the block from here
+
+    // ---- dispatch, dense over the tile's active slots (all lanes busy, one copy of the code)
+    unsigned k1 = 0, k2 = 0, km = 0, kf = 0, nc = 0, nfa = 0, nfv = 0, exact = 0;
+    for (uint32_t i = threadIdx.x; i < run; i += 256) {
+        const size_t pos = tbase + i;
+        const uint32_t t = __ldcg(&A.tl_tet[pos]);
+        uint32_t mw[W];
+        int k = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            mw[w] = __ldcg(&A.tl_mask[(size_t)w * A.tl_stride + pos]);
+            k += __popc(mw[w]);
+        }
+        k1 += (k == 1);
+        k2 += (k == 2);
+        km += (k > 2);
+        kf += k;
+        const uint4 tv = GRID ? grid_tet(A.R, A.dR, t) : __ldg(&A.tets[t]);
+        const uint32_t ref = classify_ia_tet<W, PACK>(A, tv, mw, k, exact);
+        A.tl_ref[pos] = ref;
+        if (ref & REF_GENERAL) {
+            if (k <= IACapsSmall::MAXK) {
+                const unsigned q = agg_inc(&A.gc->n_small);
+                if (q < A.list_cap)
+                    A.small_list[q] = (uint32_t)pos;
+                else
+                    atomicOr(A.overflow, OVF_LIST);
+            } else {
+                const unsigned q = agg_inc(&A.gc->n_big);
+                if (q < A.list_cap)
+                    A.big_list[q] = (uint32_t)pos;
+                else
+                    atomicOr(A.overflow, OVF_LIST);
+            }
+        } else {
+            const uint32_t h = __ldg(&A.blob32[ref]);
+            nc += h & 255;
+            nfa += (h >> 8) & 255;
+            nfv += h >> 16;
         }
     }
 #pragma unroll
@@ -557,6 +646,9 @@ __device__ __forceinline__ IsoVertInfo iso_vert_info(uint32_t e, const uint32_t*
 struct EmitArgs
 {
     const uint4* tets;
+    uint32_t R; // != 0: generated grid, the tet's vertex ids are computed (grid_tet)
+    FastDiv dR;
+    unsigned* tile_ticket;
     const uint32_t* tl_tet;
     const uint32_t* tl_mask;
     const uint32_t* tl_ref;
@@ -573,24 +665,32 @@ struct EmitArgs
     uint32_t* rec_ref;
     uint4* offs;
     uint4* cand_key;
-    uint32_t* table;
-    uint32_t table_mask;
-    uint32_t* slot_of;
+    uint32_t* cand_src; // candidate -> active tet
     const unsigned* overflow;
 };
 
 template <int W>
-__global__ void __launch_bounds__(256) emit_insert_kernel(const EmitArgs A)
+__global__ void __launch_bounds__(256) emit_kernel(const EmitArgs A)
 {
     __shared__ uint4 s_warp[8];
     __shared__ uint4 s_run, s_tot;
+    __shared__ unsigned s_tile;
     if (*A.overflow) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        const uint32_t n_act = A.tile_tot[tile].act;
-        if (n_act == 0) continue;
-        const TileTot off = A.tile_off[tile];
+    for (;;) {
+        // tiles carry very different numbers of active tets: dynamic assignment
         __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t;
+            do t = atomicAdd(A.tile_ticket, 1u);
+            while (t < A.n_tiles && A.tile_tot[t].act == 0);
+            s_tile = t;
+        }
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= A.n_tiles) return;
+        const uint32_t n_act = A.tile_tot[tile].act;
+        const TileTot off = A.tile_off[tile];
         if (threadIdx.x == 0) s_run = make_uint4(off.cand, off.face, off.fv, off.funcs);
         __syncthreads();
         for (uint32_t r0 = 0; r0 < n_act; r0 += 256) {
@@ -664,41 +764,88 @@ __global__ void __launch_bounds__(256) emit_insert_kernel(const EmitArgs A)
                 A.rec_ref[a] = ref;
                 A.offs[a] = o;
                 if (ci.x) {
-                    const uint4 tv4 = __ldg(&A.tets[t]);
+                    const uint4 tv4 = A.R ? grid_tet(A.R, A.dR, t) : __ldg(&A.tets[t]);
                     const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
                     uint32_t fl[4];
                     first_funcs<W>(m, fl);
-                    for (uint32_t i = 0; i < ci.x; ++i)
+                    for (uint32_t i = 0; i < ci.x; ++i) {
                         A.cand_key[o.x + i] = iso_vert_info<W>(rec[1 + i], tv, fl, m).key;
-                }
-            }
-            __threadfence();
-            __syncthreads();
-            // insertion, one candidate per thread
-            for (uint32_t c = base.x + threadIdx.x; c < base.x + tot.x; c += 256) {
-                const uint4 k = __ldcg(&A.cand_key[c]);
-                if (k.x == NONE32) {
-                    A.slot_of[c] = NONE32;
-                    continue;
-                }
-                uint32_t h = hash4(k) & A.table_mask;
-                for (;;) {
-                    uint32_t cur = __ldcg(&A.table[h]);
-                    if (cur == NONE32) {
-                        cur = atomicCAS(&A.table[h], NONE32, c);
-                        if (cur == NONE32) break;
+                        A.cand_src[o.x + i] = a;
                     }
-                    if (key_eq(__ldcg(&A.cand_key[cur]), k)) {
-                        atomicMin(&A.table[h], c);
-                        break;
-                    }
-                    h = (h + 1) & A.table_mask;
                 }
-                A.slot_of[c] = h;
             }
             __syncthreads();
             if (threadIdx.x == 0) s_run = make_uint4(base.x + tot.x, base.y + tot.y, base.z + tot.z, base.w + tot.w);
             __syncthreads();
+        }
+    }
+}
+
+// K6: hash-min insertion, one candidate per thread and INS_BATCH in flight (first probes of all, then the key
+// checks).  A full table (sized from the previous pass) is reported through the overflow word.
+constexpr int INS_BATCH = 4;
+struct InsertArgs
+{
+    const uint4* cand_key;
+    const PassTotals* totals;
+    uint32_t* table;
+    uint32_t table_mask;
+    uint32_t* slot_of;
+    unsigned* overflow;
+};
+
+__global__ void __launch_bounds__(256) insert_kernel(const InsertArgs A)
+{
+    if (*A.overflow) return;
+    const uint32_t n = A.totals->n_cand;
+    const uint32_t step = gridDim.x * 256 * INS_BATCH;
+    for (uint32_t c0 = blockIdx.x * 256 * INS_BATCH + threadIdx.x; c0 < n; c0 += step) {
+        uint4 k[INS_BATCH];
+        uint32_t h[INS_BATCH], cur[INS_BATCH];
+        bool act[INS_BATCH];
+#pragma unroll
+        for (int u = 0; u < INS_BATCH; ++u) {
+            const uint32_t c = c0 + u * 256;
+            act[u] = c < n;
+            if (act[u]) k[u] = A.cand_key[c];
+        }
+#pragma unroll
+        for (int u = 0; u < INS_BATCH; ++u) {
+            const uint32_t c = c0 + u * 256;
+            if (act[u] && k[u].x == NONE32) { // never shared
+                A.slot_of[c] = NONE32;
+                act[u] = false;
+            }
+            if (act[u]) {
+                h[u] = hash4(k[u]) & A.table_mask;
+                cur[u] = atomicCAS(&A.table[h[u]], NONE32, c);
+            }
+        }
+        uint4 kc[INS_BATCH];
+#pragma unroll
+        for (int u = 0; u < INS_BATCH; ++u)
+            if (act[u] && cur[u] != NONE32) kc[u] = A.cand_key[cur[u]];
+#pragma unroll
+        for (int u = 0; u < INS_BATCH; ++u) {
+            if (!act[u]) continue;
+            const uint32_t c = c0 + u * 256;
+            uint32_t hh = h[u], cc = cur[u];
+            uint4 kk = kc[u];
+            for (uint32_t probes = 0;; ++probes) {
+                if (cc == NONE32) break; // the slot was empty and is ours now
+                if (key_eq(kk, k[u])) {
+                    atomicMin(&A.table[hh], c);
+                    break;
+                }
+                if (probes > A.table_mask) {
+                    atomicOr(A.overflow, OVF_TABLE);
+                    break;
+                }
+                hh = (hh + 1) & A.table_mask;
+                cc = atomicCAS(&A.table[hh], NONE32, c);
+                if (cc != NONE32) kk = A.cand_key[cc];
+            }
+            A.slot_of[c] = hh;
         }
     }
 }
@@ -714,6 +861,8 @@ __global__ void __launch_bounds__(256) emit_insert_kernel(const EmitArgs A)
 struct RankArgs
 {
     const uint4* tets;
+    uint32_t R;
+    FastDiv dR;
     const uint32_t* act_tet;
     const uint32_t* act_mask;
     uint32_t act_cap;
@@ -722,6 +871,7 @@ struct RankArgs
     const uint32_t* blob32;
     const uint32_t* arena32;
     const PassTotals* totals;
+    const uint32_t* cand_src;
     uint32_t* table;
     uint32_t* slot_of;
     const double* vals;
@@ -787,16 +937,67 @@ __device__ __forceinline__ void iso_vert_xyz(const uint32_t* sv, const uint32_t*
 #undef FV
 }
 
-constexpr int RV_TILE = 256;
+constexpr int RV_ITEMS = 4;
+constexpr int RV_TILE = 256 * RV_ITEMS; // candidates per tile
+
+// the representative candidate c of active tet a becomes vertex `id`
+template <int W>
+__device__ __forceinline__ void write_iso_vertex(const RankArgs& A, uint32_t c, uint32_t s, uint32_t id)
+{
+    const uint32_t a = A.cand_src[c];
+    const uint32_t t = A.act_tet[a];
+    const uint32_t ref = A.rec_ref[a];
+    const uint32_t i = c - A.offs[a].x;
+    uint32_t m[W], fl[4];
+#pragma unroll
+    for (int w = 0; w < W; ++w) m[w] = A.act_mask[(size_t)w * A.act_cap + a];
+    const uint32_t* rec = (ref & REF_GENERAL) ? A.arena32 + (size_t)(ref & ~REF_FLAGS) : A.blob32 + ref;
+    const uint32_t e = rec[1 + i];
+    const uint4 tv4 = A.R ? grid_tet(A.R, A.dR, t) : __ldg(&A.tets[t]);
+    const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
+    first_funcs<W>(m, fl);
+    const IsoVertInfo vi = iso_vert_info<W>(e, tv, fl, m);
+    uint32_t sv[4];
+    if (vi.size == 4) {
+        sv[0] = tv[0];
+        sv[1] = tv[1];
+        sv[2] = tv[2];
+        sv[3] = tv[3];
+    } else {
+        sv[0] = vi.key.x;
+        sv[1] = vi.key.y;
+        sv[2] = vi.key.z;
+        sv[3] = NONE32;
+    }
+    uint32_t fi[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) fi[q] = vi.f[q] == 0xffffu ? NONE32 : vi.f[q];
+    A.v_tet[id] = t;
+    A.v_local[id] = (uint8_t)vi.local;
+    A.v_size[id] = (uint8_t)vi.size;
+    A.v_simplex[id] = make_uint4(sv[0], sv[1], sv[2], sv[3]);
+    A.v_funcs[id] = make_uint4(fi[0], fi[1], fi[2], NONE32);
+    A.v_key[id] = vi.key;
+    double out[3];
+    iso_vert_xyz(sv, fi, vi.size, A.vals, A.VS, A.pts, out);
+    A.v_xyz[3 * (size_t)id + 0] = out[0];
+    A.v_xyz[3 * (size_t)id + 1] = out[1];
+    A.v_xyz[3 * (size_t)id + 2] = out[2];
+    if (s == NONE32)
+        A.slot_of[c] = VID_FLAG | id;
+    else
+        A.table[s] = VID_FLAG | id;
+}
 
 template <int W>
 __global__ void __launch_bounds__(256) rank_verts_kernel(const RankArgs A)
 {
     __shared__ unsigned s_tile, s_base;
-    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_cnt[RV_ITEMS * 8];
+    __shared__ uint2 s_rep[RV_TILE]; // (candidate, slot) of the tile's representatives, in candidate order
     if (*A.overflow) return;
-    const uint32_t n_active = A.totals->n_active;
-    const uint32_t n_tiles = (n_active + RV_TILE - 1) / RV_TILE;
+    const uint32_t n_cand = A.totals->n_cand;
+    const uint32_t n_tiles = (n_cand + RV_TILE - 1) / RV_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;) {
         __syncthreads();
@@ -804,45 +1005,39 @@ __global__ void __launch_bounds__(256) rank_verts_kernel(const RankArgs A)
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= n_tiles) return;
-        const uint32_t a = tile * RV_TILE + threadIdx.x;
-        const bool valid = a < n_active;
-        const uint32_t* rec = A.blob32;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        int nv = 0;
-        if (valid) {
-            const uint32_t ref = A.rec_ref[a];
-            rec = (ref & REF_GENERAL) ? A.arena32 + (size_t)(ref & ~REF_FLAGS) : A.blob32 + ref;
-            nv = rec[0] & 255;
-            o = A.offs[a];
+        // candidates in candidate order: item j of thread x is candidate tile * RV_TILE + j * 256 + x
+        uint32_t slot[RV_ITEMS];
+        unsigned ball[RV_ITEMS];
+        bool rep[RV_ITEMS];
+#pragma unroll
+        for (int j = 0; j < RV_ITEMS; ++j) {
+            const uint32_t c = tile * RV_TILE + j * 256 + threadIdx.x;
+            slot[j] = (c < n_cand) ? A.slot_of[c] : 0u;
         }
-        // representatives among this tet's candidates (bit i of repmask for the first 64)
-        unsigned long long repmask = 0;
-        unsigned cnt = 0;
-        for (int i = 0; i < nv; ++i) {
-            const uint32_t c = o.x + i;
-            const uint32_t s = A.slot_of[c];
-            const bool rep = (s == NONE32) || (__ldcg(&A.table[s]) == c);
-            cnt += rep;
-            if (i < 64 && rep) repmask |= 1ull << i;
+#pragma unroll
+        for (int j = 0; j < RV_ITEMS; ++j) {
+            const uint32_t c = tile * RV_TILE + j * 256 + threadIdx.x;
+            rep[j] = (c < n_cand) && (slot[j] == NONE32 || __ldcg(&A.table[slot[j]]) == c);
         }
-        unsigned x = cnt;
+#pragma unroll
+        for (int j = 0; j < RV_ITEMS; ++j) {
+            ball[j] = __ballot_sync(0xffffffffu, rep[j]);
+            if (lane == 0) s_cnt[j * 8 + warp] = __popc(ball[j]);
+        }
+        __syncthreads();
+        // exclusive prefix over the (item, warp) sequence: RV_ITEMS * 8 = 32 entries, one warp scan each
+        const unsigned cq = s_cnt[lane];
+        unsigned x = cq;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned y = __shfl_up_sync(0xffffffffu, x, d);
             if (lane >= d) x += y;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            const unsigned tq = (lane < 8) ? s_warp[lane] : 0;
-            unsigned x8 = tq;
+        const unsigned run = __shfl_sync(0xffffffffu, x, 31);
+        unsigned my_off[RV_ITEMS];
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, x8, d);
-                if (lane >= d) x8 += y;
-            }
-            if (lane < 8) s_warp[lane] = x8 - tq;
-            const unsigned run = __shfl_sync(0xffffffffu, x8, 7);
+        for (int j = 0; j < RV_ITEMS; ++j) my_off[j] = __shfl_sync(0xffffffffu, x - cq, j * 8 + warp);
+        if (warp == 0) {
             uint32_t e0, e1;
             tile_lookback_warp(A.status, (int)tile, run, 0, e0, e1);
             if (lane == 0) {
@@ -850,57 +1045,17 @@ __global__ void __launch_bounds__(256) rank_verts_kernel(const RankArgs A)
                 if (tile == n_tiles - 1) *A.n_unique = e0 + run;
             }
         }
+#pragma unroll
+        for (int j = 0; j < RV_ITEMS; ++j)
+            if (rep[j])
+                s_rep[my_off[j] + __popc(ball[j] & ((1u << lane) - 1u))] =
+                    make_uint2(tile * RV_TILE + j * 256 + threadIdx.x, slot[j]);
         __syncthreads();
-        unsigned id = s_base + s_warp[warp] + x - cnt;
-        if (!valid || cnt == 0) continue;
-        const uint32_t t = A.act_tet[a];
-        const uint4 tv4 = __ldg(&A.tets[t]);
-        const uint32_t tv[4] = {tv4.x, tv4.y, tv4.z, tv4.w};
-        uint32_t m[W], fl[4];
-#pragma unroll
-        for (int w = 0; w < W; ++w) m[w] = A.act_mask[(size_t)w * A.act_cap + a];
-        first_funcs<W>(m, fl);
-        for (int i = 0; i < nv; ++i) {
-            const uint32_t c = o.x + i;
-            const uint32_t s = A.slot_of[c];
-            bool rep;
-            if (i < 64)
-                rep = (repmask >> i) & 1;
-            else
-                rep = (s == NONE32) || (__ldcg(&A.table[s]) == c);
-            if (!rep) continue;
-            const IsoVertInfo vi = iso_vert_info<W>(rec[1 + i], tv, fl, m);
-            uint32_t sv[4];
-            if (vi.size == 4) {
-                sv[0] = tv[0];
-                sv[1] = tv[1];
-                sv[2] = tv[2];
-                sv[3] = tv[3];
-            } else {
-                sv[0] = vi.key.x;
-                sv[1] = vi.key.y;
-                sv[2] = vi.key.z;
-                sv[3] = NONE32;
-            }
-            uint32_t fi[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) fi[q] = vi.f[q] == 0xffffu ? NONE32 : vi.f[q];
-            A.v_tet[id] = t;
-            A.v_local[id] = (uint8_t)vi.local;
-            A.v_size[id] = (uint8_t)vi.size;
-            A.v_simplex[id] = make_uint4(sv[0], sv[1], sv[2], sv[3]);
-            A.v_funcs[id] = make_uint4(fi[0], fi[1], fi[2], NONE32);
-            A.v_key[id] = vi.key;
-            double out[3];
-            iso_vert_xyz(sv, fi, vi.size, A.vals, A.VS, A.pts, out);
-            A.v_xyz[3 * (size_t)id + 0] = out[0];
-            A.v_xyz[3 * (size_t)id + 1] = out[1];
-            A.v_xyz[3 * (size_t)id + 2] = out[2];
-            if (s == NONE32)
-                A.slot_of[c] = VID_FLAG | id;
-            else
-                A.table[s] = VID_FLAG | id;
-            ++id;
+        const unsigned base = s_base;
+        // dense: consecutive lanes write consecutive vertices
+        for (unsigned i = threadIdx.x; i < run; i += 256) {
+            const uint2 q = s_rep[i];
+            write_iso_vertex<W>(A, q.x, q.y, base + i);
         }
     }
 }
@@ -933,9 +1088,12 @@ struct FaceArgs
     const unsigned* overflow;
 };
 
+constexpr int FK_NV = 8; // final ids of a tet's first FK_NV candidates are fetched up front (independent loads)
+
 template <int W, bool HDR>
 __global__ void __launch_bounds__(256) faces_kernel(const FaceArgs A)
 {
+    __shared__ uint32_t s_vid[FK_NV][256];
     if (*A.overflow) return;
     const uint32_t n_active = A.totals->n_active;
     if (!HDR && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -954,6 +1112,14 @@ __global__ void __launch_bounds__(256) faces_kernel(const FaceArgs A)
         for (int w = 0; w < W; ++w) m[w] = A.act_mask[(size_t)w * A.act_cap + a];
         first_funcs<W>(m, fl);
         const uint4 o = A.offs[a];
+        {
+            uint32_t sl[FK_NV];
+#pragma unroll
+            for (int i = 0; i < FK_NV; ++i) sl[i] = (i < nv) ? A.slot_of[o.x + i] : VID_FLAG;
+#pragma unroll
+            for (int i = 0; i < FK_NV; ++i)
+                s_vid[i][threadIdx.x] = ((sl[i] & VID_FLAG) ? sl[i] : A.table[sl[i]]) & ~VID_FLAG;
+        }
         const uint32_t* p = r + 1 + nv;
         uint32_t fvo = o.z;
         for (int j = 0; j < nf; ++j) {
@@ -997,8 +1163,10 @@ __global__ void __launch_bounds__(256) faces_kernel(const FaceArgs A)
             }
             for (int k0 = 0; k0 < n; k0 += 4) {
                 const uint32_t x = *p++;
-                for (int k = k0; k < n && k < k0 + 4; ++k)
-                    A.f_verts[fvo + k] = final_vid(o.x + ((x >> (8 * (k - k0))) & 255), A.slot_of, A.table);
+                for (int k = k0; k < n && k < k0 + 4; ++k) {
+                    const uint32_t rk = (x >> (8 * (k - k0))) & 255;
+                    A.f_verts[fvo + k] = rk < FK_NV ? s_vid[rk][threadIdx.x] : final_vid(o.x + rk, A.slot_of, A.table);
+                }
             }
             fvo += n;
         }

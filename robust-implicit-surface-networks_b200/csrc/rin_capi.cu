@@ -28,6 +28,12 @@ int fail(int code, const std::string& msg)
     return code;
 }
 
+// stage events are recorded only while stage timing is on (rin_set_stage_timing); first / last always
+#define EVREC(ev_)                                                                                 \
+    do {                                                                                           \
+        if (c->stage_timing || (ev_) == c->ev[0] || (ev_) == c->ev[ST_COUNT]) CK(cudaEventRecord((ev_), c->stream)); \
+    } while (0)
+
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -145,10 +151,10 @@ struct rin_ctx
     DevBuf tl_tet, tl_mask, tile_cnt, tile_off; // tile-local filter output
     DevBuf tl_ref, tile_tot, tile_pre;          // implicit-arrangement pass: record refs, tile totals / prefixes
     // sizes learnt from the previous pass (0 = unknown: the next pass sizes its buffers after the tile scan)
-    uint32_t h_act = 0, h_list = 0, h_cand = 0, h_face = 0, h_fv = 0;
+    uint32_t h_act = 0, h_list = 0, h_cand = 0, h_face = 0, h_fv = 0, h_unique = 0;
     uint32_t table_size = 0; // vertex hash table slots of the last IA pass
     DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
-    DevBuf cand_key, cand_pay, face_hdr, fv_ref;
+    DevBuf cand_key, cand_pay, cand_src, face_hdr, fv_ref;
     DevBuf table, slot_of, rep, vid;
     DevBuf tmp_fverts, bfkeys, frep, fdup, fpos, bf_mask; // degenerate boundary-face dedup
     DevBuf m_cnt, m_off, m_vmap, m_fmap, fpartner;        // cell-grouping maps (rin_tet_maps)
@@ -187,6 +193,7 @@ struct rin_ctx
     uint32_t run_F = 0, run_VS = 0;
     uint64_t run_V = 0, run_t_first = 0, run_t_count = 0;
     int launches = 0; // kernels launched by the last rin_run
+    bool stage_timing = true;
 };
 
 namespace {
@@ -272,7 +279,7 @@ void rin_destroy(rin_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->pts, &c->tets, &c->funcs, &c->rowmajor, &c->vals, &c->vmask, &c->vmask16, &c->counters,
         &c->status, &c->tl_tet, &c->tl_mask, &c->tile_cnt, &c->tile_off, &c->tl_ref, &c->tile_tot, &c->tile_pre, &c->axes, &c->act_tet, &c->act_mask, &c->rec_ref, &c->general_list, &c->big_list, &c->arena, &c->offs, &c->m_cnt, &c->m_off, &c->m_vmap, &c->m_fmap, &c->fpartner,
-        &c->cand_key, &c->cand_pay, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
+        &c->cand_key, &c->cand_pay, &c->cand_src, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
         &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->cx_out, &c->f_off, &c->f_verts,
@@ -318,7 +325,7 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
     c->t_count = n_tets;
     c->v_first = c->v_count = 0;
     c->have_values = false;
-    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = 0;
+    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     invalidate(c);
     return RIN_OK;
 }
@@ -348,7 +355,7 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     c->t_count = T;
     c->v_first = c->v_count = 0;
     c->have_values = false;
-    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = 0;
+    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     invalidate(c);
     return RIN_OK;
 }
@@ -364,7 +371,7 @@ int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
     c->v_first = 0;
     c->v_count = 0;
     c->x_window = false;
-    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = 0;
+    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     invalidate(c);
     if (count != 0 && (first != 0 || count != c->T)) {
         // vertex id range referenced by the tet range: only these vertices are evaluated
@@ -557,6 +564,18 @@ int rin_download_grid(rin_ctx* c, double* pts, uint32_t* tets)
     if (tets) CK(cudaMemcpyAsync(tets, c->tets.p, c->T * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return RIN_OK;
+}
+
+int rin_set_stage_timing(rin_ctx* c, int on)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    c->stage_timing = on != 0;
+    return RIN_OK;
+}
+
+int rin_get_launch_count(const rin_ctx* c)
+{
+    return c ? c->launches : 0;
 }
 
 int rin_get_stage_times(const rin_ctx* c, float* ms, int capacity)
@@ -1290,7 +1309,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         const bool sizing = (c->h_act == 0); // sizes unknown: one extra synchronisation after the tile scan
         const uint32_t list_cap = std::max<uint32_t>(c->h_list, 4096);
         CK(c->general_list.ensure((size_t)list_cap * 4));
-        CK(c->big_list.ensure((size_t)list_cap * 12)); // [big | small-tier overflow | mid-tier overflow]
+        CK(c->big_list.ensure((size_t)list_cap * 8)); // [big | small-tier overflow]
         uint32_t act_cap = 0, cand_cap = 0, face_cap = 0, fv_cap = 0, tsize = 0;
         auto size_outputs = [&]() -> int {
             act_cap = c->h_act;
@@ -1302,11 +1321,14 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
             CK(c->rec_ref.ensure((size_t)c->act_cap * 4));
             CK(c->offs.ensure((size_t)c->act_cap * 16));
-            CK(c->status.ensure(((size_t)act_cap / RV_TILE + 2) * 8 + 64));
+            CK(c->status.ensure(((size_t)cand_cap / RV_TILE + 2) * 8 + 64));
+            CK(c->cand_src.ensure((size_t)cand_cap * 4));
             CK(c->cand_key.ensure((size_t)cand_cap * 16));
             CK(c->slot_of.ensure((size_t)cand_cap * 4));
+            // slots: twice the unique keys of the previous pass (a full table is detected and the pass repeated),
+            // or twice the candidates when nothing is known
             tsize = 1024;
-            while (tsize < 2ull * cand_cap) tsize <<= 1;
+            while (tsize < 2ull * (c->h_unique ? c->h_unique : cand_cap)) tsize <<= 1;
             CK(c->table.ensure((size_t)tsize * 4));
             CK(c->v_tet.ensure((size_t)cand_cap * 4));
             CK(c->v_local.ensure(cand_cap));
@@ -1328,24 +1350,22 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         }
 
         CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
-        const unsigned top0 = 8; // the arena starts with an empty record (header + trailing word)
-        CK(cudaMemsetAsync(c->arena.p, 0, 8, s));
-        CK(cudaMemcpyAsync(&dctr->gen.arena_top, &top0, 4, cudaMemcpyHostToDevice, s));
 
         // ---- K1: values + sign masks (only the vertex range the tet range touches)
-        CK(cudaEventRecord(c->ev[ST_EVAL], s));
-        CK(cudaEventRecord(c->kev[0], s));
+        EVREC(c->ev[ST_EVAL]);
+        EVREC(c->kev[0]);
         if (!evaluated) {
             const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : V;
             if (c->have_funcs) {
                 const size_t smem = F * sizeof(rin_func_desc);
                 const int g = grid_for((vc + EV_VPT - 1) / EV_VPT, 256, sm, 8);
                 if (grid)
-                    eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1, vf, vc, VS,
+                    eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1,
+                        make_fastdiv(c->grid_R + 1), vf, vc, VS,
                         c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16,
                         &dctr->n_zero);
                 else
-                    eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, vf, vc, VS,
+                    eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, FastDiv{}, vf, vc, VS,
                         c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), vm16,
                         &dctr->n_zero);
             } else {
@@ -1355,13 +1375,14 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             CK(cudaGetLastError());
             ++c->launches;
         }
-        CK(cudaEventRecord(c->kev[1], s));
+        EVREC(c->kev[1]);
 
         // ---- K2: filter + dispatch
-        CK(cudaEventRecord(c->ev[ST_FILTER], s));
+        EVREC(c->ev[ST_FILTER]);
         FilterArgs fa{};
         fa.tets = grid ? nullptr : c->tets.as<uint4>();
         fa.R = c->grid_R;
+        fa.dR = make_fastdiv(c->grid_R);
         fa.t_first = t_first;
         fa.t_count = T;
         fa.c_first = c_first;
@@ -1374,6 +1395,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         fa.lut1 = c->lut_ia.lut1.as<uint16_t>();
         fa.lut2 = c->lut_ia.lut2.as<uint16_t>();
         fa.blob32 = c->lut_ia.blob.as<uint32_t>();
+        fa.arena32 = c->arena.as<uint32_t>();
         fa.use_lookup = use_lookup;
         fa.use_secondary = use_secondary;
         fa.tl_tet = c->tl_tet.as<uint32_t>();
@@ -1388,7 +1410,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         fa.gc = &dctr->gen;
         fa.n_exact = &dctr->n_exact_classify;
         fa.overflow = &dctr->overflow;
-        CK(cudaEventRecord(c->kev[2], s));
+        EVREC(c->kev[2]);
         if (grid) {
             if (pack && W == 1)
                 filter_classify_kernel<1, true, true><<<n_tiles, 256, 0, s>>>(fa);
@@ -1400,13 +1422,13 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             else
                 filter_classify_kernel<W, false, false><<<n_tiles, 256, 0, s>>>(fa);
         }
-        CK(cudaEventRecord(c->kev[3], s));
+        EVREC(c->kev[3]);
         CK(cudaGetLastError());
         ++c->launches;
 
         // ---- K4: general tiers; the last block of the big tier scans the tile totals
-        CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
-        CK(cudaEventRecord(c->ev[ST_GENERAL], s));
+        EVREC(c->ev[ST_CLASSIFY]);
+        EVREC(c->ev[ST_GENERAL]);
         const uint32_t acap = (uint32_t)std::min<size_t>(c->arena.cap, 0xfffffff0u);
         const uint32_t est = std::min<uint32_t>(list_cap, c->h_list ? c->h_list : list_cap);
         const int small_blocks = (int)std::max<uint32_t>(
@@ -1414,13 +1436,6 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         const int mid_blocks = (int)std::max<uint32_t>(
             1, std::min<uint32_t>((est + GEN_MID_WARPS - 1) / GEN_MID_WARPS, (uint32_t)(sm * mid_per_sm)));
         uint32_t* lists = c->big_list.as<uint32_t>();
-        general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet,
-            fa.tl_mask, (uint32_t)tl_stride, fa.small_list, lists + list_cap,
-            c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr, c->lut_ia.lut2cx.as<uint16_t>(),
-            fa.vals, VS, c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
-        general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
-            (uint32_t)tl_stride, lists, lists + list_cap, lists + 2 * (size_t)list_cap, fa.vals, VS,
-            c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
         TileScanArgs sa{};
         sa.tot = fa.tile_tot;
         sa.n_tiles = n_tiles;
@@ -1431,12 +1446,16 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         sa.face_cap = sizing ? 0xffffffffu : face_cap;
         sa.fv_cap = sizing ? 0xffffffffu : fv_cap;
         sa.overflow = &dctr->overflow;
-        general_ia_big_kernel<W><<<sm * 2, GEN_BIG_THREADS, 0, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
-            (uint32_t)tl_stride, lists + 2 * (size_t)list_cap, &dctr->gen.n_ovf2, fa.vals, VS, c->arena.as<uint8_t>(),
-            acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, sa, list_cap);
+        general_ia_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet,
+            fa.tl_mask, (uint32_t)tl_stride, fa.small_list, lists + list_cap,
+            c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr, c->lut_ia.lut2cx.as<uint16_t>(),
+            fa.vals, VS, c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
+        general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
+            (uint32_t)tl_stride, lists, lists + list_cap, nullptr, fa.vals, VS,
+            c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap, sa);
         CK(cudaGetLastError());
-        c->launches += 3;
-        CK(cudaEventRecord(c->ev[ST_SCAN], s));
+        c->launches += 2;
+        EVREC(c->ev[ST_SCAN]);
 
         auto check_general = [&](const Counters& hc, bool& again) -> int {
             again = false;
@@ -1449,7 +1468,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
                 again = true;
             }
             if (hc.overflow & OVF_LIST) {
-                const uint32_t need = std::max({hc.gen.n_small, hc.gen.n_big, hc.gen.n_ovf, hc.gen.n_ovf2});
+                const uint32_t need = std::max({hc.gen.n_small, hc.gen.n_big, hc.gen.n_ovf});
                 c->h_list = need + need / 8 + 1024;
                 again = true;
             }
@@ -1474,11 +1493,14 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         }
 
         // ---- K5 + K6: ordered active list, candidates, hash-min insertion
-        CK(cudaEventRecord(c->ev[ST_EMIT], s));
+        EVREC(c->ev[ST_EMIT]);
         CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
-        CK(cudaMemsetAsync(c->status.p, 0, ((size_t)act_cap / RV_TILE + 2) * 8, s));
+        CK(cudaMemsetAsync(c->status.p, 0, ((size_t)cand_cap / RV_TILE + 2) * 8, s));
         EmitArgs ea{};
         ea.tets = c->tets.as<uint4>();
+        ea.R = c->grid_R;
+        ea.dR = fa.dR;
+        ea.tile_ticket = &dctr->scan.tile_counter;
         ea.tl_tet = fa.tl_tet;
         ea.tl_mask = fa.tl_mask;
         ea.tl_ref = fa.tl_ref;
@@ -1495,19 +1517,29 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         ea.rec_ref = c->rec_ref.as<uint32_t>();
         ea.offs = c->offs.as<uint4>();
         ea.cand_key = c->cand_key.as<uint4>();
-        ea.table = c->table.as<uint32_t>();
-        ea.table_mask = tsize - 1;
-        ea.slot_of = c->slot_of.as<uint32_t>();
+        ea.cand_src = c->cand_src.as<uint32_t>();
         ea.overflow = &dctr->overflow;
-        emit_insert_kernel<W><<<(int)std::min<uint32_t>(n_tiles, (uint32_t)sm * 8), 256, 0, s>>>(ea);
+        emit_kernel<W><<<(int)std::min<uint32_t>(n_tiles, (uint32_t)sm * 8), 256, 0, s>>>(ea);
+        const uint32_t a_est = sizing ? h.tot.n_active : act_cap;
+        const uint32_t c_est = sizing ? h.tot.n_cand : cand_cap;
+        InsertArgs ia{};
+        ia.cand_key = ea.cand_key;
+        ia.totals = &dctr->tot;
+        ia.table = c->table.as<uint32_t>();
+        ia.table_mask = tsize - 1;
+        ia.slot_of = c->slot_of.as<uint32_t>();
+        ia.overflow = &dctr->overflow;
+        EVREC(c->ev[ST_DEDUP]);
+        insert_kernel<<<grid_for((c_est + INS_BATCH - 1) / INS_BATCH, 256, sm, 8), 256, 0, s>>>(ia);
         CK(cudaGetLastError());
-        ++c->launches;
+        c->launches += 2;
 
         // ---- K6 + K7: ranking, vertex records, coordinates
-        CK(cudaEventRecord(c->ev[ST_DEDUP], s));
-        CK(cudaEventRecord(c->ev[ST_VERTS], s));
+        EVREC(c->ev[ST_VERTS]);
         RankArgs ra{};
         ra.tets = ea.tets;
+        ra.R = ea.R;
+        ra.dR = ea.dR;
         ra.act_tet = ea.act_tet;
         ra.act_mask = ea.act_mask;
         ra.act_cap = c->act_cap;
@@ -1516,8 +1548,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         ra.blob32 = ea.blob32;
         ra.arena32 = ea.arena32;
         ra.totals = &dctr->tot;
-        ra.table = ea.table;
-        ra.slot_of = ea.slot_of;
+        ra.cand_src = ea.cand_src;
+        ra.table = ia.table;
+        ra.slot_of = ia.slot_of;
         ra.vals = fa.vals;
         ra.VS = VS;
         ra.pts = c->pts.as<double>();
@@ -1532,14 +1565,13 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         ra.tile_counter = &dctr->rank_tile;
         ra.n_unique = &dctr->n_unique;
         ra.overflow = &dctr->overflow;
-        const uint32_t a_est = sizing ? h.tot.n_active : act_cap;
-        rank_verts_kernel<W><<<(int)std::max<uint32_t>(1, std::min<uint32_t>((a_est + RV_TILE - 1) / RV_TILE,
-                                   (uint32_t)sm * 8)), 256, 0, s>>>(ra);
+        rank_verts_kernel<W><<<(int)std::max<uint32_t>(1, std::min<uint32_t>((c_est + RV_TILE - 1) / RV_TILE,
+                                   (uint32_t)sm * 6)), 256, 0, s>>>(ra);
         CK(cudaGetLastError());
         ++c->launches;
 
         // ---- faces
-        CK(cudaEventRecord(c->ev[ST_FACES], s));
+        EVREC(c->ev[ST_FACES]);
         FaceArgs fg{};
         fg.act_tet = ea.act_tet;
         fg.act_mask = ea.act_mask;
@@ -1549,8 +1581,8 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         fg.blob32 = ea.blob32;
         fg.arena32 = ea.arena32;
         fg.totals = &dctr->tot;
-        fg.table = ea.table;
-        fg.slot_of = ea.slot_of;
+        fg.table = ia.table;
+        fg.slot_of = ia.slot_of;
         fg.f_off = c->f_off.as<uint32_t>();
         fg.f_verts = c->f_verts.as<uint32_t>();
         fg.f_toff = c->f_toff.as<uint32_t>();
@@ -1561,7 +1593,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         faces_kernel<W, false><<<face_grid, 256, 0, s>>>(fg);
         CK(cudaGetLastError());
         ++c->launches;
-        CK(cudaEventRecord(c->ev[ST_COUNT], s));
+        EVREC(c->ev[ST_COUNT]);
 
         // ---- the one read-back
         CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -1574,6 +1606,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         if (rc) return rc;
         if (again || h.overflow) {
             c->h_act = 0; // size the next attempt exactly
+            c->h_unique = 0;
             continue;
         }
 
@@ -1625,12 +1658,17 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
                 c->f_tets.as<uint32_t>());
             CK(cudaGetLastError());
             c->launches += 7;
-            CK(cudaEventRecord(c->ev[ST_COUNT], s));
+            EVREC(c->ev[ST_COUNT]);
             CK(cudaStreamSynchronize(s));
         }
-        for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
-        CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
-        CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+        if (c->stage_timing) {
+            for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+            CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
+            CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+        } else {
+            for (auto& x : c->stage_ms) x = 0;
+            c->kernel_ms[0] = c->kernel_ms[1] = 0;
+        }
         CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
         // learnt sizes for the next pass over these inputs
@@ -1639,10 +1677,11 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         c->h_face = h.tot.n_faces + h.tot.n_faces / 8 + 1024;
         c->h_fv = h.tot.n_fv + h.tot.n_fv / 8 + 1024;
         {
-            const uint32_t need = std::max({h.gen.n_small, h.gen.n_big, h.gen.n_ovf, h.gen.n_ovf2});
+            const uint32_t need = std::max({h.gen.n_small, h.gen.n_big, h.gen.n_ovf});
             c->h_list = need + need / 8 + 1024;
         }
         c->table_size = tsize;
+        c->h_unique = h.n_unique + h.n_unique / 8 + 1024;
         c->ia_bndry_faces = h.gen.n_bnd_faces != 0;
         const uint32_t NV = h.tot.n_cand ? h.n_unique : 0;
         c->n_local_verts = NV;
@@ -1686,18 +1725,19 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->vals.ensure((size_t)V * F * 8));
     CK(c->vmask.ensure((size_t)V * W * 8));
     CK(cudaMemsetAsync(dctr, 0, sizeof(Counters), s));
-    CK(cudaEventRecord(c->ev[ST_EVAL], s));
+    EVREC(c->ev[ST_EVAL]);
     const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : (uint32_t)c->V;
-    CK(cudaEventRecord(c->kev[0], s));
+    EVREC(c->kev[0]);
     if (c->have_funcs) {
         const size_t smem = F * sizeof(rin_func_desc);
         const int g = grid_for((vc + EV_VPT - 1) / EV_VPT, 256, sm, 8);
         if (c->grid_R)
-            eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1, vf, vc, V,
+            eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1,
+                make_fastdiv(c->grid_R + 1), vf, vc, V,
                 c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
                 &dctr->n_zero);
         else
-            eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, vf, vc, V,
+            eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, FastDiv{}, vf, vc, V,
                 c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
                 &dctr->n_zero);
     } else {
@@ -1708,11 +1748,11 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(cudaMemsetAsync(&dctr->n_zero, 0, 8, s));
     highest_material_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->vals.as<double>(), vf, vc, V, F,
         c->vmask.as<uint2>(), &dctr->n_zero);
-    CK(cudaEventRecord(c->kev[1], s));
+    EVREC(c->kev[1]);
     CK(cudaGetLastError());
 
     // ---- K2: filter (tile-local compaction) + tile scan + ordered gather
-    CK(cudaEventRecord(c->ev[ST_FILTER], s));
+    EVREC(c->ev[ST_FILTER]);
     const uint32_t n_tiles = (T + FILT_TILE - 1) / FILT_TILE;
     const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
     const size_t tl_stride = (size_t)n_tiles * FILT_TILE;
@@ -1720,12 +1760,12 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->tl_mask.ensure(tl_stride * 4 * W));
     CK(c->tile_cnt.ensure((size_t)n_tiles * 8));
     CK(c->tile_off.ensure((size_t)(n_tiles + 1) * 8));
-    CK(cudaEventRecord(c->kev[2], s));
+    EVREC(c->kev[2]);
     (void)last_mask;
     filter_mi_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
         c->vmask.as<uint2>(), c->vals.as<double>(), V, F, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
         tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
-    CK(cudaEventRecord(c->kev[3], s));
+    EVREC(c->kev[3]);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -1754,7 +1794,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     n.num_active_funcs = h.filt.n_funcs;
 
     // ---- K3: classify
-    CK(cudaEventRecord(c->ev[ST_CLASSIFY], s));
+    EVREC(c->ev[ST_CLASSIFY]);
     CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
     CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
     CK(c->big_list.ensure((size_t)std::max(A, 1u) * 8)); // [big | small-tier overflow]
@@ -1769,7 +1809,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     (void)use_secondary;
 
     // ---- K4: general kernels (arena grows on overflow)
-    CK(cudaEventRecord(c->ev[ST_GENERAL], s));
+    EVREC(c->ev[ST_GENERAL]);
     if (A) {
         const uint32_t est = use_lookup ? (h.filt.n_kmore + h.filt.n_k2) : A;
         const int small_blocks = (int)std::max<uint32_t>(
@@ -1810,7 +1850,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     n.num_general_tets = h.gen.n_general;
 
     // ---- K5a: counts + offsets
-    CK(cudaEventRecord(c->ev[ST_SCAN], s));
+    EVREC(c->ev[ST_SCAN]);
     const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
     if (A) {
         CK(c->status.ensure((size_t)a_tiles * 16 + 64));
@@ -1825,7 +1865,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
 
     // ---- K5b: emit
-    CK(cudaEventRecord(c->ev[ST_EMIT], s));
+    EVREC(c->ev[ST_EMIT]);
     CK(c->cand_key.ensure((size_t)std::max(NC, 1u) * 16));
     CK(c->cand_pay.ensure((size_t)std::max(NC, 1u) * 16));
     CK(c->face_hdr.ensure((size_t)std::max(NFc, 1u) * 16));
@@ -1851,7 +1891,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     }
 
     // ---- K6: dedup (hash-min + rank)
-    CK(cudaEventRecord(c->ev[ST_DEDUP], s));
+    EVREC(c->ev[ST_DEDUP]);
     uint32_t NV = 0;
     if (NC) {
         uint32_t tsize = 1024;
@@ -1917,7 +1957,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     }
 
     // ---- K7: unique vertices + xyz
-    CK(cudaEventRecord(c->ev[ST_VERTS], s));
+    EVREC(c->ev[ST_VERTS]);
     CK(c->v_tet.ensure((size_t)std::max(NV, 1u) * 4));
     CK(c->v_local.ensure(std::max(NV, 1u)));
     CK(c->v_size.ensure(std::max(NV, 1u)));
@@ -1935,7 +1975,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     }
 
     // ---- faces
-    CK(cudaEventRecord(c->ev[ST_FACES], s));
+    EVREC(c->ev[ST_FACES]);
     CK(c->f_off.ensure((size_t)(NFc + 1) * 4));
     CK(c->f_verts.ensure((size_t)std::max(NFV, 1u) * 4));
     CK(c->f_toff.ensure((size_t)(NFc + 1) * 4));
@@ -1975,11 +2015,16 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         NFVout = ht[1];
         NFT = ht[2];
     }
-    CK(cudaEventRecord(c->ev[ST_COUNT], s));
+    EVREC(c->ev[ST_COUNT]);
     CK(cudaStreamSynchronize(s));
-    for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
-    CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
-    CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+    if (c->stage_timing) {
+        for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
+        CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));
+        CK(cudaEventElapsedTime(&c->kernel_ms[1], c->kev[2], c->kev[3]));
+    } else {
+        for (auto& x : c->stage_ms) x = 0;
+        c->kernel_ms[0] = c->kernel_ms[1] = 0;
+    }
     CK(cudaEventElapsedTime(&c->total_ms, c->ev[0], c->ev[ST_COUNT]));
 
     c->marked = c->finalized = false;
@@ -2124,7 +2169,7 @@ int build_ia_tables(rin_ctx* c)
     CKC(cudaMemsetAsync(d_arena.p, 0, 8, s));
     general_ia_big_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_tets.as<uint4>(), d_act_tet.as<uint32_t>(),
         d_act_mask.as<uint32_t>(), NWT, d_gl.as<uint32_t>(), &dctr->gen.n_big, d_vals.as<double>(), Vw,
-        d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen, nullptr, 1, TileScanArgs{});
+        d_arena.as<uint8_t>(), (uint32_t)d_arena.cap, d_ref.as<uint32_t>(), &dctr->gen);
     CKC(cudaGetLastError());
     GeneralCounters g1;
     CKC(cudaMemcpyAsync(&g1, &dctr->gen, sizeof(g1), cudaMemcpyDeviceToHost, s));

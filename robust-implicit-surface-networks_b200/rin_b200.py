@@ -68,6 +68,8 @@ def lib():
         L.rin_download_values.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_download_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rin_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.rin_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
+        L.rin_get_launch_count.argtypes = [C.c_void_p]
         L.rin_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                            C.POINTER(C.c_float)]
         L.rin_boundary_export.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -272,6 +274,12 @@ class Context:
         out = np.zeros(4, np.uint32)
         self._check(lib().rin_robust_test(self._h, mode, out.ctypes.data))
         return {"type1": int(out[0]), "type2": int(out[1]), "type3": int(out[2]), "tested": int(out[3])}
+
+    def set_stage_timing(self, on):
+        self._check(lib().rin_set_stage_timing(self._h, 1 if on else 0))
+
+    def launch_count(self):
+        return lib().rin_get_launch_count(self._h)
 
     def kernel_times(self):
         e, f, t = C.c_float(), C.c_float(), C.c_float()
