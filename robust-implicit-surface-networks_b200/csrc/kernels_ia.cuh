@@ -857,22 +857,25 @@ struct TileScanArgs
 
 __device__ void tile_scan_block(const TileScanArgs& S)
 {
+    // warp w owns a contiguous run of tiles and reads it 32 tiles at a time (coalesced)
     __shared__ unsigned s_w[32][5];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t per = (S.n_tiles + blockDim.x - 1) / blockDim.x;
-    const uint32_t b = min(S.n_tiles, threadIdx.x * per), e = min(S.n_tiles, b + per);
+    const uint32_t chunk = ((S.n_tiles + nwarps - 1) / nwarps + 31u) & ~31u;
+    const uint32_t b = min(S.n_tiles, warp * chunk), e = min(S.n_tiles, b + chunk);
+    // pass 1: the warp's totals
     unsigned c[5] = {0, 0, 0, 0, 0};
-    for (uint32_t t0 = b; t0 < e; t0 += 8) { // eight tiles' loads in flight
-        uint4 a[8];
-        unsigned f[8];
+    for (uint32_t t0 = b + lane; t0 < e; t0 += 32 * 4) {
+        uint4 a[4];
+        unsigned f[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const bool in = t0 + q < e;
-            a[q] = in ? __ldcg(reinterpret_cast<const uint4*>(S.tot + t0 + q)) : make_uint4(0, 0, 0, 0);
-            f[q] = in ? __ldcg(&S.tot[t0 + q].fv) : 0u;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t t = t0 + 32 * q;
+            const bool in = t < e;
+            a[q] = in ? __ldcg(reinterpret_cast<const uint4*>(S.tot + t)) : make_uint4(0, 0, 0, 0);
+            f[q] = in ? __ldcg(&S.tot[t].fv) : 0u;
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
             c[0] += a[q].x;
             c[1] += a[q].y;
             c[2] += a[q].z;
@@ -880,78 +883,69 @@ __device__ void tile_scan_block(const TileScanArgs& S)
             c[4] += f[q];
         }
     }
-    unsigned x[5];
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
-        x[q] = c[q];
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, x[q], o);
-            if (lane >= o) x[q] += y;
-        }
-        if (lane == 31) s_w[warp][q] = x[q];
+        for (int o = 16; o; o >>= 1) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
+        if (lane == 0) s_w[warp][q] = c[q];
     }
     __syncthreads();
-    if (warp == 0) {
+    unsigned run[5] = {0, 0, 0, 0, 0}, total[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < nwarps; ++w)
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            const unsigned t = lane < nwarps ? s_w[lane][q] : 0u;
-            unsigned y = t;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned z = __shfl_up_sync(0xffffffffu, y, o);
-                if (lane >= o) y += z;
-            }
-            if (lane < nwarps) s_w[lane][q] = y - t;
-            if (lane == 31) {
-                unsigned o = 0;
-                if (q == 0) {
-                    S.totals->n_active = y;
-                    if (y > S.act_cap) o = OVF_ACT;
-                } else if (q == 1)
-                    S.totals->n_funcs = y;
-                else if (q == 2) {
-                    S.totals->n_cand = y;
-                    if (y > S.cand_cap) o = OVF_CAND;
-                } else if (q == 3) {
-                    S.totals->n_faces = y;
-                    if (y > S.face_cap) o = OVF_FACE;
-                } else {
-                    S.totals->n_fv = y;
-                    if (y > S.fv_cap) o = OVF_FV;
-                }
-                if (o) atomicOr(S.overflow, o);
-            }
+            const unsigned x = s_w[w][q];
+            if (w < warp) run[q] += x;
+            total[q] += x;
         }
-    }
-    __syncthreads();
-    unsigned run[5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q) run[q] = s_w[warp][q] + x[q] - c[q];
-    for (uint32_t t0 = b; t0 < e; t0 += 8) {
-        uint4 a[8];
-        unsigned f[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const bool in = t0 + q < e;
-            a[q] = in ? __ldcg(reinterpret_cast<const uint4*>(S.tot + t0 + q)) : make_uint4(0, 0, 0, 0);
-            f[q] = in ? __ldcg(&S.tot[t0 + q].fv) : 0u;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (t0 + q < e) {
-                uint4* o4 = reinterpret_cast<uint4*>(S.off + t0 + q);
-                o4[0] = make_uint4(run[0], run[1], run[2], run[3]);
-                o4[1] = make_uint4(run[4], 0, 0, 0);
-                run[0] += a[q].x;
-                run[1] += a[q].y;
-                run[2] += a[q].z;
-                run[3] += a[q].w;
-                run[4] += f[q];
-            }
-    }
-    if (threadIdx.x == blockDim.x - 1) { // owns the tail (possibly empty): run = grand totals
+    if (threadIdx.x == 0) {
+        S.totals->n_active = total[0];
+        S.totals->n_funcs = total[1];
+        S.totals->n_cand = total[2];
+        S.totals->n_faces = total[3];
+        S.totals->n_fv = total[4];
+        unsigned o = 0;
+        if (total[0] > S.act_cap) o |= OVF_ACT;
+        if (total[2] > S.cand_cap) o |= OVF_CAND;
+        if (total[3] > S.face_cap) o |= OVF_FACE;
+        if (total[4] > S.fv_cap) o |= OVF_FV;
+        if (o) atomicOr(S.overflow, o);
         uint4* o4 = reinterpret_cast<uint4*>(S.off + S.n_tiles);
-        o4[0] = make_uint4(run[0], run[1], run[2], run[3]);
-        o4[1] = make_uint4(run[4], 0, 0, 0);
+        o4[0] = make_uint4(total[0], total[1], total[2], total[3]);
+        o4[1] = make_uint4(total[4], 0, 0, 0);
+    }
+    // pass 2: exclusive prefixes, 32 tiles per round (the next round's loads are issued before this round's scan)
+    uint4 a = make_uint4(0, 0, 0, 0);
+    unsigned f = 0;
+    if (b + lane < e) {
+        a = __ldcg(reinterpret_cast<const uint4*>(S.tot + b + lane));
+        f = __ldcg(&S.tot[b + lane].fv);
+    }
+    for (uint32_t t0 = b; t0 < e; t0 += 32) {
+        const uint32_t t = t0 + lane, tn = t + 32;
+        uint4 an = make_uint4(0, 0, 0, 0);
+        unsigned fn = 0;
+        if (tn < e) {
+            an = __ldcg(reinterpret_cast<const uint4*>(S.tot + tn));
+            fn = __ldcg(&S.tot[tn].fv);
+        }
+        unsigned v[5] = {a.x, a.y, a.z, a.w, f}, x[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            x[q] = v[q];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, x[q], o);
+                if (lane >= o) x[q] += y;
+            }
+        }
+        if (t < e) {
+            uint4* o4 = reinterpret_cast<uint4*>(S.off + t);
+            o4[0] = make_uint4(run[0] + x[0] - v[0], run[1] + x[1] - v[1], run[2] + x[2] - v[2], run[3] + x[3] - v[3]);
+            o4[1] = make_uint4(run[4] + x[4] - v[4], 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) run[q] += __shfl_sync(0xffffffffu, x[q], 31);
+        a = an;
+        f = fn;
     }
 }
 
