@@ -406,7 +406,7 @@ template <int W>
 __global__ void __launch_bounds__(256) compact_active_kernel(const uint32_t* __restrict__ tl_tet,
     const uint32_t* __restrict__ tl_mask, size_t tl_stride, const uint2* __restrict__ tile_off,
     uint32_t n_tiles, uint32_t n_active, uint32_t* __restrict__ act_tet, uint32_t* __restrict__ act_mask,
-    uint32_t cap)
+    uint32_t cap, uint32_t tile_slots = FILT_TILE)
 {
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         // tile = last one with tile_off.x <= a
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) compact_active_kernel(const uint32_t* __r
             else
                 hi = mid;
         }
-        const size_t pos = (size_t)lo * FILT_TILE + (a - __ldg(&tile_off[lo].x));
+        const size_t pos = (size_t)lo * tile_slots + (a - __ldg(&tile_off[lo].x));
         act_tet[a] = tl_tet[pos];
 #pragma unroll
         for (int w = 0; w < W; ++w) act_mask[(size_t)w * cap + a] = tl_mask[(size_t)w * tl_stride + pos];

@@ -490,18 +490,79 @@ __global__ void __launch_bounds__(GEN_THREADS) general_mi_big_kernel(const uint4
 }
 
 // ---------------------------------------------------------------------------------------------
+// Key of the interface of THREE materials (the reference's "secondary" table, dispatch at
+// src/material_interface.cpp:320-324).  The general algorithm starts with m0, inserts m1, then m2; every branch
+// it takes depends on exact signs only: the order of the three values at each corner (3 bits per corner) and,
+// for every tet edge on which m0 - m1 changes sign, the sign of m2 - m0 at the point of that edge where
+// m0 = m1 (6 bits; it is the vertex the first insertion created there).  Equal keys -> identical complexes.
+// -1: a tie at a corner or a vanishing edge predicate (degenerate: general kernel).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mi3_key(const double p0[4], const double p1[4], const double p2[4], unsigned* nex)
+{
+    int key = 0;
+    int a01 = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (p0[c] == p1[c] || p0[c] == p2[c] || p1[c] == p2[c]) return -1;
+        const int a = p0[c] > p1[c], b = p0[c] > p2[c], d = p1[c] > p2[c];
+        key |= (a | (b << 1) | (d << 2)) << (3 * c);
+        a01 |= a << c;
+    }
+    int e = 0;
+    for (int x = 0; x < 4; ++x)
+        for (int y = x + 1; y < 4; ++y, ++e) {
+            if (((a01 >> x) & 1) == ((a01 >> y) & 1)) continue;
+            // exact sign of (m2 - m0) where m0 = m1 on edge (x, y): the predicate of MIComplex::orient_vertex
+            // for the vertex {boundary, boundary, m0, m1}
+            const double qa[4] = {p0[x], p0[y], p2[x], p2[y]}, qb[4] = {p1[x], p1[y], p0[x], p0[y]};
+            const double da[4] = {p0[x], p0[y], 1.0, 1.0}, db[4] = {p1[x], p1[y], 0.0, 0.0};
+            const int sq = detn_diff_sign(2, qa, qb, nex);
+            if (sq == 0) return -1;
+            const int sd = detn_diff_sign(2, da, db, nex);
+            if (sd == 0) return -1;
+            if (sq * sd > 0) key |= 1 << (12 + e);
+        }
+    return key;
+}
+constexpr uint32_t MI3_KEYS = 1u << 18;
+constexpr uint32_t LUT3_MISS = 0xffffffffu;
+
+// table generation: witness w owns vertices 4w..4w+3 and materials 0..2 with hashed values in (0, 1)
+__global__ void __launch_bounds__(256) mi3_witness_kernel(uint32_t n, uint32_t Vw, double* __restrict__ vals,
+    int* __restrict__ keys)
+{
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+        double p[3][4];
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                unsigned long long z = ((unsigned long long)w * 12 + f * 4 + c + 1) * 0x9e3779b97f4a7c15ull;
+                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+                z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+                z ^= z >> 31;
+                p[f][c] = (double)((z >> 11) + 1) * (1.0 / 9007199254740994.0);
+                vals[(size_t)f * Vw + 4 * w + c] = p[f][c];
+            }
+        unsigned nex = 0;
+        keys[w] = mi3_key(p[0], p[1], p[2], &nex);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3 (MI): two materials without ties go to the 16-entry table (sign pattern of m0 - m1 at the
-// corners); everything else to the general kernels.  Dispatch of src/material_interface.cpp:320-328
-// (the 3-material "secondary" table is served by the general kernel: same results).
+// corners), three materials without degeneracies to the secondary table (mi3_key) when use_secondary_lookup is
+// on; everything else to the general kernels.  Dispatch of src/material_interface.cpp:320-328.
 // ---------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(256) classify_mi_kernel(const uint4* __restrict__ tets,
     const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask, uint32_t cap,
     uint32_t n_active, const double* __restrict__ vals, const uint2* __restrict__ vmask, uint32_t V, uint32_t F,
-    const uint16_t* __restrict__ lut2, int use_lookup, uint32_t* __restrict__ rec_ref,
-    uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list, GeneralCounters* __restrict__ gc,
-    unsigned* __restrict__ n_gated)
+    const uint16_t* __restrict__ lut2, const uint32_t* __restrict__ lut3, int use_lookup, int use_secondary,
+    uint32_t* __restrict__ rec_ref, uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list,
+    GeneralCounters* __restrict__ gc, unsigned* __restrict__ n_gated)
 {
+    unsigned exact = 0;
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         uint32_t m[W];
         int k = 0;
@@ -553,6 +614,21 @@ __global__ void __launch_bounds__(256) classify_mi_kernel(const uint4* __restric
                 key |= (x > y ? 1 : 0) << c;
             }
             if (key >= 0) ref = lut2[key];
+        } else if (use_lookup && use_secondary && k == 3 && lut3) {
+            // the 3-material ("secondary") table, src/material_interface.cpp:320-324
+            const int f0 = nth_set_bit(m, W, 0), f1 = nth_set_bit(m, W, 1), f2 = nth_set_bit(m, W, 2);
+            double p0[4], p1[4], p2[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                p0[c] = __ldg(&vals[(size_t)f0 * V + vv[c]]);
+                p1[c] = __ldg(&vals[(size_t)f1 * V + vv[c]]);
+                p2[c] = __ldg(&vals[(size_t)f2 * V + vv[c]]);
+            }
+            const int key = mi3_key(p0, p1, p2, &exact);
+            if (key >= 0) {
+                const uint32_t off = __ldg(&lut3[key]);
+                if (off != LUT3_MISS) ref = off;
+            }
         }
         if (ref & REF_GENERAL) {
             atomicAdd(&gc->n_general, 1u);
@@ -563,6 +639,7 @@ __global__ void __launch_bounds__(256) classify_mi_kernel(const uint4* __restric
         }
         rec_ref[a] = ref;
     }
+    if (exact) atomicAdd(&gc->n_exact, exact);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ struct MICaps
 struct MICapsSmall
 {
     using idx = uint8_t;
-    static constexpr int MAXK = 5;
+    static constexpr int MAXK = 8;
     static constexpr int MAXV = 44;
     static constexpr int MAXE = 96;
     static constexpr int MAXF = 64;

@@ -1173,4 +1173,197 @@ __global__ void __launch_bounds__(256) faces_kernel(const FaceArgs A)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K2b on a generated grid: material filter (src/material_interface.cpp:99-152) with the cube structure of the
+// implicit-arrangement filter above.  S = union of the corners' maximal materials; a tet is active iff S has at
+// least two members (:120-123) - that needs the eight corner masks of the cube only, so the ordered compaction
+// is exact after the streaming phase.  The value test (every material exceeding min_h at >= 2 corners joins S,
+// :125-145) then runs densely over the tile's active slots.  Output in the layout of filter_mi_tiles_kernel
+// (tile-local slots + per-tile (active, CRS length) counts) with MI_GRID_SLOTS slots per tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int MI_GRID_ROUNDS = 4;
+constexpr int MI_GRID_SLOTS = MI_GRID_ROUNDS * 256 * 5;
+
+template <int W>
+__global__ void __launch_bounds__(256) filter_mi_grid_kernel(uint32_t R, const FastDiv dR, uint32_t t_first,
+    uint32_t t_count, uint32_t c_first, uint32_t n_units, const uint2* __restrict__ vmask,
+    const double* __restrict__ vals, uint32_t VS, uint32_t F, uint32_t* __restrict__ tl_tet,
+    uint32_t* __restrict__ tl_mask, size_t tl_stride, uint2* __restrict__ tile_cnt, FilterCounters* __restrict__ ctr)
+{
+    constexpr int ROUNDS = (W == 1) ? MI_GRID_ROUNDS : 1; // more words: fewer cubes per thread in registers
+    constexpr int UNITS = MI_GRID_ROUNDS * 256;
+    constexpr int NE = MI_GRID_ROUNDS * 8;
+    __shared__ unsigned s_cnt[NE];
+    __shared__ unsigned s_tot[4];
+    const unsigned tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) s_tot[threadIdx.x] = 0;
+    const uint32_t t_end = t_first + t_count, N = R + 1;
+    const size_t tbase = (size_t)tile * MI_GRID_SLOTS;
+    unsigned run_total = 0;
+    // W == 1: all four rounds in registers, one barrier.  W > 1: round by round with a running offset.
+    for (int r0 = 0; r0 < MI_GRID_ROUNDS; r0 += ROUNDS) {
+        uint32_t m[ROUNDS][5][W];
+#pragma unroll
+        for (int rr = 0; rr < ROUNDS; ++rr) {
+            const uint32_t u = tile * UNITS + (r0 + rr) * 256 + threadIdx.x;
+            const bool in = u < n_units;
+            const uint32_t cube = c_first + (in ? u : 0u);
+            const uint32_t ij = fd_div(cube, dR), k = cube - ij * R, i = fd_div(ij, dR), j = ij - i * R;
+            const uint32_t base = (i * N + j) * N + k;
+            const bool odd = (i + j + k) & 1;
+            uint32_t cv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                cv[q] = base + (((q & 3) == 1 || (q & 3) == 2) ? N * N : 0u) + (((q & 3) >= 2) ? N : 0u) + (q >> 2);
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                uint32_t c8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) c8[q] = __ldg(&vmask[(size_t)w * VS + cv[q]]).x;
+#define RIN_TS(a, b, c, d) (c8[a] | c8[b] | c8[c] | c8[d])
+                uint32_t x[5];
+                if (!odd) {
+                    x[0] = RIN_TS(4, 6, 1, 3);
+                    x[1] = RIN_TS(6, 3, 4, 7);
+                    x[2] = RIN_TS(1, 3, 0, 4);
+                    x[3] = RIN_TS(3, 1, 2, 6);
+                    x[4] = RIN_TS(4, 1, 6, 5);
+                } else {
+                    x[0] = RIN_TS(7, 0, 2, 5);
+                    x[1] = RIN_TS(2, 3, 0, 7);
+                    x[2] = RIN_TS(5, 7, 0, 4);
+                    x[3] = RIN_TS(7, 2, 6, 5);
+                    x[4] = RIN_TS(0, 1, 2, 5);
+                }
+#undef RIN_TS
+#pragma unroll
+                for (int s = 0; s < 5; ++s) {
+                    const uint32_t t = 5 * cube + s;
+                    m[rr][s][w] = (!in || t < t_first || t >= t_end) ? 0u : x[s];
+                }
+            }
+        }
+        // active iff the union has >= 2 members
+        unsigned pr[ROUNDS];
+        uint32_t act[ROUNDS];
+#pragma unroll
+        for (int rr = 0; rr < ROUNDS; ++rr) {
+            unsigned cnt = 0;
+            act[rr] = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                int ns = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) ns += __popc(m[rr][s][w]);
+                if (ns >= 2) {
+                    act[rr] |= 1u << s;
+                    ++cnt;
+                }
+            }
+            unsigned x = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            pr[rr] = x - cnt;
+            if (lane == 31) s_cnt[(r0 + rr) * 8 + warp] = x;
+        }
+        __syncthreads();
+        // prefix over the (round, warp) entries written so far in this pass: rounds r0 .. r0 + ROUNDS - 1
+        unsigned my_off[ROUNDS];
+        {
+            const int e = lane; // NE == 32
+            const bool mine = e >= r0 * 8 && e < (r0 + ROUNDS) * 8;
+            const unsigned c = mine ? s_cnt[e] : 0u;
+            unsigned x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+#pragma unroll
+            for (int rr = 0; rr < ROUNDS; ++rr)
+                my_off[rr] = run_total + __shfl_sync(0xffffffffu, x - c, (r0 + rr) * 8 + warp);
+            run_total += __shfl_sync(0xffffffffu, x, 31);
+        }
+#pragma unroll
+        for (int rr = 0; rr < ROUNDS; ++rr) {
+            if (s_cnt[(r0 + rr) * 8 + warp] == 0) continue;
+            unsigned rank = 0;
+#pragma unroll
+            for (int s = 0; s < 5; ++s)
+                if ((act[rr] >> s) & 1) {
+                    const uint32_t u = tile * UNITS + (r0 + rr) * 256 + threadIdx.x;
+                    const size_t pos = tbase + my_off[rr] + pr[rr] + rank++;
+                    tl_tet[pos] = 5 * (c_first + u) + s;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) tl_mask[(size_t)w * tl_stride + pos] = m[rr][s][w];
+                }
+        }
+        __syncthreads();
+    }
+    // ---- value test, dense over the tile's active slots
+    unsigned k1 = 0, k2 = 0, km = 0, kf = 0;
+    for (uint32_t i = threadIdx.x; i < run_total; i += 256) {
+        const size_t pos = tbase + i;
+        const uint4 tv = grid_tet(R, dR, __ldcg(&tl_tet[pos]));
+        const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
+        uint32_t mw[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) mw[w] = __ldcg(&tl_mask[(size_t)w * tl_stride + pos]);
+        double min_h[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) min_h[c] = 1.7976931348623157e308;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            uint32_t sset = mw[w];
+            while (sset) {
+                const int f = w * 32 + __ffs(sset) - 1;
+                sset &= sset - 1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) min_h[c] = fmin(min_h[c], __ldg(&vals[(size_t)f * VS + vv[c]]));
+            }
+        }
+        int kq = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            for (uint32_t f = w * 32; f < F && f < (uint32_t)w * 32 + 32; ++f) {
+                int greater = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) greater += (__ldg(&vals[(size_t)f * VS + vv[c]]) > min_h[c]);
+                if (greater > 1) mw[w] |= 1u << (f & 31);
+            }
+            tl_mask[(size_t)w * tl_stride + pos] = mw[w];
+            kq += __popc(mw[w]);
+        }
+        k1 += (kq == 2);
+        k2 += (kq == 3);
+        km += (kq > 3);
+        kf += kq;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        k1 += __shfl_xor_sync(0xffffffffu, k1, o);
+        k2 += __shfl_xor_sync(0xffffffffu, k2, o);
+        km += __shfl_xor_sync(0xffffffffu, km, o);
+        kf += __shfl_xor_sync(0xffffffffu, kf, o);
+    }
+    if (lane == 0) {
+        if (k1) atomicAdd(&s_tot[0], k1);
+        if (k2) atomicAdd(&s_tot[1], k2);
+        if (km) atomicAdd(&s_tot[2], km);
+        if (kf) atomicAdd(&s_tot[3], kf);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tile_cnt[tile] = make_uint2(run_total, s_tot[3]);
+        if (s_tot[0]) atomicAdd(&ctr->n_k1, s_tot[0]);
+        if (s_tot[1]) atomicAdd(&ctr->n_k2, s_tot[1]);
+        if (s_tot[2]) atomicAdd(&ctr->n_kmore, s_tot[2]);
+    }
+}
+
 } // namespace rin

@@ -106,6 +106,7 @@ struct Lut
     DevBuf lut1, lut2, blob;
     DevBuf cx2, lut2cx; // complete 2-plane complexes (start state of the general kernel) + key -> entry
     uint32_t blob_bytes = 0;
+    uint32_t n_keys3 = 0; // MI: realised keys of the 3-material table
     bool built = false;
     // host copies (tests / introspection)
     std::vector<uint16_t> h_lut1, h_lut2;
@@ -1710,6 +1711,20 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
 {
     const uint32_t V = c->VS, F = c->F; // V: row stride of vals / vmask
     const uint32_t T = (uint32_t)c->t_count, t_first = (uint32_t)c->t_first;
+    if (T == 0) { // empty tet range: a valid empty result
+        c->counts = rin_counts{};
+        c->counts.num_pts = c->V;
+        c->counts.num_funcs = F;
+        CK(c->f_off.ensure(4));
+        CK(c->f_toff.ensure(4));
+        CK(cudaMemsetAsync(c->f_off.p, 0, 4, c->stream));
+        CK(cudaMemsetAsync(c->f_toff.p, 0, 4, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->n_local_verts = c->n_own = 0;
+        for (auto& x : c->stage_ms) x = 0;
+        c->kernel_ms[0] = c->kernel_ms[1] = c->total_ms = 0;
+        return RIN_OK;
+    }
     const int use_lookup = (flags & RIN_FLAG_USE_LOOKUP) ? 1 : 0;
     const int use_secondary = (flags & RIN_FLAG_USE_SECONDARY_LOOKUP) ? 1 : 0;
     const int negate = (flags & RIN_FLAG_NEGATE) ? 1 : 0;
@@ -1753,18 +1768,27 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
 
     // ---- K2: filter (tile-local compaction) + tile scan + ordered gather
     EVREC(c->ev[ST_FILTER]);
-    const uint32_t n_tiles = (T + FILT_TILE - 1) / FILT_TILE;
-    const uint32_t last_mask = (F % 32) ? ((1u << (F % 32)) - 1u) : 0xffffffffu;
-    const size_t tl_stride = (size_t)n_tiles * FILT_TILE;
+    // generated grids: cube-structured filter (the tet index stream is not read)
+    const bool mgrid = c->grid_R != 0;
+    const uint32_t tile_slots = mgrid ? (uint32_t)MI_GRID_SLOTS : (uint32_t)FILT_TILE;
+    const uint32_t c_first = mgrid ? t_first / 5 : 0;
+    const uint32_t n_units = mgrid ? ((t_first + T - 1) / 5 - c_first + 1) : T;
+    const uint32_t n_tiles = mgrid ? (n_units + MI_GRID_ROUNDS * 256 - 1) / (MI_GRID_ROUNDS * 256)
+                                   : (T + FILT_TILE - 1) / FILT_TILE;
+    const size_t tl_stride = (size_t)n_tiles * tile_slots;
     CK(c->tl_tet.ensure(tl_stride * 4));
     CK(c->tl_mask.ensure(tl_stride * 4 * W));
     CK(c->tile_cnt.ensure((size_t)n_tiles * 8));
     CK(c->tile_off.ensure((size_t)(n_tiles + 1) * 8));
     EVREC(c->kev[2]);
-    (void)last_mask;
-    filter_mi_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
-        c->vmask.as<uint2>(), c->vals.as<double>(), V, F, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
-        tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
+    if (mgrid)
+        filter_mi_grid_kernel<W><<<n_tiles, 256, 0, s>>>(c->grid_R, make_fastdiv(c->grid_R), t_first, T, c_first,
+            n_units, c->vmask.as<uint2>(), c->vals.as<double>(), V, F, c->tl_tet.as<uint32_t>(),
+            c->tl_mask.as<uint32_t>(), tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
+    else
+        filter_mi_tiles_kernel<W><<<n_tiles, FILT_THREADS, 0, s>>>(c->tets.as<uint4>(), t_first, T,
+            c->vmask.as<uint2>(), c->vals.as<double>(), V, F, c->tl_tet.as<uint32_t>(), c->tl_mask.as<uint32_t>(),
+            tl_stride, c->tile_cnt.as<uint2>(), &dctr->filt);
     EVREC(c->kev[3]);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
@@ -1777,7 +1801,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     if (A) {
         compact_active_kernel<W><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tl_tet.as<uint32_t>(),
             c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, A, c->act_tet.as<uint32_t>(),
-            c->act_mask.as<uint32_t>(), c->act_cap);
+            c->act_mask.as<uint32_t>(), c->act_cap, tile_slots);
         CK(cudaGetLastError());
     }
 
@@ -1802,11 +1826,11 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     if (A) {
         classify_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
             c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vals.as<double>(),
-            c->vmask.as<uint2>(), V, F, c->lut_mi.lut1.as<uint16_t>(), use_lookup, c->rec_ref.as<uint32_t>(),
+            c->vmask.as<uint2>(), V, F, c->lut_mi.lut1.as<uint16_t>(), c->lut_mi.lut2.as<uint32_t>(), use_lookup,
+            use_secondary, c->rec_ref.as<uint32_t>(),
             c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_tie_faces);
         CK(cudaGetLastError());
     }
-    (void)use_secondary;
 
     // ---- K4: general kernels (arena grows on overflow)
     EVREC(c->ev[ST_GENERAL]);
@@ -2336,6 +2360,99 @@ int build_mi_tables(rin_ctx* c)
         L.h_lut1[w] = (uint16_t)(L.h_blob.size() / 4);
         const uint8_t* r = reinterpret_cast<const uint8_t*>(rw);
         L.h_blob.insert(L.h_blob.end(), r, r + 4 * words);
+    }
+    // ---- three materials (the "secondary" table): hashed witnesses, the first witness of every key goes through
+    // this library's general kernel; a key no witness realises stays LUT3_MISS and takes the general kernel
+    {
+        const uint32_t NW3 = 1u << 19, Vw3 = 4 * NW3;
+        DevBuf d_v3, d_k3, d_t3, d_a3, d_m3, d_r3, d_g3, d_ar3;
+        auto cleanup3 = [&]() {
+            for (DevBuf* b : {&d_v3, &d_k3, &d_t3, &d_a3, &d_m3, &d_r3, &d_g3, &d_ar3}) b->release();
+        };
+#define CK3(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup3();                                                                            \
+            cleanup();                                                                             \
+            return fail(RIN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                          \
+    } while (0)
+        CK3(d_v3.ensure((size_t)3 * Vw3 * 8));
+        CK3(d_k3.ensure((size_t)NW3 * 4));
+        mi3_witness_kernel<<<grid_for(NW3, 256, sm), 256, 0, s>>>(NW3, Vw3, d_v3.as<double>(), d_k3.as<int>());
+        CK3(cudaGetLastError());
+        std::vector<int> keys(NW3);
+        CK3(cudaMemcpyAsync(keys.data(), d_k3.p, (size_t)NW3 * 4, cudaMemcpyDeviceToHost, s));
+        CK3(cudaStreamSynchronize(s));
+        std::map<int, uint32_t> first; // key -> first witness
+        for (uint32_t w = 0; w < NW3; ++w)
+            if (keys[w] >= 0) first.emplace(keys[w], w);
+        const uint32_t NCH = (uint32_t)first.size();
+        std::vector<uint4> t3(NCH);
+        std::vector<uint32_t> a3(NCH), m3(NCH, 7u), g3(NCH);
+        {
+            uint32_t i = 0;
+            for (auto& kv : first) {
+                const uint32_t w = kv.second;
+                t3[i] = make_uint4(4 * w, 4 * w + 1, 4 * w + 2, 4 * w + 3);
+                a3[i] = g3[i] = i;
+                ++i;
+            }
+        }
+        CK3(d_t3.ensure((size_t)NCH * 16));
+        CK3(d_a3.ensure((size_t)NCH * 4));
+        CK3(d_m3.ensure((size_t)NCH * 4));
+        CK3(d_r3.ensure((size_t)NCH * 4));
+        CK3(d_g3.ensure((size_t)NCH * 4));
+        CK3(d_ar3.ensure((size_t)NCH * 512 + 4096));
+        CK3(cudaMemcpyAsync(d_t3.p, t3.data(), (size_t)NCH * 16, cudaMemcpyHostToDevice, s));
+        CK3(cudaMemcpyAsync(d_a3.p, a3.data(), (size_t)NCH * 4, cudaMemcpyHostToDevice, s));
+        CK3(cudaMemcpyAsync(d_m3.p, m3.data(), (size_t)NCH * 4, cudaMemcpyHostToDevice, s));
+        CK3(cudaMemcpyAsync(d_g3.p, g3.data(), (size_t)NCH * 4, cudaMemcpyHostToDevice, s));
+        CK3(cudaMemsetAsync(d_r3.p, 0, (size_t)NCH * 4, s));
+        CK3(cudaMemsetAsync(d_ar3.p, 0, 4, s));
+        GeneralCounters g3c{};
+        g3c.n_general = g3c.n_big = NCH;
+        g3c.arena_top = 4;
+        CK3(cudaMemcpyAsync(&dctr->gen, &g3c, sizeof(g3c), cudaMemcpyHostToDevice, s));
+        general_mi_big_kernel<1><<<sm * 4, GEN_THREADS, 0, s>>>(d_t3.as<uint4>(), d_a3.as<uint32_t>(),
+            d_m3.as<uint32_t>(), NCH, d_g3.as<uint32_t>(), d_g3.as<uint32_t>(), d_v3.as<double>(), Vw3,
+            d_ar3.as<uint8_t>(), (uint32_t)d_ar3.cap, d_r3.as<uint32_t>(), &dctr->gen);
+        CK3(cudaGetLastError());
+        GeneralCounters g3r;
+        std::vector<uint32_t> refs3(NCH);
+        CK3(cudaMemcpyAsync(&g3r, &dctr->gen, sizeof(g3r), cudaMemcpyDeviceToHost, s));
+        CK3(cudaMemcpyAsync(refs3.data(), d_r3.p, (size_t)NCH * 4, cudaMemcpyDeviceToHost, s));
+        CK3(cudaStreamSynchronize(s));
+        if (g3r.err || g3r.arena_overflow) {
+            cleanup3();
+            cleanup();
+            return fail(RIN_ERR_STATE, "MI 3-material table generation failed");
+        }
+        std::vector<uint8_t> ar3(g3r.arena_top);
+        CK3(cudaMemcpyAsync(ar3.data(), d_ar3.p, g3r.arena_top, cudaMemcpyDeviceToHost, s));
+        CK3(cudaStreamSynchronize(s));
+        std::vector<uint32_t> lut3(MI3_KEYS, LUT3_MISS);
+        uint32_t i = 0;
+        for (auto& kv : first) {
+            const uint32_t ref = refs3[i++];
+            if ((ref & REF_FLAGS) != REF_GENERAL || (size_t)(ref & ~REF_FLAGS) * 4 + 4 > ar3.size()) continue;
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(ar3.data() + (size_t)(ref & ~REF_FLAGS) * 4);
+            const int nv = rw[0] & 255, nf = (rw[0] >> 8) & 255;
+            uint32_t words = 1 + 2 * nv;
+            for (int f = 0; f < nf; ++f) words += 1 + rec_face_words((rw[words] >> 24) & 127);
+            words += 1; // trailing word: faces of the whole complex
+            lut3[kv.first] = (uint32_t)(L.h_blob.size() / 4);
+            const uint8_t* r = reinterpret_cast<const uint8_t*>(rw);
+            L.h_blob.insert(L.h_blob.end(), r, r + 4 * words);
+        }
+        CK3(L.lut2.ensure((size_t)MI3_KEYS * 4));
+        CK3(cudaMemcpyAsync(L.lut2.p, lut3.data(), (size_t)MI3_KEYS * 4, cudaMemcpyHostToDevice, s));
+        CK3(cudaStreamSynchronize(s));
+        L.n_keys3 = NCH;
+        cleanup3();
+#undef CK3
     }
     L.blob_bytes = (uint32_t)L.h_blob.size();
     CKC(L.lut1.ensure(32));

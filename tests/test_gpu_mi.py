@@ -42,7 +42,7 @@ def gpu_digest(mesh):
 
 
 @pytest.mark.parametrize("R", [6, 21, 48])
-@pytest.mark.parametrize("flags", [0, FLAG_LOOKUP | FLAG_SECONDARY])
+@pytest.mark.parametrize("flags", [0, FLAG_LOOKUP, FLAG_LOOKUP | FLAG_SECONDARY])
 def test_c3_six_spheres(ctx, rin, R, flags):
     """BASELINE C3 function set (6 overlapping spheres, triple junctions) on generated grids."""
     funcs = make_funcs(synthetic_functions("C3"))
@@ -53,6 +53,11 @@ def test_c3_six_spheres(ctx, rin, R, flags):
     ctx.generate_grid(R)
     ctx.set_functions(funcs)
     cnt = ctx.run(rin.MODE_MI, flags)
+    if flags == (FLAG_LOOKUP | FLAG_SECONDARY):
+        # the 3-material ("secondary") table serves the 3-material tets: only >= 4 materials are left over
+        assert cnt.num_k2 > 0 and cnt.num_general_tets <= cnt.num_kmore + cnt.num_k2 // 20 + cnt.num_k1 // 50
+    elif flags == FLAG_LOOKUP:
+        assert cnt.num_general_tets >= cnt.num_k2  # 3-material tets take the general kernel (:320-324)
     compare_mi(ctx, ctx.download_mesh(), port, cnt)
     if R == 48:
         assert cnt.num_k2 > 0  # three-material tets exist
