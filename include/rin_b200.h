@@ -214,6 +214,10 @@ int rin_nccl_unique_id(uint8_t id[128]);
 int rin_nccl_init(rin_ctx*, const uint8_t id[128], int rank, int world);
 int rin_exchange_nccl(rin_ctx*, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
                       uint64_t* n_faces_total);
+/* offsets of this rank's slice in the merged mesh after rin_exchange_nccl:
+ * out = {vertex offset, vertices total, face offset, faces total, face-vertex offset, face-vertex total,
+ *        face-tet-pair offset, face-tet-pair total} */
+int rin_get_exchange_offsets(const rin_ctx*, uint64_t out[8]);
 /* vertex id range referenced by the current tet range */
 int rin_get_vertex_range(const rin_ctx*, uint32_t* v_lo, uint32_t* v_hi);
 

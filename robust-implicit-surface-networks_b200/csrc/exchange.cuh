@@ -6,21 +6,24 @@
 
 namespace rin {
 
-// message layout per rank (uint32 words): header[4] = {count, n_own, n_faces, 0},
+// message layout per rank (uint32 words): header[XHDR] = {count, n_own, n_faces, n_face_verts, n_face_tets, 0..},
 // keys[cap][4], ids[cap]
+constexpr uint32_t XHDR = 8;
 __host__ __device__ inline size_t xmsg_words(uint32_t cap)
 {
-    return 4 + (size_t)cap * 5;
+    return XHDR + (size_t)cap * 5;
 }
 
 __global__ void x_header_kernel(uint32_t* msg, const unsigned* count, uint32_t cap, const unsigned* n_own,
-    uint32_t n_faces, unsigned* overflow)
+    uint32_t n_faces, unsigned* overflow, uint32_t n_fv = 0, uint32_t n_ft = 0)
 {
     const unsigned c = *count;
     msg[0] = c;
     msg[1] = n_own ? *n_own : 0;
     msg[2] = n_faces;
-    msg[3] = 0;
+    msg[3] = n_fv;
+    msg[4] = n_ft;
+    msg[5] = msg[6] = msg[7] = 0;
     if (c > cap) *overflow = c;
 }
 
@@ -29,8 +32,8 @@ __global__ void __launch_bounds__(256) x_select_kernel(const uint4* __restrict__
     const uint8_t* __restrict__ v_size, uint32_t n, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ own_idx,
     uint32_t* __restrict__ msg, uint32_t cap, unsigned* __restrict__ n_out)
 {
-    uint4* out_keys = reinterpret_cast<uint4*>(msg + 4);
-    uint32_t* out_ids = msg + 4 + (size_t)cap * 4;
+    uint4* out_keys = reinterpret_cast<uint4*>(msg + XHDR);
+    uint32_t* out_ids = msg + XHDR + (size_t)cap * 4;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int sz = v_size[i];
         if (sz >= 4) continue;
@@ -63,12 +66,12 @@ __global__ void __launch_bounds__(256) x_insert_kernel(const uint32_t* __restric
         const uint32_t s = c / cap, i = c % cap;
         const uint32_t* m = all + s * stride;
         if (i >= min(m[0], cap)) continue;
-        const uint4 k = reinterpret_cast<const uint4*>(m + 4)[i];
+        const uint4 k = reinterpret_cast<const uint4*>(m + XHDR)[i];
         uint32_t h = hash4(k) & mask;
         for (;;) {
             const uint32_t cur = atomicCAS(&table[h], NONE32, c);
             if (cur == NONE32) break;
-            const uint4 kc = reinterpret_cast<const uint4*>(all + (cur / cap) * stride + 4)[cur % cap];
+            const uint4 kc = reinterpret_cast<const uint4*>(all + (cur / cap) * stride + XHDR)[cur % cap];
             if (key_eq(kc, k)) break;
             h = (h + 1) & mask;
         }
@@ -83,7 +86,7 @@ __device__ __forceinline__ uint32_t x_lookup(const uint32_t* all, uint32_t cap, 
     for (;;) {
         const uint32_t cur = table[h];
         if (cur == NONE32) return NONE32;
-        const uint4 kc = reinterpret_cast<const uint4*>(all + (cur / cap) * stride + 4)[cur % cap];
+        const uint4 kc = reinterpret_cast<const uint4*>(all + (cur / cap) * stride + XHDR)[cur % cap];
         if (key_eq(kc, k)) return cur;
         h = (h + 1) & mask;
     }
@@ -155,20 +158,28 @@ __global__ void x_offsets_kernel(const uint32_t* __restrict__ first, const uint3
 {
     if (threadIdx.x || blockIdx.x) return;
     const size_t stride = xmsg_words(cap);
-    uint32_t v = 0, f = 0;
+    uint32_t v = 0, f = 0, fv = 0, ft = 0;
+    uint32_t* fvoff = foff + (world + 1);
+    uint32_t* ftoff = fvoff + (world + 1);
     unsigned ovf = 0;
     for (int s = 0; s < world; ++s) {
         voff[s] = v;
         foff[s] = f;
+        fvoff[s] = fv;
+        ftoff[s] = ft;
         const uint32_t* m = all + s * stride;
         v += m[1];
         f += m[2];
+        fv += m[3];
+        ft += m[4];
         if (m[0] > cap) ovf = max(ovf, m[0]);
         if (first[s * stride] > cap) ovf = max(ovf, first[s * stride]);
     }
     *overflow = ovf;
     voff[world] = v;
     foff[world] = f;
+    fvoff[world] = fv;
+    ftoff[world] = ft;
 }
 
 // global id of every local vertex: own -> offset + own index; foreign -> owner's offset + its own index
@@ -190,8 +201,85 @@ __global__ void __launch_bounds__(256) x_global_ids_kernel(const uint4* __restri
             gid[i] = NONE32;
         } else {
             const uint32_t s = f / cap, j = f % cap;
-            gid[i] = voff[s] + (all + s * stride + 4 + (size_t)cap * 4)[j];
+            gid[i] = voff[s] + (all + s * stride + XHDR + (size_t)cap * 4)[j];
         }
+    }
+}
+
+// ---- neighbour protocol (slab sharding: a rank shares vertices with ranks r-1 and r+1 only) ----------------
+// message layout as above: header[4] = {count, n_own, n_faces, 0}, keys[cap][4], ids[cap]
+
+// own indices of the vertices this rank sent upwards (it owns all of them: it is the lowest rank on that plane)
+__global__ void __launch_bounds__(256) x_own_ids_kernel(const uint32_t* __restrict__ sent, uint32_t cap,
+    const uint32_t* __restrict__ own_idx, uint32_t* __restrict__ out, unsigned* __restrict__ n_bad)
+{
+    const uint32_t n = min(sent[0], cap);
+    const uint32_t* ids = sent + XHDR + (size_t)cap * 4;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t o = own_idx[ids[j]];
+        if (o == NONE32) atomicAdd(n_bad, 1u);
+        out[j] = o;
+    }
+}
+
+// record of the count exchange: {n_own, n_faces, candidates sent upwards, n_face_verts, n_face_tets, 0, 0, 0}
+__global__ void x_counts_kernel(uint32_t* out, const unsigned* n_own, uint32_t n_faces, const unsigned* n_up,
+    uint32_t n_fv, uint32_t n_ft)
+{
+    out[0] = *n_own;
+    out[1] = n_faces;
+    out[2] = *n_up;
+    out[3] = n_fv;
+    out[4] = n_ft;
+    out[5] = out[6] = out[7] = 0;
+}
+
+// prefixes of the gathered records (vertices, faces, face-vertex entries, face-tet pairs: four arrays of
+// world + 1 entries behind each other); overflow = largest n_up beyond the capacity
+__global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, int world, uint32_t cap,
+    uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t v = 0, f = 0, fv = 0, ft = 0;
+    uint32_t* fvoff = foff + (world + 1);
+    uint32_t* ftoff = fvoff + (world + 1);
+    unsigned ovf = 0;
+    for (int s = 0; s < world; ++s) {
+        voff[s] = v;
+        foff[s] = f;
+        fvoff[s] = fv;
+        ftoff[s] = ft;
+        v += all[8 * s];
+        f += all[8 * s + 1];
+        fv += all[8 * s + 3];
+        ft += all[8 * s + 4];
+        if (all[8 * s + 2] > cap) ovf = max(ovf, all[8 * s + 2]);
+    }
+    voff[world] = v;
+    foff[world] = f;
+    fvoff[world] = fv;
+    ftoff[world] = ft;
+    *overflow = ovf;
+}
+
+// global ids: own -> offset + own index; foreign -> offset of the lower neighbour + its own index
+__global__ void __launch_bounds__(256) x_global_ids_nb_kernel(const uint4* __restrict__ v_key,
+    const uint32_t* __restrict__ own_idx, uint32_t n, int rank, const uint32_t* __restrict__ voff,
+    const uint32_t* __restrict__ recv_low, const uint32_t* __restrict__ ids_low, uint32_t cap,
+    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t o = own_idx[i];
+        if (o != NONE32) {
+            gid[i] = voff[rank] + o;
+            continue;
+        }
+        const uint32_t f = x_lookup(recv_low, cap, table, mask, v_key[i]);
+        if (f == NONE32 || ids_low[f] == NONE32) {
+            atomicAdd(n_unresolved, 1u);
+            gid[i] = NONE32;
+        } else
+            gid[i] = voff[rank - 1] + ids_low[f];
     }
 }
 

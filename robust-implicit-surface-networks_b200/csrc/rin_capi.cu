@@ -92,6 +92,10 @@ struct NcclApi
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, char[128], int) = nullptr; // ncclUniqueId is passed by value
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -173,6 +177,11 @@ struct rin_ctx
     int x_rank = 0, x_world = 1;
     uint32_t x_cap = 0, x_lo = 1, x_hi = 0;
     bool x_window = false;
+    bool x_neighbours = false;          // every rank shares vertices with ranks r-1 / r+1 only (slab sharding)
+    uint32_t x_up_lo = 1, x_up_hi = 0;  // vertex window shared with rank r+1 (empty: lo > hi)
+    bool x_has_low = false, x_has_up = false;
+    DevBuf x_ids_up, x_ids_low, x_cnt;
+    uint64_t x_offsets[8] = {}; // offset / total of vertices, faces, face-vertex entries, face-tet pairs (last exchange)
     DevBuf x_send, x_recv1, x_recv2, x_table, x_small;
     DevBuf cx_out; // rin_get_complexes output arena
     void* h_pinned = nullptr; // pinned host mirror of the device counters (cheap read-back)
@@ -283,7 +292,7 @@ void rin_destroy(rin_ctx* c)
         &c->cand_key, &c->cand_pay, &c->cand_src, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
-        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->cx_out, &c->f_off, &c->f_verts,
+        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->x_ids_up, &c->x_ids_low, &c->x_cnt, &c->cx_out, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob, &c->lut_ia.cx2, &c->lut_ia.lut2cx,
         &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
@@ -1023,9 +1032,15 @@ int load_nccl()
     g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
     void* init = dlsym(h, "ncclCommInitRank");
-    if (!g_nccl.GetUniqueId || !g_nccl.AllGather || !init) return fail(RIN_ERR_STATE, "NCCL symbols missing");
+    if (!g_nccl.GetUniqueId || !g_nccl.AllGather || !init || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
+        !g_nccl.GroupEnd)
+        return fail(RIN_ERR_STATE, "NCCL symbols missing");
     memcpy(&g_nccl.CommInitRank, &init, sizeof(init));
     g_nccl.handle = h;
     return RIN_OK;
@@ -1058,12 +1073,147 @@ int rin_nccl_init(rin_ctx* c, const uint8_t id[128], int rank, int world)
     memcpy(&init, &g_nccl.CommInitRank, sizeof(init));
     UniqueId u;
     memcpy(u.internal, id, 128);
+    if (c->nccl_comm && g_nccl.CommDestroy) {
+        g_nccl.CommDestroy(c->nccl_comm);
+        c->nccl_comm = nullptr;
+    }
     NK(init(&c->nccl_comm, world, u, rank));
     c->x_rank = rank;
     c->x_world = world;
     c->x_window = false;
     return RIN_OK;
 }
+
+// Neighbour protocol for slab sharding: rank r shares vertices with r-1 and r+1 only and owns everything on the
+// plane it shares with r+1 (first occurrence in tet order).  Per pass: one ncclSend/ncclRecv pair with the keys of
+// the upper plane, one with their own indices, one 16-byte-per-rank ncclAllGather of (owned vertices, faces,
+// candidates sent) for the global offsets; all stream-ordered, ONE host synchronisation at the end.
+extern "C++" {
+namespace {
+int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
+    uint64_t* n_faces_total)
+{
+    cudaStream_t s = c->stream;
+    const int rank = c->x_rank, world = c->x_world, sm = c->sm_count;
+    const uint32_t NV = c->n_local_verts;
+    const uint32_t NFV = (uint32_t)c->counts.num_face_verts;
+    uint32_t* small = c->x_small.as<uint32_t>(); // [0..15] counters, [64..] offsets
+    for (int attempt = 0;; ++attempt) {
+        const uint32_t cap = c->x_cap;
+        const size_t words = xmsg_words(cap);
+        CK(c->x_send.ensure(words * 4));
+        CK(c->x_recv1.ensure(words * 4));
+        CK(c->x_ids_up.ensure((size_t)cap * 4));
+        CK(c->x_ids_low.ensure((size_t)cap * 4));
+        CK(c->x_cnt.ensure((size_t)(world + 1) * 32));
+        uint32_t tsize = 64;
+        while (tsize < 2ull * cap) tsize <<= 1;
+        CK(c->x_table.ensure((size_t)tsize * 4));
+        CK(c->own_idx.ensure((size_t)std::max(NV, 1u) * 4));
+        CK(c->gid.ensure((size_t)std::max(NV, 1u) * 4));
+        const uint32_t tiles = (NV + 1023) / 1024;
+        CK(c->status.ensure((size_t)std::max(tiles, 1u) * 8 + 64));
+        const size_t no1 = std::max(NV, 1u); // owned vertices <= local vertices
+        CK(c->o_tet.ensure(no1 * 4));
+        CK(c->o_local.ensure(no1));
+        CK(c->o_size.ensure(no1));
+        CK(c->o_simplex.ensure(no1 * 16));
+        CK(c->o_funcs.ensure(no1 * 16));
+        CK(c->o_xyz.ensure(no1 * 24));
+        CK(c->o_key.ensure(no1 * 16));
+        CK(cudaMemsetAsync(small, 0, 64, s));
+        unsigned* d_up = small + 0;
+        unsigned* d_nown = small + 2;
+        unsigned* d_ovf = small + 3;
+        unsigned* d_tile = small + 4;
+        unsigned* d_bad = small + 5;
+        uint32_t* d_voff = small + 64;
+        uint32_t* d_foff = small + 64 + (world + 1);
+        uint32_t* up = c->x_send.as<uint32_t>();
+        uint32_t* low = c->x_recv1.as<uint32_t>();
+        uint32_t* mine4 = c->x_cnt.as<uint32_t>(); // this rank's 8-word count record
+        uint32_t* all4 = mine4 + 8;                // gathered
+        // 1. keys (+ local indices) of the vertices on the plane shared with r+1 -> r+1
+        if (NV && c->x_up_lo <= c->x_up_hi)
+            x_select_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
+                c->x_up_lo, c->x_up_hi, nullptr, up, cap, d_up);
+        x_header_kernel<<<1, 1, 0, s>>>(up, d_up, cap, nullptr, 0, d_ovf);
+        NK(g_nccl.GroupStart());
+        if (c->x_has_up) NK(g_nccl.Send(up, words, 3 /*ncclUint32*/, rank + 1, c->nccl_comm, s));
+        if (c->x_has_low) NK(g_nccl.Recv(low, words, 3, rank - 1, c->nccl_comm, s));
+        NK(g_nccl.GroupEnd());
+        // 2. what the lower neighbour found first is foreign; ordered own index of the rest
+        CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+        if (c->x_has_low)
+            x_insert_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(low, cap, 1, c->x_table.as<uint32_t>(), tsize - 1);
+        CK(cudaMemsetAsync(c->status.p, 0, (size_t)std::max(tiles, 1u) * 8, s));
+        if (NV)
+            x_mark_scan_kernel<<<tiles, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV, low, cap,
+                c->x_table.as<uint32_t>(), tsize - 1, c->x_has_low ? 1 : 0, c->own_idx.as<uint32_t>(),
+                c->status.as<unsigned long long>(), d_tile, d_nown);
+        // 3. own indices of what was sent upwards -> r+1; (n_own, n_faces, n_up) of every rank -> offsets
+        x_own_ids_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(up, cap, c->own_idx.as<uint32_t>(),
+            c->x_ids_up.as<uint32_t>(), d_bad);
+        x_counts_kernel<<<1, 1, 0, s>>>(mine4, d_nown, (uint32_t)c->counts.num_faces, d_up,
+            (uint32_t)c->counts.num_face_verts, (uint32_t)c->counts.num_face_tets);
+        NK(g_nccl.GroupStart());
+        if (c->x_has_up) NK(g_nccl.Send(c->x_ids_up.p, cap, 3, rank + 1, c->nccl_comm, s));
+        if (c->x_has_low) NK(g_nccl.Recv(c->x_ids_low.p, cap, 3, rank - 1, c->nccl_comm, s));
+        NK(g_nccl.GroupEnd());
+        NK(g_nccl.AllGather(mine4, all4, 8, 3, c->nccl_comm, s));
+        x_offsets_nb_kernel<<<1, 1, 0, s>>>(all4, world, cap, d_voff, d_foff, d_ovf);
+        // 4. global ids, face vertex lists, owned vertices (skipped by every rank alike when a message overflowed:
+        //    the decision comes from the gathered counts)
+        if (NV) {
+            x_global_ids_nb_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(),
+                c->own_idx.as<uint32_t>(), NV, rank, d_voff, low, c->x_ids_low.as<uint32_t>(), cap,
+                c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad);
+            compact_own_verts_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->own_idx.as<uint32_t>(), NV,
+                c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(),
+                c->v_funcs.as<uint4>(), c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(),
+                c->o_local.as<uint8_t>(), c->o_size.as<uint8_t>(), c->o_simplex.as<uint4>(), c->o_funcs.as<uint4>(),
+                c->o_xyz.as<double>(), c->o_key.as<uint4>());
+        }
+        std::vector<uint32_t> hsmall(64 + 4 * (world + 1));
+        CK(cudaMemcpyAsync(hsmall.data(), small, hsmall.size() * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s)); // the one synchronisation of the exchange
+        if (hsmall[3]) { // a rank's message outgrew the capacity: every rank sees it in the gathered counts
+            if (attempt > 3) return fail(RIN_ERR_STATE, "exchange: capacity negotiation failed");
+            c->x_cap = (hsmall[3] + hsmall[3] / 4 + 1024 + 3u) & ~3u;
+            continue;
+        }
+        if (hsmall[5])
+            return fail(RIN_ERR_STATE, "exchange: " + std::to_string(hsmall[5]) + " shared vertices have no owner");
+        // only now (nothing can fail any more) the face vertex lists are rewritten in place
+        if (NV && NFV) {
+            apply_gids_kernel<<<grid_for(NFV, 256, sm), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
+                c->gid.as<uint32_t>());
+            CK(cudaGetLastError());
+        }
+        const uint32_t NO = hsmall[2];
+        std::swap(c->v_tet, c->o_tet);
+        std::swap(c->v_local, c->o_local);
+        std::swap(c->v_size, c->o_size);
+        std::swap(c->v_simplex, c->o_simplex);
+        std::swap(c->v_funcs, c->o_funcs);
+        std::swap(c->v_xyz, c->o_xyz);
+        std::swap(c->v_key, c->o_key);
+        c->n_own = NO;
+        c->counts.num_verts = NO;
+        c->marked = c->finalized = true;
+        for (int q = 0; q < 4; ++q) {
+            c->x_offsets[2 * q] = hsmall[64 + q * (world + 1) + rank];
+            c->x_offsets[2 * q + 1] = hsmall[64 + q * (world + 1) + world];
+        }
+        if (vert_offset) *vert_offset = c->x_offsets[0];
+        if (n_verts_total) *n_verts_total = c->x_offsets[1];
+        if (face_offset) *face_offset = c->x_offsets[2];
+        if (n_faces_total) *n_faces_total = c->x_offsets[3];
+        return RIN_OK;
+    }
+}
+} // namespace
+} // extern "C++"
 
 // The whole slab-boundary protocol on the device (see sharding.py): two ncclAllGather calls.
 int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
@@ -1077,11 +1227,15 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
     const int rank = c->x_rank, world = c->x_world, sm = c->sm_count;
     const uint32_t NV = c->n_local_verts;
     const uint32_t NFV = (uint32_t)c->counts.num_face_verts;
-    CK(c->x_small.ensure(4096));
+    CK(c->x_small.ensure(4096 + 64 * (size_t)c->x_world));
     uint32_t* small = c->x_small.as<uint32_t>(); // [0..15] counters, [16..16+2*world] ranges, [64..] offsets
     if (!c->x_window) {
         // shared vertex window: all-gather of the ranks' vertex ranges (once per mesh / range)
         uint32_t lo = c->v_count ? c->v_first : 0, hi = c->v_count ? c->v_first + c->v_count - 1 : (uint32_t)c->V - 1;
+        if (c->t_count == 0) { // an empty tet range touches no vertex
+            lo = 1;
+            hi = 0;
+        }
         uint32_t mine[2] = {lo, hi};
         std::vector<uint32_t> all(2 * world);
         CK(cudaMemcpyAsync(small + 16, mine, 8, cudaMemcpyHostToDevice, s));
@@ -1101,12 +1255,35 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         c->x_lo = any ? wl : 1;
         c->x_hi = any ? wh : 0;
         c->x_window = true;
+        // the same decision on every rank (all see all ranges): do non-adjacent ranks ever share a vertex?
+        bool nb = true;
+        for (int a = 0; a < world && nb; ++a)
+            for (int b = a + 2; b < world && nb; ++b)
+                if (std::max(all[2 * a], all[2 * b]) <= std::min(all[2 * a + 1], all[2 * b + 1]) &&
+                    all[2 * a] <= all[2 * a + 1] && all[2 * b] <= all[2 * b + 1])
+                    nb = false;
+        for (int a = 0; a + 1 < world && nb; ++a) // ranges must ascend with the rank (the lower rank owns)
+            if (all[2 * a] <= all[2 * a + 1] && all[2 * a + 2] <= all[2 * a + 3] && all[2 * a] > all[2 * a + 2]) nb = false;
+        c->x_neighbours = nb && getenv("RIN_X_ALLGATHER") == nullptr;
+        c->x_has_low = c->x_has_up = false;
+        c->x_up_lo = 1;
+        c->x_up_hi = 0;
+        if (rank + 1 < world) {
+            const uint32_t a = std::max(lo, all[2 * (rank + 1)]), b = std::min(hi, all[2 * (rank + 1) + 1]);
+            c->x_has_up = true; // the message is exchanged even when the window is empty (sizes must match)
+            if (a <= b && lo <= hi) {
+                c->x_up_lo = a;
+                c->x_up_hi = b;
+            }
+        }
+        if (rank > 0) c->x_has_low = true;
     }
     if (c->x_cap == 0) {
         const char* env = getenv("RIN_XCAP"); // test hook: a tiny capacity forces the renegotiation path
         c->x_cap = env ? (uint32_t)std::max(4, atoi(env)) : 4096;
     }
     c->x_cap = (c->x_cap + 3u) & ~3u; // keys are read as uint4: keep every rank's segment 16-byte aligned
+    if (c->x_neighbours) return exchange_neighbours(c, vert_offset, n_verts_total, face_offset, n_faces_total);
     for (int attempt = 0;; ++attempt) {
         const uint32_t cap = c->x_cap;
         const size_t words = xmsg_words(cap);
@@ -1150,7 +1327,8 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         if (NV)
             x_select_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
                 c->x_lo, c->x_hi, c->own_idx.as<uint32_t>(), msg, cap, d_cnt2);
-        x_header_kernel<<<1, 1, 0, s>>>(msg, d_cnt2, cap, d_nown, (uint32_t)c->counts.num_faces, d_ovf);
+        x_header_kernel<<<1, 1, 0, s>>>(msg, d_cnt2, cap, d_nown, (uint32_t)c->counts.num_faces, d_ovf,
+            (uint32_t)c->counts.num_face_verts, (uint32_t)c->counts.num_face_tets);
         NK(g_nccl.AllGather(msg, c->x_recv2.p, words, 3, c->nccl_comm, s));
         x_offsets_kernel<<<1, 1, 0, s>>>(c->x_recv1.as<uint32_t>(), c->x_recv2.as<uint32_t>(), cap, world, d_voff, d_foff,
             d_ovf);
@@ -1159,7 +1337,7 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         if (rank > 0)
             x_insert_kernel<<<grid_for((uint64_t)rank * cap, 256, sm), 256, 0, s>>>(c->x_recv2.as<uint32_t>(), cap,
                 rank, c->x_table.as<uint32_t>(), tsize - 1);
-        std::vector<uint32_t> hsmall(64 + 2 * (world + 1));
+        std::vector<uint32_t> hsmall(64 + 4 * (world + 1));
         CK(cudaMemcpyAsync(hsmall.data(), small, hsmall.size() * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         if (hsmall[3]) { // a rank's payload outgrew the capacity: every rank sees it, redo larger
@@ -1204,12 +1382,24 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         c->n_own = NO;
         c->counts.num_verts = NO;
         c->marked = c->finalized = true;
-        if (vert_offset) *vert_offset = hsmall[64 + rank];
-        if (n_verts_total) *n_verts_total = hsmall[64 + world];
-        if (face_offset) *face_offset = hsmall[64 + (world + 1) + rank];
-        if (n_faces_total) *n_faces_total = hsmall[64 + (world + 1) + world];
+        for (int q = 0; q < 4; ++q) {
+            c->x_offsets[2 * q] = hsmall[64 + q * (world + 1) + rank];
+            c->x_offsets[2 * q + 1] = hsmall[64 + q * (world + 1) + world];
+        }
+        if (vert_offset) *vert_offset = c->x_offsets[0];
+        if (n_verts_total) *n_verts_total = c->x_offsets[1];
+        if (face_offset) *face_offset = c->x_offsets[2];
+        if (n_faces_total) *n_faces_total = c->x_offsets[3];
         return RIN_OK;
     }
+}
+
+int rin_get_exchange_offsets(const rin_ctx* c, uint64_t out[8])
+{
+    if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->finalized) return fail(RIN_ERR_STATE, "rin_get_exchange_offsets: no finished exchange");
+    for (int q = 0; q < 8; ++q) out[q] = c->x_offsets[q];
+    return RIN_OK;
 }
 
 // introspection for tests: host copy of the IA tables

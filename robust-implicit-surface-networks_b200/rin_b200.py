@@ -80,6 +80,7 @@ def lib():
         L.rin_nccl_unique_id.argtypes = [C.c_void_p]
         L.rin_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rin_exchange_nccl.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+        L.rin_get_exchange_offsets.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_robust_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_uint64, C.c_int, C.c_void_p, C.c_uint32, C.POINTER(Counts)]
@@ -240,11 +241,15 @@ class Context:
         self._check(lib().rin_nccl_init(self._h, uid.ctypes.data, rank, world))
 
     def exchange_nccl(self):
-        """Device-side slab-boundary exchange (two ncclAllGather calls on the context's stream)."""
+        """Device-side slab-boundary exchange on the context's stream (neighbour send/recv for slabs, all-gather
+        otherwise); returns this rank's offsets in the merged mesh."""
         v = [C.c_uint64() for _ in range(4)]
         self._check(lib().rin_exchange_nccl(self._h, *[C.byref(x) for x in v]))
+        o = (C.c_uint64 * 8)()
+        self._check(lib().rin_get_exchange_offsets(self._h, o))
         return {"vert_offset": v[0].value, "n_verts_total": v[1].value, "face_offset": v[2].value,
-                "n_faces_total": v[3].value}
+                "n_faces_total": v[3].value, "fv_offset": o[4], "n_fv_total": o[5], "ft_offset": o[6],
+                "n_ft_total": o[7]}
 
     def get_complexes(self, mode, tet_ids):
         """Full per-tet complexes (layout in include/rin_b200.h) -> (offsets, words)."""

@@ -141,3 +141,37 @@ class NumpyEngine:
         table = {tuple(k): int(g) for k, g in zip(np.asarray(keys).reshape(-1, 4).tolist(), gids)}
         self.gid = np.array([offset + o if o >= 0 else table[tuple(k)]
                              for o, k in zip(self.own_idx, self.keys.tolist())], np.int64)
+
+
+MESH_VERT_KEYS = ("vert_tet", "vert_local", "vert_simplex_size", "vert_simplex", "vert_funcs", "vert_xyz")
+
+
+def merged_layout(info):
+    """Sizes of the merged mesh arrays from one rank's exchange result (identical on every rank)."""
+    nv, nf, nfv, nft = info["n_verts_total"], info["n_faces_total"], info["n_fv_total"], info["n_ft_total"]
+    return {"vert_tet": ((nv,), np.uint32), "vert_local": ((nv,), np.uint8), "vert_simplex_size": ((nv,), np.uint8),
+            "vert_simplex": ((nv, 4), np.uint32), "vert_funcs": ((nv, 4), np.uint32), "vert_xyz": ((nv, 3), np.float64),
+            "face_offsets": ((nf + 1,), np.uint32), "face_verts": ((nfv,), np.uint32),
+            "face_tet_offsets": ((nf + 1,), np.uint32), "face_tets": ((nft, 2), np.uint32),
+            "face_funcs": ((nf, 2), np.uint32)}
+
+
+def slice_views(merged, info, counts):
+    """Views of this rank's slice inside the merged arrays (what rin_download_mesh writes into).  The offset
+    arrays of a slice are local; fix_offsets() rebases them once every rank has written."""
+    v0, f0, fv0, ft0 = info["vert_offset"], info["face_offset"], info["fv_offset"], info["ft_offset"]
+    nv, nf, nfv, nft = counts.num_verts, counts.num_faces, counts.num_face_verts, counts.num_face_tets
+    out = {k: merged[k][v0:v0 + nv] for k in MESH_VERT_KEYS}
+    out["face_verts"] = merged["face_verts"][fv0:fv0 + nfv]
+    out["face_tets"] = merged["face_tets"][ft0:ft0 + nft]
+    out["face_funcs"] = merged["face_funcs"][f0:f0 + nf]
+    # every slice writes nf + 1 offsets; the last one of a slice is overwritten by its successor's first
+    out["face_offsets"] = merged["face_offsets"][f0:f0 + nf + 1]
+    out["face_tet_offsets"] = merged["face_tet_offsets"][f0:f0 + nf + 1]
+    return out
+
+
+def rebase_offsets(views, info):
+    """Local offsets -> offsets into the merged face_verts / face_tets (this rank's slice only)."""
+    views["face_offsets"] += np.uint32(info["fv_offset"])
+    views["face_tet_offsets"] += np.uint32(info["ft_offset"])
