@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the per-tetrahedron hot path (BASELINE.json metric: arranged tets/sec, end to end
-to mesh).
+"""Benchmark of the per-tetrahedron hot path (BASELINE.json metric: arranged tets/sec, end to end to mesh).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4|C5]
+                  [--scaling weak|strong]
 
-A step = one pass of the hot path (function evaluation -> signs -> filter -> per-tet arrangement
--> mesh extraction + xyz) over one synthetic tet5 grid.  Workload: implicit
-arrangement, 8 random spheres + planes (seed 1), grid resolution R = round(128 * N^(1/3)) so that
-every GPU owns ~10.5 M tets (N=1: BASELINE C2, 128^3; N=8: BASELINE C5, 256^3), x-slab sharded.
-Inputs (grid + function description) are resident in HBM for `value`; `e2e` goes through the
-legacy host-array entry point (rin_run_host: pts, size_t tets, row-major funcVals from pinned
-host memory, mesh arrays copied back), host<->device copies inside the timed region.
+A step = one pass of the hot path (function evaluation -> signs / highest material -> filter -> per-tet
+arrangement -> mesh extraction + xyz) over one synthetic tet5 grid (SURVEY section 8(d) generators).
+  N = 1: BASELINE C2 (implicit arrangement, 128^3, 8 functions) unless --config says otherwise
+         (C3 material interface 128^3, C4 32 dense functions 128^3, C5 256^3 on one GPU).
+  N > 1: x-slab sharding, weak scaling R = round(128 N^(1/3)) (N = 8 is BASELINE C5, 256^3);
+         --scaling strong keeps 256^3 for every N.
+`value`: inputs (grid + function description) resident in HBM, device-side slab exchange included for N > 1.
+`e2e`: the reference-shaped entry point with HOST buffers (points, size_t tets, row-major function values, all
+pinned; for N > 1 every rank uploads its slab's slice) and the mesh copied back to the host (N > 1: every rank
+DMA-writes its slice of the merged mesh into one pinned POSIX shared-memory segment that rank 0 reads).
+The merged mesh is checked against the committed oracle digest of the same configuration
+(tests/golden/fullsize_golden.json) outside the timed region.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +34,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "arranged tets/sec (end-to-end to mesh)"
 UNIT = "tets/s"
+FUNCTION_SET = {"C2": "C2", "C5": "C2", "C3": "C3", "C4": "C4"}
+MESH_KEYS = ("vert_tet", "vert_local", "vert_simplex_size", "vert_simplex", "vert_funcs", "vert_xyz", "face_offsets",
+             "face_verts", "face_tet_offsets", "face_tets", "face_funcs")
 
 
 def measured_peak():
@@ -73,23 +82,72 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def grid_resolution(n_gpus):
-    return int(round(128 * n_gpus ** (1.0 / 3.0)))
+def grid_resolution(config, n_gpus, scaling):
+    if n_gpus == 1:
+        return 256 if config == "C5" else 128
+    return 256 if scaling == "strong" else int(round(128 * n_gpus ** (1.0 / 3.0)))
 
 
-def slab_range(R, rank, world):
-    import sharding
-    return sharding.slab_range(R, rank, world)
+def golden_name(config, R):
+    """Committed oracle digest of this (function set, grid) combination, if there is one."""
+    if config in ("C2", "C5"):
+        return {128: "C2", 161: "W2", 203: "W4", 256: "C5"}.get(R)
+    return config if R == 128 else None
 
 
-def cpu_reference_run(config, seconds_budget=20.0):
-    """Times the reference's CPU implementation of the path on a bounded sample of the workload:
-    the first x-slabs of the SAME grid (same vertices, same functions), single-threaded like the
-    reference.  Uses oracle/_ref (reference sources compiled in place) when present, else the port."""
+def workload_text(config, R, mi):
+    F = {"C2": 8, "C5": 8, "C3": 6, "C4": 32}[config]
+    return "%s, generated tet5 grid %d^3 (%d tets), %d synthetic functions of BASELINE config %s (SURVEY 8(d) " \
+           "generator), lookup tables on" % ("material interface" if mi else "implicit arrangement", R, 5 * R ** 3, F,
+                                            config)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def mesh_digest(mesh, mi):
+    ff = mesh["face_funcs"].astype(np.int64)
+    ff[ff == 0xFFFFFFFF] = -1
+    d = {"face_offsets": sha(mesh["face_offsets"].astype(np.int64)),
+         "face_verts": sha(mesh["face_verts"].astype(np.int64)),
+         "face_tets": sha(mesh["face_tets"].astype(np.int64).ravel()),
+         "face_funcs_first": sha(ff[:, 0]), "vert_xyz": sha(mesh["vert_xyz"])}
+    if mi:
+        d["face_funcs"] = sha(ff.ravel())
+    return d
+
+
+def check_digest(mesh, config, R, mi):
+    name = golden_name(config, R)
+    p = os.path.join(ROOT, "tests", "golden", "fullsize_golden.json")
+    if name is None or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        gold = json.load(f)
+    if name not in gold:
+        return None
+    return {"golden": "tests/golden/fullsize_golden.json:" + name, "pinned_by": gold[name]["pinned_by"],
+            "equal": mesh_digest(mesh, mi) == gold[name]["digest"]}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation of the path (oracle/_ref = its sources
+# compiled in place, else the oracle port), one thread (the reference is single-threaded by construction), on a
+# bounded sample of the workload: the first x-slabs of the same grid with the same functions
+# ---------------------------------------------------------------------------------------------------------------
+CPU_SLABS = {"C2": (128, 128), "C3": (128, 128), "C4": (128, 20), "C5": (256, 96)}  # (R, slabs in the sample)
+CPU_LABELS = {"ia": ("func signs", "filter", "simp_arr(other)", "simp_arr(1 func)", "simp_arr(2 func)",
+                     "simp_arr(>=3 func)", "extract mesh", "compute xyz"),
+              "mi": ("highest func", "filter", "MI(other)", "MI(2 func)", "MI(3 func)", "MI(>=4 func)", "extract mesh",
+                     "compute xyz")}
+
+
+def cpu_reference_run(config):
     from helpers import make_funcs, orc_eval, orc_grid, orc_run, ref_lib, ref_run, synthetic_functions
-    R = 128
-    funcs = make_funcs(synthetic_functions(config))
-    slabs = 128  # the whole 128^3 grid: 10.5 M tets, ~2.5 s of single-core CPU work per step
+    R, slabs = CPU_SLABS[config]
+    mode = "mi" if config == "C3" else "ia"
+    funcs = make_funcs(synthetic_functions(FUNCTION_SET[config]))
     N = R + 1
     pts, tets = orc_grid(R)
     n_t = slabs * 5 * R * R
@@ -102,48 +160,54 @@ def cpu_reference_run(config, seconds_budget=20.0):
     kind = "port"
     if ref_lib() is not None:
         kind = "reference"
-        b = ref_run("ia", pts_s, tets_s, vals)
+        b = ref_run(mode, pts_s, tets_s, vals)
         lab = dict(zip(b.timing_labels, b["timings"].tolist()))
-        hot = sum(lab.get(k, 0.0) for k in ("func signs", "filter", "simp_arr(other)", "simp_arr(1 func)",
-                                            "simp_arr(2 func)", "simp_arr(>=3 func)", "extract mesh",
-                                            "compute xyz"))
+        hot = sum(lab.get(k, 0.0) for k in CPU_LABELS[mode])
     else:
-        b = orc_run("ia", pts_s, tets_s, vals)
+        b = orc_run(mode, pts_s, tets_s, vals)
         hot = float(np.sum(b["timings"]))
     total = t_eval + hot
     return {"value": n_t / total, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "first %d of %d x-slabs of the 128^3 grid (%d tets, %d functions); stages: function "
-                      "evaluation + func signs + filter + simp_arr + extract mesh + compute xyz; "
-                      "%.2f s CPU" % (slabs, R, n_t, len(funcs), total),
-            "seconds": total, "host_cores_total": os.cpu_count()}
+            "sample": "first %d of %d x-slabs of the %d^3 grid (%d tets, %d functions); stages: function evaluation + "
+                      "%s + filter + per-tet arrangement + extract mesh + compute xyz; %.2f s CPU" % (
+                          slabs, R, R, n_t, len(funcs), "highest func" if mode == "mi" else "func signs", total),
+            "seconds": total, "tets": n_t, "host_cores_total": os.cpu_count()}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    last = None
+    config = args.config
+    if args.gpus > 1 and config == "C2" and (args.scaling == "strong" or args.gpus == 8):
+        config = "C5"  # the N-GPU workload of the repo arm is the 256^3 grid
+    secs, last = [], None
     for it in range(args.warmup + args.steps):
-        last = cpu_reference_run(args.config)
+        last = cpu_reference_run(config)
         if it >= args.warmup:
-            vals.append(last["seconds"])
-    n_t = 128 * 5 * 128 * 128
-    v = n_t / (sum(vals) / len(vals))
+            secs.append(last["seconds"])
+    v = last["tets"] / (sum(secs) / len(secs))
     last["value"] = v
+    R_ours = grid_resolution(args.config, args.gpus, args.scaling)
+    R_ref = CPU_SLABS[config][0]
+    note = ""
+    if R_ours != R_ref:
+        note = "; the repo arm at %d GPUs runs the %d^3 instance of the same generator, this arm samples the %d^3 " \
+               "instance (tets/s is size-normalised)" % (args.gpus, R_ours, R_ref)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(vals) / len(vals),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "implicit arrangement, generated tet5 grid 128^3 (10485760 tets), 8 synthetic functions "
-                                   "of BASELINE config C2 (SURVEY 8(d) generator), lookup tables on",
-                       "baseline_config": "C2",
-                       "sample": last["sample"] + ("" if args.gpus == 1 else
-                                                   "; bounded sample of the %d-GPU weak-scaling workload (grid %d^3): its "
-                                                   "single-GPU instance" % (args.gpus, grid_resolution(args.gpus)))},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_text(config, R_ref, config == "C3"), "baseline_config": config,
+                       "sample": last["sample"] + note},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def pinned(shape, dtype):
+    import torch
+    tdt = {np.float64: torch.float64, np.uint32: torch.int32, np.uint64: torch.int64, np.uint8: torch.uint8}[dtype]
+    return torch.empty(shape, dtype=tdt, pin_memory=True).numpy().view(dtype)
 
 
 def main():
@@ -153,6 +217,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--resolution", type=int, default=0, help="override the grid resolution (tests)")
@@ -165,6 +230,7 @@ def main():
 
     import torch
     import rin_b200 as rin
+    import sharding
     from helpers import make_funcs, synthetic_functions
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,61 +244,71 @@ def main():
         dist = None
         torch.cuda.set_device(0)
 
-    R = args.resolution or grid_resolution(world)
-    funcs = make_funcs(synthetic_functions(args.config))
+    config = args.config
+    R = args.resolution or grid_resolution(config, world, args.scaling)
+    funcs = make_funcs(synthetic_functions(FUNCTION_SET[config]))
     F = len(funcs)
+    mi = config == "C3"
+    mode = rin.MODE_MI if mi else rin.MODE_IA
+    flags = rin.FLAG_LOOKUP | rin.FLAG_SECONDARY
     ctx = rin.Context(local)
     ctx.generate_grid(R)
     ctx.set_functions(funcs)
-    t_first, t_count = slab_range(R, rank, world)
+    t_first, t_count = sharding.slab_range(R, rank, world)
     if world > 1:
         ctx.set_tet_range(t_first, t_count)
     T_total = 5 * R ** 3
-    mode = rin.MODE_MI if args.config == "C3" else rin.MODE_IA  # C3 is the material-interface configuration
-    flags = rin.FLAG_LOOKUP | rin.FLAG_SECONDARY
+    N1 = R + 1
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    import sharding
-    gather = sharding.torch_gather(dist, torch.device("cuda", local)) if dist is not None else None
-    xstate = sharding.ExchangeState()
-    if dist is not None:
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def new_uid():
         # NCCL communicator of the engine itself (device-side exchange): rank 0's id to everyone
         uid = torch.from_numpy(rin.nccl_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
         dist.broadcast(uid, 0)
-        ctx.nccl_init(uid.cpu().numpy(), rank, world)
+        return uid.cpu().numpy()
+
+    if dist is not None:
+        ctx.nccl_init(new_uid(), rank, world)
 
     def step():
-        """One pass: local hot path on this rank's slab, then (N > 1) the slab-boundary key
-        exchange over NCCL and the rewrite to global vertex ids."""
+        """One pass: hot path on this rank's slab, then (N > 1) the slab-boundary exchange on the device."""
         c = ctx.run(mode, flags)
-        if dist is not None:
-            ctx.exchange_nccl()
-        return c
+        return ctx.exchange_nccl() if dist is not None else c
 
-    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     ctx.set_stage_timing(False)  # the timed region records two events per pass, not a dozen
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    dev_ms, eval_ms, filt_ms = [], [], []
+    dev_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cnt = step()
+        info = step()
         dev_ms.append(ctx.kernel_times()["total_ms"])
     barrier()
-    wall = time.perf_counter() - t0
+    wall = allmax(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    cnt = ctx.counts()
     launches_per_step = ctx.launch_count()
+    ms_per_step = 1e3 * wall / args.steps
+    value = T_total / (wall / args.steps)
+
     # separate profiled passes (per-stage events on) for the stage table and the kernel brackets
     ctx.set_stage_timing(True)
-    stage_acc = None
+    eval_ms, filt_ms, stage_acc = [], [], None
     for _ in range(5):
         step()
         kt = ctx.kernel_times()
@@ -242,157 +318,195 @@ def main():
         stage_acc = st if stage_acc is None else {k: stage_acc[k] + v for k, v in st.items()}
     stage = {k: v / 5 for k, v in stage_acc.items()}
     ctx.set_stage_timing(False)
-    wall_t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(wall_t, op=dist.ReduceOp.MAX)
-    wall = float(wall_t.item())
-    ms_per_step = 1e3 * wall / args.steps
-    value = T_total / (wall / args.steps)
 
-    # ---- N > 1: the device-side NCCL exchange against the host-driven protocol of sharding.py -----
-    exchange_verified = None
-    if dist is not None:
-        ctx.run(mode, flags)
-        info_a = ctx.exchange_nccl()
-        mesh_a = ctx.download_mesh()
-        c_b = ctx.run(mode, flags)
-        info_b = sharding.exchange(ctx, rank, world, gather, c_b.num_faces, xstate)
-        mesh_b = ctx.download_mesh()
-        same = all(np.array_equal(mesh_a[k], mesh_b[k]) for k in mesh_a) and \
-            info_a["vert_offset"] == info_b["vert_offset"] and info_a["n_verts_total"] == info_b["n_verts_total"]
-        ok = torch.tensor([1 if same else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        exchange_verified = bool(ok.item())
-        n_verts_total = info_a["n_verts_total"]
+    # ---- the merged mesh on rank 0's host (also the destination of the e2e legs) ------------------------------
+    if dist is None:
+        info = {"vert_offset": 0, "face_offset": 0, "fv_offset": 0, "ft_offset": 0, "n_verts_total": cnt.num_verts,
+                "n_faces_total": cnt.num_faces, "n_fv_total": cnt.num_face_verts, "n_ft_total": cnt.num_face_tets}
+    layout = sharding.merged_layout(info)
+    sizes = {k: int(np.prod(sh)) * np.dtype(dt).itemsize for k, (sh, dt) in layout.items()}
+    total_bytes = max(4096, sum((s + 255) & ~255 for s in sizes.values()))
+    shm = None
+    if dist is None:
+        hostbuf = pinned((total_bytes,), np.uint8)
+    else:
+        from multiprocessing import shared_memory
+        name = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=total_bytes)
+            name[0] = shm.name
+        dist.broadcast_object_list(name, 0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        hostbuf = np.ndarray((total_bytes,), np.uint8, buffer=shm.buf)
+        # page-lock the shared segment so that every rank's D2H copy is a plain DMA into "rank 0's" host memory
+        rc = torch.cuda.cudart().cudaHostRegister(hostbuf.ctypes.data, total_bytes, 0)
+        assert int(rc) == 0, "cudaHostRegister failed: %s" % rc
+    merged, off = {}, 0
+    for k, (sh, dt) in layout.items():
+        merged[k] = np.ndarray(sh, dt, buffer=hostbuf, offset=off)
+        off += (sizes[k] + 255) & ~255
+    views = sharding.slice_views(merged, info, cnt)
+    ctx.download_mesh(views)
+    barrier()
+    verified = check_digest(merged, config, R, mi) if rank == 0 else None
 
-    # ---- roofline of the dominant streaming kernel (filter: reads every tet's index record) -----
-    peak, peak_src = measured_peak()
-    V_rank = (R + 1) ** 3 if world == 1 else ((R * (rank + 1) // world - R * rank // world) + 1) * (R + 1) ** 2
-    # algorithmic bytes per launch: 16 B index record + 4 B result per tet, and each
-    # function value once (8F per vertex); this implementation reads 8 B of sign masks per vertex
-    # instead of the values, so the bytes it can possibly move are the smaller figure below.
-    alg_survey = 20.0 * t_count + 8.0 * F * V_rank
-    mask_bytes = 4.0 if F <= 16 else 8.0 * ((F + 31) // 32)  # packed P|N word when F <= 16
-    alg_masks = 16.0 * t_count + mask_bytes * V_rank + 8.0 * cnt.num_intersecting_tet
-    filt = float(np.mean(filt_ms))
-    evl = float(np.mean(eval_ms))
-    achieved = min(alg_survey, alg_masks) / (filt * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tp) and world == 1 and args.config == "C2" and not args.resolution:
-        with open(tp) as f:
-            traffic = json.load(f).get("filter_tiles_kernel", {}).get("dram_bytes")
-    roofline = {"bound": "hbm", "kernel": "filter_tiles_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": min(alg_survey, alg_masks),
-                "algorithmic_bytes_survey_formula": alg_survey, "kernel_ms": filt,
-                "eval_kernel": {"ms": evl, "bytes": (24.0 + 8.0 * F + 8.0) * V_rank,
-                                "achieved": (24.0 + 8.0 * F + 8.0) * V_rank / (evl * 1e-3) / 1e9,
-                                "frac": (24.0 + 8.0 * F + 8.0) * V_rank / (evl * 1e-3) / 1e9 / peak},
-                "eval_plus_filter": {"ms": evl + filt,
-                                     "bytes_survey": (20.0 + (24.0 + 16.0 * F) / 5.0) * t_count,
-                                     "frac_survey": (20.0 + (24.0 + 16.0 * F) / 5.0) * t_count /
-                                     ((evl + filt) * 1e-3) / 1e9 / peak}}
-
-    # ---- e2e: legacy host-array entry point, pinned host buffers, copies inside the timed region --
+    # ---- e2e: host buffers in, merged mesh on the host out ----------------------------------------------------
     e2e = None
-    if world == 1 and not args.no_e2e and mode == rin.MODE_IA:
-        V = (R + 1) ** 3
-        pts_h = torch.empty((V, 3), dtype=torch.float64, pin_memory=True).numpy()
-        tets_h = torch.empty((T_total, 4), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
-        vals_h = torch.empty((V, F), dtype=torch.float64, pin_memory=True).numpy()
-        gp, gt = ctx.download_grid(V, T_total)
-        pts_h[:] = gp
-        tets_h[:] = gt
-        vals_h[:] = ctx.download_values()
+    d2h = sum(views[k].nbytes for k in MESH_KEYS)
+    if not args.no_e2e:
+        # this rank's slice of the reference-shaped inputs: the vertex planes its slab touches
+        i0, i1 = R * rank // world, R * (rank + 1) // world
+        v_first, v_count = i0 * N1 * N1, (i1 - i0 + 1) * N1 * N1
+        gp, gt = ctx.download_grid(N1 ** 3, T_total)
+        pts_h = pinned((v_count, 3), np.float64)
+        tets_h = pinned((t_count, 4), np.uint64)
+        vals_h = pinned((v_count, F), np.float64)
+        pts_h[:] = gp[v_first:v_first + v_count]
+        tets_h[:] = gt[t_first:t_first + t_count]
         del gp, gt
-        n = ctx.counts()
-        cap = lambda x: int(x * 1.05) + 16
-        out = {
-            "vert_tet": torch.empty(cap(n.num_verts), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "vert_local": torch.empty(cap(n.num_verts), dtype=torch.uint8, pin_memory=True).numpy(),
-            "vert_simplex_size": torch.empty(cap(n.num_verts), dtype=torch.uint8, pin_memory=True).numpy(),
-            "vert_simplex": torch.empty((cap(n.num_verts), 4), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "vert_funcs": torch.empty((cap(n.num_verts), 4), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "vert_xyz": torch.empty((cap(n.num_verts), 3), dtype=torch.float64, pin_memory=True).numpy(),
-            "face_offsets": torch.empty(cap(n.num_faces) + 1, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "face_verts": torch.empty(cap(n.num_face_verts), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "face_tet_offsets": torch.empty(cap(n.num_faces) + 1, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "face_tets": torch.empty((cap(n.num_face_tets), 2), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-            "face_funcs": torch.empty((cap(n.num_faces), 2), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
-        }
-        ctx2 = rin.Context(local)
-        for _ in range(2):
-            ctx2.run_host(mode, flags, pts_h, tets_h, vals_h)
-            ctx2.download_mesh(out)
-        torch.cuda.synchronize()
-        k = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(k):
-            c2 = ctx2.run_host(mode, flags, pts_h, tets_h, vals_h)
-            ctx2.download_mesh(out)
-        torch.cuda.synchronize()
-        e_wall = (time.perf_counter() - t0) / k
-        assert c2.num_verts == cnt.num_verts and c2.num_faces == cnt.num_faces
+        vals_h[:] = ctx.download_values()[v_first:v_first + v_count]
         h2d = pts_h.nbytes + tets_h.nbytes + vals_h.nbytes
-        d2h = (n.num_verts * (4 + 1 + 1 + 16 + 16 + 24) + (n.num_faces + 1) * 8 + n.num_face_verts * 4 +
-               n.num_face_tets * 8 + n.num_faces * 8)
-        e2e = {"value": T_total / e_wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e_wall,
-               "api": "rin_run_host (pts, size_t tets, row-major funcVals) + rin_download_mesh"}
-        # same call sequence when the caller keeps the tet mesh on the device between calls (several function
-        # sets on one grid): only the V x F values go up per step.  Reported beside the headline, not as it.
-        ctx2.set_mesh(pts_h, tets_h)
-        for _ in range(2):
-            ctx2.set_values(vals_h)
-            ctx2.run(mode, flags)
-            ctx2.download_mesh(out)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(k):
-            ctx2.set_values(vals_h)
-            c3 = ctx2.run(mode, flags)
-            ctx2.download_mesh(out)
-        torch.cuda.synchronize()
-        r_wall = (time.perf_counter() - t0) / k
-        assert c3.num_verts == cnt.num_verts and c3.num_faces == cnt.num_faces
-        e2e["resident_mesh"] = {"value": T_total / r_wall, "unit": UNIT, "h2d_bytes_per_step": int(vals_h.nbytes),
-                                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * r_wall,
-                                "api": "rin_set_mesh_host once; per step rin_set_values_host + rin_run + rin_download_mesh"}
+        ctx2 = rin.Context(local)
+        ctx2.set_stage_timing(False)
+        if dist is not None:
+            ctx2.nccl_init(new_uid(), rank, world)
+
+        def e2e_step(upload_mesh=True):
+            if dist is None:
+                if upload_mesh:
+                    ctx2.run_host(mode, flags, pts_h, tets_h, vals_h)
+                else:
+                    ctx2.set_values(vals_h)
+                    ctx2.run(mode, flags)
+            else:
+                if upload_mesh:
+                    ctx2.set_mesh_range(N1 ** 3, T_total, pts_h, v_first, tets_h, t_first)
+                ctx2.set_values_range(vals_h, v_first)
+                ctx2.run(mode, flags)
+                ctx2.exchange_nccl()
+            ctx2.download_mesh(views)
+
+        def timed(fn, k):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                fn()
+            barrier()
+            return allmax(time.perf_counter() - t0) / k
+
+        k = max(3, min(args.steps, 10))
+        if dist is None:
+            ctx2.set_mesh(pts_h, tets_h)  # shapes for the "resident" variant exist before its first call
+        e_wall = timed(e2e_step, k)
+        c2 = ctx2.counts()
+        assert c2.num_verts == cnt.num_verts and c2.num_faces == cnt.num_faces
+        tot = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tot)
+        e2e = {"value": T_total / e_wall, "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()),
+               "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": 1e3 * e_wall,
+               "api": "rin_run_host (pts, size_t tets, row-major funcVals) + rin_download_mesh" if dist is None else
+                      "per rank: rin_set_mesh_host_range + rin_set_values_host_range (its slab's slice) + rin_run + "
+                      "rin_exchange_nccl + rin_download_mesh into its slice of the merged mesh in a pinned "
+                      "shared-memory segment read by rank 0"}
+        barrier()
+        if rank == 0:
+            e2e["verified"] = check_digest(merged, config, R, mi)
+        # the caller keeps the tet mesh on the device between calls (several function sets on one grid): only the
+        # V x F values go up per step.  Reported beside the headline, not as it.
+        r_wall = timed(lambda: e2e_step(False), k)
+        e2e["resident_mesh"] = {"value": T_total / r_wall, "unit": UNIT, "ms_per_step": 1e3 * r_wall,
+                                "h2d_bytes_per_step": int(vals_h.nbytes) * world,
+                                "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
+                                "api": "mesh uploaded once; per step the V x F values up, run, mesh down"}
+        # the application-level call (impl_arrangement config.json): grid resolution + function parameters in,
+        # mesh on the host out - the same inputs the reference arm starts from
+        if dist is None:
+            def app_step():
+                ctx2.generate_grid(R)
+                ctx2.set_functions(funcs)
+                ctx2.run(mode, flags)
+                ctx2.download_mesh(views)
+            a_wall = timed(app_step, k)
+            e2e["app_level"] = {"value": T_total / a_wall, "unit": UNIT, "ms_per_step": 1e3 * a_wall,
+                                "h2d_bytes_per_step": int(funcs.nbytes), "d2h_bytes_per_step": int(d2h),
+                                "api": "rin_generate_grid + rin_set_functions + rin_run + rin_download_mesh "
+                                       "(what the app does for a config with gridResolution + funcFile)"}
         ctx2.close()
 
-    # ---- CPU baseline on the host cores of this box (rank 0, N=1 only) ---------------------------
+    # ---- roofline of the dominant HBM kernel -------------------------------------------------------------------
+    # IA / MI on a generated grid: the evaluation kernel writes the SoA values (8F bytes per vertex) and the sign
+    # masks; nothing is read (coordinates come from three axis tables).  SURVEY 8(d) K1 with an implicit grid:
+    # V * 8F (+ the masks this implementation adds).  The filter no longer streams the index records.
+    peak, peak_src = measured_peak()
+    V_rank = N1 ** 3 if world == 1 else ((R * (rank + 1) // world - R * rank // world) + 1) * N1 * N1
+    mask_bytes = 4.0 if (F <= 16 and not mi) else 8.0 * ((F + 31) // 32)
+    evl, filt = float(np.mean(eval_ms)), float(np.mean(filt_ms))
+    alg_eval = (8.0 * F + mask_bytes) * V_rank
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")  # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp) and world == 1 and not args.resolution:
+        with open(tp) as f:
+            t = json.load(f).get(config, {}).get("eval_kernel")
+        if t:
+            traffic, traffic_src = t["dram_bytes"], t["source"]
+    moved = alg_eval if traffic is None else min(alg_eval, traffic)
+    achieved = moved / (evl * 1e-3) / 1e9
+    survey_bytes = (20.0 + (24.0 + 16.0 * F) / 5.0) * t_count
+    dev = float(np.mean(dev_ms))
+    roofline = {"bound": "hbm", "kernel": "eval_kernel" + ("+highest_material_kernel" if mi else ""),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_eval,
+                "kernel_ms": evl,
+                "bytes_model": "V * (8F values + %d B sign masks) written, nothing read (generated grid); achieved = "
+                               "min(algorithmic, measured DRAM bytes) / kernel time" % int(mask_bytes),
+                "filter_kernel": {"name": "filter_mi_grid_kernel" if mi else "filter_classify_kernel", "ms": filt,
+                                  "note": "cube-structured: reads the per-vertex masks once per cube corner through "
+                                          "L1/L2, never the 16 B/tet index stream; instruction-bound, not HBM-bound"},
+                "eval_plus_filter": {"ms": evl + filt, "bytes_survey": survey_bytes,
+                                     "frac_survey": survey_bytes / ((evl + filt) * 1e-3) / 1e9 / peak},
+                "whole_step": {"ms": dev, "frac_survey": survey_bytes / (dev * 1e-3) / 1e9 / peak,
+                               "note": "SURVEY 8(d) eval+filter bytes (reference-shaped formulation) over the device "
+                                       "time of the whole pass"}}
+
+    # ---- CPU baseline on the host cores of this box (rank 0, N = 1 only) --------------------------------------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and args.config == "C2":
+    if world == 1 and not args.no_cpu_baseline and not args.resolution:
         try:
-            cpu = cpu_reference_run(args.config)
+            cpu = cpu_reference_run(config)
         except Exception as ex:  # the baseline is reported, never required
             cpu = {"value": None, "error": str(ex)}
 
     if rank == 0:
-        # kernels launched by this library per step (counted from the orchestrator in rin_capi.cu):
-        # eval, filter, classify, general small, general big, count_scan, emit, hash_insert, rank_reps,
-        # write_verts, remap_face_verts, write_faces
+        x_launches = 10 if world > 1 else 0  # kernels of the neighbour exchange (rin_capi.cu exchange_neighbours)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s, generated tet5 grid %d^3 (%d tets), %d synthetic functions of BASELINE "
-                                       "config %s (SURVEY 8(d) generator), lookup tables on" % (
-                                           "material interface" if mode == rin.MODE_MI else "implicit arrangement",
-                                           R, T_total, F, args.config),
-                           "baseline_config": args.config if world == 1 else ("C5" if world == 8 else "C2-weak"),
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_text(config, R, mi),
+                           "baseline_config": config if world == 1 else ("C5" if R == 256 else "C2-weak"),
                            "sharding": "x-slabs, one contiguous tet range per GPU" if world > 1 else "none",
-                           "cache": "inputs (%.0f MB) + intermediates exceed the 126 MB L2" %
-                                    ((16.0 * T_total + 88.0 * (R + 1) ** 3) / 1e6)},
-                "device_ms_per_step": float(np.mean(dev_ms)), "stage_ms": stage,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": (launches_per_step + (13 if world > 1 else 0)) * args.steps,
-                "launches_per_step": launches_per_step,
-                "clocks": sampler.summary(), "counts": cnt.as_dict(),
+                           "cache": "outputs of every stage (values %.0f MB, candidates, mesh) exceed the 126 MB L2 "
+                                    "or are produced by the previous kernel" % (8.0 * F * N1 ** 3 / 1e6)},
+                "device_ms_per_step": dev, "stage_ms": stage,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": (launches_per_step + x_launches) * args.steps,
+                "launches_per_step": launches_per_step + x_launches,
+                "clocks": sampler.summary(), "counts": cnt.as_dict(), "verified": verified,
                 "exchange": None if dist is None else {
-                    "what": "slab-boundary vertex keys, 2 ncclAllGather per step (device-side, rin_exchange_nccl)",
-                    "verified_against_host_protocol": exchange_verified, "n_verts_total": n_verts_total}}
+                    "what": "slab-boundary vertex keys: ncclSend/ncclRecv with the neighbour ranks + one 32-byte-per-"
+                            "rank ncclAllGather of the counts (rin_exchange_nccl, one host synchronisation)",
+                    "n_verts_total": info["n_verts_total"], "n_faces_total": info["n_faces_total"]}}
         print(json.dumps(line))
     if dist is not None:
+        barrier()
+        torch.cuda.cudart().cudaHostUnregister(hostbuf.ctypes.data)
+        del merged, views, hostbuf
+        shm.close()
+        if rank == 0:
+            shm.unlink()
         dist.destroy_process_group()
 
 

@@ -118,6 +118,15 @@ void rin_destroy(rin_ctx* ctx);
  * reference's std::array<size_t,4>, or 32-bit) */
 int rin_set_mesh_host(rin_ctx*, const double* pts, uint64_t n_pts, const void* tets,
                       uint64_t n_tets, int index_bytes /* 4 or 8 */);
+/* one rank's slice of a mesh sharded by contiguous tet ranges: pts_slice = points [v_first, v_first + v_count)
+ * (the vertices the tet range references), tets_slice = tets [t_first, t_first + t_count) with GLOBAL vertex
+ * indices; only the slice crosses PCIe, the tet range of the run is set to the slice */
+int rin_set_mesh_host_range(rin_ctx*, uint64_t n_pts, uint64_t n_tets, const double* pts_slice, uint64_t v_first,
+                            uint64_t v_count, const void* tets_slice, uint64_t t_first, uint64_t t_count,
+                            int index_bytes);
+/* rows [v_first, v_first + v_count) of the row-major V x F value matrix */
+int rin_set_values_host_range(rin_ctx*, const double* vals_slice, uint64_t v_first, uint64_t v_count,
+                              uint32_t n_funcs);
 /* generate_tet_mesh() on the device (same vertex and tet order as src/io.cpp:95-152) */
 int rin_generate_grid(rin_ctx*, uint32_t resolution, const double bbox_min[3], const double bbox_max[3]);
 /* restrict the run to tets [first, first+count) (slab sharding).  count == RIN_TET_RANGE_ALL: up to the last
@@ -216,7 +225,10 @@ int rin_exchange_nccl(rin_ctx*, uint64_t* vert_offset, uint64_t* n_verts_total, 
                       uint64_t* n_faces_total);
 /* offsets of this rank's slice in the merged mesh after rin_exchange_nccl:
  * out = {vertex offset, vertices total, face offset, faces total, face-vertex offset, face-vertex total,
- *        face-tet-pair offset, face-tet-pair total} */
+ *        face-tet-pair offset, face-tet-pair total}
+ * After the exchange rin_download_mesh returns face_verts as global vertex ids and face_offsets /
+ * face_tet_offsets rebased into the merged arrays: every rank can write its slice straight into shared arrays
+ * of the merged sizes. */
 int rin_get_exchange_offsets(const rin_ctx*, uint64_t out[8]);
 /* vertex id range referenced by the current tet range */
 int rin_get_vertex_range(const rin_ctx*, uint32_t* v_lo, uint32_t* v_hi);

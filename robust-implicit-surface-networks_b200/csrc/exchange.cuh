@@ -206,6 +206,11 @@ __global__ void __launch_bounds__(256) x_global_ids_kernel(const uint4* __restri
     }
 }
 
+__global__ void __launch_bounds__(256) add_offset_kernel(uint32_t* __restrict__ a, uint32_t n, uint32_t off)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] += off;
+}
+
 // ---- neighbour protocol (slab sharding: a rank shares vertices with ranks r-1 and r+1 only) ----------------
 // message layout as above: header[4] = {count, n_own, n_faces, 0}, keys[cap][4], ids[cap]
 

@@ -327,6 +327,7 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
             c->rowmajor.as<uint64_t>(), n_tets, c->tets.as<uint4>());
         CK(cudaGetLastError());
     }
+    const bool same_shape = c->V == n_pts && c->T == n_tets && c->t_first == 0 && c->t_count == n_tets && c->grid_R == 0;
     c->V = n_pts;
     c->VS = (uint32_t)((n_pts + 15) & ~15ull);
     c->grid_R = 0;
@@ -335,7 +336,72 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
     c->t_count = n_tets;
     c->v_first = c->v_count = 0;
     c->have_values = false;
-    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+    if (!same_shape) { // sizes learnt from the previous pass stay valid hints for a mesh of the same shape
+        c->x_window = false;
+        c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+    }
+    invalidate(c);
+    return RIN_OK;
+}
+
+// One rank's slice of a mesh that is sharded by contiguous tet ranges: device buffers are allocated for the
+// whole mesh (indices stay global, so keys agree between ranks) but only the slice crosses PCIe.
+int rin_set_mesh_host_range(rin_ctx* c, uint64_t n_pts, uint64_t n_tets, const double* pts_slice, uint64_t v_first,
+    uint64_t v_count, const void* tets_slice, uint64_t t_first, uint64_t t_count, int index_bytes)
+{
+    if (!c || (v_count && !pts_slice) || (t_count && !tets_slice)) return fail(RIN_ERR_ARG, "rin_set_mesh_host_range: null argument");
+    if (index_bytes != 4 && index_bytes != 8) return fail(RIN_ERR_ARG, "index_bytes must be 4 or 8");
+    if (n_pts >= 0xffffffffull || n_tets >= 0x7fffffffull) return fail(RIN_ERR_ARG, "mesh too large for 32-bit device indices");
+    if (v_first > n_pts || v_count > n_pts - v_first || t_first > n_tets || t_count > n_tets - t_first)
+        return fail(RIN_ERR_ARG, "rin_set_mesh_host_range: slice out of bounds");
+    CK(cudaSetDevice(c->device));
+    CK(c->pts.ensure(n_pts * 24));
+    CK(c->tets.ensure(n_tets * 16));
+    if (v_count)
+        CK(cudaMemcpyAsync(c->pts.as<double>() + 3 * v_first, pts_slice, v_count * 24, cudaMemcpyHostToDevice, c->stream));
+    if (t_count) {
+        if (index_bytes == 4) {
+            CK(cudaMemcpyAsync(c->tets.as<uint4>() + t_first, tets_slice, t_count * 16, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            CK(c->rowmajor.ensure(t_count * 32));
+            CK(cudaMemcpyAsync(c->rowmajor.p, tets_slice, t_count * 32, cudaMemcpyHostToDevice, c->stream));
+            narrow_tets_kernel<<<grid_for(t_count, 256, c->sm_count), 256, 0, c->stream>>>(
+                c->rowmajor.as<uint64_t>(), t_count, c->tets.as<uint4>() + t_first);
+            CK(cudaGetLastError());
+        }
+    }
+    const bool same_shape = c->V == n_pts && c->T == n_tets && c->t_first == t_first && c->t_count == t_count &&
+                            c->grid_R == 0;
+    c->V = n_pts;
+    c->VS = (uint32_t)((n_pts + 15) & ~15ull);
+    c->grid_R = 0;
+    c->T = n_tets;
+    c->t_first = t_first;
+    c->t_count = t_count;
+    c->v_first = (uint32_t)v_first;
+    c->v_count = (uint32_t)v_count;
+    c->have_values = false;
+    if (!same_shape) {
+        c->x_window = false;
+        c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+    }
+    invalidate(c);
+    return RIN_OK;
+}
+
+int rin_set_values_host_range(rin_ctx* c, const double* vals_slice, uint64_t v_first, uint64_t v_count, uint32_t F)
+{
+    if (!c || (v_count && !vals_slice) || F == 0) return fail(RIN_ERR_ARG, "rin_set_values_host_range: bad argument");
+    if (v_first > c->V || v_count > c->V - v_first) return fail(RIN_ERR_ARG, "rin_set_values_host_range: slice out of bounds");
+    if (F > RIN_MAX_FUNCS) return fail(RIN_ERR_ARG, "more than 128 functions are not supported by this build");
+    CK(cudaSetDevice(c->device));
+    CK(c->rowmajor.ensure(c->V * F * 8));
+    if (v_count)
+        CK(cudaMemcpyAsync(c->rowmajor.as<double>() + v_first * F, vals_slice, v_count * F * 8, cudaMemcpyHostToDevice,
+            c->stream));
+    c->F = F;
+    c->have_values = true;
+    c->have_funcs = false;
     invalidate(c);
     return RIN_OK;
 }
@@ -1205,6 +1271,15 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
             c->x_offsets[2 * q] = hsmall[64 + q * (world + 1) + rank];
             c->x_offsets[2 * q + 1] = hsmall[64 + q * (world + 1) + world];
         }
+        {
+            // face offset arrays -> offsets into the merged face_verts / face_tets arrays
+            const uint32_t nf1 = (uint32_t)c->counts.num_faces + 1;
+            add_offset_kernel<<<grid_for(nf1, 256, sm), 256, 0, s>>>(c->f_off.as<uint32_t>(), nf1,
+                (uint32_t)c->x_offsets[4]);
+            add_offset_kernel<<<grid_for(nf1, 256, sm), 256, 0, s>>>(c->f_toff.as<uint32_t>(), nf1,
+                (uint32_t)c->x_offsets[6]);
+            CK(cudaGetLastError());
+        }
         if (vert_offset) *vert_offset = c->x_offsets[0];
         if (n_verts_total) *n_verts_total = c->x_offsets[1];
         if (face_offset) *face_offset = c->x_offsets[2];
@@ -1385,6 +1460,15 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         for (int q = 0; q < 4; ++q) {
             c->x_offsets[2 * q] = hsmall[64 + q * (world + 1) + rank];
             c->x_offsets[2 * q + 1] = hsmall[64 + q * (world + 1) + world];
+        }
+        {
+            // face offset arrays -> offsets into the merged face_verts / face_tets arrays
+            const uint32_t nf1 = (uint32_t)c->counts.num_faces + 1;
+            add_offset_kernel<<<grid_for(nf1, 256, sm), 256, 0, s>>>(c->f_off.as<uint32_t>(), nf1,
+                (uint32_t)c->x_offsets[4]);
+            add_offset_kernel<<<grid_for(nf1, 256, sm), 256, 0, s>>>(c->f_toff.as<uint32_t>(), nf1,
+                (uint32_t)c->x_offsets[6]);
+            CK(cudaGetLastError());
         }
         if (vert_offset) *vert_offset = c->x_offsets[0];
         if (n_verts_total) *n_verts_total = c->x_offsets[1];

@@ -56,6 +56,9 @@ def lib():
         L.rin_destroy.argtypes = [C.c_void_p]
         L.rin_set_mesh_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
         L.rin_generate_grid.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.rin_set_mesh_host_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
+                                              C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
+        L.rin_set_values_host_range.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
         L.rin_set_tet_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.rin_set_functions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.rin_set_values_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
@@ -133,6 +136,17 @@ class Context:
         tets = np.ascontiguousarray(tets)
         self._check(lib().rin_set_mesh_host(self._h, pts.ctypes.data, len(pts), tets.ctypes.data, len(tets),
                                             tets.dtype.itemsize))
+
+    def set_mesh_range(self, n_pts, n_tets, pts_slice, v_first, tets_slice, t_first):
+        assert tets_slice.dtype in (np.uint32, np.uint64) and pts_slice.dtype == np.float64
+        self._check(lib().rin_set_mesh_host_range(self._h, n_pts, n_tets, pts_slice.ctypes.data, v_first,
+                                                  len(pts_slice), tets_slice.ctypes.data, t_first, len(tets_slice),
+                                                  tets_slice.dtype.itemsize))
+
+    def set_values_range(self, vals_slice, v_first):
+        assert vals_slice.dtype == np.float64 and vals_slice.flags.c_contiguous
+        self._check(lib().rin_set_values_host_range(self._h, vals_slice.ctypes.data, v_first, vals_slice.shape[0],
+                                                    vals_slice.shape[1]))
 
     def generate_grid(self, R, bmin=(-1, -1, -1), bmax=(1, 1, 1)):
         a = np.asarray(bmin, np.float64)

@@ -157,8 +157,8 @@ def merged_layout(info):
 
 
 def slice_views(merged, info, counts):
-    """Views of this rank's slice inside the merged arrays (what rin_download_mesh writes into).  The offset
-    arrays of a slice are local; fix_offsets() rebases them once every rank has written."""
+    """Views of this rank's slice inside the merged arrays (what rin_download_mesh writes into).  After
+    rin_exchange_nccl the offset arrays arrive rebased into the merged arrays."""
     v0, f0, fv0, ft0 = info["vert_offset"], info["face_offset"], info["fv_offset"], info["ft_offset"]
     nv, nf, nfv, nft = counts.num_verts, counts.num_faces, counts.num_face_verts, counts.num_face_tets
     out = {k: merged[k][v0:v0 + nv] for k in MESH_VERT_KEYS}
@@ -169,9 +169,3 @@ def slice_views(merged, info, counts):
     out["face_offsets"] = merged["face_offsets"][f0:f0 + nf + 1]
     out["face_tet_offsets"] = merged["face_tet_offsets"][f0:f0 + nf + 1]
     return out
-
-
-def rebase_offsets(views, info):
-    """Local offsets -> offsets into the merged face_verts / face_tets (this rank's slice only)."""
-    views["face_offsets"] += np.uint32(info["fv_offset"])
-    views["face_tet_offsets"] += np.uint32(info["ft_offset"])

@@ -27,6 +27,10 @@ CASES = {  # name -> (mode, function set, R, run the hybrid reference too)
     "C3": ("mi", "C3", 128, True),
     "C4": ("ia", "C4", 128, True),
     "C5": ("ia", "C5", 256, True),
+    # weak-scaling instances of bench.py: R = round(128 N^(1/3)) for N = 1, 2, 4 (N = 8 is C5)
+    "C2": ("ia", "C2", 128, True),
+    "W2": ("ia", "C2", 161, False),
+    "W4": ("ia", "C2", 203, False),
 }
 
 
