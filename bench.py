@@ -254,7 +254,8 @@ def main():
     ctx = rin.Context(local)
     ctx.generate_grid(R)
     ctx.set_functions(funcs)
-    t_first, t_count = sharding.slab_range(R, rank, world)
+    i0, i1 = R * rank // world, R * (rank + 1) // world  # this rank's x-planes of cubes [i0, i1)
+    t_first, t_count = sharding.slab_of_planes(R, i0, i1)
     if world > 1:
         ctx.set_tet_range(t_first, t_count)
     T_total = 5 * R ** 3
@@ -277,13 +278,35 @@ def main():
         dist.broadcast(uid, 0)
         return uid.cpu().numpy()
 
+    slab_plan = None
     if dist is not None:
         ctx.nccl_init(new_uid(), rank, world)
+        # calibration pass (outside the timed region): where the surface is decides what a slab costs; slabs are
+        # re-cut so that the estimated cost is even (sharding.balanced_slab_planes), every rank from the same data
+        ctx.run(mode, flags)
+        hist = torch.zeros(R, dtype=torch.float64, device="cuda")
+        act = ctx.download_active_tets() // np.uint32(5 * R * R)
+        hist += torch.from_numpy(np.bincount(act, minlength=R).astype(np.float64)).cuda()
+        dist.all_reduce(hist)
+        slab_plan = sharding.balanced_slab_planes(hist.cpu().numpy(), world)
+        i0, i1 = slab_plan[rank], slab_plan[rank + 1]
+        t_first, t_count = sharding.slab_of_planes(R, i0, i1)
+        ctx.set_tet_range(t_first, t_count)
+
+    split = {"run": 0.0, "exchange": 0.0, "n": 0}
 
     def step():
         """One pass: hot path on this rank's slab, then (N > 1) the slab-boundary exchange on the device."""
+        ta = time.perf_counter()
         c = ctx.run(mode, flags)
-        return ctx.exchange_nccl() if dist is not None else c
+        if dist is None:
+            return c
+        tb = time.perf_counter()
+        r = ctx.exchange_nccl()
+        split["run"] += tb - ta
+        split["exchange"] += time.perf_counter() - tb
+        split["n"] += 1
+        return r
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------
     ctx.set_stage_timing(False)  # the timed region records two events per pass, not a dozen
@@ -293,6 +316,7 @@ def main():
     sampler.start()
     barrier()
     dev_ms = []
+    split.update(run=0.0, exchange=0.0, n=0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         info = step()
@@ -302,6 +326,13 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     cnt = ctx.counts()
+    split_ms = None
+    if dist is not None:  # host wall time of the two calls on this rank (the exchange includes waiting for the peers)
+        split_ms = {"run_ms": 1e3 * split["run"] / split["n"], "exchange_ms": 1e3 * split["exchange"] / split["n"]}
+        both = torch.tensor([split_ms["run_ms"], split_ms["exchange_ms"]], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(both) for _ in range(world)]
+        dist.all_gather(allr, both)
+        split_ms = {"per_rank_run_ms": [float(x[0]) for x in allr], "per_rank_exchange_ms": [float(x[1]) for x in allr]}
     launches_per_step = ctx.launch_count()
     ms_per_step = 1e3 * wall / args.steps
     value = T_total / (wall / args.steps)
@@ -356,7 +387,6 @@ def main():
     d2h = sum(views[k].nbytes for k in MESH_KEYS)
     if not args.no_e2e:
         # this rank's slice of the reference-shaped inputs: the vertex planes its slab touches
-        i0, i1 = R * rank // world, R * (rank + 1) // world
         v_first, v_count = i0 * N1 * N1, (i1 - i0 + 1) * N1 * N1
         gp, gt = ctx.download_grid(N1 ** 3, T_total)
         pts_h = pinned((v_count, 3), np.float64)
@@ -442,7 +472,7 @@ def main():
     # masks; nothing is read (coordinates come from three axis tables).  SURVEY 8(d) K1 with an implicit grid:
     # V * 8F (+ the masks this implementation adds).  The filter no longer streams the index records.
     peak, peak_src = measured_peak()
-    V_rank = N1 ** 3 if world == 1 else ((R * (rank + 1) // world - R * rank // world) + 1) * N1 * N1
+    V_rank = N1 ** 3 if world == 1 else (i1 - i0 + 1) * N1 * N1
     mask_bytes = 4.0 if (F <= 16 and not mi) else 8.0 * ((F + 31) // 32)
     evl, filt = float(np.mean(eval_ms)), float(np.mean(filt_ms))
     alg_eval = (8.0 * F + mask_bytes) * V_rank
@@ -487,7 +517,9 @@ def main():
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_text(config, R, mi),
                            "baseline_config": config if world == 1 else ("C5" if R == 256 else "C2-weak"),
-                           "sharding": "x-slabs, one contiguous tet range per GPU" if world > 1 else "none",
+                           "sharding": ("x-slabs, one contiguous tet range per GPU, cut at the cube planes %s so that the "
+                                        "estimated cost (tets and active tets of a calibration pass) is even" % slab_plan)
+                           if world > 1 else "none",
                            "cache": "outputs of every stage (values %.0f MB, candidates, mesh) exceed the 126 MB L2 "
                                     "or are produced by the previous kernel" % (8.0 * F * N1 ** 3 / 1e6)},
                 "device_ms_per_step": dev, "stage_ms": stage,
@@ -498,7 +530,8 @@ def main():
                 "exchange": None if dist is None else {
                     "what": "slab-boundary vertex keys: ncclSend/ncclRecv with the neighbour ranks + one 32-byte-per-"
                             "rank ncclAllGather of the counts (rin_exchange_nccl, one host synchronisation)",
-                    "n_verts_total": info["n_verts_total"], "n_faces_total": info["n_faces_total"]}}
+                    "n_verts_total": info["n_verts_total"], "n_faces_total": info["n_faces_total"],
+                    "host_wall": split_ms}}
         print(json.dumps(line))
     if dist is not None:
         barrier()

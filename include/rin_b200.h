@@ -146,6 +146,8 @@ int rin_download_mesh(rin_ctx*, rin_mesh_out* out);
 /* func_in_tet / start_index_of_tet (src/implicit_arrangement.cpp:84-85) for the tet range:
  * start has count+1 entries; either pointer may be NULL */
 int rin_download_active(rin_ctx*, uint32_t* func_in_tet, uint64_t* start_index_of_tet);
+/* ids of the active tets of the last run, ascending (num_intersecting_tet entries): what a load balancer needs */
+int rin_download_active_tets(rin_ctx*, uint32_t* tet_ids);
 /* row-major V x F function values as evaluated on the device */
 int rin_download_values(rin_ctx*, double* vals_rowmajor);
 int rin_download_grid(rin_ctx*, double* pts, uint32_t* tets);

@@ -215,33 +215,32 @@ __global__ void __launch_bounds__(256) add_offset_kernel(uint32_t* __restrict__ 
 // message layout as above: header[4] = {count, n_own, n_faces, 0}, keys[cap][4], ids[cap]
 
 // own indices of the vertices this rank sent upwards (it owns all of them: it is the lowest rank on that plane)
+// out = this rank's record of the count exchange: 8 header words {n_own, n_faces, candidates sent upwards,
+// n_face_verts, n_face_tets, 0, 0, 0} followed by the own indices (one all-gather moves both)
 __global__ void __launch_bounds__(256) x_own_ids_kernel(const uint32_t* __restrict__ sent, uint32_t cap,
-    const uint32_t* __restrict__ own_idx, uint32_t* __restrict__ out, unsigned* __restrict__ n_bad)
+    const uint32_t* __restrict__ own_idx, uint32_t* __restrict__ out, unsigned* __restrict__ n_bad,
+    const unsigned* __restrict__ n_own, uint32_t n_faces, uint32_t n_fv, uint32_t n_ft)
 {
     const uint32_t n = min(sent[0], cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[0] = *n_own;
+        out[1] = n_faces;
+        out[2] = sent[0];
+        out[3] = n_fv;
+        out[4] = n_ft;
+        out[5] = out[6] = out[7] = 0;
+    }
     const uint32_t* ids = sent + XHDR + (size_t)cap * 4;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t o = own_idx[ids[j]];
         if (o == NONE32) atomicAdd(n_bad, 1u);
-        out[j] = o;
+        out[8 + j] = o;
     }
-}
-
-// record of the count exchange: {n_own, n_faces, candidates sent upwards, n_face_verts, n_face_tets, 0, 0, 0}
-__global__ void x_counts_kernel(uint32_t* out, const unsigned* n_own, uint32_t n_faces, const unsigned* n_up,
-    uint32_t n_fv, uint32_t n_ft)
-{
-    out[0] = *n_own;
-    out[1] = n_faces;
-    out[2] = *n_up;
-    out[3] = n_fv;
-    out[4] = n_ft;
-    out[5] = out[6] = out[7] = 0;
 }
 
 // prefixes of the gathered records (vertices, faces, face-vertex entries, face-tet pairs: four arrays of
 // world + 1 entries behind each other); overflow = largest n_up beyond the capacity
-__global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, int world, uint32_t cap,
+__global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, size_t stride, int world, uint32_t cap,
     uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
 {
     if (threadIdx.x || blockIdx.x) return;
@@ -254,11 +253,11 @@ __global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, int world,
         foff[s] = f;
         fvoff[s] = fv;
         ftoff[s] = ft;
-        v += all[8 * s];
-        f += all[8 * s + 1];
-        fv += all[8 * s + 3];
-        ft += all[8 * s + 4];
-        if (all[8 * s + 2] > cap) ovf = max(ovf, all[8 * s + 2]);
+        v += all[stride * s];
+        f += all[stride * s + 1];
+        fv += all[stride * s + 3];
+        ft += all[stride * s + 4];
+        if (all[stride * s + 2] > cap) ovf = max(ovf, all[stride * s + 2]);
     }
     voff[world] = v;
     foff[world] = f;

@@ -617,6 +617,17 @@ int rin_download_active(rin_ctx* c, uint32_t* func_in_tet, uint64_t* start)
     return RIN_OK;
 }
 
+int rin_download_active_tets(rin_ctx* c, uint32_t* out)
+{
+    if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->ran) return fail(RIN_ERR_STATE, "no finished run");
+    CK(cudaSetDevice(c->device));
+    const size_t A = (size_t)c->counts.num_intersecting_tet;
+    if (A) CK(cudaMemcpyAsync(out, c->act_tet.p, A * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RIN_OK;
+}
+
 int rin_download_values(rin_ctx* c, double* out)
 {
     if (!c || !out) return fail(RIN_ERR_ARG, "null argument");
@@ -1152,8 +1163,8 @@ int rin_nccl_init(rin_ctx* c, const uint8_t id[128], int rank, int world)
 
 // Neighbour protocol for slab sharding: rank r shares vertices with r-1 and r+1 only and owns everything on the
 // plane it shares with r+1 (first occurrence in tet order).  Per pass: one ncclSend/ncclRecv pair with the keys of
-// the upper plane, one with their own indices, one 16-byte-per-rank ncclAllGather of (owned vertices, faces,
-// candidates sent) for the global offsets; all stream-ordered, ONE host synchronisation at the end.
+// the upper plane and one ncclAllGather of (counts, own indices of those keys) for the global offsets and ids;
+// all stream-ordered, ONE host synchronisation at the end.
 extern "C++" {
 namespace {
 int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
@@ -1169,9 +1180,8 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
         const size_t words = xmsg_words(cap);
         CK(c->x_send.ensure(words * 4));
         CK(c->x_recv1.ensure(words * 4));
-        CK(c->x_ids_up.ensure((size_t)cap * 4));
-        CK(c->x_ids_low.ensure((size_t)cap * 4));
-        CK(c->x_cnt.ensure((size_t)(world + 1) * 32));
+        const size_t rec_words = 8 + (size_t)cap; // count record + own indices of the vertices sent upwards
+        CK(c->x_cnt.ensure((size_t)(world + 1) * rec_words * 4));
         uint32_t tsize = 64;
         while (tsize < 2ull * cap) tsize <<= 1;
         CK(c->x_table.ensure((size_t)tsize * 4));
@@ -1197,8 +1207,8 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
         uint32_t* d_foff = small + 64 + (world + 1);
         uint32_t* up = c->x_send.as<uint32_t>();
         uint32_t* low = c->x_recv1.as<uint32_t>();
-        uint32_t* mine4 = c->x_cnt.as<uint32_t>(); // this rank's 8-word count record
-        uint32_t* all4 = mine4 + 8;                // gathered
+        uint32_t* mine4 = c->x_cnt.as<uint32_t>(); // this rank's record
+        uint32_t* all4 = mine4 + rec_words;        // gathered
         // 1. keys (+ local indices) of the vertices on the plane shared with r+1 -> r+1
         if (NV && c->x_up_lo <= c->x_up_hi)
             x_select_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
@@ -1218,21 +1228,17 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
                 c->x_table.as<uint32_t>(), tsize - 1, c->x_has_low ? 1 : 0, c->own_idx.as<uint32_t>(),
                 c->status.as<unsigned long long>(), d_tile, d_nown);
         // 3. own indices of what was sent upwards -> r+1; (n_own, n_faces, n_up) of every rank -> offsets
-        x_own_ids_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(up, cap, c->own_idx.as<uint32_t>(),
-            c->x_ids_up.as<uint32_t>(), d_bad);
-        x_counts_kernel<<<1, 1, 0, s>>>(mine4, d_nown, (uint32_t)c->counts.num_faces, d_up,
-            (uint32_t)c->counts.num_face_verts, (uint32_t)c->counts.num_face_tets);
-        NK(g_nccl.GroupStart());
-        if (c->x_has_up) NK(g_nccl.Send(c->x_ids_up.p, cap, 3, rank + 1, c->nccl_comm, s));
-        if (c->x_has_low) NK(g_nccl.Recv(c->x_ids_low.p, cap, 3, rank - 1, c->nccl_comm, s));
-        NK(g_nccl.GroupEnd());
-        NK(g_nccl.AllGather(mine4, all4, 8, 3, c->nccl_comm, s));
-        x_offsets_nb_kernel<<<1, 1, 0, s>>>(all4, world, cap, d_voff, d_foff, d_ovf);
+        x_own_ids_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(up, cap, c->own_idx.as<uint32_t>(), mine4, d_bad,
+            d_nown, (uint32_t)c->counts.num_faces, (uint32_t)c->counts.num_face_verts,
+            (uint32_t)c->counts.num_face_tets);
+        NK(g_nccl.AllGather(mine4, all4, rec_words, 3, c->nccl_comm, s));
+        x_offsets_nb_kernel<<<1, 1, 0, s>>>(all4, rec_words, world, cap, d_voff, d_foff, d_ovf);
+        const uint32_t* ids_low = all4 + (size_t)std::max(rank - 1, 0) * rec_words + 8;
         // 4. global ids, face vertex lists, owned vertices (skipped by every rank alike when a message overflowed:
         //    the decision comes from the gathered counts)
         if (NV) {
             x_global_ids_nb_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(),
-                c->own_idx.as<uint32_t>(), NV, rank, d_voff, low, c->x_ids_low.as<uint32_t>(), cap,
+                c->own_idx.as<uint32_t>(), NV, rank, d_voff, low, ids_low, cap,
                 c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad);
             compact_own_verts_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->own_idx.as<uint32_t>(), NV,
                 c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(),

@@ -69,6 +69,7 @@ def lib():
         L.rin_download_mesh.argtypes = [C.c_void_p, C.POINTER(MeshOut)]
         L.rin_download_active.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rin_download_values.argtypes = [C.c_void_p, C.c_void_p]
+        L.rin_download_active_tets.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_download_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rin_get_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.rin_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
@@ -208,6 +209,11 @@ class Context:
         start = np.empty(n.num_tets + 1, np.uint64)
         self._check(lib().rin_download_active(self._h, fit.ctypes.data, start.ctypes.data))
         return fit, start
+
+    def download_active_tets(self):
+        out = np.empty(self.counts().num_intersecting_tet, np.uint32)
+        self._check(lib().rin_download_active_tets(self._h, out.ctypes.data))
+        return out
 
     def download_values(self):
         n = self.counts()
