@@ -189,6 +189,19 @@ int rin_tet_maps(rin_ctx*, uint64_t* n_active, uint64_t* n_vert_entries, uint64_
 int rin_download_tet_maps(rin_ctx*, uint32_t* active_tets, uint32_t* vert_offsets, int64_t* vert_ids,
                           uint32_t* face_offsets, uint32_t* face_ids);
 
+/* ---- N1: edges of the extracted mesh (compute_mesh_edges, src/mesh_connectivity.cpp:10-56) ----
+ * Edge ids follow the first occurrence scanning (face, position in face).  edges_of_face[p] is the edge between
+ * entries p and p + 1 (cyclically) of the face-vertex array; edge_faces lists, per edge and ascending, the
+ * (face, position in face) pairs = Edge::face_edge_indices (src/mesh.h:62-71). */
+typedef struct rin_edges_out {
+    uint32_t* edge_verts;        /* [num_edges*2]      v1 <= v2 */
+    uint32_t* edges_of_face;     /* [num_face_verts]   same offsets as face_verts */
+    uint32_t* edge_face_offsets; /* [num_edges+1] */
+    uint32_t* edge_faces;        /* [num_face_verts*2] (face, position) pairs */
+} rin_edges_out;
+int rin_mesh_edges(rin_ctx*, uint64_t* n_edges);
+int rin_download_edges(rin_ctx*, rin_edges_out* out);
+
 /* robust_test (-R) of the reference (src/implicit_arrangement.cpp:137-243): every active tet of the
  * last run is computed with its functions in forward and in reversed order.
  * out = {type 1 (inconsistent counts), type 2 (forward run failed), type 3 (reversed run failed), tets tested} */

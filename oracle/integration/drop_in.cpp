@@ -4,9 +4,10 @@
 // (/root/reference/src/implicit_arrangement.h:39-62, src/material_interface.h:38-61) re-implemented
 // as a maintainer would after adopting librin_b200: the hot stages (:53-402 / :53-447) are ONE call
 // into the GPU library through the C++ host layer (robust-implicit-surface-networks_b200/host),
-// the per-tet complexes come from rin_get_complexes, and every host topology stage after
-// "compute xyz" is the reference's OWN code (mesh_connectivity / pair_faces / topo_ray_shooting
-// objects compiled in place from /root/reference/src and linked here).  The reference's csg.cpp is
+// the per-tet complexes come from rin_get_complexes, edges / patches / chains come from this
+// repository (rin_mesh_edges on the device, rin_host::mesh_patches / mesh_chains), and the host topology stages
+// behind them (face ordering, shells, ray shooting, labels) are the reference's OWN code (pair_faces /
+// topo_ray_shooting / mesh_connectivity objects compiled in place from /root/reference/src and linked here).  The reference's csg.cpp is
 // linked unchanged and therefore calls THIS implicit_arrangement: a literal drop-in.
 // The oracle's CPU engine (oracle/sa/*.cpp) is NOT linked into this library.
 #include <simplicial_arrangement/lookup_table.h>
@@ -151,20 +152,21 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
 
     // ---- from here on: the reference's own host stages (src/implicit_arrangement.cpp:404-647)
     Topology T;
-    compute_mesh_edges(iso_faces, T.edges_of_face, iso_edges);
+    // N1 (edges on the device, patches / chains in the host layer of this repository, not the reference's)
+    {
+        std::string err;
+        if (!rin_host::mesh_edges(T.edges_of_face, iso_edges, err)) {
+            std::cout << err << std::endl;
+            return false;
+        }
+    }
     push_stat(stats_labels, stats, "num_iso_edges", iso_edges.size());
-    compute_patches(T.edges_of_face, iso_edges, iso_faces, patches, patch_function_label);
+    rin_host::mesh_patches(T.edges_of_face, iso_edges, iso_faces, patches, patch_function_label);
     push_stat(stats_labels, stats, "num_patches", patches.size());
     T.patch_of_face.resize(iso_faces.size());
     for (size_t p = 0; p < patches.size(); ++p)
         for (size_t f : patches[p]) T.patch_of_face[f] = p;
-    non_manifold_edges_of_vert.resize(iso_pts.size());
-    for (size_t e = 0; e < iso_edges.size(); ++e)
-        if (iso_edges[e].face_edge_indices.size() > 2) {
-            non_manifold_edges_of_vert[iso_edges[e].v1].push_back(e);
-            non_manifold_edges_of_vert[iso_edges[e].v2].push_back(e);
-        }
-    compute_chains(iso_edges, non_manifold_edges_of_vert, chains);
+    rin_host::mesh_chains(iso_pts.size(), iso_edges, non_manifold_edges_of_vert, chains);
     push_stat(stats_labels, stats, "num_chains", chains.size());
     absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets;
     if (hot.num_degenerate_vertex > 0) {
@@ -258,20 +260,20 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
 
     // ---- the reference's own host stages (src/material_interface.cpp:449-695)
     Topology T;
-    compute_mesh_edges(MI_faces, T.edges_of_face, MI_edges);
+    {
+        std::string err;
+        if (!rin_host::mesh_edges(T.edges_of_face, MI_edges, err)) {
+            std::cout << err << std::endl;
+            return false;
+        }
+    }
     push_stat(stats_labels, stats, "num_MI_edges", MI_edges.size());
-    compute_patches(T.edges_of_face, MI_edges, MI_faces, patches, patch_function_label);
+    rin_host::mesh_patches(T.edges_of_face, MI_edges, MI_faces, patches, patch_function_label);
     push_stat(stats_labels, stats, "num_patches", patches.size());
     T.patch_of_face.resize(MI_faces.size());
     for (size_t p = 0; p < patches.size(); ++p)
         for (size_t f : patches[p]) T.patch_of_face[f] = p;
-    non_manifold_edges_of_vert.resize(MI_pts.size());
-    for (size_t e = 0; e < MI_edges.size(); ++e)
-        if (MI_edges[e].face_edge_indices.size() > 2) {
-            non_manifold_edges_of_vert[MI_edges[e].v1].push_back(e);
-            non_manifold_edges_of_vert[MI_edges[e].v2].push_back(e);
-        }
-    compute_chains(MI_edges, non_manifold_edges_of_vert, chains);
+    rin_host::mesh_chains(MI_pts.size(), MI_edges, non_manifold_edges_of_vert, chains);
     push_stat(stats_labels, stats, "num_chains", chains.size());
     absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets; // only filled for tied vertices upstream
     T.half_patch_pairs.resize(chains.size());

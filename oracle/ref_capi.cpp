@@ -142,9 +142,17 @@ void* ref_ia_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
     auto& pl = bag->i64["patch_function_label"];
     for (auto x : patch_label) pl.push_back(int64_t(x));
     auto& ed = bag->i64["edges"];
+    auto& ef = bag->i64["edge_faces"];
+    auto& efo = bag->i64["edge_faces_offsets"];
+    efo.push_back(0);
     for (auto& e : edges) {
         ed.push_back(int64_t(e.v1));
         ed.push_back(int64_t(e.v2));
+        for (auto& q : e.face_edge_indices) {
+            ef.push_back(int64_t(q.first));
+            ef.push_back(int64_t(q.second));
+        }
+        efo.push_back(int64_t(ef.size() / 2));
     }
     auto& cl = bag->i64["cell_function_label"]; // cells x F, row-major 0/1
     for (auto& row : cell_label)
@@ -314,9 +322,17 @@ void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
         pl.push_back(int64_t(x.second));
     }
     auto& ed = bag->i64["edges"];
+    auto& ef = bag->i64["edge_faces"];
+    auto& efo = bag->i64["edge_faces_offsets"];
+    efo.push_back(0);
     for (auto& e : edges) {
         ed.push_back(int64_t(e.v1));
         ed.push_back(int64_t(e.v2));
+        for (auto& q : e.face_edge_indices) {
+            ef.push_back(int64_t(q.first));
+            ef.push_back(int64_t(q.second));
+        }
+        efo.push_back(int64_t(ef.size() / 2));
     }
     auto& cl = bag->i64["cell_function_label"];
     for (auto x : cell_label) cl.push_back(x == Mesh_None ? -1 : int64_t(x));

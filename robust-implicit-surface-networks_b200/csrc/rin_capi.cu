@@ -6,6 +6,7 @@
 #include "pipeline_ia.cuh"
 #include "complexes.cuh"
 #include "exchange.cuh"
+#include "edges.cuh"
 
 #include <dlfcn.h>
 
@@ -184,6 +185,9 @@ struct rin_ctx
     uint64_t x_offsets[8] = {}; // offset / total of vertices, faces, face-vertex entries, face-tet pairs (last exchange)
     DevBuf x_send, x_recv1, x_recv2, x_table, x_small;
     DevBuf cx_out; // rin_get_complexes output arena
+    DevBuf e_key, e_slot, e_table, e_verts, e_of_face, e_cnt, e_off, e_pairs; // rin_mesh_edges
+    uint64_t n_edges = 0;
+    bool edges_ready = false;
     void* h_pinned = nullptr; // pinned host mirror of the device counters (cheap read-back)
     uint32_t n_local_verts = 0, n_own = 0;
     DevBuf f_off, f_verts, f_toff, f_tets, f_funcs;
@@ -215,6 +219,7 @@ void invalidate(rin_ctx* c)
 {
     c->ran = false;
     c->maps_ready = false;
+    c->edges_ready = false;
     c->marked = c->finalized = false;
 }
 
@@ -292,7 +297,8 @@ void rin_destroy(rin_ctx* c)
         &c->cand_key, &c->cand_pay, &c->cand_src, &c->face_hdr, &c->fv_ref, &c->table, &c->slot_of, &c->rep, &c->vid, &c->tmp_fverts, &c->bfkeys, &c->frep, &c->fdup, &c->fpos, &c->bf_mask,
         &c->v_tet, &c->v_local, &c->v_size, &c->v_simplex, &c->v_funcs, &c->v_xyz, &c->v_key, &c->o_tet, &c->o_local,
         &c->o_size, &c->o_simplex, &c->o_funcs, &c->o_xyz, &c->o_key, &c->own_flag, &c->own_idx, &c->gid, &c->fkeys,
-        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->x_ids_up, &c->x_ids_low, &c->x_cnt, &c->cx_out, &c->f_off, &c->f_verts,
+        &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->x_ids_up, &c->x_ids_low, &c->x_cnt, &c->e_key, &c->e_slot, &c->e_table, &c->e_verts, &c->e_of_face,
+        &c->e_cnt, &c->e_off, &c->e_pairs, &c->cx_out, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob, &c->lut_ia.cx2, &c->lut_ia.lut2cx,
         &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
     for (auto* b : bufs) b->release();
@@ -912,6 +918,91 @@ int rin_download_tet_maps(rin_ctx* c, uint32_t* active_tets, uint32_t* vert_offs
     if (vert_ids && c->m_nv) CK(cudaMemcpyAsync(vert_ids, c->m_vmap.p, c->m_nv * 8, cudaMemcpyDeviceToHost, s));
     if (face_ids && c->m_nf) CK(cudaMemcpyAsync(face_ids, c->m_fmap.p, c->m_nf * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return RIN_OK;
+}
+
+// N1: compute_mesh_edges (src/mesh_connectivity.cpp:10-56) of the last run's mesh on the device (edges.cuh)
+int rin_mesh_edges(rin_ctx* c, uint64_t* n_edges)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->ran) return fail(RIN_ERR_STATE, "rin_mesh_edges: no finished run");
+    CK(cudaSetDevice(c->device));
+    if (!c->edges_ready) {
+        cudaStream_t s = c->stream;
+        const int sm = c->sm_count;
+        const uint32_t NF = (uint32_t)c->counts.num_faces, NP = (uint32_t)c->counts.num_face_verts;
+        c->n_edges = 0;
+        if (NP) {
+            uint32_t tsize = 1024;
+            while (tsize < 2ull * NP) tsize <<= 1;
+            CK(c->e_key.ensure((size_t)NP * 8));
+            CK(c->e_slot.ensure((size_t)NP * 4));
+            CK(c->e_table.ensure((size_t)tsize * 4));
+            CK(c->e_verts.ensure((size_t)NP * 8));
+            CK(c->e_of_face.ensure((size_t)NP * 4));
+            CK(c->e_cnt.ensure((size_t)NP * 8 + 64)); // counts | cursors
+            CK(c->e_off.ensure((size_t)(NP + 1) * 4));
+            CK(c->e_pairs.ensure((size_t)NP * 8));
+            const uint32_t tiles = (NP + 1023) / 1024;
+            CK(c->status.ensure((size_t)tiles * 8 + 64));
+            CK(c->counters.ensure(sizeof(Counters)));
+            Counters* dctr = c->counters.as<Counters>();
+            CK(cudaMemsetAsync(c->e_table.p, 0xff, (size_t)tsize * 4, s));
+            CK(cudaMemsetAsync(c->e_cnt.p, 0, (size_t)NP * 8, s));
+            CK(cudaMemsetAsync(c->status.p, 0, (size_t)tiles * 8, s));
+            CK(cudaMemsetAsync(&dctr->rank_tile, 0, 8, s)); // rank_tile, n_unique
+            edge_keys_kernel<<<grid_for(NF, 256, sm), 256, 0, s>>>(c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), NF,
+                c->e_key.as<uint2>());
+            edge_insert_kernel<<<grid_for(NP, 256, sm), 256, 0, s>>>(c->e_key.as<uint2>(), NP, c->e_table.as<uint32_t>(),
+                tsize - 1, c->e_slot.as<uint32_t>());
+            edge_rank_kernel<<<grid_for(tiles, 1, sm, 6), 256, 0, s>>>(c->e_key.as<uint2>(), NP,
+                c->e_table.as<uint32_t>(), c->e_slot.as<uint32_t>(), c->e_verts.as<uint32_t>(),
+                c->status.as<unsigned long long>(), &dctr->rank_tile, &dctr->n_unique);
+            edge_assign_kernel<<<grid_for(NP, 256, sm), 256, 0, s>>>(NP, c->e_table.as<uint32_t>(),
+                c->e_slot.as<uint32_t>(), c->e_of_face.as<uint32_t>(), c->e_cnt.as<uint32_t>());
+            CK(cudaGetLastError());
+            unsigned ne = 0;
+            CK(cudaMemcpyAsync(&ne, &dctr->n_unique, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            const uint32_t etiles = (ne + 1023) / 1024;
+            CK(cudaMemsetAsync(c->status.p, 0, (size_t)std::max(etiles, 1u) * 8, s));
+            CK(cudaMemsetAsync(&dctr->rank_tile, 0, 4, s));
+            scan_u32_kernel<<<grid_for(std::max(etiles, 1u), 1, sm, 6), 256, 0, s>>>(c->e_cnt.as<uint32_t>(), ne,
+                c->e_off.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile);
+            edge_fill_kernel<<<grid_for(NF, 256, sm), 256, 0, s>>>(c->f_off.as<uint32_t>(), NF,
+                c->e_of_face.as<uint32_t>(), c->e_off.as<uint32_t>(), c->e_cnt.as<uint32_t>() + NP,
+                c->e_pairs.as<uint2>());
+            edge_sort_kernel<<<grid_for(ne, 256, sm), 256, 0, s>>>(ne, c->e_off.as<uint32_t>(), c->e_pairs.as<uint2>());
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(s));
+            c->n_edges = ne;
+        }
+        c->edges_ready = true;
+    }
+    if (n_edges) *n_edges = c->n_edges;
+    return RIN_OK;
+}
+
+int rin_download_edges(rin_ctx* c, rin_edges_out* o)
+{
+    if (!c || !o) return fail(RIN_ERR_ARG, "null argument");
+    if (!c->edges_ready) return fail(RIN_ERR_STATE, "rin_download_edges: call rin_mesh_edges first");
+    CK(cudaSetDevice(c->device));
+    const size_t NE = c->n_edges, NP = (size_t)c->counts.num_face_verts;
+    auto dl = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
+        if (!dst || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
+    CK(dl(o->edge_verts, c->e_verts, NE * 8));
+    CK(dl(o->edges_of_face, c->e_of_face, NP * 4));
+    if (o->edge_face_offsets) {
+        if (NE)
+            CK(dl(o->edge_face_offsets, c->e_off, (NE + 1) * 4));
+        else
+            o->edge_face_offsets[0] = 0;
+    }
+    CK(dl(o->edge_faces, c->e_pairs, NP * 8));
+    CK(cudaStreamSynchronize(c->stream));
     return RIN_OK;
 }
 

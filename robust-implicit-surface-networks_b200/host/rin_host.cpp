@@ -106,7 +106,7 @@ void stage_times(bool mi, std::vector<std::string>& labels, std::vector<double>&
     timings.push_back(s(1));
     labels.emplace_back(mi ? "MI(other)" : "simp_arr(other)");
     timings.push_back(0.0);
-    labels.emplace_back(mi ? "MI(2 func)" : "simp_arr(1 func)");
+    labels.emplace_back(mi ? "MI(2 func)" : "simp_arr(1 func)"); // table dispatch (IA: fused into the filter)
     timings.push_back(s(2));
     labels.emplace_back(mi ? "MI(3 func)" : "simp_arr(2 func)");
     timings.push_back(0.0);
@@ -317,6 +317,118 @@ bool fetch_tet_maps(size_t n_tets, std::vector<long long>& global_vId_of_tet_ver
         if (active) ++a;
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// N1: edges (device), patches and chains (host: order-dependent breadth-first traversals over a mesh that is tiny
+// next to the tet grid)
+// ---------------------------------------------------------------------------------------------------------------
+bool mesh_edges(std::vector<std::vector<size_t>>& edges_of_face, std::vector<Edge>& edges, std::string& error)
+{
+    if (!ensure_ctx(error)) return false;
+    uint64_t ne = 0;
+    rin_counts n{};
+    if (rin_mesh_edges(g_ctx, &ne) != RIN_OK || rin_get_counts(g_ctx, &n) != RIN_OK) {
+        error = rin_last_error();
+        return false;
+    }
+    std::vector<uint32_t> ev(2 * ne), eof(n.num_face_verts), eoff(ne + 1), ef(2 * n.num_face_verts), fo(n.num_faces + 1);
+    rin_edges_out eo{ev.data(), eof.data(), eoff.data(), ef.data()};
+    rin_mesh_out mo{};
+    mo.face_offsets = fo.data();
+    if (rin_download_edges(g_ctx, &eo) != RIN_OK || rin_download_mesh(g_ctx, &mo) != RIN_OK) {
+        error = rin_last_error();
+        return false;
+    }
+    edges.resize(ne);
+    for (size_t e = 0; e < ne; ++e) {
+        edges[e].v1 = ev[2 * e];
+        edges[e].v2 = ev[2 * e + 1];
+        edges[e].face_edge_indices.clear();
+        edges[e].face_edge_indices.reserve(eoff[e + 1] - eoff[e]);
+        for (uint32_t q = eoff[e]; q < eoff[e + 1]; ++q) edges[e].face_edge_indices.emplace_back(ef[2 * q], ef[2 * q + 1]);
+    }
+    edges_of_face.resize(n.num_faces);
+    for (size_t f = 0; f < n.num_faces; ++f) edges_of_face[f].assign(eof.begin() + fo[f], eof.begin() + fo[f + 1]);
+    return true;
+}
+
+namespace {
+// breadth-first grouping of faces; `label_of(face)` is recorded for the seed of every patch
+template <typename Label, typename LabelOf>
+void group_patches(const std::vector<std::vector<size_t>>& edges_of_face, const std::vector<Edge>& edges,
+    std::vector<std::vector<size_t>>& patches, std::vector<Label>& labels, LabelOf label_of)
+{
+    const size_t nf = edges_of_face.size();
+    std::vector<char> seen(nf, 0);
+    for (size_t seed = 0; seed < nf; ++seed) {
+        if (seen[seed]) continue;
+        patches.emplace_back();
+        std::vector<size_t>& patch = patches.back(); // doubles as the queue: faces are appended in discovery order
+        patch.push_back(seed);
+        seen[seed] = 1;
+        labels.push_back(label_of(seed));
+        for (size_t head = 0; head < patch.size(); ++head) {
+            const size_t f = patch[head];
+            for (size_t e : edges_of_face[f]) {
+                const auto& inc = edges[e].face_edge_indices;
+                if (inc.size() != 2) continue; // only manifold edges connect the faces of a patch
+                const size_t g = inc[0].first == f ? inc[1].first : inc[0].first;
+                if (!seen[g]) {
+                    seen[g] = 1;
+                    patch.push_back(g);
+                }
+            }
+        }
+    }
+}
+} // namespace
+
+void mesh_patches(const std::vector<std::vector<size_t>>& edges_of_face, const std::vector<Edge>& edges,
+    const std::vector<PolygonFace>& faces, std::vector<std::vector<size_t>>& patches,
+    std::vector<size_t>& patch_function_label)
+{
+    group_patches(edges_of_face, edges, patches, patch_function_label,
+        [&](size_t f) { return faces[f].func_index.first; });
+}
+
+void mesh_patches(const std::vector<std::vector<size_t>>& edges_of_face, const std::vector<Edge>& edges,
+    const std::vector<PolygonFace>& faces, std::vector<std::vector<size_t>>& patches,
+    std::vector<std::pair<size_t, size_t>>& patch_function_label)
+{
+    group_patches(edges_of_face, edges, patches, patch_function_label, [&](size_t f) { return faces[f].func_index; });
+}
+
+void mesh_chains(size_t n_verts, const std::vector<Edge>& edges,
+    std::vector<std::vector<size_t>>& non_manifold_edges_of_vert, std::vector<std::vector<size_t>>& chains)
+{
+    non_manifold_edges_of_vert.resize(n_verts);
+    const size_t ne = edges.size();
+    for (size_t e = 0; e < ne; ++e)
+        if (edges[e].face_edge_indices.size() > 2) { // boundary edges (one face) take no part in the ordering
+            non_manifold_edges_of_vert[edges[e].v1].push_back(e);
+            non_manifold_edges_of_vert[edges[e].v2].push_back(e);
+        }
+    std::vector<char> seen(ne, 0);
+    for (size_t seed = 0; seed < ne; ++seed) {
+        if (seen[seed] || edges[seed].face_edge_indices.size() <= 2) continue;
+        chains.emplace_back();
+        std::vector<size_t>& chain = chains.back();
+        chain.push_back(seed);
+        seen[seed] = 1;
+        for (size_t head = 0; head < chain.size(); ++head) {
+            const size_t e = chain[head];
+            for (const size_t v : {edges[e].v1, edges[e].v2}) {
+                const auto& at = non_manifold_edges_of_vert[v];
+                if (at.size() != 2) continue; // a junction (or a dangling end) closes the chain
+                const size_t o = at[0] == e ? at[1] : at[0];
+                if (!seen[o]) {
+                    seen[o] = 1;
+                    chain.push_back(o);
+                }
+            }
+        }
+    }
 }
 
 } // namespace rin_host

@@ -75,4 +75,25 @@ bool fetch_tet_maps(size_t n_tets, std::vector<long long>& global_vId_of_tet_ver
     std::vector<size_t>& global_vId_start_index_of_tet, std::vector<size_t>& iso_fId_of_tet_face,
     std::vector<size_t>& iso_fId_start_index_of_tet, std::string& error);
 
+// ---- N1: the stages right behind the hot path (src/implicit_arrangement.cpp:406-465) -----------------------------
+// Edges of the LAST hot-path call's mesh, computed on the device (rin_mesh_edges): the same ids, edges_of_face and
+// face_edge_indices as compute_mesh_edges (src/mesh_connectivity.cpp:10-56).
+bool mesh_edges(std::vector<std::vector<size_t>>& edges_of_face, std::vector<Edge>& mesh_edges, std::string& error);
+
+// Faces grouped into patches across manifold edges (exactly two incident faces), in the reference's discovery
+// order: patches by lowest face id, faces of a patch in breadth-first order, neighbours in the order of the
+// face's edges (compute_patches, src/mesh_connectivity.cpp:58-94).  Label of a patch = label of its first face.
+void mesh_patches(const std::vector<std::vector<size_t>>& edges_of_face, const std::vector<Edge>& mesh_edges,
+    const std::vector<PolygonFace>& faces, std::vector<std::vector<size_t>>& patches,
+    std::vector<size_t>& patch_function_label);
+void mesh_patches(const std::vector<std::vector<size_t>>& edges_of_face, const std::vector<Edge>& mesh_edges,
+    const std::vector<PolygonFace>& faces, std::vector<std::vector<size_t>>& patches,
+    std::vector<std::pair<size_t, size_t>>& patch_function_label);
+
+// Non-manifold edges (more than two incident faces) of every vertex, then chains: non-manifold edges linked
+// through vertices with exactly two of them, breadth-first from the lowest edge id, end v1 before v2
+// (src/implicit_arrangement.cpp:446-462, compute_chains src/mesh_connectivity.cpp:196-241).
+void mesh_chains(size_t n_verts, const std::vector<Edge>& mesh_edges,
+    std::vector<std::vector<size_t>>& non_manifold_edges_of_vert, std::vector<std::vector<size_t>>& chains);
+
 } // namespace rin_host

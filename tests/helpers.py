@@ -142,7 +142,7 @@ MAP_I64 = ["global_vId_of_tet_vert", "global_vId_start_index_of_tet", "iso_fId_o
 PORT_I64 = MESH_I64 + ["func_in_tet", "start_index_of_tet", "vert_rec", "engine"] + MAP_I64
 REF_I64 = MESH_I64 + ["success", "threw", "patches", "patches_offsets", "chains", "chains_offsets",
                       "shells", "shells_offsets", "cells", "cells_offsets", "patch_function_label",
-                      "cell_function_label", "edges", "timing_label_bytes", "stats_label_bytes",
+                      "cell_function_label", "edges", "edge_faces", "edge_faces_offsets", "timing_label_bytes", "stats_label_bytes",
                       "non_manifold_edges_of_vert", "non_manifold_edges_of_vert_offsets"]
 
 

@@ -162,3 +162,35 @@ def test_mi_cell_grouping_mode_through_the_gpu_drop_in():
     assert np.array_equal(gpu["cell_function_label"], cpu["cell_function_label"])
     shot = ref_run("mi", pts, tets, vals, ray=True, lib=dropin_lib())
     assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 4
+
+
+N1_CASES = [("ia", "C2", 24), ("ia", "3-sphere-3", 40), ("ia", "2-planesphere", 31), ("mi", "C3", 21),
+            ("mi", "3-sphere-1", 36)]
+
+
+@pytest.mark.parametrize("mode,fset,R", N1_CASES)
+def test_edges_patches_chains_equal_the_reference_own_functions(mode, fset, R):
+    """edges from the device (rin_mesh_edges), patches / chains from this repository's host layer,
+    element-wise against compute_mesh_edges / compute_patches / compute_chains of the reference
+    (src/mesh_connectivity.cpp:10-56, 58-94, 196-241) run by the hybrid on the same inputs: edge ids, end
+    vertices, face_edge_indices, patch order and the order of faces inside a patch, chain order."""
+    from helpers import synthetic_functions
+    pts, tets = orc_grid(R)
+    if fset == "degenerate":
+        funcs = make_funcs([{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
+                            {"type": "sphere", "center": [0, 0, 0], "radius": 0.5, "squared": True},
+                            {"type": "plane", "point": [0, 0, 0], "normal": [0, 1, 0]}])
+    elif fset in ("C2", "C3"):
+        funcs = make_funcs(synthetic_functions(fset))
+    else:
+        funcs = load_funcs(os.path.join(G, "functions", fset + ".json"))
+    vals = orc_eval(funcs, pts)
+    ref = ref_run(mode, pts, tets, vals)
+    got = ref_run(mode, pts, tets, vals, lib=dropin_lib())
+    # (the reference's MI face ordering gives up when an edge's faces span several tets, src/pair_faces.cpp:131-134:
+    #  both sides then report the same failure, after the N1 stages have run)
+    assert ref.error == "" and got.error == "" and got["success"][0] == ref["success"][0]
+    for k in ("edges", "edge_faces", "edge_faces_offsets", "patches", "patches_offsets", "chains", "chains_offsets",
+              "non_manifold_edges_of_vert", "non_manifold_edges_of_vert_offsets", "patch_function_label"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert len(ref["edges"]) > 0
