@@ -1,22 +1,22 @@
-// INTEGRATION DEMONSTRATION (test infrastructure, NOT product code).
-//
 // The reference's entry points implicit_arrangement() / material_interface()
-// (/root/reference/src/implicit_arrangement.h:39-62, src/material_interface.h:38-61) re-implemented
-// as a maintainer would after adopting librin_b200: the hot stages (:53-402 / :53-447) are ONE call
-// into the GPU library through the C++ host layer (robust-implicit-surface-networks_b200/host),
-// the per-tet complexes come from rin_get_complexes, edges / patches / chains come from this
-// repository (rin_mesh_edges on the device, rin_host::mesh_patches / mesh_chains), and the host topology stages
-// behind them (face ordering, shells, ray shooting, labels) are the reference's OWN code (pair_faces /
-// topo_ray_shooting / mesh_connectivity objects compiled in place from /root/reference/src and linked here).  The reference's csg.cpp is
-// linked unchanged and therefore calls THIS implicit_arrangement: a literal drop-in.
-// The oracle's CPU engine (oracle/sa/*.cpp) is NOT linked into this library.
+// (/root/reference/src/implicit_arrangement.h:39-62, src/material_interface.h:38-61), signatures verbatim, on top
+// of librin_b200.  This file is compiled INSIDE the reference's source tree in place of
+// src/implicit_arrangement.cpp and src/material_interface.cpp: it includes the reference's own
+// headers and is linked with the reference's remaining objects.  What comes from this repository:
+//   * the hot stages (:53-402 / :53-447): ONE call into the GPU library through the host layer (rin_host.h);
+//   * the per-tet complexes the later stages look at: rin_get_complexes on demand;
+//   * edges / patches / chains: rin_mesh_edges on the device, rin_host::mesh_patches / mesh_chains.
+// What stays the reference's own code (out of scope, host side by north_star): face ordering around chains
+// (pair_faces), shells / components, topological ray shooting, cell grouping, label propagation, and csg.cpp, which
+// is linked unchanged and therefore calls THIS implicit_arrangement: a literal drop-in.
+// No CPU engine is linked: without a CUDA device every call returns false with the library's message.
 #include <simplicial_arrangement/lookup_table.h>
 #include <simplicial_arrangement/simplicial_arrangement.h>
 
 #include "implicit_arrangement.h"
 #include "material_interface.h"
 
-#include "../../robust-implicit-surface-networks_b200/host/rin_host.h"
+#include "rin_host.h"
 
 #include <iostream>
 
