@@ -16,6 +16,9 @@
 #include "material_interface.h"
 
 #include "result_bag.h"
+#ifdef RIN_GPU_DROPIN
+#include "../robust-implicit-surface-networks_b200/host/rin_host.h"
+#endif
 
 #include <functional>
 #include <iostream>
@@ -141,6 +144,9 @@ void* ref_ia_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
     pack_crs(bag, "cells", cells);
     auto& pl = bag->i64["patch_function_label"];
     for (auto x : patch_label) pl.push_back(int64_t(x));
+#ifdef RIN_GPU_DROPIN
+    bag->i64["complexes_fetched"].push_back(int64_t(rin_host::complexes_fetched()));
+#endif
     auto& ed = bag->i64["edges"];
     auto& ef = bag->i64["edge_faces"];
     auto& efo = bag->i64["edge_faces_offsets"];
@@ -321,6 +327,9 @@ void* ref_mi_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
         pl.push_back(int64_t(x.first));
         pl.push_back(int64_t(x.second));
     }
+#ifdef RIN_GPU_DROPIN
+    bag->i64["complexes_fetched"].push_back(int64_t(rin_host::complexes_fetched()));
+#endif
     auto& ed = bag->i64["edges"];
     auto& ef = bag->i64["edge_faces"];
     auto& efo = bag->i64["edge_faces_offsets"];

@@ -82,27 +82,112 @@ void to_reference(const rin_host::TetComplex& in, simplicial_arrangement::Materi
     }
 }
 
-// cut_results / cut_result_index of the reference, filled from the device on demand
+// cut_results / cut_result_index of the reference, filled from the device ON DEMAND: the host
+// stages look at the complexes of a handful of tets only - the tets around the representative edge of every chain
+// (compute_face_order, src/pair_faces.cpp:16-108) and, when there are several components, tets that own an
+// iso-vertex on an edge of the ray-shooting spanning forest (src/topo_ray_shooting.cpp:332-353, 385-390).
 template <typename Complex>
-bool materialise_complexes(int mode, const rin_host::HotPathOutput& hot, size_t n_tets, std::vector<Complex>& cut_results,
-    std::vector<size_t>& cut_result_index)
+struct LazyComplexes
 {
-    std::vector<size_t> active;
-    cut_result_index.assign(n_tets, Complex::None);
-    for (size_t t = 0; t < n_tets; ++t)
-        if (hot.start_index_of_tet[t + 1] > hot.start_index_of_tet[t]) {
-            cut_result_index[t] = active.size();
-            active.push_back(t);
-        }
-    std::vector<rin_host::TetComplex> raw;
-    std::string err;
-    if (!rin_host::fetch_complexes(mode, active, raw, err)) {
-        std::cout << err << std::endl;
-        return false;
+    int mode;
+    std::vector<Complex> cut_results;
+    std::vector<size_t> cut_result_index;
+    size_t n_active = 0;
+
+    LazyComplexes(int mode_, const rin_host::HotPathOutput& hot, size_t n_tets) : mode(mode_)
+    {
+        cut_result_index.assign(n_tets, Complex::None);
+        active.assign(n_tets, false);
+        for (size_t t = 0; t < n_tets; ++t)
+            if (hot.start_index_of_tet[t + 1] > hot.start_index_of_tet[t]) {
+                active[t] = true;
+                ++n_active;
+            }
     }
-    cut_results.resize(raw.size());
-    for (size_t i = 0; i < raw.size(); ++i) to_reference(raw[i], cut_results[i]);
-    return true;
+    // makes the complexes of the given tets available (inactive tets keep None, as in the reference)
+    bool need(std::vector<size_t> tets)
+    {
+        std::sort(tets.begin(), tets.end());
+        tets.erase(std::unique(tets.begin(), tets.end()), tets.end());
+        std::vector<size_t> missing;
+        for (size_t t : tets)
+            if (active[t] && cut_result_index[t] == Complex::None) missing.push_back(t);
+        if (missing.empty()) return true;
+        std::vector<rin_host::TetComplex> raw;
+        std::string err;
+        if (!rin_host::fetch_complexes(mode, missing, raw, err)) {
+            std::cout << err << std::endl;
+            return false;
+        }
+        for (size_t i = 0; i < raw.size(); ++i) {
+            cut_result_index[missing[i]] = cut_results.size();
+            cut_results.emplace_back();
+            to_reference(raw[i], cut_results.back());
+        }
+        return true;
+    }
+    bool need_all()
+    {
+        std::vector<size_t> all;
+        for (size_t t = 0; t < active.size(); ++t)
+            if (active[t]) all.push_back(t);
+        return need(std::move(all));
+    }
+    void report() const
+    {
+        std::cout << "per-tet complexes fetched from the device: " << cut_results.size() << " of " << n_active
+                  << " active tets" << std::endl;
+    }
+
+private:
+    std::vector<bool> active;
+};
+
+// tets whose complexes compute_face_order may read for the chain represented by `edge`
+template <typename Vert>
+void face_order_tets(const Edge& edge, const std::vector<PolygonFace>& faces, const std::vector<Vert>& verts,
+    const absl::flat_hash_map<size_t, std::vector<size_t>>& incident_tets, std::vector<size_t>& out)
+{
+    const size_t before = out.size();
+    for (const auto& fe : edge.face_edge_indices)
+        for (const auto& t : faces[fe.first].tet_face_indices) out.push_back(t.first);
+    std::sort(out.begin() + before, out.end());
+    const bool one_tet = std::unique(out.begin() + before, out.end()) - (out.begin() + before) == 1;
+    if (one_tet) {
+        out.resize(before + 1);
+        return;
+    }
+    // the edge lies on a tet edge or face: every tet around the grid vertices its end points sit on
+    for (size_t v : {edge.v1, edge.v2})
+        for (size_t k = 0; k < verts[v].simplex_size && k < 4; ++k) {
+            auto it = incident_tets.find(verts[v].simplex_vert_indices[k]);
+            if (it != incident_tets.end()) out.insert(out.end(), it->second.begin(), it->second.end());
+        }
+}
+
+// tets that own an iso-vertex on an edge (v -> next[v]) of the spanning forest topo_ray_shooting walks:
+// next[v] = the smallest (x, y, z) vertex of the last tet that lists v (src/topo_ray_shooting.cpp:332-353)
+template <typename Vert>
+void ray_shooting_tets(const std::vector<std::array<double, 3>>& pts, const std::vector<std::array<size_t, 4>>& tets,
+    const std::vector<Vert>& verts, std::vector<size_t>& out)
+{
+    std::vector<size_t> next(pts.size(), Mesh_None);
+    auto less = [&](size_t a, size_t b) {
+        const auto &p = pts[a], &q = pts[b];
+        return p[0] != q[0] ? p[0] < q[0] : (p[1] != q[1] ? p[1] < q[1] : p[2] < q[2]);
+    };
+    for (const auto& tet : tets) {
+        size_t m = 0;
+        for (size_t i = 1; i < 4; ++i)
+            if (less(tet[i], tet[m])) m = i;
+        for (size_t i = 0; i < 4; ++i)
+            if (i != m) next[tet[i]] = tet[m];
+    }
+    for (const auto& v : verts)
+        if (v.simplex_size == 2) {
+            const size_t a = v.simplex_vert_indices[0], b = v.simplex_vert_indices[1];
+            if (next[a] == b || next[b] == a) out.push_back(v.tet_index);
+        }
 }
 
 struct Topology
@@ -146,9 +231,9 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
         std::string err;
         return rin_host::robust_test_verdict(0, err);
     }
-    std::vector<simplicial_arrangement::Arrangement<3>> cut_results;
-    std::vector<size_t> cut_result_index;
-    if (!materialise_complexes(0, hot, tets.size(), cut_results, cut_result_index)) return false;
+    LazyComplexes<simplicial_arrangement::Arrangement<3>> lazy(0, hot, tets.size());
+    const auto& cut_results = lazy.cut_results;
+    const auto& cut_result_index = lazy.cut_result_index;
 
     // ---- from here on: the reference's own host stages (src/implicit_arrangement.cpp:404-647)
     Topology T;
@@ -178,6 +263,11 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
             for (size_t v : tets[t])
                 if (degenerate[v]) incident_tets[v].push_back(t);
     }
+    {
+        std::vector<size_t> wanted;
+        for (size_t c = 0; c < chains.size(); ++c) face_order_tets(iso_edges[chains[c][0]], iso_faces, iso_verts, incident_tets, wanted);
+        if (!lazy.need(std::move(wanted))) return false;
+    }
     T.half_patch_pairs.resize(chains.size());
     for (size_t c = 0; c < chains.size(); ++c) {
         std::vector<HalfFacePair> face_pairs;
@@ -199,11 +289,15 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     if (T.components.size() < 2) {
         for (size_t s = 0; s < shells.size(); ++s) arrangement_cells.push_back({s});
     } else if (use_topo_ray_shooting) {
+        std::vector<size_t> wanted;
+        ray_shooting_tets(pts, tets, iso_verts, wanted);
+        if (!lazy.need(std::move(wanted))) return false;
         topo_ray_shooting(pts, tets, cut_results, cut_result_index, iso_verts, iso_faces, patches, T.patch_of_face, shells,
             T.shell_of_half_patch, T.components, T.component_of_patch, arrangement_cells);
     } else {
         // cell grouping (src/implicit_arrangement.cpp:590-622): the maps of the second extract_iso_mesh overload
         // come from the device (rin_tet_maps), the grouping itself is the reference's own code
+        if (!lazy.need_all()) return false; // the simplicial-cell graph spans every active tet
         std::vector<long long> global_vId_of_tet_vert;
         std::vector<size_t> global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet;
         std::string err;
@@ -222,6 +316,7 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
             simp_hFace_start_index, arrangement_cells);
     }
     push_stat(stats_labels, stats, "num_cells", arrangement_cells.size());
+    lazy.report();
     std::vector<bool> sample(n_func);
     for (size_t f = 0; f < n_func; ++f) sample[f] = funcVals(0, f) > 0;
     cell_function_label =
@@ -254,9 +349,9 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
         std::string err;
         return rin_host::robust_test_verdict(1, err);
     }
-    std::vector<simplicial_arrangement::MaterialInterface<3>> cut_results;
-    std::vector<size_t> cut_result_index;
-    if (!materialise_complexes(1, hot, tets.size(), cut_results, cut_result_index)) return false;
+    LazyComplexes<simplicial_arrangement::MaterialInterface<3>> lazy(1, hot, tets.size());
+    const auto& cut_results = lazy.cut_results;
+    const auto& cut_result_index = lazy.cut_result_index;
 
     // ---- the reference's own host stages (src/material_interface.cpp:449-695)
     Topology T;
@@ -276,6 +371,11 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     rin_host::mesh_chains(MI_pts.size(), MI_edges, non_manifold_edges_of_vert, chains);
     push_stat(stats_labels, stats, "num_chains", chains.size());
     absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets; // only filled for tied vertices upstream
+    {
+        std::vector<size_t> wanted;
+        for (size_t c = 0; c < chains.size(); ++c) face_order_tets(MI_edges[chains[c][0]], MI_faces, MI_verts, incident_tets, wanted);
+        if (!lazy.need(std::move(wanted))) return false;
+    }
     T.half_patch_pairs.resize(chains.size());
     for (size_t c = 0; c < chains.size(); ++c) {
         std::vector<HalfFacePair> face_pairs;
@@ -297,11 +397,15 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
         for (size_t s = 0; s < shells.size(); ++s) material_cells.push_back({s});
         if (material_cells.empty()) material_cells.push_back({Mesh_None}); // no interface at all (:619-623)
     } else if (use_topo_ray_shooting) {
+        std::vector<size_t> wanted;
+        ray_shooting_tets(pts, tets, MI_verts, wanted);
+        if (!lazy.need(std::move(wanted))) return false;
         topo_ray_shooting(pts, tets, cut_results, cut_result_index, MI_verts, MI_faces, patches, T.patch_of_face, shells,
             T.shell_of_half_patch, T.components, T.component_of_patch, material_cells);
     } else {
         // cell grouping (src/material_interface.cpp:640-672): maps of the second extract_MI_mesh overload from
         // the device (rin_tet_maps), the grouping itself is the reference's own code
+        if (!lazy.need_all()) return false;
         std::vector<long long> global_vId_of_tet_vert;
         std::vector<size_t> global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet;
         std::string err;
@@ -320,6 +424,7 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
             simp_hFace_start_index, material_cells);
     }
     push_stat(stats_labels, stats, "num_cells", material_cells.size());
+    lazy.report();
     std::vector<double> sample(n_func);
     for (size_t f = 0; f < n_func; ++f) sample[f] = funcVals(0, f);
     cell_function_label =

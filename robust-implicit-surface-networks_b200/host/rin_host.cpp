@@ -8,6 +8,7 @@ namespace rin_host {
 namespace {
 
 rin_ctx* g_ctx = nullptr;
+size_t g_complexes_fetched = 0; // per-tet complexes fetched since the last hot-path call
 
 bool ensure_ctx(std::string& err)
 {
@@ -37,6 +38,7 @@ bool run_and_download(int mode, uint32_t flags, const std::vector<std::array<dou
     std::vector<std::array<double, 3>>& out_pts, Downloaded& d, HotPathOutput& out)
 {
     if (!ensure_ctx(out.error)) return false;
+    g_complexes_fetched = 0;
     static_assert(sizeof(size_t) == 8, "the reference's tets are 64-bit indices");
     if (rin_run_host(g_ctx, mode, flags, pts.empty() ? nullptr : pts[0].data(), pts.size(),
             tets.empty() ? nullptr : tets[0].data(), tets.size(), 8, funcVals, (uint32_t)n_func, &d.n) != RIN_OK) {
@@ -224,12 +226,18 @@ bool robust_test_verdict(int mode, std::string& error)
     return true;
 }
 
+size_t complexes_fetched()
+{
+    return g_complexes_fetched;
+}
+
 bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<TetComplex>& out, std::string& error)
 {
     if (!g_ctx) {
         error = "no hot-path run";
         return false;
     }
+    g_complexes_fetched += tet_ids.size();
     std::vector<uint64_t> ids(tet_ids.begin(), tet_ids.end()), off(tet_ids.size() + 1);
     uint64_t nw = 0;
     if (rin_get_complexes(g_ctx, mode, 0, ids.data(), ids.size(), off.data(), nullptr, &nw) != RIN_OK) {

@@ -68,6 +68,9 @@ bool robust_test_verdict(int mode, std::string& error);
 // an empty complex.  This is the lazy replacement of cut_results[cut_result_index[tet]].
 bool fetch_complexes(int mode, const std::vector<size_t>& tet_ids, std::vector<TetComplex>& out, std::string& error);
 
+// number of per-tet complexes fetched since the last hot-path call (what "lazy" amounts to)
+size_t complexes_fetched();
+
 // Cell-grouping maps of the LAST implicit-arrangement call, in the shape the reference's second
 // extract_iso_mesh overload returns them (src/extract_mesh.cpp:268-566) and build_simplicial_cell_adjacency
 // consumes them (src/cell_connectivity.h:13-26): start arrays have n_tets + 1 entries.

@@ -194,3 +194,26 @@ def test_edges_patches_chains_equal_the_reference_own_functions(mode, fset, R):
               "non_manifold_edges_of_vert", "non_manifold_edges_of_vert_offsets", "patch_function_label"):
         assert np.array_equal(got[k], ref[k]), k
     assert len(ref["edges"]) > 0
+
+
+def test_complexes_are_fetched_lazily(grid101):
+    """the host stages read the complexes of a few tets only (one per chain, plus the owners of
+    iso-vertices on spanning-forest edges when there are several components); the drop-in fetches exactly those
+    from the device instead of all active tets - and the reference's known answers still come out."""
+    pts, tets = grid101
+    for name, bound in (("2-planesphere", 0.01), ("3-sphere-3", 0.01), ("3-sphere-1", 0.35)):
+        vals = orc_eval(load_funcs(os.path.join(G, "functions", name + ".json")), pts)
+        b = ref_run("ia", pts, tets, vals, lib=dropin_lib())
+        assert b.error == "" and b["success"][0] == 1
+        exp = IA_GOLD[name]["reference_test_expectation"]
+        assert len(crs(b, "cells")) == exp["cells"] and len(crs(b, "chains")) == exp["chains"]
+        active = b.stats["num_intersecting_tet"]
+        n = _fetched(b)
+        assert n is not None and n <= bound * active + 64, (name, n, active)
+
+
+def _fetched(bag):
+    import ctypes as C
+    n = C.c_uint64()
+    p = bag._lib.ref_i64(bag._h, b"complexes_fetched", C.byref(n))
+    return int(p[0]) if n.value else None
