@@ -133,6 +133,16 @@ int rin_generate_grid(rin_ctx*, uint32_t resolution, const double bbox_min[3], c
  * tet; count == 0: an empty range (rin_run then returns an empty result); out-of-range -> RIN_ERR_ARG */
 #define RIN_TET_RANGE_ALL UINT64_MAX
 int rin_set_tet_range(rin_ctx*, uint64_t first, uint64_t count);
+/* Ghost tets of a sharded run on DEGENERATE inputs (a function vanishing at grid vertices, materials tying there):
+ * an iso-face can then lie on a tet face of the slab plane, where the reference pairs the two incident tets
+ * (src/extract_mesh.cpp:240-253) or matches their materials (:833-981).  The run processes
+ * [first - below, first + count + above) but keeps only what the rank's OWN tets create: vertices first created by a
+ * ghost below are foreign (the lower rank owns them), everything created by a ghost above is dropped, faces keep
+ * their complete tet lists.  `below` / `above` must cover every tet of the neighbouring ranks that touches a shared
+ * vertex: one layer of cubes (5 R^2 tets) for x-slabs of a generated grid.  Call after rin_set_tet_range (which
+ * resets the ghosts to 0); the values are clamped to the mesh.  rin_exchange_nccl enables one cube layer by itself
+ * and repeats the run when any rank reports degenerate vertices on a generated grid. */
+int rin_set_ghost_tets(rin_ctx*, uint64_t below, uint64_t above);
 
 /* function values: either parametric (evaluated on the device) ... */
 int rin_set_functions(rin_ctx*, const rin_func_desc* funcs, uint32_t n_funcs);

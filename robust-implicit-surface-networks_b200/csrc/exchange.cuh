@@ -15,7 +15,7 @@ __host__ __device__ inline size_t xmsg_words(uint32_t cap)
 }
 
 __global__ void x_header_kernel(uint32_t* msg, const unsigned* count, uint32_t cap, const unsigned* n_own,
-    uint32_t n_faces, unsigned* overflow, uint32_t n_fv = 0, uint32_t n_ft = 0)
+    uint32_t n_faces, unsigned* overflow, uint32_t n_fv = 0, uint32_t n_ft = 0, uint32_t need_ghost = 0)
 {
     const unsigned c = *count;
     msg[0] = c;
@@ -23,7 +23,8 @@ __global__ void x_header_kernel(uint32_t* msg, const unsigned* count, uint32_t c
     msg[2] = n_faces;
     msg[3] = n_fv;
     msg[4] = n_ft;
-    msg[5] = msg[6] = msg[7] = 0;
+    msg[5] = need_ghost; // degenerate vertices seen by a run without ghost tets
+    msg[6] = msg[7] = 0;
     if (c > cap) *overflow = c;
 }
 
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) x_mark_scan_kernel(const uint4* __restric
     const uint8_t* __restrict__ v_size, uint32_t n, const uint32_t* __restrict__ all, uint32_t cap,
     const uint32_t* __restrict__ table, uint32_t mask, int rank, uint32_t* __restrict__ own_idx,
     volatile unsigned long long* __restrict__ status, unsigned* __restrict__ tile_counter,
-    unsigned* __restrict__ n_own)
+    unsigned* __restrict__ n_own, uint32_t v_lo)
 {
     __shared__ unsigned s_tile, s_base;
     __shared__ unsigned s_warp[8];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) x_mark_scan_kernel(const uint4* __restric
         if (i < n) {
             own[j] = true;
             if (rank > 0 && v_size[i] < 4 && x_lookup(all, cap, table, mask, v_key[i]) != NONE32) own[j] = false;
+            if (i < v_lo) own[j] = false; // first created by a ghost tet of the rank below
             cnt += own[j];
         }
     }
@@ -154,14 +156,15 @@ __global__ void __launch_bounds__(256) x_mark_scan_kernel(const uint4* __restric
 // `first` is the gathered buffer of the first collective: every rank derives the SAME overflow
 // decision from the same gathered headers (a rank deciding alone would desynchronise the collectives)
 __global__ void x_offsets_kernel(const uint32_t* __restrict__ first, const uint32_t* __restrict__ all, uint32_t cap,
-    int world, uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
+    int world, uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow,
+    unsigned* __restrict__ need_ghost)
 {
     if (threadIdx.x || blockIdx.x) return;
     const size_t stride = xmsg_words(cap);
     uint32_t v = 0, f = 0, fv = 0, ft = 0;
     uint32_t* fvoff = foff + (world + 1);
     uint32_t* ftoff = fvoff + (world + 1);
-    unsigned ovf = 0;
+    unsigned ovf = 0, ng = 0;
     for (int s = 0; s < world; ++s) {
         voff[s] = v;
         foff[s] = f;
@@ -172,10 +175,12 @@ __global__ void x_offsets_kernel(const uint32_t* __restrict__ first, const uint3
         f += m[2];
         fv += m[3];
         ft += m[4];
+        ng |= m[5];
         if (m[0] > cap) ovf = max(ovf, m[0]);
         if (first[s * stride] > cap) ovf = max(ovf, first[s * stride]);
     }
     *overflow = ovf;
+    *need_ghost = ng;
     voff[world] = v;
     foff[world] = f;
     fvoff[world] = fv;
@@ -186,7 +191,7 @@ __global__ void x_offsets_kernel(const uint32_t* __restrict__ first, const uint3
 __global__ void __launch_bounds__(256) x_global_ids_kernel(const uint4* __restrict__ v_key,
     const uint32_t* __restrict__ own_idx, uint32_t n, int rank, const uint32_t* __restrict__ voff,
     const uint32_t* __restrict__ all, uint32_t cap, const uint32_t* __restrict__ table, uint32_t mask,
-    uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved)
+    uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved, uint32_t v_lo)
 {
     const size_t stride = xmsg_words(cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(256) x_global_ids_kernel(const uint4* __restri
         }
         const uint32_t f = x_lookup(all, cap, table, mask, v_key[i]);
         if (f == NONE32) {
-            atomicAdd(n_unresolved, 1u);
+            if (i >= v_lo) atomicAdd(n_unresolved, 1u); // a ghost's vertex off the shared plane: no kept face uses it
             gid[i] = NONE32;
         } else {
             const uint32_t s = f / cap, j = f % cap;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(256) add_offset_kernel(uint32_t* __restrict__ 
 // n_face_verts, n_face_tets, 0, 0, 0} followed by the own indices (one all-gather moves both)
 __global__ void __launch_bounds__(256) x_own_ids_kernel(const uint32_t* __restrict__ sent, uint32_t cap,
     const uint32_t* __restrict__ own_idx, uint32_t* __restrict__ out, unsigned* __restrict__ n_bad,
-    const unsigned* __restrict__ n_own, uint32_t n_faces, uint32_t n_fv, uint32_t n_ft)
+    const unsigned* __restrict__ n_own, uint32_t n_faces, uint32_t n_fv, uint32_t n_ft, uint32_t need_ghost)
 {
     const uint32_t n = min(sent[0], cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -228,7 +233,8 @@ __global__ void __launch_bounds__(256) x_own_ids_kernel(const uint32_t* __restri
         out[2] = sent[0];
         out[3] = n_fv;
         out[4] = n_ft;
-        out[5] = out[6] = out[7] = 0;
+        out[5] = need_ghost; // degenerate vertices seen by a run without ghost tets
+        out[6] = out[7] = 0;
     }
     const uint32_t* ids = sent + XHDR + (size_t)cap * 4;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -241,13 +247,14 @@ __global__ void __launch_bounds__(256) x_own_ids_kernel(const uint32_t* __restri
 // prefixes of the gathered records (vertices, faces, face-vertex entries, face-tet pairs: four arrays of
 // world + 1 entries behind each other); overflow = largest n_up beyond the capacity
 __global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, size_t stride, int world, uint32_t cap,
-    uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow)
+    uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow,
+    unsigned* __restrict__ need_ghost)
 {
     if (threadIdx.x || blockIdx.x) return;
     uint32_t v = 0, f = 0, fv = 0, ft = 0;
     uint32_t* fvoff = foff + (world + 1);
     uint32_t* ftoff = fvoff + (world + 1);
-    unsigned ovf = 0;
+    unsigned ovf = 0, ng = 0;
     for (int s = 0; s < world; ++s) {
         voff[s] = v;
         foff[s] = f;
@@ -257,8 +264,10 @@ __global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, size_t str
         f += all[stride * s + 1];
         fv += all[stride * s + 3];
         ft += all[stride * s + 4];
+        ng |= all[stride * s + 5];
         if (all[stride * s + 2] > cap) ovf = max(ovf, all[stride * s + 2]);
     }
+    *need_ghost = ng;
     voff[world] = v;
     foff[world] = f;
     fvoff[world] = fv;
@@ -270,7 +279,8 @@ __global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, size_t str
 __global__ void __launch_bounds__(256) x_global_ids_nb_kernel(const uint4* __restrict__ v_key,
     const uint32_t* __restrict__ own_idx, uint32_t n, int rank, const uint32_t* __restrict__ voff,
     const uint32_t* __restrict__ recv_low, const uint32_t* __restrict__ ids_low, uint32_t cap,
-    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved)
+    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved,
+    uint32_t v_lo)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t o = own_idx[i];
@@ -278,13 +288,74 @@ __global__ void __launch_bounds__(256) x_global_ids_nb_kernel(const uint4* __res
             gid[i] = voff[rank] + o;
             continue;
         }
-        const uint32_t f = x_lookup(recv_low, cap, table, mask, v_key[i]);
+        const uint32_t f = (rank > 0) ? x_lookup(recv_low, cap, table, mask, v_key[i]) : NONE32;
         if (f == NONE32 || ids_low[f] == NONE32) {
-            atomicAdd(n_unresolved, 1u);
+            if (i >= v_lo) atomicAdd(n_unresolved, 1u);
             gid[i] = NONE32;
         } else
             gid[i] = voff[rank - 1] + ids_low[f];
     }
+}
+
+// ---- ghost tets (sharded runs on degenerate inputs, rin_set_ghost_tets) ------------------------------------
+// Vertices are numbered in the order of their creating tet and faces are listed in the order of theirs (first
+// entry of the tet list), so what the ghosts below / above created is a prefix / suffix of both arrays.
+struct GhostBounds
+{
+    uint32_t v_lo, v_hi;   // vertices created by own tets: [v_lo, v_hi)
+    uint32_t f_lo, f_hi;   // faces created by own tets
+    uint32_t fv_lo, fv_hi; // their entries in the face-vertex array
+    uint32_t ft_lo, ft_hi; // and in the (tet, local face) array
+};
+
+__global__ void ghost_bounds_kernel(const uint32_t* __restrict__ v_tet, uint32_t nv, const uint32_t* __restrict__ f_off,
+    const uint32_t* __restrict__ f_toff, const uint32_t* __restrict__ f_tets, uint32_t nf, uint32_t own_first,
+    uint32_t own_end, GhostBounds* __restrict__ out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    auto first_vert = [&](uint32_t t) { // first vertex whose creating tet is >= t
+        uint32_t lo = 0, hi = nv;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (v_tet[mid] < t) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    auto first_face = [&](uint32_t t) {
+        uint32_t lo = 0, hi = nf;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (f_tets[2 * (size_t)f_toff[mid]] < t) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    GhostBounds b;
+    b.v_lo = first_vert(own_first);
+    b.v_hi = first_vert(own_end);
+    b.f_lo = first_face(own_first);
+    b.f_hi = first_face(own_end);
+    b.fv_lo = f_off[b.f_lo];
+    b.fv_hi = f_off[b.f_hi];
+    b.ft_lo = f_toff[b.f_lo];
+    b.ft_hi = f_toff[b.f_hi];
+    *out = b;
+}
+
+// faces [f_lo, f_hi) with their offsets rebased to 0
+__global__ void __launch_bounds__(256) ghost_slice_faces_kernel(const GhostBounds b, const uint32_t* __restrict__ f_off,
+    const uint32_t* __restrict__ f_verts, const uint32_t* __restrict__ f_toff, const uint32_t* __restrict__ f_tets,
+    const uint32_t* __restrict__ f_funcs, uint32_t* __restrict__ o_off, uint32_t* __restrict__ o_verts,
+    uint32_t* __restrict__ o_toff, uint32_t* __restrict__ o_tets, uint32_t* __restrict__ o_funcs)
+{
+    const uint32_t nf = b.f_hi - b.f_lo, nfv = b.fv_hi - b.fv_lo, nft = b.ft_hi - b.ft_lo;
+    const uint32_t step = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = i0; i <= nf; i += step) {
+        o_off[i] = f_off[b.f_lo + i] - b.fv_lo;
+        o_toff[i] = f_toff[b.f_lo + i] - b.ft_lo;
+    }
+    for (uint32_t i = i0; i < 2 * nf; i += step) o_funcs[i] = f_funcs[2 * (size_t)b.f_lo + i];
+    for (uint32_t i = i0; i < nfv; i += step) o_verts[i] = f_verts[b.fv_lo + i];
+    for (uint32_t i = i0; i < 2 * nft; i += step) o_tets[i] = f_tets[2 * (size_t)b.ft_lo + i];
 }
 
 } // namespace rin

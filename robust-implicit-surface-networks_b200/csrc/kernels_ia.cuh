@@ -1842,11 +1842,12 @@ __device__ __forceinline__ uint32_t foreign_lookup(const uint4* fkeys, const uin
 // flag[i] = 1 when vertex i is owned by this rank (not found among the lower ranks' keys)
 __global__ void __launch_bounds__(256) mark_foreign_kernel(const uint4* __restrict__ v_key,
     const uint8_t* __restrict__ v_size, uint32_t n, const uint4* __restrict__ fkeys,
-    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ own_flag)
+    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ own_flag, uint32_t v_lo)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t own = 1;
         if (v_size[i] < 4 && mask && foreign_lookup(fkeys, table, mask, v_key[i]) != NONE32) own = 0;
+        if (i < v_lo) own = 0; // first created by a ghost tet of the rank below (rin_set_ghost_tets)
         own_flag[i] = own;
     }
 }
@@ -1892,7 +1893,7 @@ __global__ void __launch_bounds__(1024) own_scan_kernel(const uint32_t* __restri
 __global__ void __launch_bounds__(256) global_ids_kernel(const uint4* __restrict__ v_key,
     const uint32_t* __restrict__ own_idx, uint32_t n, uint32_t offset, const uint4* __restrict__ fkeys,
     const uint32_t* __restrict__ fgids, const uint32_t* __restrict__ table, uint32_t mask,
-    uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved)
+    uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved, uint32_t v_lo)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t o = own_idx[i];
@@ -1902,7 +1903,7 @@ __global__ void __launch_bounds__(256) global_ids_kernel(const uint4* __restrict
         }
         const uint32_t f = mask ? foreign_lookup(fkeys, table, mask, v_key[i]) : NONE32;
         if (f == NONE32) {
-            atomicAdd(n_unresolved, 1u);
+            if (i >= v_lo) atomicAdd(n_unresolved, 1u); // a ghost's vertex off the shared plane: unused
             gid[i] = NONE32;
         } else
             gid[i] = fgids[f];
@@ -1914,6 +1915,14 @@ __global__ void __launch_bounds__(256) apply_gids_kernel(uint32_t* __restrict__ 
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         f_verts[i] = gid[f_verts[i]];
+}
+
+// ghost runs: a kept face must not use a vertex that has no global id
+__global__ void __launch_bounds__(256) check_gids_kernel(const uint32_t* __restrict__ f_verts, uint32_t n,
+    const uint32_t* __restrict__ gid, unsigned* __restrict__ n_bad)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (gid[f_verts[i]] == NONE32) atomicAdd(n_bad, 1u);
 }
 
 // keep the owned vertices (order preserved)

@@ -144,7 +144,11 @@ struct rin_ctx
     uint32_t VS = 0;      // row stride of vals / vmask: V rounded up to 16 entries (128-byte rows)
     uint32_t grid_R = 0;  // != 0: the mesh is generate_tet_mesh(grid_R) (structured filter, axis tables)
     DevBuf pts, tets, axes;
-    uint64_t t_first = 0, t_count = 0;
+    uint64_t t_first = 0, t_count = 0; // tets processed by a run (own range + ghosts)
+    uint64_t own_first = 0, own_count = 0, ghost_lo = 0, ghost_hi = 0; // rin_set_ghost_tets
+    uint64_t res_first = 0, res_count = 0; // tets resident on the device (a slice after rin_set_mesh_host_range)
+    uint32_t ghost_v_lo = 0; // local vertices [0, ghost_v_lo) of the last run were first created by a ghost below
+    DevBuf g_off, g_verts, g_toff, g_tets, g_funcs; // face arrays without the faces created by ghosts
     // functions / values
     uint32_t F = 0;
     DevBuf funcs;
@@ -338,8 +342,9 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
     c->VS = (uint32_t)((n_pts + 15) & ~15ull);
     c->grid_R = 0;
     c->T = n_tets;
-    c->t_first = 0;
-    c->t_count = n_tets;
+    c->t_first = c->own_first = c->res_first = 0;
+    c->t_count = c->own_count = c->res_count = n_tets;
+    c->ghost_lo = c->ghost_hi = 0;
     c->v_first = c->v_count = 0;
     c->have_values = false;
     if (!same_shape) { // sizes learnt from the previous pass stay valid hints for a mesh of the same shape
@@ -382,8 +387,9 @@ int rin_set_mesh_host_range(rin_ctx* c, uint64_t n_pts, uint64_t n_tets, const d
     c->VS = (uint32_t)((n_pts + 15) & ~15ull);
     c->grid_R = 0;
     c->T = n_tets;
-    c->t_first = t_first;
-    c->t_count = t_count;
+    c->t_first = c->own_first = c->res_first = t_first;
+    c->t_count = c->own_count = c->res_count = t_count;
+    c->ghost_lo = c->ghost_hi = 0;
     c->v_first = (uint32_t)v_first;
     c->v_count = (uint32_t)v_count;
     c->have_values = false;
@@ -433,8 +439,9 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     c->VS = (uint32_t)((V + 15) & ~15ull);
     c->grid_R = R;
     c->T = T;
-    c->t_first = 0;
-    c->t_count = T;
+    c->t_first = c->own_first = c->res_first = 0;
+    c->t_count = c->own_count = c->res_count = T;
+    c->ghost_lo = c->ghost_hi = 0;
     c->v_first = c->v_count = 0;
     c->have_values = false;
     c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
@@ -442,28 +449,29 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     return RIN_OK;
 }
 
-int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
+namespace {
+// tets processed = own range widened by the ghosts; only the vertices they reference are evaluated
+int apply_tet_range(rin_ctx* c)
 {
-    if (!c) return fail(RIN_ERR_ARG, "null ctx");
-    if (first > c->T) return fail(RIN_ERR_ARG, "tet range out of bounds");
-    if (count == RIN_TET_RANGE_ALL) count = c->T - first;
-    if (count > c->T - first) return fail(RIN_ERR_ARG, "tet range out of bounds");
-    c->t_first = first;
-    c->t_count = count; // 0: an empty range, rin_run then returns an empty result
+    const uint64_t lo = std::min<uint64_t>(c->ghost_lo, c->own_first);
+    const uint64_t hi = std::min<uint64_t>(c->ghost_hi, c->T - (c->own_first + c->own_count));
+    if (c->own_count && (c->own_first - lo < c->res_first || c->own_first + c->own_count + hi > c->res_first + c->res_count))
+        return fail(RIN_ERR_STATE, "tet range (with ghosts) outside the slice uploaded by rin_set_mesh_host_range");
+    c->t_first = c->own_first - lo;
+    c->t_count = c->own_count ? c->own_count + lo + hi : 0; // an empty rank stays empty
     c->v_first = 0;
     c->v_count = 0;
     c->x_window = false;
     c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     invalidate(c);
-    if (count != 0 && (first != 0 || count != c->T)) {
-        // vertex id range referenced by the tet range: only these vertices are evaluated
+    if (c->t_count != 0 && (c->t_first != 0 || c->t_count != c->T)) {
         CK(cudaSetDevice(c->device));
         CK(c->counters.ensure(sizeof(Counters)));
         uint32_t init[2] = {0xffffffffu, 0u};
         uint32_t* d = c->counters.as<uint32_t>();
         CK(cudaMemcpyAsync(d, init, 8, cudaMemcpyHostToDevice, c->stream));
-        vertex_range_kernel<<<grid_for(count, 256, c->sm_count), 256, 0, c->stream>>>(c->tets.as<uint4>(),
-            (uint32_t)first, (uint32_t)count, d);
+        vertex_range_kernel<<<grid_for(c->t_count, 256, c->sm_count), 256, 0, c->stream>>>(c->tets.as<uint4>(),
+            (uint32_t)c->t_first, (uint32_t)c->t_count, d);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(init, d, 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -471,6 +479,28 @@ int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
         c->v_count = init[1] - init[0] + 1;
     }
     return RIN_OK;
+}
+} // namespace
+
+int rin_set_tet_range(rin_ctx* c, uint64_t first, uint64_t count)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (first > c->T) return fail(RIN_ERR_ARG, "tet range out of bounds");
+    if (count == RIN_TET_RANGE_ALL) count = c->T - first;
+    if (count > c->T - first) return fail(RIN_ERR_ARG, "tet range out of bounds");
+    c->own_first = first;
+    c->own_count = count; // 0: an empty range, rin_run then returns an empty result
+    c->ghost_lo = c->ghost_hi = 0;
+    return apply_tet_range(c);
+}
+
+int rin_set_ghost_tets(rin_ctx* c, uint64_t below, uint64_t above)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (c->T == 0) return fail(RIN_ERR_STATE, "rin_set_ghost_tets: no mesh");
+    c->ghost_lo = below;
+    c->ghost_hi = above;
+    return apply_tet_range(c);
 }
 
 int rin_set_functions(rin_ctx* c, const rin_func_desc* funcs, uint32_t F)
@@ -501,6 +531,48 @@ int rin_set_values_host(rin_ctx* c, const double* vals, uint64_t n_pts, uint32_t
     invalidate(c);
     return RIN_OK;
 }
+
+namespace {
+// rin_set_ghost_tets: keep what the rank's own tets created (exchange.cuh, GhostBounds)
+int trim_ghosts(rin_ctx* c)
+{
+    c->ghost_v_lo = 0;
+    if (c->t_first == c->own_first && c->t_count == c->own_count) return RIN_OK;
+    cudaStream_t s = c->stream;
+    const uint32_t NV = c->n_local_verts, NF = (uint32_t)c->counts.num_faces;
+    CK(c->x_small.ensure(4096 + 64 * (size_t)std::max(c->x_world, 1)));
+    GhostBounds* d_b = reinterpret_cast<GhostBounds*>(c->x_small.as<uint32_t>() + 512);
+    ghost_bounds_kernel<<<1, 1, 0, s>>>(c->v_tet.as<uint32_t>(), NV, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(),
+        c->f_tets.as<uint32_t>(), NF, (uint32_t)c->own_first, (uint32_t)(c->own_first + c->own_count), d_b);
+    CK(cudaGetLastError());
+    GhostBounds b;
+    CK(cudaMemcpyAsync(&b, d_b, sizeof(b), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t nf = b.f_hi - b.f_lo, nfv = b.fv_hi - b.fv_lo, nft = b.ft_hi - b.ft_lo;
+    CK(c->g_off.ensure(((size_t)nf + 1) * 4));
+    CK(c->g_toff.ensure(((size_t)nf + 1) * 4));
+    CK(c->g_funcs.ensure(std::max<size_t>(nf, 1) * 8));
+    CK(c->g_verts.ensure(std::max<size_t>(nfv, 1) * 4));
+    CK(c->g_tets.ensure(std::max<size_t>(nft, 1) * 8));
+    ghost_slice_faces_kernel<<<grid_for(std::max<uint64_t>({nf + 1ull, nfv, 2ull * nft}), 256, c->sm_count), 256, 0, s>>>(b,
+        c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(),
+        c->f_funcs.as<uint32_t>(), c->g_off.as<uint32_t>(), c->g_verts.as<uint32_t>(), c->g_toff.as<uint32_t>(),
+        c->g_tets.as<uint32_t>(), c->g_funcs.as<uint32_t>());
+    CK(cudaGetLastError());
+    std::swap(c->f_off, c->g_off);
+    std::swap(c->f_verts, c->g_verts);
+    std::swap(c->f_toff, c->g_toff);
+    std::swap(c->f_tets, c->g_tets);
+    std::swap(c->f_funcs, c->g_funcs);
+    c->ghost_v_lo = b.v_lo;
+    c->n_local_verts = c->n_own = b.v_hi; // what the ghosts above created is gone
+    c->counts.num_verts = b.v_hi;
+    c->counts.num_faces = nf;
+    c->counts.num_face_verts = nfv;
+    c->counts.num_face_tets = nft;
+    return RIN_OK;
+}
+} // namespace
 
 int rin_run(rin_ctx* c, int mode, uint32_t flags)
 {
@@ -533,6 +605,7 @@ int rin_run(rin_ctx* c, int mode, uint32_t flags)
         case 4: rc = run_ia_w<4>(c, flags); break;
         default: return fail(RIN_ERR_ARG, "more than 128 functions are not supported by this build");
         }
+        if (rc == RIN_OK) rc = trim_ghosts(c);
         if (rc == RIN_OK) snapshot();
         return rc;
     }
@@ -549,6 +622,7 @@ int rin_run(rin_ctx* c, int mode, uint32_t flags)
         case 4: rc = run_mi_w<4>(c, flags); break;
         default: return fail(RIN_ERR_ARG, "more than 128 materials are not supported by this build");
         }
+        if (rc == RIN_OK) rc = trim_ghosts(c);
         if (rc == RIN_OK) snapshot();
         return rc;
     }
@@ -848,6 +922,7 @@ int rin_tet_maps(rin_ctx* c, uint64_t* n_active, uint64_t* n_vert_entries, uint6
     const bool mi = c->last_mode == RIN_MODE_MI;
     const uint8_t* blob = mi ? c->lut_mi.blob.as<uint8_t>() : c->lut_ia.blob.as<uint8_t>();
     if (c->marked || c->finalized) return fail(RIN_ERR_STATE, "rin_tet_maps: not available after a sharded exchange");
+    if (c->t_count != c->own_count) return fail(RIN_ERR_STATE, "rin_tet_maps: not available for a run with ghost tets");
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const uint32_t A = (uint32_t)c->counts.num_intersecting_tet;
@@ -1114,7 +1189,7 @@ int rin_mark_foreign(rin_ctx* c, const uint32_t* keys, uint64_t m, uint64_t* n_o
     if (NV) {
         mark_foreign_kernel<<<grid_for(NV, 256, c->sm_count), 256, 0, s>>>(c->v_key.as<uint4>(),
             c->v_size.as<uint8_t>(), NV, c->fkeys.as<uint4>(), c->ftable.as<uint32_t>(), mask,
-            c->own_flag.as<uint32_t>());
+            c->own_flag.as<uint32_t>(), c->ghost_v_lo);
         own_scan_kernel<<<1, 1024, 0, s>>>(c->own_flag.as<uint32_t>(), NV, c->own_idx.as<uint32_t>(), d_n);
         CK(cudaGetLastError());
     } else
@@ -1145,8 +1220,11 @@ int rin_finalize_sharded(rin_ctx* c, uint64_t vert_offset, const uint32_t* keys,
     if (NV) {
         global_ids_kernel<<<grid_for(NV, 256, c->sm_count), 256, 0, s>>>(c->v_key.as<uint4>(),
             c->own_idx.as<uint32_t>(), NV, (uint32_t)vert_offset, c->fkeys.as<uint4>(), c->fgids.as<uint32_t>(),
-            c->ftable.as<uint32_t>(), mask, c->gid.as<uint32_t>(), d_bad);
+            c->ftable.as<uint32_t>(), mask, c->gid.as<uint32_t>(), d_bad, c->ghost_v_lo);
         const uint32_t NFV = (uint32_t)c->counts.num_face_verts;
+        if (NFV && c->ghost_v_lo)
+            check_gids_kernel<<<grid_for(NFV, 256, c->sm_count), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
+                c->gid.as<uint32_t>(), d_bad);
         if (NFV)
             apply_gids_kernel<<<grid_for(NFV, 256, c->sm_count), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
                 c->gid.as<uint32_t>());
@@ -1258,6 +1336,11 @@ int rin_nccl_init(rin_ctx* c, const uint8_t id[128], int rank, int world)
 // all stream-ordered, ONE host synchronisation at the end.
 extern "C++" {
 namespace {
+constexpr int X_NEED_GHOST = 1000; // internal: a rank saw degenerate vertices, the run has to be repeated with ghost tets
+uint32_t need_ghost(const rin_ctx* c)
+{
+    return (c->counts.num_degenerate_vertex != 0 && c->ghost_lo == 0 && c->ghost_hi == 0) ? 1u : 0u;
+}
 int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
     uint64_t* n_faces_total)
 {
@@ -1317,20 +1400,23 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
         if (NV)
             x_mark_scan_kernel<<<tiles, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV, low, cap,
                 c->x_table.as<uint32_t>(), tsize - 1, c->x_has_low ? 1 : 0, c->own_idx.as<uint32_t>(),
-                c->status.as<unsigned long long>(), d_tile, d_nown);
+                c->status.as<unsigned long long>(), d_tile, d_nown, c->ghost_v_lo);
         // 3. own indices of what was sent upwards -> r+1; (n_own, n_faces, n_up) of every rank -> offsets
         x_own_ids_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(up, cap, c->own_idx.as<uint32_t>(), mine4, d_bad,
             d_nown, (uint32_t)c->counts.num_faces, (uint32_t)c->counts.num_face_verts,
-            (uint32_t)c->counts.num_face_tets);
+            (uint32_t)c->counts.num_face_tets, need_ghost(c));
         NK(g_nccl.AllGather(mine4, all4, rec_words, 3, c->nccl_comm, s));
-        x_offsets_nb_kernel<<<1, 1, 0, s>>>(all4, rec_words, world, cap, d_voff, d_foff, d_ovf);
+        x_offsets_nb_kernel<<<1, 1, 0, s>>>(all4, rec_words, world, cap, d_voff, d_foff, d_ovf, small + 6);
         const uint32_t* ids_low = all4 + (size_t)std::max(rank - 1, 0) * rec_words + 8;
         // 4. global ids, face vertex lists, owned vertices (skipped by every rank alike when a message overflowed:
         //    the decision comes from the gathered counts)
         if (NV) {
             x_global_ids_nb_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(),
                 c->own_idx.as<uint32_t>(), NV, rank, d_voff, low, ids_low, cap,
-                c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad);
+                c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad, c->ghost_v_lo);
+            if (NFV && c->ghost_v_lo)
+                check_gids_kernel<<<grid_for(NFV, 256, sm), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
+                    c->gid.as<uint32_t>(), d_bad);
             compact_own_verts_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->own_idx.as<uint32_t>(), NV,
                 c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(),
                 c->v_funcs.as<uint4>(), c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(),
@@ -1345,6 +1431,7 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
             c->x_cap = (hsmall[3] + hsmall[3] / 4 + 1024 + 3u) & ~3u;
             continue;
         }
+        if (hsmall[6]) return X_NEED_GHOST; // every rank sees the same gathered flags
         if (hsmall[5])
             return fail(RIN_ERR_STATE, "exchange: " + std::to_string(hsmall[5]) + " shared vertices have no owner");
         // only now (nothing can fail any more) the face vertex lists are rewritten in place
@@ -1387,11 +1474,43 @@ int exchange_neighbours(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_tot
 } // namespace
 } // extern "C++"
 
-// The whole slab-boundary protocol on the device (see sharding.py): two ncclAllGather calls.
+extern "C++" {
+namespace {
+int exchange_once(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
+    uint64_t* n_faces_total);
+}
+}
+
+// The whole slab-boundary protocol on the device (see sharding.py).  When any rank reports degenerate vertices
+// and the run had no ghost tets, every rank (they all see the same gathered flags) widens its range by one cube
+// layer of the generated grid, repeats the run and the exchange: iso-faces lying on the slab plane then get both
+// incident tets and the material matching across the plane happens (rin_set_ghost_tets).
 int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
     uint64_t* n_faces_total)
 {
     if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    int rc = exchange_once(c, vert_offset, n_verts_total, face_offset, n_faces_total);
+    if (rc != X_NEED_GHOST) return rc;
+    if (c->grid_R == 0)
+        return fail(RIN_ERR_STATE, "degenerate vertices in a sharded run on an unstructured mesh: give every rank the "
+                                   "ghost tets that touch its shared vertices (rin_set_ghost_tets) and run again");
+    const uint64_t layer = 5ull * c->grid_R * c->grid_R;
+    const int mode = c->last_mode;
+    const uint32_t flags = c->last_flags;
+    rc = rin_set_ghost_tets(c, layer, layer);
+    if (rc) return rc;
+    rc = rin_run(c, mode, flags);
+    if (rc) return rc;
+    rc = exchange_once(c, vert_offset, n_verts_total, face_offset, n_faces_total);
+    if (rc == X_NEED_GHOST) return fail(RIN_ERR_STATE, "exchange: ghost negotiation failed");
+    return rc;
+}
+
+extern "C++" {
+namespace {
+int exchange_once(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
+    uint64_t* n_faces_total)
+{
     if (!c->nccl_comm) return fail(RIN_ERR_STATE, "rin_exchange_nccl: call rin_nccl_init first");
     if (!c->ran || c->finalized) return fail(RIN_ERR_STATE, "rin_exchange_nccl: no fresh run");
     CK(cudaSetDevice(c->device));
@@ -1494,16 +1613,16 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         if (NV)
             x_mark_scan_kernel<<<tiles, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
                 c->x_recv1.as<uint32_t>(), cap, c->x_table.as<uint32_t>(), tsize - 1, rank, c->own_idx.as<uint32_t>(),
-                c->status.as<unsigned long long>(), d_tile, d_nown);
+                c->status.as<unsigned long long>(), d_tile, d_nown, c->ghost_v_lo);
         // 3. owned shared keys with their own index + (n_own, n_faces) -> all ranks
         if (NV)
             x_select_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), NV,
                 c->x_lo, c->x_hi, c->own_idx.as<uint32_t>(), msg, cap, d_cnt2);
         x_header_kernel<<<1, 1, 0, s>>>(msg, d_cnt2, cap, d_nown, (uint32_t)c->counts.num_faces, d_ovf,
-            (uint32_t)c->counts.num_face_verts, (uint32_t)c->counts.num_face_tets);
+            (uint32_t)c->counts.num_face_verts, (uint32_t)c->counts.num_face_tets, need_ghost(c));
         NK(g_nccl.AllGather(msg, c->x_recv2.p, words, 3, c->nccl_comm, s));
         x_offsets_kernel<<<1, 1, 0, s>>>(c->x_recv1.as<uint32_t>(), c->x_recv2.as<uint32_t>(), cap, world, d_voff, d_foff,
-            d_ovf);
+            d_ovf, small + 6);
         // 4. global ids, rewrite the face vertex lists, keep the owned vertices
         CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
         if (rank > 0)
@@ -1517,11 +1636,15 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
             c->x_cap = (hsmall[3] + hsmall[3] / 4 + 1024 + 3u) & ~3u;
             continue;
         }
+        if (hsmall[6]) return X_NEED_GHOST;
         const uint32_t NO = hsmall[2];
         if (NV) {
             x_global_ids_kernel<<<grid_for(NV, 256, sm), 256, 0, s>>>(c->v_key.as<uint4>(), c->own_idx.as<uint32_t>(),
                 NV, rank, d_voff, c->x_recv2.as<uint32_t>(), cap, c->x_table.as<uint32_t>(), tsize - 1,
-                c->gid.as<uint32_t>(), d_bad);
+                c->gid.as<uint32_t>(), d_bad, c->ghost_v_lo);
+            if (NFV && c->ghost_v_lo)
+                check_gids_kernel<<<grid_for(NFV, 256, sm), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
+                    c->gid.as<uint32_t>(), d_bad);
             if (NFV)
                 apply_gids_kernel<<<grid_for(NFV, 256, sm), 256, 0, s>>>(c->f_verts.as<uint32_t>(), NFV,
                     c->gid.as<uint32_t>());
@@ -1574,6 +1697,9 @@ int rin_exchange_nccl(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total
         return RIN_OK;
     }
 }
+
+} // namespace
+} // extern "C++"
 
 int rin_get_exchange_offsets(const rin_ctx* c, uint64_t out[8])
 {

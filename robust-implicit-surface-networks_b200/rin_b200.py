@@ -60,6 +60,7 @@ def lib():
                                               C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
         L.rin_set_values_host_range.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
         L.rin_set_tet_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.rin_set_ghost_tets.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.rin_set_functions.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.rin_set_values_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         L.rin_run.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
@@ -157,6 +158,10 @@ class Context:
 
     def set_tet_range(self, first, count):
         self._check(lib().rin_set_tet_range(self._h, first, count))
+
+    def set_ghost_tets(self, below, above):
+        """Ghost tets of a sharded run on degenerate inputs (include/rin_b200.h); call after set_tet_range."""
+        self._check(lib().rin_set_ghost_tets(self._h, below, above))
 
     def set_functions(self, funcs):
         funcs = np.ascontiguousarray(funcs, FUNC_DESC)

@@ -72,11 +72,22 @@ class ExchangeState:
         self.window = None
 
 
-def exchange(engine, rank, world, gather, n_faces, state=None):
+def exchange(engine, rank, world, gather, n_faces, state=None, degenerate=0, ghost_rerun=None):
     """Runs the boundary protocol (two all-gathers per pass).  Returns dict(vert_offset,
-    face_offset, n_verts_total, n_faces_total, n_own)."""
+    face_offset, n_verts_total, n_faces_total, n_own).
+
+    Degenerate inputs (a function vanishing at grid vertices, materials tying there) can put an iso-face on a
+    tet face of the slab plane, where the reference pairs the two incident tets (src/extract_mesh.cpp:240-253) or
+    matches their materials (:833-981).  `degenerate` is this rank's num_degenerate_vertex; when any rank reports
+    one, every rank calls `ghost_rerun()` (rin_set_ghost_tets with one cube layer + rin_run; returns the new face
+    count) before the exchange - the same negotiation rin_exchange_nccl does on the device."""
     if state is None:
         state = ExchangeState()
+    if ghost_rerun is not None:
+        flags = gather(np.array([1 if degenerate else 0], np.int64))
+        if any(int(f[0]) for f in flags):
+            n_faces = ghost_rerun()
+            state.window = None
     if state.window is None:
         lo, hi = engine.vertex_range()
         ranges = gather(np.array([lo, hi], np.int64))

@@ -27,14 +27,22 @@ def main():
     dist.broadcast_object_list(uid, 0)
     ctx.nccl_init(uid[0], rank, world)
 
-    cases = [("ia", "C2", 20), ("mi", "C3", 18), ("ia", "C2", 33)]
+    # degenerate inputs: iso-faces / material interfaces ON the slab planes (ghost-layer negotiation inside
+    # rin_exchange_nccl, src/extract_mesh.cpp:240-253, 833-981)
+    special = {"ia_x0": [{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
+                         {"type": "sphere", "center": [0, 0, 0], "radius": 0.5, "squared": True},
+                         {"type": "plane", "point": [0, 0, 0], "normal": [0, 1, 0]}],
+               "mi_x0": [{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
+                         {"type": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]},
+                         {"type": "sphere", "center": [0, 0.5, 0], "radius": 0.6}]}
+    cases = [("ia", "C2", 20), ("mi", "C3", 18), ("ia", "C2", 33), ("ia", "ia_x0", 16), ("mi", "mi_x0", 16)]
     for mode, fset, R in cases:
         for allgather in (False, True):
             if allgather:
                 os.environ["RIN_X_ALLGATHER"] = "1"  # the general (non-slab) protocol on the same input
             else:
                 os.environ.pop("RIN_X_ALLGATHER", None)
-            funcs = make_funcs(synthetic_functions(fset))
+            funcs = make_funcs(special[fset] if fset in special else synthetic_functions(fset))
             ctx.generate_grid(R)  # resets the cached vertex windows
             ctx.set_functions(funcs)
             ctx.set_tet_range(*sharding.slab_range(R, rank, world))

@@ -71,3 +71,84 @@ def test_sharded_run_equals_single_run(world, R, mode):
     assert np.array_equal(fv, ref["face_verts"])
     assert np.array_equal(ft.ravel(), ref["face_tets"])
     assert sum(m["face_offsets"].shape[0] - 1 for _, m in results) == ref["stats"][8]
+
+
+# Degenerate inputs whose iso-faces / material interfaces lie on tet faces of the slab planes (even R, cuts at grid
+# planes through the origin): the reference pairs the two tets of such a face (src/extract_mesh.cpp:240-253) and
+# matches materials across it (:833-981).  Sharded runs negotiate one ghost cube layer (rin_set_ghost_tets).
+DEGENERATE = {
+    "ia_plane_x0": ("ia", [{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
+                           {"type": "sphere", "center": [0, 0, 0], "radius": 0.5, "squared": True},
+                           {"type": "plane", "point": [0, 0, 0], "normal": [0, 1, 0]}]),
+    "ia_planes_at_cuts": ("ia", [{"type": "plane", "point": [-0.5, 0, 0], "normal": [1, 0, 0]},
+                                 {"type": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]},
+                                 {"type": "plane", "point": [0.5, 0, 0], "normal": [1, 0, 0]},
+                                 {"type": "sphere", "center": [0.1, 0, 0], "radius": 0.7, "squared": False}]),
+    "mi_x_vs_negx": ("mi", [{"type": "plane", "point": [0, 0, 0], "normal": [1, 0, 0]},
+                            {"type": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]}]),
+    "mi_sym_spheres": ("mi", [{"type": "sphere", "center": [-0.5, 0, 0], "radius": 0.7},
+                              {"type": "sphere", "center": [0.5, 0, 0], "radius": 0.7},
+                              {"type": "sphere", "center": [0, 0.5, 0], "radius": 0.6},
+                              {"type": "sphere", "center": [0, -0.5, 0], "radius": 0.6}]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(DEGENERATE))
+@pytest.mark.parametrize("world,R", [(2, 8), (4, 16)])
+def test_sharded_degenerate_faces_on_the_slab_plane(name, world, R):
+    import rin_b200 as rin
+    import sharding
+    mode, specs = DEGENERATE[name]
+    funcs = make_funcs(specs)
+    pts, tets = orc_grid(R)
+    vals = orc_eval(funcs, pts)
+    ref = orc_run(mode, pts, tets, vals)
+    assert ref.error == ""
+    lg = LocalGather(world)
+    results = [None] * world
+    errors = []
+
+    def rank_main(rank):
+        try:
+            ctx = rin.Context(0)
+            ctx.generate_grid(R)
+            ctx.set_functions(funcs)
+            ctx.set_tet_range(*sharding.slab_range(R, rank, world))
+            m = rin.MODE_IA if mode == "ia" else rin.MODE_MI
+            cnt = ctx.run(m)
+
+            def ghost_rerun():
+                ctx.set_ghost_tets(5 * R * R, 5 * R * R)
+                return ctx.run(m).num_faces
+
+            info = sharding.exchange(ctx, rank, world, lg.for_rank(rank), cnt.num_faces,
+                                     degenerate=cnt.num_degenerate_vertex, ghost_rerun=ghost_rerun)
+            results[rank] = (info, ctx.download_mesh())
+            ctx.close()
+        except Exception as ex:
+            errors.append(ex)
+            lg.barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    cat = lambda k: np.concatenate([m[k] for _, m in results])
+    assert np.array_equal(cat("vert_xyz"), ref["vert_xyz"].reshape(-1, 3))
+    assert np.array_equal(cat("face_verts").astype(np.int64), ref["face_verts"])
+    assert np.array_equal(cat("face_tets").astype(np.int64).ravel(), ref["face_tets"])
+    ff = cat("face_funcs").astype(np.int64)
+    ff[ff == 0xFFFFFFFF] = -1
+    assert np.array_equal(ff.ravel(), ref["face_funcs"])
+    # per-face sizes (offsets are rank-local here: compare the differences)
+    sizes = np.concatenate([np.diff(m["face_offsets"].astype(np.int64)) for _, m in results])
+    assert np.array_equal(sizes, np.diff(ref["face_offsets"]))
+    tsz = np.concatenate([np.diff(m["face_tet_offsets"].astype(np.int64)) for _, m in results])
+    assert np.array_equal(tsz, np.diff(ref["face_tet_offsets"]))
+    assert tsz.max() == 2 or mode == "mi"  # IA: some face is shared by two tets
+    nrec = 11 if mode == "mi" else 10
+    rec = ref["vert_rec"].reshape(-1, nrec)
+    assert np.array_equal(cat("vert_tet").astype(np.int64), rec[:, 0])
+    assert np.array_equal(cat("vert_simplex_size").astype(np.int64), rec[:, 2])
