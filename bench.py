@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--two-call-exchange", action="store_true",
+                    help="N > 1: rin_run then rin_exchange_nccl (two synchronisations) instead of rin_run_exchange")
     ap.add_argument("--resolution", type=int, default=0, help="override the grid resolution (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -297,10 +299,12 @@ def main():
 
     def step():
         """One pass: hot path on this rank's slab, then (N > 1) the slab-boundary exchange on the device."""
-        ta = time.perf_counter()
-        c = ctx.run(mode, flags)
         if dist is None:
-            return c
+            return ctx.run(mode, flags)
+        if not args.two_call_exchange:
+            return ctx.run_exchange(mode, flags)  # one synchronisation: the exchange rides behind the run
+        ta = time.perf_counter()
+        ctx.run(mode, flags)
         tb = time.perf_counter()
         r = ctx.exchange_nccl()
         split["run"] += tb - ta
@@ -318,21 +322,33 @@ def main():
     dev_ms = []
     split.update(run=0.0, exchange=0.0, n=0)
     t0 = time.perf_counter()
+    x_ms = []
     for _ in range(args.steps):
         info = step()
         dev_ms.append(ctx.kernel_times()["total_ms"])
+        if dist is not None:
+            x_ms.append(ctx.exchange_time())
     barrier()
     wall = allmax(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     cnt = ctx.counts()
     split_ms = None
-    if dist is not None:  # host wall time of the two calls on this rank (the exchange includes waiting for the peers)
+    if dist is not None and split["n"]:  # host wall time of the two calls on this rank (the exchange includes waiting for the peers)
         split_ms = {"run_ms": 1e3 * split["run"] / split["n"], "exchange_ms": 1e3 * split["exchange"] / split["n"]}
         both = torch.tensor([split_ms["run_ms"], split_ms["exchange_ms"]], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(both) for _ in range(world)]
         dist.all_gather(allr, both)
         split_ms = {"per_rank_run_ms": [float(x[0]) for x in allr], "per_rank_exchange_ms": [float(x[1]) for x in allr]}
+    per_rank = None
+    if dist is not None:  # device times of every rank: the run's kernels and the forked exchange chain
+        both = torch.tensor([float(np.mean(dev_ms)), float(np.mean(x_ms)), float(cnt.num_intersecting_tet), float(t_count)],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(both) for _ in range(world)]
+        dist.all_gather(allr, both)
+        per_rank = {"run_device_ms": [round(float(x[0]), 4) for x in allr],
+                    "exchange_chain_device_ms": [round(float(x[1]), 4) for x in allr],
+                    "active_tets": [int(x[2]) for x in allr], "tets": [int(x[3]) for x in allr]}
     launches_per_step = ctx.launch_count()
     ms_per_step = 1e3 * wall / args.steps
     value = T_total / (wall / args.steps)
@@ -413,8 +429,7 @@ def main():
                 if upload_mesh:
                     ctx2.set_mesh_range(N1 ** 3, T_total, pts_h, v_first, tets_h, t_first)
                 ctx2.set_values_range(vals_h, v_first)
-                ctx2.run(mode, flags)
-                ctx2.exchange_nccl()
+                ctx2.run_exchange(mode, flags)
             ctx2.download_mesh(views)
 
         def timed(fn, k):
@@ -511,7 +526,8 @@ def main():
             cpu = {"value": None, "error": str(ex)}
 
     if rank == 0:
-        x_launches = 10 if world > 1 else 0  # kernels of the neighbour exchange (rin_capi.cu exchange_neighbours)
+        # kernels of the neighbour exchange: counted by the library when it rides behind the run (rin_run_exchange)
+        x_launches = 10 if (world > 1 and args.two_call_exchange) else 0
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -528,10 +544,14 @@ def main():
                 "launches_per_step": launches_per_step + x_launches,
                 "clocks": sampler.summary(), "counts": cnt.as_dict(), "verified": verified,
                 "exchange": None if dist is None else {
-                    "what": "slab-boundary vertex keys: ncclSend/ncclRecv with the neighbour ranks + one 32-byte-per-"
-                            "rank ncclAllGather of the counts (rin_exchange_nccl, one host synchronisation)",
+                    "what": "slab-boundary vertex keys: ncclSend/ncclRecv with the neighbour ranks + one ncclAllGather of "
+                            "the counts and own indices; " + ("rin_run then rin_exchange_nccl (two synchronisations)"
+                                                               if args.two_call_exchange else
+                                                               "enqueued behind the run's kernels, counts read from "
+                                                               "device memory, ONE host synchronisation per step "
+                                                               "(rin_run_exchange)"),
                     "n_verts_total": info["n_verts_total"], "n_faces_total": info["n_faces_total"],
-                    "host_wall": split_ms}}
+                    "host_wall": split_ms, "per_rank": per_rank}}
         print(json.dumps(line))
     if dist is not None:
         barrier()

@@ -248,6 +248,11 @@ int rin_nccl_unique_id(uint8_t id[128]);
 int rin_nccl_init(rin_ctx*, const uint8_t id[128], int rank, int world);
 int rin_exchange_nccl(rin_ctx*, uint64_t* vert_offset, uint64_t* n_verts_total, uint64_t* face_offset,
                       uint64_t* n_faces_total);
+/* rin_run + rin_exchange_nccl as one call with one host synchronisation (the exchange is enqueued behind the run's
+ * kernels and reads its counts from device memory); falls back to the two calls when the fused path does not apply
+ * (first pass over new inputs, material interface, degenerate inputs).  Collective: every rank calls it. */
+int rin_run_exchange(rin_ctx*, int mode, uint32_t flags, uint64_t* vert_offset, uint64_t* n_verts_total,
+                     uint64_t* face_offset, uint64_t* n_faces_total);
 /* offsets of this rank's slice in the merged mesh after rin_exchange_nccl:
  * out = {vertex offset, vertices total, face offset, faces total, face-vertex offset, face-vertex total,
  *        face-tet-pair offset, face-tet-pair total}
@@ -255,6 +260,9 @@ int rin_exchange_nccl(rin_ctx*, uint64_t* vert_offset, uint64_t* n_verts_total, 
  * face_tet_offsets rebased into the merged arrays: every rank can write its slice straight into shared arrays
  * of the merged sizes. */
 int rin_get_exchange_offsets(const rin_ctx*, uint64_t out[8]);
+/* device time (ms) of the exchange chain of the last fused rin_run_exchange (vertex kernel done -> owned vertices
+ * compacted, including the wait for the neighbours); 0 when the pass was not fused */
+int rin_get_exchange_time(const rin_ctx*, float* ms);
 /* vertex id range referenced by the current tet range */
 int rin_get_vertex_range(const rin_ctx*, uint32_t* v_lo, uint32_t* v_hi);
 

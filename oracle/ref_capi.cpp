@@ -16,6 +16,10 @@
 #include "material_interface.h"
 
 #include "result_bag.h"
+#ifndef RIN_GPU_DROPIN
+#include "cell_connectivity.h"
+#include "../robust-implicit-surface-networks_b200/host/cell_graph.h"
+#endif
 #ifdef RIN_GPU_DROPIN
 #include "../robust-implicit-surface-networks_b200/host/rin_host.h"
 #endif
@@ -167,6 +171,40 @@ void* ref_ia_run(const double* pts_in, uint64_t V, const uint64_t* tets_in, uint
 }
 
 #ifndef RIN_GPU_DROPIN // the drop-in library does not link the reference's extraction
+extern "C++" {
+namespace {
+// The product's simplicial-cell graph (host/cell_graph.h) against the reference's own build_simplicial_cell_adjacency
+// + compute_simplicial_cell_connected_components (src/cell_connectivity.cpp) on the same inputs.  The adjacency only
+// looks patches and shells up, so synthetic patch / shell numberings exercise it as well as real ones.
+// Returns {adjacency arrays equal, components equal as shell sets, #simplicial cells, #components}.
+template <typename Complex, typename PositiveSide>
+std::vector<int64_t> check_cell_graph(const std::vector<std::array<size_t, 4>>& tets, const std::vector<Complex>& cut_results,
+    const std::vector<size_t>& cut_result_index, const std::vector<long long>& gv, const std::vector<size_t>& gv_start,
+    const std::vector<size_t>& ff, const std::vector<size_t>& ff_start, size_t n_faces, PositiveSide side)
+{
+    std::vector<size_t> patch_of_face(n_faces), shell_of_half_patch;
+    size_t n_patches = 0;
+    for (size_t f = 0; f < n_faces; ++f) {
+        patch_of_face[f] = (f * 2654435761u) % (n_faces / 3 + 1);
+        n_patches = std::max(n_patches, patch_of_face[f] + 1);
+    }
+    for (size_t h = 0; h < 2 * n_patches; ++h) shell_of_half_patch.push_back((h * 40503u) % (n_patches / 2 + 2));
+    std::vector<std::pair<size_t, size_t>> tc_ref, tc_own;
+    std::vector<long long> info_ref, info_own;
+    std::vector<size_t> start_ref, start_own;
+    build_simplicial_cell_adjacency(tets, cut_results, cut_result_index, gv, gv_start, ff, ff_start, patch_of_face,
+        shell_of_half_patch, tc_ref, info_ref, start_ref);
+    rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, gv, gv_start, ff, ff_start, patch_of_face,
+        shell_of_half_patch, side, tc_own, info_own, start_own);
+    std::vector<std::vector<size_t>> cells_ref, cells_own;
+    compute_simplicial_cell_connected_components(tc_ref, info_ref, start_ref, cells_ref);
+    rin_host::simplicial_cell_components(tc_own, info_own, start_own, cells_own);
+    for (auto& c : cells_ref) std::sort(c.begin(), c.end()); // the reference's order inside a cell is a hash set's
+    return {int64_t(tc_ref == tc_own && info_ref == info_own && start_ref == start_own), int64_t(cells_ref == cells_own),
+        int64_t(tc_own.size()), int64_t(cells_own.size())};
+}
+} // namespace
+} // extern "C++"
 // The reference's cell-grouping extraction (second extract_iso_mesh overload, src/extract_mesh.cpp:268-566)
 // called directly: its inputs are produced here the way implicit_arrangement() produces them (active
 // function lists per tet, one arrangement per active tet), its maps are returned for the parity test of
@@ -218,6 +256,8 @@ void* ref_ia_cellgroup_maps(const uint64_t* tets_in, uint64_t T, uint64_t V, con
         auto& d = bag->i64["iso_fId_start_index_of_tet"];
         for (auto x : ff_start) d.push_back(int64_t(x));
         bag->i64["counts"] = {int64_t(iso_verts.size()), int64_t(iso_faces.size())};
+        bag->i64["cell_graph"] = check_cell_graph(tets, cut_results, cut_result_index, gv, gv_start, ff, ff_start,
+            iso_faces.size(), [](const Arrangement<3>& cx, size_t f, size_t cell) { return cx.faces[f].positive_cell == cell; });
     } catch (std::exception& e) {
         bag->error = e.what();
     }
@@ -269,6 +309,10 @@ void* ref_mi_cellgroup_maps(const uint64_t* tets_in, uint64_t T, const double* v
         auto& d = bag->i64["iso_fId_start_index_of_tet"];
         for (auto x : ff_start) d.push_back(int64_t(x));
         bag->i64["counts"] = {int64_t(verts.size()), int64_t(faces.size())};
+        bag->i64["cell_graph"] = check_cell_graph(tets, cut_results, cut_result_index, gv, gv_start, ff, ff_start,
+            faces.size(), [](const MaterialInterface<3>& cx, size_t f, size_t cell) {
+                return cx.faces[f].positive_material_label == cx.cells[cell].material_label;
+            });
     } catch (std::exception& e) {
         bag->error = e.what();
     }

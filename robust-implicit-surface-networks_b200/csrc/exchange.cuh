@@ -31,8 +31,9 @@ __global__ void x_header_kernel(uint32_t* msg, const unsigned* count, uint32_t c
 // select into a message buffer (keys at msg+4, ids at msg+4+4*cap)
 __global__ void __launch_bounds__(256) x_select_kernel(const uint4* __restrict__ v_key,
     const uint8_t* __restrict__ v_size, uint32_t n, uint32_t lo, uint32_t hi, const uint32_t* __restrict__ own_idx,
-    uint32_t* __restrict__ msg, uint32_t cap, unsigned* __restrict__ n_out)
+    uint32_t* __restrict__ msg, uint32_t cap, unsigned* __restrict__ n_out, const unsigned* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) n = *n_dev; // fused run + exchange: the vertex count has not reached the host yet
     uint4* out_keys = reinterpret_cast<uint4*>(msg + XHDR);
     uint32_t* out_ids = msg + XHDR + (size_t)cap * 4;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -98,13 +99,15 @@ __global__ void __launch_bounds__(256) x_mark_scan_kernel(const uint4* __restric
     const uint8_t* __restrict__ v_size, uint32_t n, const uint32_t* __restrict__ all, uint32_t cap,
     const uint32_t* __restrict__ table, uint32_t mask, int rank, uint32_t* __restrict__ own_idx,
     volatile unsigned long long* __restrict__ status, unsigned* __restrict__ tile_counter,
-    unsigned* __restrict__ n_own, uint32_t v_lo)
+    unsigned* __restrict__ n_own, uint32_t v_lo, const unsigned* __restrict__ n_dev = nullptr)
 {
     __shared__ unsigned s_tile, s_base;
     __shared__ unsigned s_warp[8];
+    if (n_dev) n = *n_dev;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
     const unsigned tile = s_tile;
+    if ((size_t)tile * 1024 >= n) return; // launched for the capacity: no later tile depends on this one
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int ITEMS = 4;
     const uint32_t base = tile * 256 * ITEMS + threadIdx.x * ITEMS;
@@ -254,7 +257,7 @@ __global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, size_t str
     uint32_t v = 0, f = 0, fv = 0, ft = 0;
     uint32_t* fvoff = foff + (world + 1);
     uint32_t* ftoff = fvoff + (world + 1);
-    unsigned ovf = 0, ng = 0;
+    unsigned ovf = 0, ng = 0, bad = 0;
     for (int s = 0; s < world; ++s) {
         voff[s] = v;
         foff[s] = f;
@@ -265,9 +268,11 @@ __global__ void x_offsets_nb_kernel(const uint32_t* __restrict__ all, size_t str
         fv += all[stride * s + 3];
         ft += all[stride * s + 4];
         ng |= all[stride * s + 5];
+        bad |= all[stride * s + 6];
         if (all[stride * s + 2] > cap) ovf = max(ovf, all[stride * s + 2]);
     }
     *need_ghost = ng;
+    need_ghost[1] = bad; // fused run + exchange: some rank's run has to be repeated
     voff[world] = v;
     foff[world] = f;
     fvoff[world] = fv;
@@ -280,8 +285,9 @@ __global__ void __launch_bounds__(256) x_global_ids_nb_kernel(const uint4* __res
     const uint32_t* __restrict__ own_idx, uint32_t n, int rank, const uint32_t* __restrict__ voff,
     const uint32_t* __restrict__ recv_low, const uint32_t* __restrict__ ids_low, uint32_t cap,
     const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ gid, unsigned* __restrict__ n_unresolved,
-    uint32_t v_lo)
+    uint32_t v_lo, const unsigned* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) n = *n_dev;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t o = own_idx[i];
         if (o != NONE32) {
@@ -356,6 +362,225 @@ __global__ void __launch_bounds__(256) ghost_slice_faces_kernel(const GhostBound
     for (uint32_t i = i0; i < 2 * nf; i += step) o_funcs[i] = f_funcs[2 * (size_t)b.f_lo + i];
     for (uint32_t i = i0; i < nfv; i += step) o_verts[i] = f_verts[b.fv_lo + i];
     for (uint32_t i = i0; i < 2 * nft; i += step) o_tets[i] = f_tets[2 * (size_t)b.ft_lo + i];
+}
+
+// ---- peer-memory exchange (rin_run_exchange on one NVLink / NVSwitch node) --------------------------------
+// The same neighbour protocol without NCCL on the data path: every rank owns an INBOX in its HBM that the other
+// ranks map through CUDA IPC; a sender stores its message straight into the receiver's inbox over NVLink, fences
+// (system scope) and then stores the pass number into the receiver's flag word; the receiving kernel spins on that
+// flag.  Lower rank -> upper rank for the keys (no cycle), everyone -> everyone for the 8-word count records (a rank
+// publishes before it waits).  Inboxes are double-buffered by the parity of the pass number: a rank can be at most
+// one pass ahead of a peer, because finishing a pass needs every peer's record of that pass.
+//
+// inbox layout (uint32 words): flags[PX_FLAG_WORDS] | per parity: keys message xmsg_words(cap) | world records of
+// rec_words = 8 + cap
+constexpr uint32_t PX_FLAG_WORDS = 128; // [parity * 64 + 0] keys flag, [parity * 64 + 1 + s] record flag of rank s
+constexpr int PX_MAX_WORLD = 32;
+struct PeerInboxes
+{
+    uint32_t* p[PX_MAX_WORLD];
+};
+__host__ __device__ inline size_t px_parity_words(uint32_t cap, int world)
+{
+    return xmsg_words(cap) + (size_t)world * (8 + (size_t)cap);
+}
+__host__ __device__ inline size_t px_inbox_words(uint32_t cap, int world)
+{
+    return PX_FLAG_WORDS + 2 * px_parity_words(cap, world);
+}
+__host__ __device__ __forceinline__ uint32_t* px_keys(uint32_t* inbox, uint32_t cap, int world, uint32_t parity)
+{
+    return inbox + PX_FLAG_WORDS + parity * px_parity_words(cap, world);
+}
+__host__ __device__ __forceinline__ uint32_t* px_record(uint32_t* inbox, uint32_t cap, int world, uint32_t parity, int s)
+{
+    return px_keys(inbox, cap, world, parity) + xmsg_words(cap) + (size_t)s * (8 + (size_t)cap);
+}
+__device__ __forceinline__ void px_signal(uint32_t* flag, uint32_t pass)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(flag) = pass;
+}
+// spins until the flag reaches the pass number; gives up after ~2 s (a peer died) and reports through *timeout
+__device__ __forceinline__ void px_wait(const uint32_t* flag, uint32_t pass, unsigned* timeout)
+{
+    const long long t0 = clock64();
+    while ((int32_t)(*reinterpret_cast<const volatile uint32_t*>(flag) - pass) < 0) {
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(timeout, 1u);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// keys of the vertices on the plane shared with rank + 1, stored straight into its inbox; their local ids stay here
+__global__ void __launch_bounds__(256) px_send_keys_kernel(const uint4* __restrict__ v_key,
+    const uint8_t* __restrict__ v_size, const unsigned* __restrict__ n_dev, uint32_t lo, uint32_t hi,
+    uint32_t* __restrict__ remote_inbox, uint32_t cap, int world, uint32_t pass, uint32_t* __restrict__ local_ids,
+    unsigned* __restrict__ n_out, unsigned* __restrict__ done, unsigned* __restrict__ overflow)
+{
+    const uint32_t n = *n_dev;
+    uint32_t* msg = remote_inbox ? px_keys(remote_inbox, cap, world, pass & 1u) : nullptr;
+    uint4* out_keys = reinterpret_cast<uint4*>(msg + XHDR);
+    if (msg && lo <= hi)
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int sz = v_size[i];
+            if (sz >= 4) continue;
+            const uint4 k = v_key[i];
+            bool in = k.x >= lo && k.x <= hi;
+            if (sz >= 2) in &= k.y >= lo && k.y <= hi;
+            if (sz >= 3) in &= k.z >= lo && k.z <= hi;
+            if (!in) continue;
+            const unsigned p = atomicAdd(n_out, 1u);
+            if (p < cap) {
+                out_keys[p] = k;
+                local_ids[p] = i;
+            }
+        }
+    // last block: header, then the flag (every block's stores are fenced before its ticket)
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last || threadIdx.x) return;
+    const unsigned c = *reinterpret_cast<volatile unsigned*>(n_out);
+    if (c > cap) *overflow = c;
+    if (msg) {
+        msg[0] = c;
+        px_signal(remote_inbox + (pass & 1u) * 64, pass);
+    }
+}
+
+// waits for the lower neighbour's keys of this pass, then inserts them into the foreign table
+__global__ void __launch_bounds__(256) px_recv_insert_kernel(uint32_t* __restrict__ inbox, uint32_t cap, int world,
+    uint32_t pass, uint32_t* __restrict__ table, uint32_t mask, unsigned* __restrict__ timeout)
+{
+    if (threadIdx.x == 0) px_wait(inbox + (pass & 1u) * 64, pass, timeout);
+    __syncthreads();
+    const uint32_t* m = px_keys(inbox, cap, world, pass & 1u);
+    const uint32_t n = min(__ldcg(m), cap);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const uint4 k = __ldcg(reinterpret_cast<const uint4*>(m + XHDR) + c);
+        uint32_t h = hash4(k) & mask;
+        for (;;) {
+            const uint32_t cur = atomicCAS(&table[h], NONE32, c);
+            if (cur == NONE32) break;
+            const uint4 kc = __ldcg(reinterpret_cast<const uint4*>(m + XHDR) + cur);
+            if (key_eq(kc, k)) break;
+            h = (h + 1) & mask;
+        }
+    }
+}
+
+// this rank's count record {n_own, n_faces, n_up, n_fv, n_ft, degenerate, run incomplete, 0} into every inbox, the
+// own indices of the vertices sent upwards into the upper neighbour's (and this rank's own) copy, then the flags
+__global__ void __launch_bounds__(256) px_publish_record_kernel(const PeerInboxes peers, int rank, int world,
+    uint32_t cap, uint32_t pass, const uint32_t* __restrict__ local_ids, const unsigned* __restrict__ n_up,
+    const uint32_t* __restrict__ own_idx, const unsigned* __restrict__ n_own, const unsigned* __restrict__ n_faces,
+    const unsigned* __restrict__ n_fv, const unsigned long long* __restrict__ n_zero, uint32_t known_degenerate,
+    const unsigned* __restrict__ run_overflow, const unsigned* __restrict__ gen_err,
+    const unsigned* __restrict__ gen_arena_overflow, const unsigned* __restrict__ n_bnd_faces,
+    unsigned* __restrict__ n_bad, unsigned* __restrict__ done)
+{
+    const uint32_t parity = pass & 1u;
+    const uint32_t sent = *n_up, n = min(sent, cap);
+    uint32_t* up_rec = (rank + 1 < world) ? px_record(peers.p[rank + 1], cap, world, parity, rank) : nullptr;
+    if (up_rec)
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            const uint32_t o = own_idx[local_ids[j]];
+            if (o == NONE32) atomicAdd(n_bad, 1u);
+            up_rec[8 + j] = o;
+        }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if ((int)threadIdx.x < world) {
+        uint32_t* rec = px_record(peers.p[threadIdx.x], cap, world, parity, rank);
+        rec[0] = *n_own;
+        rec[1] = *n_faces;
+        rec[2] = sent;
+        rec[3] = *n_fv;
+        rec[4] = *n_faces; // interior iso-faces: one (tet, local face) pair each
+        rec[5] = (known_degenerate || *n_zero != 0 || *n_bnd_faces != 0) ? 1u : 0u;
+        rec[6] = (*run_overflow || *gen_err || *gen_arena_overflow) ? 1u : 0u;
+        rec[7] = 0;
+        px_signal(peers.p[threadIdx.x] + parity * 64 + 1 + rank, pass);
+    }
+}
+
+// waits for every rank's record of this pass, then the prefixes (x_offsets_nb_kernel on the inbox)
+__global__ void px_offsets_kernel(uint32_t* __restrict__ inbox, int world, uint32_t cap, uint32_t pass,
+    uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ overflow,
+    unsigned* __restrict__ need_ghost, unsigned* __restrict__ timeout)
+{
+    const uint32_t parity = pass & 1u;
+    if ((int)threadIdx.x < world) px_wait(inbox + parity * 64 + 1 + threadIdx.x, pass, timeout);
+    __syncthreads();
+    if (threadIdx.x) return;
+    uint32_t v = 0, f = 0, fv = 0, ft = 0;
+    uint32_t* fvoff = foff + (world + 1);
+    uint32_t* ftoff = fvoff + (world + 1);
+    unsigned ovf = *overflow, ng = 0, bad = 0;
+    for (int s = 0; s < world; ++s) {
+        const uint32_t* r = px_record(inbox, cap, world, parity, s);
+        voff[s] = v;
+        foff[s] = f;
+        fvoff[s] = fv;
+        ftoff[s] = ft;
+        v += __ldcg(r + 0);
+        f += __ldcg(r + 1);
+        fv += __ldcg(r + 3);
+        ft += __ldcg(r + 4);
+        ng |= __ldcg(r + 5);
+        bad |= __ldcg(r + 6);
+        if (__ldcg(r + 2) > cap) ovf = max(ovf, __ldcg(r + 2));
+    }
+    voff[world] = v;
+    foff[world] = f;
+    fvoff[world] = fv;
+    ftoff[world] = ft;
+    *overflow = ovf;
+    *need_ghost = ng;
+    need_ghost[1] = bad;
+}
+
+// ---- fused run + exchange (rin_run_exchange): the exchange is enqueued behind the run's kernels before the
+// run's counts have reached the host, so every count is read from device memory ------------------------------
+// header of this rank's count record from the device counters of the run
+__global__ void fx_header_kernel(uint32_t* __restrict__ rec, const unsigned* __restrict__ n_faces,
+    const unsigned* __restrict__ n_fv, const unsigned long long* __restrict__ n_zero, uint32_t known_degenerate,
+    const unsigned* __restrict__ run_overflow, const unsigned* __restrict__ gen_err,
+    const unsigned* __restrict__ gen_arena_overflow, const unsigned* __restrict__ n_bnd_faces)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    rec[1] = *n_faces;
+    rec[3] = *n_fv;
+    rec[4] = *n_faces; // interior iso-faces: one (tet, local face) pair each
+    rec[5] = (known_degenerate || *n_zero != 0 || *n_bnd_faces != 0) ? 1u : 0u;
+    rec[6] = (*run_overflow || *gen_err || *gen_arena_overflow) ? 1u : 0u;
+}
+
+// global vertex ids into the face vertex lists and the rebased face offsets, only when every rank's pass is
+// complete (flags = {capacity overflow, -, unresolved vertices, degenerate, some run incomplete})
+__global__ void __launch_bounds__(256) fx_apply_kernel(const unsigned* __restrict__ flags, uint32_t* __restrict__ f_verts,
+    const uint32_t* __restrict__ gid, const unsigned* __restrict__ n_fv, uint32_t* __restrict__ f_off,
+    uint32_t* __restrict__ f_toff, const unsigned* __restrict__ n_faces, const uint32_t* __restrict__ fv_off,
+    const uint32_t* __restrict__ ft_off)
+{
+    if (flags[3] | flags[5] | flags[6] | flags[7]) return;
+    const uint32_t nfv = *n_fv, nf1 = *n_faces + 1, a = *fv_off, b = *ft_off;
+    const uint32_t step = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = i0; i < nfv; i += step) f_verts[i] = gid[f_verts[i]];
+    for (uint32_t i = i0; i < nf1; i += step) {
+        f_off[i] += a;
+        f_toff[i] += b;
+    }
 }
 
 } // namespace rin

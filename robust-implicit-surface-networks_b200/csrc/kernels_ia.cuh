@@ -1931,8 +1931,9 @@ __global__ void __launch_bounds__(256) compact_own_verts_kernel(const uint32_t* 
     const uint4* __restrict__ v_simplex, const uint4* __restrict__ v_funcs, const double* __restrict__ v_xyz,
     const uint4* __restrict__ v_key, uint32_t* __restrict__ o_tet, uint8_t* __restrict__ o_local,
     uint8_t* __restrict__ o_size, uint4* __restrict__ o_simplex, uint4* __restrict__ o_funcs,
-    double* __restrict__ o_xyz, uint4* __restrict__ o_key)
+    double* __restrict__ o_xyz, uint4* __restrict__ o_key, const unsigned* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) n = *n_dev;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t d = own_idx[i];
         if (d == NONE32) continue;

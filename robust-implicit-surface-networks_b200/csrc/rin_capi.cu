@@ -137,6 +137,15 @@ struct rin_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // fused run + exchange: the vertex exchange runs beside the face kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    float x_chain_ms = 0; // device time of the forked exchange chain of the last fused pass
+    // peer-memory exchange (exchange.cuh): this rank's inbox and the peers' inboxes mapped through CUDA IPC
+    uint32_t* p_inbox = nullptr;
+    uint32_t* p_peer[PX_MAX_WORLD] = {};
+    uint32_t p_cap = 0, p_pass = 0;
+    bool p_ready = false, p_failed = false;
+    DevBuf p_stage;
     int sm_count = 148;
     size_t smem_per_sm = 227 * 1024;
     // mesh
@@ -185,9 +194,13 @@ struct rin_ctx
     bool x_neighbours = false;          // every rank shares vertices with ranks r-1 / r+1 only (slab sharding)
     uint32_t x_up_lo = 1, x_up_hi = 0;  // vertex window shared with rank r+1 (empty: lo > hi)
     bool x_has_low = false, x_has_up = false;
+    bool x_fusable = false;   // neighbour protocol and no empty rank: rin_run_exchange may fuse
+    bool fuse = false;        // the current rin_run enqueues the exchange behind its kernels
+    bool fuse_disabled = false; // degenerate inputs: the ranks agreed to use the two-call path
+    uint32_t* h_xsmall = nullptr; // pinned mirror of x_small
     DevBuf x_ids_up, x_ids_low, x_cnt;
     uint64_t x_offsets[8] = {}; // offset / total of vertices, faces, face-vertex entries, face-tet pairs (last exchange)
-    DevBuf x_send, x_recv1, x_recv2, x_table, x_small;
+    DevBuf x_send, x_recv1, x_recv2, x_table, x_small, x_status;
     DevBuf cx_out; // rin_get_complexes output arena
     DevBuf e_key, e_slot, e_table, e_verts, e_of_face, e_cnt, e_off, e_pairs; // rin_mesh_edges
     uint64_t n_edges = 0;
@@ -291,6 +304,22 @@ int rin_create(int device, rin_ctx** out)
     return RIN_OK;
 }
 
+extern "C++" {
+namespace {
+void release_peers(rin_ctx* c)
+{
+    for (int s = 0; s < PX_MAX_WORLD; ++s) {
+        if (c->p_peer[s] && c->p_peer[s] != c->p_inbox) cudaIpcCloseMemHandle(c->p_peer[s]);
+        c->p_peer[s] = nullptr;
+    }
+    if (c->p_inbox) cudaFree(c->p_inbox);
+    c->p_inbox = nullptr;
+    c->p_ready = false;
+    c->p_cap = 0;
+}
+} // namespace
+}
+
 void rin_destroy(rin_ctx* c)
 {
     if (!c) return;
@@ -311,8 +340,13 @@ void rin_destroy(rin_ctx* c)
     for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_xsmall) cudaFreeHost(c->h_xsmall);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     if (c->stream) cudaStreamDestroy(c->stream);
+    release_peers(c);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
 }
 
@@ -1327,6 +1361,8 @@ int rin_nccl_init(rin_ctx* c, const uint8_t id[128], int rank, int world)
     c->x_rank = rank;
     c->x_world = world;
     c->x_window = false;
+    release_peers(c);
+    c->p_failed = false;
     return RIN_OK;
 }
 
@@ -1556,6 +1592,10 @@ int exchange_once(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, ui
         for (int a = 0; a + 1 < world && nb; ++a) // ranges must ascend with the rank (the lower rank owns)
             if (all[2 * a] <= all[2 * a + 1] && all[2 * a + 2] <= all[2 * a + 3] && all[2 * a] > all[2 * a + 2]) nb = false;
         c->x_neighbours = nb && getenv("RIN_X_ALLGATHER") == nullptr;
+        bool none_empty = true;
+        for (int a = 0; a < world; ++a) none_empty &= all[2 * a] <= all[2 * a + 1];
+        c->x_fusable = c->x_neighbours && none_empty && getenv("RIN_NO_FUSED_EXCHANGE") == nullptr;
+        c->fuse_disabled = false;
         c->x_has_low = c->x_has_up = false;
         c->x_up_lo = 1;
         c->x_up_hi = 0;
@@ -1700,6 +1740,327 @@ int exchange_once(rin_ctx* c, uint64_t* vert_offset, uint64_t* n_verts_total, ui
 
 } // namespace
 } // extern "C++"
+
+
+extern "C++" {
+namespace {
+constexpr int X_NOT_FUSED = 1001; // internal: degenerate inputs, every rank falls back to rin_run + rin_exchange_nccl
+
+// The neighbour exchange enqueued behind the kernels of a run whose counts are still on the device
+// (exchange_neighbours with every count read from device memory).  vcap = capacity of the vertex arrays.
+int enqueue_fused_exchange(rin_ctx* c, Counters* dctr, bool known_degenerate, uint32_t vcap)
+{
+    // forked behind the vertex kernel: everything up to the global ids needs the vertices and the totals only
+    if (!c->stream2) {
+        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c->ev_fork));
+        CK(cudaEventCreate(&c->ev_join));
+    }
+    cudaStream_t s = c->stream2;
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(s, c->ev_fork, 0));
+    const int rank = c->x_rank, world = c->x_world, sm = c->sm_count;
+    const uint32_t cap = c->x_cap;
+    const size_t words = xmsg_words(cap);
+    CK(c->x_small.ensure(4096 + 64 * (size_t)world));
+    CK(c->x_send.ensure(words * 4));
+    CK(c->x_recv1.ensure(words * 4));
+    const size_t rec_words = 8 + (size_t)cap;
+    CK(c->x_cnt.ensure((size_t)(world + 1) * rec_words * 4));
+    uint32_t tsize = 64;
+    while (tsize < 2ull * cap) tsize <<= 1;
+    CK(c->x_table.ensure((size_t)tsize * 4));
+    const size_t nv1 = std::max(vcap, 1u);
+    CK(c->own_idx.ensure(nv1 * 4));
+    CK(c->gid.ensure(nv1 * 4));
+    const uint32_t tiles = (vcap + 1023) / 1024;
+    CK(c->x_status.ensure((size_t)std::max(tiles, 1u) * 8 + 64));
+    CK(c->o_tet.ensure(nv1 * 4));
+    CK(c->o_local.ensure(nv1));
+    CK(c->o_size.ensure(nv1));
+    CK(c->o_simplex.ensure(nv1 * 16));
+    CK(c->o_funcs.ensure(nv1 * 16));
+    CK(c->o_xyz.ensure(nv1 * 24));
+    CK(c->o_key.ensure(nv1 * 16));
+    if (!c->h_xsmall) CK(cudaHostAlloc((void**)&c->h_xsmall, 4096 + 64 * 64, cudaHostAllocDefault));
+    uint32_t* small = c->x_small.as<uint32_t>();
+    CK(cudaMemsetAsync(small, 0, 64, s));
+    unsigned* d_up = small + 0;
+    unsigned* d_nown = small + 2;
+    unsigned* d_ovf = small + 3;
+    unsigned* d_tile = small + 4;
+    unsigned* d_bad = small + 5;
+    uint32_t* d_voff = small + 64;
+    uint32_t* d_foff = small + 64 + (world + 1);
+    uint32_t* up = c->x_send.as<uint32_t>();
+    uint32_t* low = c->x_recv1.as<uint32_t>();
+    uint32_t* mine4 = c->x_cnt.as<uint32_t>();
+    uint32_t* all4 = mine4 + rec_words;
+    const unsigned* d_nv = &dctr->n_unique;
+    const int gv = grid_for(vcap, 256, sm);
+    if (c->x_up_lo <= c->x_up_hi)
+        x_select_kernel<<<gv, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), vcap, c->x_up_lo, c->x_up_hi,
+            nullptr, up, cap, d_up, d_nv);
+    x_header_kernel<<<1, 1, 0, s>>>(up, d_up, cap, nullptr, 0, d_ovf);
+    NK(g_nccl.GroupStart());
+    if (c->x_has_up) NK(g_nccl.Send(up, words, 3 /*ncclUint32*/, rank + 1, c->nccl_comm, s));
+    if (c->x_has_low) NK(g_nccl.Recv(low, words, 3, rank - 1, c->nccl_comm, s));
+    NK(g_nccl.GroupEnd());
+    CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+    if (c->x_has_low)
+        x_insert_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(low, cap, 1, c->x_table.as<uint32_t>(), tsize - 1);
+    CK(cudaMemsetAsync(c->x_status.p, 0, (size_t)std::max(tiles, 1u) * 8, s));
+    x_mark_scan_kernel<<<std::max(tiles, 1u), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), vcap, low, cap,
+        c->x_table.as<uint32_t>(), tsize - 1, c->x_has_low ? 1 : 0, c->own_idx.as<uint32_t>(),
+        c->x_status.as<unsigned long long>(), d_tile, d_nown, 0u, d_nv);
+    x_own_ids_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(up, cap, c->own_idx.as<uint32_t>(), mine4, d_bad, d_nown, 0, 0,
+        0, 0);
+    fx_header_kernel<<<1, 1, 0, s>>>(mine4, &dctr->tot.n_faces, &dctr->tot.n_fv, &dctr->n_zero, known_degenerate ? 1u : 0u,
+        &dctr->overflow, reinterpret_cast<const unsigned*>(&dctr->gen.err), &dctr->gen.arena_overflow,
+        &dctr->gen.n_bnd_faces);
+    NK(g_nccl.AllGather(mine4, all4, rec_words, 3, c->nccl_comm, s));
+    x_offsets_nb_kernel<<<1, 1, 0, s>>>(all4, rec_words, world, cap, d_voff, d_foff, d_ovf, small + 6);
+    const uint32_t* ids_low = all4 + (size_t)std::max(rank - 1, 0) * rec_words + 8;
+    x_global_ids_nb_kernel<<<gv, 256, 0, s>>>(c->v_key.as<uint4>(), c->own_idx.as<uint32_t>(), vcap, rank, d_voff, low,
+        ids_low, cap, c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad, 0u, d_nv);
+    compact_own_verts_kernel<<<gv, 256, 0, s>>>(c->own_idx.as<uint32_t>(), vcap, c->v_tet.as<uint32_t>(),
+        c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(),
+        c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(), c->o_local.as<uint8_t>(),
+        c->o_size.as<uint8_t>(), c->o_simplex.as<uint4>(), c->o_funcs.as<uint4>(), c->o_xyz.as<double>(),
+        c->o_key.as<uint4>(), d_nv);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_join, s));
+    c->launches += 9;
+    return RIN_OK;
+}
+
+
+// Collective: every rank allocates its inbox, the CUDA IPC handles travel through one ncclAllGather, every rank maps
+// its peers' inboxes; a second all-gather tells every rank whether ALL mappings succeeded (otherwise every rank keeps
+// the NCCL data path) and doubles as the barrier between "inbox zeroed" and "first remote store".
+int peer_setup(rin_ctx* c)
+{
+    const int world = c->x_world, rank = c->x_rank;
+    cudaStream_t s = c->stream;
+    release_peers(c);
+    c->p_failed = true; // until proven otherwise
+    if (world > PX_MAX_WORLD || getenv("RIN_NO_PEER_EXCHANGE")) return RIN_OK;
+    const uint32_t pcap = (std::max<uint32_t>(2 * c->x_cap, 16384) + 3u) & ~3u;
+    const size_t bytes = px_inbox_words(pcap, world) * 4;
+    bool ok = cudaMalloc((void**)&c->p_inbox, bytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine{};
+    if (ok) ok = cudaMemsetAsync(c->p_inbox, 0, bytes, s) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine, c->p_inbox) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CK(c->p_stage.ensure((size_t)(world + 1) * 64 + (size_t)(world + 1) * 4));
+    uint8_t* st = c->p_stage.as<uint8_t>();
+    CK(cudaMemcpyAsync(st, &mine, 64, cudaMemcpyHostToDevice, s));
+    NK(g_nccl.AllGather(st, st + 64, 16, 3 /*ncclUint32*/, c->nccl_comm, s));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    CK(cudaMemcpyAsync(all.data(), st + 64, (size_t)world * 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == rank) {
+            c->p_peer[r] = c->p_inbox;
+            continue;
+        }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+        } else
+            c->p_peer[r] = static_cast<uint32_t*>(ptr);
+    }
+    uint32_t flag = ok ? 1u : 0u;
+    uint32_t* fl = reinterpret_cast<uint32_t*>(st + (size_t)(world + 1) * 64);
+    CK(cudaMemcpyAsync(fl, &flag, 4, cudaMemcpyHostToDevice, s));
+    NK(g_nccl.AllGather(fl, fl + 1, 1, 3, c->nccl_comm, s));
+    std::vector<uint32_t> flags(world);
+    CK(cudaMemcpyAsync(flags.data(), fl + 1, (size_t)world * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    bool all_ok = true;
+    for (uint32_t f : flags) all_ok &= f != 0;
+    if (!all_ok) {
+        release_peers(c);
+        return RIN_OK; // NCCL data path
+    }
+    c->p_cap = pcap;
+    c->p_pass = 0;
+    c->p_ready = true;
+    c->p_failed = false;
+    return RIN_OK;
+}
+
+// the exchange chain with peer-memory kernels instead of NCCL calls (see exchange.cuh); same products as
+// enqueue_fused_exchange
+int enqueue_peer_exchange(rin_ctx* c, Counters* dctr, bool known_degenerate, uint32_t vcap)
+{
+    if (!c->stream2) {
+        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c->ev_fork));
+        CK(cudaEventCreate(&c->ev_join));
+    }
+    cudaStream_t s = c->stream2;
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(s, c->ev_fork, 0));
+    const int rank = c->x_rank, world = c->x_world, sm = c->sm_count;
+    const uint32_t cap = c->x_cap;
+    const uint32_t pass = ++c->p_pass, parity = pass & 1u;
+    CK(c->x_small.ensure(4096 + 64 * (size_t)world));
+    CK(c->x_send.ensure(std::max<size_t>(cap, 1) * 4)); // local ids of the vertices sent upwards
+    uint32_t tsize = 64;
+    while (tsize < 2ull * cap) tsize <<= 1;
+    CK(c->x_table.ensure((size_t)tsize * 4));
+    const size_t nv1 = std::max(vcap, 1u);
+    CK(c->own_idx.ensure(nv1 * 4));
+    CK(c->gid.ensure(nv1 * 4));
+    const uint32_t tiles = (vcap + 1023) / 1024;
+    CK(c->x_status.ensure((size_t)std::max(tiles, 1u) * 8 + 64));
+    CK(c->o_tet.ensure(nv1 * 4));
+    CK(c->o_local.ensure(nv1));
+    CK(c->o_size.ensure(nv1));
+    CK(c->o_simplex.ensure(nv1 * 16));
+    CK(c->o_funcs.ensure(nv1 * 16));
+    CK(c->o_xyz.ensure(nv1 * 24));
+    CK(c->o_key.ensure(nv1 * 16));
+    if (!c->h_xsmall) CK(cudaHostAlloc((void**)&c->h_xsmall, 4096 + 64 * 64, cudaHostAllocDefault));
+    uint32_t* small = c->x_small.as<uint32_t>();
+    CK(cudaMemsetAsync(small, 0, 64, s));
+    unsigned* d_up = small + 0;
+    unsigned* d_nown = small + 2;
+    unsigned* d_ovf = small + 3;
+    unsigned* d_tile = small + 4;
+    unsigned* d_bad = small + 5;
+    unsigned* d_done1 = small + 8;
+    unsigned* d_done2 = small + 9;
+    unsigned* d_timeout = small + 10;
+    uint32_t* d_voff = small + 64;
+    uint32_t* d_foff = small + 64 + (world + 1);
+    uint32_t* local_ids = c->x_send.as<uint32_t>();
+    uint32_t* low = px_keys(c->p_inbox, cap, world, parity);
+    const uint32_t* ids_low = px_record(c->p_inbox, cap, world, parity, std::max(rank - 1, 0)) + 8;
+    PeerInboxes peers{};
+    for (int r = 0; r < world; ++r) peers.p[r] = c->p_peer[r];
+    const unsigned* d_nv = &dctr->n_unique;
+    const int gv = grid_for(vcap, 256, sm);
+    px_send_keys_kernel<<<gv, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), d_nv, c->x_up_lo, c->x_up_hi,
+        c->x_has_up ? c->p_peer[rank + 1] : nullptr, cap, world, pass, local_ids, d_up, d_done1, d_ovf);
+    CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+    if (c->x_has_low)
+        px_recv_insert_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(c->p_inbox, cap, world, pass,
+            c->x_table.as<uint32_t>(), tsize - 1, d_timeout);
+    CK(cudaMemsetAsync(c->x_status.p, 0, (size_t)std::max(tiles, 1u) * 8, s));
+    x_mark_scan_kernel<<<std::max(tiles, 1u), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), vcap, low, cap,
+        c->x_table.as<uint32_t>(), tsize - 1, c->x_has_low ? 1 : 0, c->own_idx.as<uint32_t>(),
+        c->x_status.as<unsigned long long>(), d_tile, d_nown, 0u, d_nv);
+    px_publish_record_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(peers, rank, world, cap, pass, local_ids, d_up,
+        c->own_idx.as<uint32_t>(), d_nown, &dctr->tot.n_faces, &dctr->tot.n_fv, &dctr->n_zero, known_degenerate ? 1u : 0u,
+        &dctr->overflow, reinterpret_cast<const unsigned*>(&dctr->gen.err), &dctr->gen.arena_overflow,
+        &dctr->gen.n_bnd_faces, d_bad, d_done2);
+    px_offsets_kernel<<<1, 32, 0, s>>>(c->p_inbox, world, cap, pass, d_voff, d_foff, d_ovf, small + 6, d_timeout);
+    x_global_ids_nb_kernel<<<gv, 256, 0, s>>>(c->v_key.as<uint4>(), c->own_idx.as<uint32_t>(), vcap, rank, d_voff, low,
+        ids_low, cap, c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad, 0u, d_nv);
+    compact_own_verts_kernel<<<gv, 256, 0, s>>>(c->own_idx.as<uint32_t>(), vcap, c->v_tet.as<uint32_t>(),
+        c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(),
+        c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(), c->o_local.as<uint8_t>(),
+        c->o_size.as<uint8_t>(), c->o_simplex.as<uint4>(), c->o_funcs.as<uint4>(), c->o_xyz.as<double>(),
+        c->o_key.as<uint4>(), d_nv);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_join, s));
+    c->launches += 7;
+    return RIN_OK;
+}
+
+// joined behind the face kernel: global vertex ids into the face vertex lists, rebased face offsets
+int enqueue_fused_apply(rin_ctx* c, Counters* dctr)
+{
+    cudaStream_t s = c->stream;
+    const int rank = c->x_rank, world = c->x_world;
+    uint32_t* small = c->x_small.as<uint32_t>();
+    uint32_t* d_foff = small + 64 + (world + 1);
+    CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+    fx_apply_kernel<<<c->sm_count * 4, 256, 0, s>>>(small, c->f_verts.as<uint32_t>(), c->gid.as<uint32_t>(),
+        &dctr->tot.n_fv, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), &dctr->tot.n_faces,
+        d_foff + (world + 1) + rank, d_foff + 2 * (world + 1) + rank);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_xsmall, small, (64 + 4 * (size_t)(world + 1)) * 4, cudaMemcpyDeviceToHost, s));
+    ++c->launches;
+    return RIN_OK;
+}
+
+// after the synchronisation, every rank alike: 0 = done, 1 = repeat the pass, X_NOT_FUSED = use the two-call path
+int finish_fused_exchange(rin_ctx* c, bool my_run_ok)
+{
+    const uint32_t* hs = c->h_xsmall;
+    const int rank = c->x_rank, world = c->x_world;
+    if (hs[10]) return fail(RIN_ERR_STATE, "peer exchange: a peer's message did not arrive within the time limit");
+    if (hs[6]) return X_NOT_FUSED;
+    if (hs[3]) { // a message outgrew the capacity
+        c->x_cap = (hs[3] + hs[3] / 4 + 1024 + 3u) & ~3u;
+        return 1;
+    }
+    if (hs[7] || !my_run_ok) return 1;
+    if (hs[5]) return fail(RIN_ERR_STATE, "exchange: " + std::to_string(hs[5]) + " shared vertices have no owner");
+    std::swap(c->v_tet, c->o_tet);
+    std::swap(c->v_local, c->o_local);
+    std::swap(c->v_size, c->o_size);
+    std::swap(c->v_simplex, c->o_simplex);
+    std::swap(c->v_funcs, c->o_funcs);
+    std::swap(c->v_xyz, c->o_xyz);
+    std::swap(c->v_key, c->o_key);
+    c->n_own = hs[2];
+    for (int q = 0; q < 4; ++q) {
+        c->x_offsets[2 * q] = hs[64 + q * (world + 1) + rank];
+        c->x_offsets[2 * q + 1] = hs[64 + q * (world + 1) + world];
+    }
+    return RIN_OK;
+}
+} // namespace
+} // extern "C++"
+
+// rin_run + rin_exchange_nccl as ONE call with ONE host synchronisation: the exchange kernels and the NCCL calls are
+// enqueued behind the run's kernels (their launch cost hides behind the run) and read every count from device
+// memory.  Falls back to the two calls whenever the fused path does not apply (first pass over new inputs, material
+// interface, unstructured neighbourhoods, empty ranks, degenerate inputs); every rank takes the same branch.
+int rin_run_exchange(rin_ctx* c, int mode, uint32_t flags, uint64_t* vert_offset, uint64_t* n_verts_total,
+    uint64_t* face_offset, uint64_t* n_faces_total)
+{
+    if (!c) return fail(RIN_ERR_ARG, "null ctx");
+    if (!c->nccl_comm) return fail(RIN_ERR_STATE, "rin_run_exchange: call rin_nccl_init first");
+    const bool can = mode == RIN_MODE_IA && c->x_window && c->x_fusable && !c->fuse_disabled && c->ghost_lo == 0 &&
+                     c->ghost_hi == 0 && c->h_act != 0 && c->x_cap != 0 && c->t_count != 0;
+    if (can && !c->p_failed && (!c->p_ready || c->x_cap > c->p_cap)) {
+        int rc = peer_setup(c); // collective; on any failure every rank keeps the NCCL data path
+        if (rc) return rc;
+    }
+    if (can) {
+        c->fuse = true;
+        int rc = rin_run(c, mode, flags);
+        c->fuse = false;
+        if (rc == RIN_OK) {
+            if (vert_offset) *vert_offset = c->x_offsets[0];
+            if (n_verts_total) *n_verts_total = c->x_offsets[1];
+            if (face_offset) *face_offset = c->x_offsets[2];
+            if (n_faces_total) *n_faces_total = c->x_offsets[3];
+            return RIN_OK;
+        }
+        if (rc != X_NOT_FUSED) return rc;
+        c->fuse_disabled = true; // degenerate inputs (every rank saw the flag): ghost tets, two calls
+    }
+    int rc = rin_run(c, mode, flags);
+    if (rc) return rc;
+    return rin_exchange_nccl(c, vert_offset, n_verts_total, face_offset, n_faces_total);
+}
+
+// device time (ms) of the exchange chain of the last fused rin_run_exchange: from the end of the vertex kernel to
+// the owned-vertex compaction, including the wait for the neighbours (0 when the pass was not fused)
+int rin_get_exchange_time(const rin_ctx* c, float* ms)
+{
+    if (!c || !ms) return fail(RIN_ERR_ARG, "null argument");
+    *ms = c->x_chain_ms;
+    return RIN_OK;
+}
 
 int rin_get_exchange_offsets(const rin_ctx* c, uint64_t out[8])
 {
@@ -2067,6 +2428,12 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
                                    (uint32_t)sm * 6)), 256, 0, s>>>(ra);
         CK(cudaGetLastError());
         ++c->launches;
+        if (c->fuse) { // rin_run_exchange: the vertex exchange starts here, on a second stream beside the face kernel
+            const bool peer = c->p_ready && c->x_cap <= c->p_cap; // the same on every rank
+            int rc = peer ? enqueue_peer_exchange(c, dctr, evaluated && n_zero != 0, cand_cap)
+                          : enqueue_fused_exchange(c, dctr, evaluated && n_zero != 0, cand_cap);
+            if (rc) return rc;
+        }
 
         // ---- faces
         EVREC(c->ev[ST_FACES]);
@@ -2092,6 +2459,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         CK(cudaGetLastError());
         ++c->launches;
         EVREC(c->ev[ST_COUNT]);
+        if (c->fuse) { // ... and is joined here, same synchronisation as the run's
+            int rc = enqueue_fused_apply(c, dctr);
+            if (rc) return rc;
+        }
 
         // ---- the one read-back
         CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
@@ -2102,11 +2473,19 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         bool again;
         int rc = check_general(h, again);
         if (rc) return rc;
-        if (again || h.overflow) {
+        const bool my_ok = !(again || h.overflow);
+        int fr = RIN_OK;
+        if (c->fuse) { // the same decision on every rank (it comes from the gathered records)
+            fr = finish_fused_exchange(c, my_ok);
+            if (fr == X_NOT_FUSED || fr < 0) return fr;
+            cudaEventElapsedTime(&c->x_chain_ms, c->ev_fork, c->ev_join);
+        }
+        if (!my_ok) {
             c->h_act = 0; // size the next attempt exactly
             c->h_unique = 0;
             continue;
         }
+        if (fr == 1) continue; // another rank has to repeat its pass
 
         uint32_t NF = h.tot.n_faces, NFVout = h.tot.n_fv, NFT = h.tot.n_faces;
         if (h.gen.n_bnd_faces) {
@@ -2196,6 +2575,11 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         n.num_face_verts = NFVout;
         n.num_face_tets = NFT;
         n.num_exact_fallbacks = (uint64_t)h.gen.n_exact + h.n_exact_classify;
+        if (c->fuse) { // the exchange is done: owned vertices only, offsets rebased into the merged mesh
+            c->n_own = c->h_xsmall[2];
+            n.num_verts = c->n_own;
+            c->marked = c->finalized = true;
+        }
         return RIN_OK;
     }
 }

@@ -5,9 +5,10 @@
 // headers and is linked with the reference's remaining objects.  What comes from this repository:
 //   * the hot stages (:53-402 / :53-447): ONE call into the GPU library through the host layer (rin_host.h);
 //   * the per-tet complexes the later stages look at: rin_get_complexes on demand;
-//   * edges / patches / chains: rin_mesh_edges on the device, rin_host::mesh_patches / mesh_chains.
+//   * edges / patches / chains: rin_mesh_edges on the device, rin_host::mesh_patches / mesh_chains;
+//   * the simplicial-cell graph of the cell-grouping path (N4): host/cell_graph.h.
 // What stays the reference's own code (out of scope, host side by north_star): face ordering around chains
-// (pair_faces), shells / components, topological ray shooting, cell grouping, label propagation, and csg.cpp, which
+// (pair_faces), shells / components, topological ray shooting, label propagation, and csg.cpp, which
 // is linked unchanged and therefore calls THIS implicit_arrangement: a literal drop-in.
 // No CPU engine is linked: without a CUDA device every call returns false with the library's message.
 #include <simplicial_arrangement/lookup_table.h>
@@ -16,6 +17,7 @@
 #include "implicit_arrangement.h"
 #include "material_interface.h"
 
+#include "cell_graph.h"
 #include "rin_host.h"
 
 #include <iostream>
@@ -296,7 +298,7 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
             T.shell_of_half_patch, T.components, T.component_of_patch, arrangement_cells);
     } else {
         // cell grouping (src/implicit_arrangement.cpp:590-622): the maps of the second extract_iso_mesh overload
-        // come from the device (rin_tet_maps), the grouping itself is the reference's own code
+        // come from the device (rin_tet_maps), the simplicial-cell graph from this repository (host/cell_graph.h)
         if (!lazy.need_all()) return false; // the simplicial-cell graph spans every active tet
         std::vector<long long> global_vId_of_tet_vert;
         std::vector<size_t> global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet;
@@ -309,11 +311,15 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
         std::vector<std::pair<size_t, size_t>> tet_cell_of_simp_cell;
         std::vector<long long> simp_half_face_info;
         std::vector<size_t> simp_hFace_start_index;
-        build_simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
+        rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
             global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet, T.patch_of_face,
-            T.shell_of_half_patch, tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
-        compute_simplicial_cell_connected_components(tet_cell_of_simp_cell, simp_half_face_info,
-            simp_hFace_start_index, arrangement_cells);
+            T.shell_of_half_patch,
+            [](const simplicial_arrangement::Arrangement<3>& cx, size_t f, size_t cell) {
+                return cx.faces[f].positive_cell == cell; // src/cell_connectivity.cpp:78
+            },
+            tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
+        rin_host::simplicial_cell_components(tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index,
+            arrangement_cells);
     }
     push_stat(stats_labels, stats, "num_cells", arrangement_cells.size());
     lazy.report();
@@ -404,7 +410,7 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
             T.shell_of_half_patch, T.components, T.component_of_patch, material_cells);
     } else {
         // cell grouping (src/material_interface.cpp:640-672): maps of the second extract_MI_mesh overload from
-        // the device (rin_tet_maps), the grouping itself is the reference's own code
+        // the device (rin_tet_maps), the simplicial-cell graph from this repository (host/cell_graph.h)
         if (!lazy.need_all()) return false;
         std::vector<long long> global_vId_of_tet_vert;
         std::vector<size_t> global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet;
@@ -417,11 +423,15 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
         std::vector<std::pair<size_t, size_t>> tet_cell_of_simp_cell;
         std::vector<long long> simp_half_face_info;
         std::vector<size_t> simp_hFace_start_index;
-        build_simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
+        rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
             global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet, T.patch_of_face,
-            T.shell_of_half_patch, tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
-        compute_simplicial_cell_connected_components(tet_cell_of_simp_cell, simp_half_face_info,
-            simp_hFace_start_index, material_cells);
+            T.shell_of_half_patch,
+            [](const simplicial_arrangement::MaterialInterface<3>& cx, size_t f, size_t cell) {
+                return cx.faces[f].positive_material_label == cx.cells[cell].material_label; // :227
+            },
+            tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
+        rin_host::simplicial_cell_components(tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index,
+            material_cells);
     }
     push_stat(stats_labels, stats, "num_cells", material_cells.size());
     lazy.report();

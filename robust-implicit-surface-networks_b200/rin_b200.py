@@ -85,6 +85,8 @@ def lib():
         L.rin_nccl_unique_id.argtypes = [C.c_void_p]
         L.rin_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rin_exchange_nccl.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+        L.rin_get_exchange_time.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.rin_run_exchange.argtypes = [C.c_void_p, C.c_int, C.c_uint32] + [C.POINTER(C.c_uint64)] * 4
         L.rin_get_exchange_offsets.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_robust_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.rin_run_host.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
@@ -275,6 +277,21 @@ class Context:
         return {"vert_offset": v[0].value, "n_verts_total": v[1].value, "face_offset": v[2].value,
                 "n_faces_total": v[3].value, "fv_offset": o[4], "n_fv_total": o[5], "ft_offset": o[6],
                 "n_ft_total": o[7]}
+
+    def run_exchange(self, mode=MODE_IA, flags=FLAG_LOOKUP | FLAG_SECONDARY):
+        """rin_run + rin_exchange_nccl with one host synchronisation (fused when the library can, see the header)."""
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(lib().rin_run_exchange(self._h, mode, flags, *[C.byref(x) for x in v]))
+        o = (C.c_uint64 * 8)()
+        self._check(lib().rin_get_exchange_offsets(self._h, o))
+        return {"vert_offset": v[0].value, "n_verts_total": v[1].value, "face_offset": v[2].value,
+                "n_faces_total": v[3].value, "fv_offset": o[4], "n_fv_total": o[5], "ft_offset": o[6],
+                "n_ft_total": o[7]}
+
+    def exchange_time(self):
+        ms = C.c_float()
+        self._check(lib().rin_get_exchange_time(self._h, C.byref(ms)))
+        return ms.value
 
     def get_complexes(self, mode, tet_ids):
         """Full per-tet complexes (layout in include/rin_b200.h) -> (offsets, words)."""

@@ -245,7 +245,7 @@ def ref_cellgroup_maps(tets, vals, n_pts):
     lib.ref_ia_cellgroup_maps.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32]
     h = lib.ref_ia_cellgroup_maps(tets.ctypes.data, len(tets), n_pts, vals.ctypes.data, vals.shape[1])
     return Bag(lib, "ref", h, ["global_vId_of_tet_vert", "global_vId_start_index_of_tet", "iso_fId_of_tet_face",
-                               "iso_fId_start_index_of_tet", "counts"], [])
+                               "iso_fId_start_index_of_tet", "counts", "cell_graph"], [])
 
 
 def ref_mi_cellgroup_maps(tets, vals, material_in_tet, start_index_of_tet):
@@ -261,7 +261,7 @@ def ref_mi_cellgroup_maps(tets, vals, material_in_tet, start_index_of_tet):
     h = lib.ref_mi_cellgroup_maps(tets.ctypes.data, len(tets), vals.ctypes.data, vals.shape[1], mit.ctypes.data,
                                   len(mit), st.ctypes.data)
     return Bag(lib, "ref", h, ["global_vId_of_tet_vert", "global_vId_start_index_of_tet", "iso_fId_of_tet_face",
-                               "iso_fId_start_index_of_tet", "counts"], [])
+                               "iso_fId_start_index_of_tet", "counts", "cell_graph"], [])
 
 
 def ref_csg(pts, tets, vals, expr, positive_inside=True, lib=None):

@@ -47,3 +47,17 @@ def test_port_maps_equal_the_reference_function(name):
     ref = reference_maps(mode, R, specs)
     for k in MAP_I64:
         assert np.array_equal(port[k], ref[k]), k
+
+
+@pytest.mark.skipif(ref_lib() is None, reason="hybrid reference not built")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_product_cell_graph_equals_the_reference_functions(name):
+    """host/cell_graph.h (simplicial-cell adjacency + connected components) against the reference's
+    build_simplicial_cell_adjacency / compute_simplicial_cell_connected_components (src/cell_connectivity.cpp:15-372)
+    on the same complexes and maps: adjacency arrays element-wise, components as shell sets."""
+    mode, R, specs = CASES[name]
+    ref = reference_maps(mode, R, specs)
+    assert ref.error == ""
+    adjacency_equal, components_equal, n_cells, n_components = ref["cell_graph"].tolist()
+    assert adjacency_equal == 1 and components_equal == 1
+    assert n_cells >= 5 * R ** 3 and 1 <= n_components < n_cells
