@@ -136,7 +136,9 @@ def check_digest(mesh, config, R, mi):
 # compiled in place, else the oracle port), one thread (the reference is single-threaded by construction), on a
 # bounded sample of the workload: the first x-slabs of the same grid with the same functions
 # ---------------------------------------------------------------------------------------------------------------
-CPU_SLABS = {"C2": (128, 128), "C3": (128, 128), "C4": (128, 20), "C5": (256, 96)}  # (R, slabs in the sample)
+# (R, slabs in the sample).  C4: the 32 spheres sit around the origin (radius ~0.5), the first 20 slabs hold no surface at
+# all (and the reference crashes on an empty mesh): half the grid is the smallest sample with the whole grid's density
+CPU_SLABS = {"C2": (128, 128), "C3": (128, 128), "C4": (128, 64), "C5": (256, 96)}
 CPU_LABELS = {"ia": ("func signs", "filter", "simp_arr(other)", "simp_arr(1 func)", "simp_arr(2 func)",
                      "simp_arr(>=3 func)", "extract mesh", "compute xyz"),
               "mi": ("highest func", "filter", "MI(other)", "MI(2 func)", "MI(3 func)", "MI(>=4 func)", "extract mesh",
