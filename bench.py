@@ -358,8 +358,12 @@ def main():
     # separate profiled passes (per-stage events on) for the stage table and the kernel brackets
     ctx.set_stage_timing(True)
     eval_ms, filt_ms, stage_acc = [], [], None
+    x_parts = None
     for _ in range(5):
         step()
+        if dist is not None:
+            p = np.array(ctx.exchange_parts())
+            x_parts = p if x_parts is None else x_parts + p
         kt = ctx.kernel_times()
         eval_ms.append(kt["eval_ms"])
         filt_ms.append(kt["filter_ms"])
@@ -553,7 +557,11 @@ def main():
                                                                "device memory, ONE host synchronisation per step "
                                                                "(rin_run_exchange)"),
                     "n_verts_total": info["n_verts_total"], "n_faces_total": info["n_faces_total"],
-                    "host_wall": split_ms, "per_rank": per_rank}}
+                    "host_wall": split_ms, "per_rank": per_rank,
+                    "chain_kernels_ms_rank0": None if x_parts is None else dict(zip(
+                        ("send_keys", "recv_insert(waits for r-1)", "mark_scan_publish",
+                         "finish(waits for all records; ids + owned vertices)"),
+                        [round(float(x) / 5, 4) for x in x_parts[:4]]))}}
         print(json.dumps(line))
     if dist is not None:
         barrier()

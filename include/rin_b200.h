@@ -263,6 +263,9 @@ int rin_get_exchange_offsets(const rin_ctx*, uint64_t out[8]);
 /* device time (ms) of the exchange chain of the last fused rin_run_exchange (vertex kernel done -> owned vertices
  * compacted, including the wait for the neighbours); 0 when the pass was not fused */
 int rin_get_exchange_time(const rin_ctx*, float* ms);
+/* with stage timing on: device times (ms) of the kernels of the peer exchange chain {send keys, receive + insert, mark +
+ * scan + publish record, offsets + global ids + owned vertices, 0, ...}, each from the end of the previous one */
+int rin_get_exchange_parts(const rin_ctx*, float ms[10]);
 /* vertex id range referenced by the current tet range */
 int rin_get_vertex_range(const rin_ctx*, uint32_t* v_lo, uint32_t* v_hi);
 

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(256) px_send_keys_kernel(const uint4* __restri
     const uint32_t n = *n_dev;
     uint32_t* msg = remote_inbox ? px_keys(remote_inbox, cap, world, pass & 1u) : nullptr;
     uint4* out_keys = reinterpret_cast<uint4*>(msg + XHDR);
+    bool wrote = false;
     if (msg && lo <= hi)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const int sz = v_size[i];
@@ -437,10 +438,12 @@ __global__ void __launch_bounds__(256) px_send_keys_kernel(const uint4* __restri
             if (p < cap) {
                 out_keys[p] = k;
                 local_ids[p] = i;
+                wrote = true;
             }
         }
-    // last block: header, then the flag (every block's stores are fenced before its ticket)
-    __threadfence_system();
+    // last block: header, then the flag (the stores of every thread that wrote are fenced before its block's ticket;
+    // a system-scope fence is expensive, most threads have nothing to fence)
+    if (wrote) __threadfence_system();
     __syncthreads();
     __shared__ unsigned s_last;
     if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
@@ -511,6 +514,205 @@ __global__ void __launch_bounds__(256) px_publish_record_kernel(const PeerInboxe
         rec[6] = (*run_overflow || *gen_err || *gen_arena_overflow) ? 1u : 0u;
         rec[7] = 0;
         px_signal(peers.p[threadIdx.x] + parity * 64 + 1 + rank, pass);
+    }
+}
+
+// px_publish_record_kernel's work as a device function for ONE block (the last block of the mark + scan kernel calls
+// it: the sent vertices are a few thousand at most)
+struct PublishArgs
+{
+    PeerInboxes peers;
+    int rank, world;
+    uint32_t cap, pass;
+    const uint32_t* local_ids;
+    const unsigned* n_up;
+    const unsigned* n_faces;
+    const unsigned* n_fv;
+    const unsigned long long* n_zero;
+    uint32_t known_degenerate;
+    const unsigned* run_overflow;
+    const unsigned* gen_err;
+    const unsigned* gen_arena_overflow;
+    const unsigned* n_bnd_faces;
+    unsigned* n_bad;
+};
+__device__ void px_publish_block(const PublishArgs& A, const uint32_t* __restrict__ own_idx, unsigned n_own)
+{
+    const uint32_t parity = A.pass & 1u;
+    const uint32_t sent = *reinterpret_cast<const volatile unsigned*>(A.n_up), n = min(sent, A.cap);
+    uint32_t* up_rec = (A.rank + 1 < A.world) ? px_record(A.peers.p[A.rank + 1], A.cap, A.world, parity, A.rank) : nullptr;
+    bool wrote = false;
+    if (up_rec)
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+            const uint32_t o = __ldcg(&own_idx[A.local_ids[j]]);
+            if (o == NONE32) atomicAdd(A.n_bad, 1u);
+            up_rec[8 + j] = o;
+            wrote = true;
+        }
+    if (wrote) __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < A.world) {
+        uint32_t* rec = px_record(A.peers.p[threadIdx.x], A.cap, A.world, parity, A.rank);
+        rec[0] = n_own;
+        rec[1] = *A.n_faces;
+        rec[2] = sent;
+        rec[3] = *A.n_fv;
+        rec[4] = *A.n_faces; // interior iso-faces: one (tet, local face) pair each
+        rec[5] = (A.known_degenerate || *A.n_zero != 0 || *A.n_bnd_faces != 0) ? 1u : 0u;
+        rec[6] = (*A.run_overflow || *A.gen_err || *A.gen_arena_overflow) ? 1u : 0u;
+        rec[7] = 0;
+        px_signal(A.peers.p[threadIdx.x] + parity * 64 + 1 + A.rank, A.pass);
+    }
+}
+
+// own flag + ordered own index like x_mark_scan_kernel, persistent blocks taking tile tickets (the look-back only
+// ever waits for lower tickets, which resident blocks hold); the block that finishes last publishes the record
+__global__ void __launch_bounds__(256) px_mark_scan_publish_kernel(const uint4* __restrict__ v_key,
+    const uint8_t* __restrict__ v_size, const unsigned* __restrict__ n_dev, const uint32_t* __restrict__ low,
+    uint32_t cap, const uint32_t* __restrict__ table, uint32_t mask, int has_low, uint32_t* __restrict__ own_idx,
+    volatile unsigned long long* __restrict__ status, unsigned* __restrict__ tile_counter,
+    unsigned* __restrict__ n_own, unsigned* __restrict__ done, const PublishArgs P)
+{
+    __shared__ unsigned s_tile, s_base, s_last;
+    __shared__ unsigned s_warp[8];
+    const uint32_t n = *n_dev;
+    const uint32_t n_tiles = (n + 1023) / 1024;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ITEMS = 4;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const unsigned tile = s_tile;
+        if (tile >= n_tiles) break;
+        const uint32_t base = tile * 256 * ITEMS + threadIdx.x * ITEMS;
+        bool own[ITEMS];
+        unsigned cnt = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t i = base + j;
+            own[j] = false;
+            if (i < n) {
+                own[j] = true;
+                if (has_low && v_size[i] < 4 && x_lookup(low, cap, table, mask, v_key[i]) != NONE32) own[j] = false;
+                cnt += own[j];
+            }
+        }
+        unsigned x = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned t = (lane < 8) ? s_warp[lane] : 0, x8 = t;
+            for (int o = 1; o < 8; o <<= 1) {
+                unsigned y = __shfl_up_sync(0xffffffffu, x8, o);
+                if (lane >= o) x8 += y;
+            }
+            if (lane < 8) s_warp[lane] = x8 - t;
+            const unsigned run = __shfl_sync(0xffffffffu, x8, 7);
+            uint32_t e0, e1;
+            tile_lookback_warp(status, (int)tile, run, 0, e0, e1);
+            if (lane == 0) {
+                s_base = e0;
+                if (tile == n_tiles - 1) *n_own = e0 + run;
+            }
+        }
+        __syncthreads();
+        unsigned id = s_base + s_warp[warp] + x - cnt;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const uint32_t i = base + j;
+            if (i < n) own_idx[i] = own[j] ? id++ : NONE32;
+        }
+    }
+    // every block signs off once its tiles are written; the last one publishes
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    px_publish_block(P, own_idx, *reinterpret_cast<volatile unsigned*>(n_own));
+}
+
+// waits for every rank's record of this pass, computes the prefixes (every block for itself, block 0 also stores
+// them for the host), then global ids and the compaction of the owned vertices in one sweep
+__global__ void __launch_bounds__(256) px_finish_kernel(uint32_t* __restrict__ inbox, int rank, int world, uint32_t cap,
+    uint32_t pass, uint32_t* __restrict__ voff, uint32_t* __restrict__ foff, unsigned* __restrict__ flags /* small */,
+    const unsigned* __restrict__ n_dev, const uint4* __restrict__ v_key, const uint32_t* __restrict__ own_idx,
+    const uint32_t* __restrict__ table, uint32_t mask, uint32_t* __restrict__ gid,
+    const uint32_t* __restrict__ v_tet, const uint8_t* __restrict__ v_local, const uint8_t* __restrict__ v_size,
+    const uint4* __restrict__ v_simplex, const uint4* __restrict__ v_funcs, const double* __restrict__ v_xyz,
+    uint32_t* __restrict__ o_tet, uint8_t* __restrict__ o_local, uint8_t* __restrict__ o_size,
+    uint4* __restrict__ o_simplex, uint4* __restrict__ o_funcs, double* __restrict__ o_xyz, uint4* __restrict__ o_key)
+{
+    const uint32_t parity = pass & 1u;
+    __shared__ uint32_t s_voff[PX_MAX_WORLD + 1];
+    if ((int)threadIdx.x < world) px_wait(inbox + parity * 64 + 1 + threadIdx.x, pass, flags + 10);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t v = 0, f = 0, fv = 0, ft = 0;
+        unsigned ovf = 0, ng = 0, bad = 0;
+        const bool store = blockIdx.x == 0;
+        uint32_t* fvoff = foff + (world + 1);
+        uint32_t* ftoff = fvoff + (world + 1);
+        for (int s = 0; s < world; ++s) {
+            const uint32_t* r = px_record(inbox, cap, world, parity, s);
+            s_voff[s] = v;
+            if (store) {
+                voff[s] = v;
+                foff[s] = f;
+                fvoff[s] = fv;
+                ftoff[s] = ft;
+            }
+            v += __ldcg(r + 0);
+            f += __ldcg(r + 1);
+            fv += __ldcg(r + 3);
+            ft += __ldcg(r + 4);
+            ng |= __ldcg(r + 5);
+            bad |= __ldcg(r + 6);
+            if (__ldcg(r + 2) > cap) ovf = max(ovf, __ldcg(r + 2));
+        }
+        s_voff[world] = v;
+        if (store) {
+            voff[world] = v;
+            foff[world] = f;
+            fvoff[world] = fv;
+            ftoff[world] = ft;
+            if (ovf > flags[3]) flags[3] = ovf;
+            flags[6] = ng;
+            flags[7] = bad;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = *n_dev;
+    const uint32_t* low = px_keys(inbox, cap, world, parity);
+    const uint32_t* ids_low = px_record(inbox, cap, world, parity, max(rank - 1, 0)) + 8;
+    const uint32_t my_off = s_voff[rank], low_off = s_voff[max(rank - 1, 0)];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t d = own_idx[i];
+        if (d != NONE32) {
+            gid[i] = my_off + d;
+            o_tet[d] = v_tet[i];
+            o_local[d] = v_local[i];
+            o_size[d] = v_size[i];
+            o_simplex[d] = v_simplex[i];
+            o_funcs[d] = v_funcs[i];
+            o_xyz[3 * (size_t)d] = v_xyz[3 * (size_t)i];
+            o_xyz[3 * (size_t)d + 1] = v_xyz[3 * (size_t)i + 1];
+            o_xyz[3 * (size_t)d + 2] = v_xyz[3 * (size_t)i + 2];
+            o_key[d] = v_key[i];
+            continue;
+        }
+        const uint32_t f = (rank > 0) ? x_lookup(low, cap, table, mask, v_key[i]) : NONE32;
+        if (f == NONE32 || __ldcg(&ids_low[f]) == NONE32) {
+            atomicAdd(flags + 5, 1u);
+            gid[i] = NONE32;
+        } else
+            gid[i] = low_off + __ldcg(&ids_low[f]);
     }
 }
 

@@ -60,6 +60,7 @@ __device__ __forceinline__ uint4 grid_tet(uint32_t R, const FastDiv dR, uint32_t
 // ---------------------------------------------------------------------------------------------
 constexpr int EV_VPT = 4;
 
+template <int NVX = EV_VPT>
 __device__ __forceinline__ void eval_func_n(const rin_func_desc& f, const double* x, const double* y,
     const double* z, double* v)
 {
@@ -67,7 +68,7 @@ __device__ __forceinline__ void eval_func_n(const rin_func_desc& f, const double
     case RIN_FN_PLANE: {
         const double p0 = f.p[0], p1 = f.p[1], p2 = f.p[2], n0 = f.p[3], n1 = f.p[4], n2 = f.p[5];
 #pragma unroll
-        for (int j = 0; j < EV_VPT; ++j) {
+        for (int j = 0; j < NVX; ++j) {
             const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
             v[j] = (n0 * dx + n1 * dy) + n2 * dz;
         }
@@ -78,13 +79,13 @@ __device__ __forceinline__ void eval_func_n(const rin_func_desc& f, const double
         if (f.p[4] != 0.0) { // squared
             const double r2 = r * r;
 #pragma unroll
-            for (int j = 0; j < EV_VPT; ++j) {
+            for (int j = 0; j < NVX; ++j) {
                 const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
                 v[j] = r2 - ((dx * dx + dy * dy) + dz * dz);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < EV_VPT; ++j) {
+            for (int j = 0; j < NVX; ++j) {
                 const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
                 v[j] = r - sqrt((dx * dx + dy * dy) + dz * dz);
             }
@@ -97,7 +98,7 @@ __device__ __forceinline__ void eval_func_n(const rin_func_desc& f, const double
         const bool torus = f.type == RIN_FN_TORUS;
         const double r2 = f.p[7];
 #pragma unroll
-        for (int j = 0; j < EV_VPT; ++j) {
+        for (int j = 0; j < NVX; ++j) {
             const double dx = x[j] - p0, dy = y[j] - p1, dz = z[j] - p2;
             const double t = (a0 * dx + a1 * dy) + a2 * dz;
             const double px = dx - t * a0, py = dy - t * a1, pz = dz - t * a2;
@@ -112,12 +113,12 @@ __device__ __forceinline__ void eval_func_n(const rin_func_desc& f, const double
     }
     default:
 #pragma unroll
-        for (int j = 0; j < EV_VPT; ++j) v[j] = 0.0;
+        for (int j = 0; j < NVX; ++j) v[j] = 0.0;
         break;
     }
     if (f.flip) {
 #pragma unroll
-        for (int j = 0; j < EV_VPT; ++j) v[j] = -v[j];
+        for (int j = 0; j < NVX; ++j) v[j] = -v[j];
     }
 }
 
@@ -185,6 +186,91 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ pt
     // num_degenerate_vertex counts (vertex, function) pairs with value 0 (src/implicit_arrangement.cpp:69-73)
     for (int o = 16; o; o >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
     if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(n_zero, (unsigned long long)zeros);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (material interface, up to MI_EVAL_MAXF materials): evaluation fused with the "highest func" loop
+// (src/material_interface.cpp:59-92).  The F values of a vertex stay in registers, so the maximal-material mask,
+// the "some two materials are exactly equal" flag (tie gate) and the tie count cost no second pass over the
+// 8F bytes per vertex that highest_material_kernel re-reads.  Same arithmetic as eval_kernel / eval_func.
+// ---------------------------------------------------------------------------------------------
+constexpr int MI_EVAL_MAXF = 8;
+constexpr int MI_EVAL_VPT = 4;
+__host__ __device__ constexpr size_t mi_eval_smem(uint32_t F)
+{
+    // function descriptors (rounded up to 16 bytes) + the block's values [material][vertex slot][thread]
+    return ((F * sizeof(rin_func_desc) + 15) & ~(size_t)15) + (size_t)F * MI_EVAL_VPT * 256 * sizeof(double);
+}
+template <bool GRID>
+__global__ void __launch_bounds__(256) eval_mi_kernel(const double* __restrict__ pts, const double* __restrict__ axes,
+    uint32_t N, const FastDiv dN, uint32_t v_first, uint32_t v_count, uint32_t VS,
+    const rin_func_desc* __restrict__ funcs, uint32_t F, int negate, double* __restrict__ vals,
+    uint2* __restrict__ vmask, unsigned long long* __restrict__ n_tied)
+{
+    extern __shared__ __align__(16) rin_func_desc s_funcs[];
+    double* s_val = reinterpret_cast<double*>(
+        reinterpret_cast<uint8_t*>(s_funcs) + ((F * sizeof(rin_func_desc) + 15) & ~(size_t)15));
+    for (uint32_t i = threadIdx.x; i < F * (sizeof(rin_func_desc) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(s_funcs)[i] = reinterpret_cast<const double*>(funcs)[i];
+    __syncthreads();
+    unsigned tied = 0;
+    const uint32_t step = gridDim.x * blockDim.x * MI_EVAL_VPT;
+    for (uint32_t i0 = blockIdx.x * blockDim.x * MI_EVAL_VPT + threadIdx.x; i0 < v_count; i0 += step) {
+        double x[MI_EVAL_VPT], y[MI_EVAL_VPT], z[MI_EVAL_VPT];
+        uint32_t v[MI_EVAL_VPT];
+        bool ok[MI_EVAL_VPT];
+#pragma unroll
+        for (int j = 0; j < MI_EVAL_VPT; ++j) {
+            const uint32_t idx = i0 + j * blockDim.x;
+            ok[j] = idx < v_count;
+            v[j] = v_first + (ok[j] ? idx : 0u);
+            if (GRID) {
+                const uint32_t ij = fd_div(v[j], dN), k = v[j] - ij * N, ii = fd_div(ij, dN), jj = ij - ii * N;
+                x[j] = __ldg(&axes[ii]);
+                y[j] = __ldg(&axes[N + jj]);
+                z[j] = __ldg(&axes[2 * N + k]);
+            } else {
+                x[j] = __ldg(&pts[3 * (size_t)v[j]]);
+                y[j] = __ldg(&pts[3 * (size_t)v[j] + 1]);
+                z[j] = __ldg(&pts[3 * (size_t)v[j] + 2]);
+            }
+        }
+        // running maximum and the set of materials attaining it (first index on ties is bit order), :66-76;
+        // the values are parked in the thread's own shared-memory column for the pairwise test below
+        double mx[MI_EVAL_VPT];
+        uint32_t H[MI_EVAL_VPT];
+        for (uint32_t f = 0; f < F; ++f) {
+            double tmp[MI_EVAL_VPT];
+            eval_func_n<MI_EVAL_VPT>(s_funcs[f], x, y, z, tmp);
+            double* __restrict__ row = vals + (size_t)f * VS;
+#pragma unroll
+            for (int j = 0; j < MI_EVAL_VPT; ++j) {
+                if (negate) tmp[j] = tmp[j] * -1;
+                if (ok[j]) row[v[j]] = tmp[j];
+                s_val[(f * MI_EVAL_VPT + j) * 256 + threadIdx.x] = tmp[j];
+                if (f == 0 || tmp[j] > mx[j] || mx[j] != mx[j]) {
+                    mx[j] = tmp[j];
+                    H[j] = 1u << f;
+                } else if (tmp[j] == mx[j])
+                    H[j] |= 1u << f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MI_EVAL_VPT; ++j) {
+            if (!ok[j]) continue;
+            // "some two materials are exactly equal here" (tie gate of classify_mi_kernel)
+            bool any_equal = false;
+            for (uint32_t f = 0; f + 1 < F; ++f) {
+                const double a = s_val[(f * MI_EVAL_VPT + j) * 256 + threadIdx.x];
+                for (uint32_t g = f + 1; g < F; ++g) any_equal |= (a == s_val[(g * MI_EVAL_VPT + j) * 256 + threadIdx.x]);
+            }
+            if (mx[j] != mx[j]) H[j] = 0; // every value NaN: nothing compares equal to the maximum
+            vmask[v[j]] = make_uint2(H[j], any_equal ? 1u : 0u);
+            tied += (__popc(H[j]) > 1);
+        }
+    }
+    for (int o = 16; o; o >>= 1) tied += __shfl_xor_sync(0xffffffffu, tied, o);
+    if ((threadIdx.x & 31) == 0 && tied) atomicAdd(n_tied, (unsigned long long)tied);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -140,6 +140,9 @@ struct rin_ctx
     cudaStream_t stream2 = nullptr;          // fused run + exchange: the vertex exchange runs beside the face kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float x_chain_ms = 0; // device time of the forked exchange chain of the last fused pass
+    cudaEvent_t ev_x[10] = {}; // per-kernel brackets of the peer exchange chain (stage timing on)
+    float x_part_ms[10] = {};
+    int x_parts = 0;
     // peer-memory exchange (exchange.cuh): this rank's inbox and the peers' inboxes mapped through CUDA IPC
     uint32_t* p_inbox = nullptr;
     uint32_t* p_peer[PX_MAX_WORLD] = {};
@@ -1746,16 +1749,30 @@ extern "C++" {
 namespace {
 constexpr int X_NOT_FUSED = 1001; // internal: degenerate inputs, every rank falls back to rin_run + rin_exchange_nccl
 
+// second stream of the fused run + exchange, HIGH priority: its (small, latency-bound) kernels get the SM slots the
+// face kernel's blocks free first, so the exchange really runs beside the face kernel instead of behind it
+int ensure_stream2(rin_ctx* c)
+{
+    if (c->stream2) return RIN_OK;
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, greatest));
+    CK(cudaEventCreate(&c->ev_fork));
+    CK(cudaEventCreate(&c->ev_join));
+    return RIN_OK;
+}
+#define CK_RC(call)            \
+    do {                       \
+        int rc__ = (call);     \
+        if (rc__) return rc__; \
+    } while (0)
+
 // The neighbour exchange enqueued behind the kernels of a run whose counts are still on the device
 // (exchange_neighbours with every count read from device memory).  vcap = capacity of the vertex arrays.
 int enqueue_fused_exchange(rin_ctx* c, Counters* dctr, bool known_degenerate, uint32_t vcap)
 {
     // forked behind the vertex kernel: everything up to the global ids needs the vertices and the totals only
-    if (!c->stream2) {
-        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&c->ev_fork));
-        CK(cudaEventCreate(&c->ev_join));
-    }
+    CK_RC(ensure_stream2(c));
     cudaStream_t s = c->stream2;
     CK(cudaEventRecord(c->ev_fork, c->stream));
     CK(cudaStreamWaitEvent(s, c->ev_fork, 0));
@@ -1896,14 +1913,8 @@ int peer_setup(rin_ctx* c)
 // enqueue_fused_exchange
 int enqueue_peer_exchange(rin_ctx* c, Counters* dctr, bool known_degenerate, uint32_t vcap)
 {
-    if (!c->stream2) {
-        CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&c->ev_fork));
-        CK(cudaEventCreate(&c->ev_join));
-    }
+    CK_RC(ensure_stream2(c));
     cudaStream_t s = c->stream2;
-    CK(cudaEventRecord(c->ev_fork, c->stream));
-    CK(cudaStreamWaitEvent(s, c->ev_fork, 0));
     const int rank = c->x_rank, world = c->x_world, sm = c->sm_count;
     const uint32_t cap = c->x_cap;
     const uint32_t pass = ++c->p_pass, parity = pass & 1u;
@@ -1926,7 +1937,13 @@ int enqueue_peer_exchange(rin_ctx* c, Counters* dctr, bool known_degenerate, uin
     CK(c->o_key.ensure(nv1 * 16));
     if (!c->h_xsmall) CK(cudaHostAlloc((void**)&c->h_xsmall, 4096 + 64 * 64, cudaHostAllocDefault));
     uint32_t* small = c->x_small.as<uint32_t>();
+    // the clears run EARLY (the second stream is idle while the run's kernels execute), the chain itself starts
+    // behind the vertex kernel
     CK(cudaMemsetAsync(small, 0, 64, s));
+    CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+    CK(cudaMemsetAsync(c->x_status.p, 0, (size_t)std::max(tiles, 1u) * 8, s));
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    CK(cudaStreamWaitEvent(s, c->ev_fork, 0));
     unsigned* d_up = small + 0;
     unsigned* d_nown = small + 2;
     unsigned* d_ovf = small + 3;
@@ -1943,32 +1960,57 @@ int enqueue_peer_exchange(rin_ctx* c, Counters* dctr, bool known_degenerate, uin
     PeerInboxes peers{};
     for (int r = 0; r < world; ++r) peers.p[r] = c->p_peer[r];
     const unsigned* d_nv = &dctr->n_unique;
-    const int gv = grid_for(vcap, 256, sm);
+    // grid-stride kernels over the (device-side) vertex count: a few blocks per SM are plenty, and every block of the
+    // send / publish kernels pays a system-scope fence
+    const int gv = grid_for(std::max<uint32_t>(c->h_unique, 4096), 256, sm, 2);
+    int xe = 0;
+    auto XEV = [&]() {
+        if (c->stage_timing && xe < 10) {
+            if (!c->ev_x[xe]) cudaEventCreate(&c->ev_x[xe]);
+            cudaEventRecord(c->ev_x[xe++], s);
+        }
+    };
     px_send_keys_kernel<<<gv, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), d_nv, c->x_up_lo, c->x_up_hi,
         c->x_has_up ? c->p_peer[rank + 1] : nullptr, cap, world, pass, local_ids, d_up, d_done1, d_ovf);
-    CK(cudaMemsetAsync(c->x_table.p, 0xff, (size_t)tsize * 4, s));
+    XEV(); // 0: send keys
     if (c->x_has_low)
         px_recv_insert_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(c->p_inbox, cap, world, pass,
             c->x_table.as<uint32_t>(), tsize - 1, d_timeout);
-    CK(cudaMemsetAsync(c->x_status.p, 0, (size_t)std::max(tiles, 1u) * 8, s));
-    x_mark_scan_kernel<<<std::max(tiles, 1u), 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), vcap, low, cap,
+    XEV(); // 1: receive + insert (waits for the lower neighbour)
+    PublishArgs pa{};
+    pa.peers = peers;
+    pa.rank = rank;
+    pa.world = world;
+    pa.cap = cap;
+    pa.pass = pass;
+    pa.local_ids = local_ids;
+    pa.n_up = d_up;
+    pa.n_faces = &dctr->tot.n_faces;
+    pa.n_fv = &dctr->tot.n_fv;
+    pa.n_zero = &dctr->n_zero;
+    pa.known_degenerate = known_degenerate ? 1u : 0u;
+    pa.run_overflow = &dctr->overflow;
+    pa.gen_err = reinterpret_cast<const unsigned*>(&dctr->gen.err);
+    pa.gen_arena_overflow = &dctr->gen.arena_overflow;
+    pa.n_bnd_faces = &dctr->gen.n_bnd_faces;
+    pa.n_bad = d_bad;
+    // persistent blocks take tile tickets until the device-side vertex count is covered
+    const uint32_t ms_blocks = std::max<uint32_t>(1, std::min<uint32_t>((c->h_unique + 1023) / 1024, (uint32_t)sm * 4));
+    px_mark_scan_publish_kernel<<<ms_blocks, 256, 0, s>>>(c->v_key.as<uint4>(), c->v_size.as<uint8_t>(), d_nv, low, cap,
         c->x_table.as<uint32_t>(), tsize - 1, c->x_has_low ? 1 : 0, c->own_idx.as<uint32_t>(),
-        c->x_status.as<unsigned long long>(), d_tile, d_nown, 0u, d_nv);
-    px_publish_record_kernel<<<grid_for(cap, 256, sm), 256, 0, s>>>(peers, rank, world, cap, pass, local_ids, d_up,
-        c->own_idx.as<uint32_t>(), d_nown, &dctr->tot.n_faces, &dctr->tot.n_fv, &dctr->n_zero, known_degenerate ? 1u : 0u,
-        &dctr->overflow, reinterpret_cast<const unsigned*>(&dctr->gen.err), &dctr->gen.arena_overflow,
-        &dctr->gen.n_bnd_faces, d_bad, d_done2);
-    px_offsets_kernel<<<1, 32, 0, s>>>(c->p_inbox, world, cap, pass, d_voff, d_foff, d_ovf, small + 6, d_timeout);
-    x_global_ids_nb_kernel<<<gv, 256, 0, s>>>(c->v_key.as<uint4>(), c->own_idx.as<uint32_t>(), vcap, rank, d_voff, low,
-        ids_low, cap, c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(), d_bad, 0u, d_nv);
-    compact_own_verts_kernel<<<gv, 256, 0, s>>>(c->own_idx.as<uint32_t>(), vcap, c->v_tet.as<uint32_t>(),
-        c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(),
-        c->v_xyz.as<double>(), c->v_key.as<uint4>(), c->o_tet.as<uint32_t>(), c->o_local.as<uint8_t>(),
+        c->x_status.as<unsigned long long>(), d_tile, d_nown, d_done2, pa);
+    XEV(); // 2: mark + scan + publish the record
+    px_finish_kernel<<<gv, 256, 0, s>>>(c->p_inbox, rank, world, cap, pass, d_voff, d_foff, small, d_nv,
+        c->v_key.as<uint4>(), c->own_idx.as<uint32_t>(), c->x_table.as<uint32_t>(), tsize - 1, c->gid.as<uint32_t>(),
+        c->v_tet.as<uint32_t>(), c->v_local.as<uint8_t>(), c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(),
+        c->v_funcs.as<uint4>(), c->v_xyz.as<double>(), c->o_tet.as<uint32_t>(), c->o_local.as<uint8_t>(),
         c->o_size.as<uint8_t>(), c->o_simplex.as<uint4>(), c->o_funcs.as<uint4>(), c->o_xyz.as<double>(),
-        c->o_key.as<uint4>(), d_nv);
+        c->o_key.as<uint4>());
+    XEV(); // 3: offsets (waits for every rank's record) + global ids + owned vertices
+    c->x_parts = xe;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_join, s));
-    c->launches += 7;
+    c->launches += c->x_has_low ? 4 : 3;
     return RIN_OK;
 }
 
@@ -2059,6 +2101,15 @@ int rin_get_exchange_time(const rin_ctx* c, float* ms)
 {
     if (!c || !ms) return fail(RIN_ERR_ARG, "null argument");
     *ms = c->x_chain_ms;
+    return RIN_OK;
+}
+
+// per-kernel device times (ms) of the peer exchange chain of the last fused pass with stage timing on:
+// {send keys, receive + insert, mark + scan + publish record, offsets + global ids + owned vertices}
+int rin_get_exchange_parts(const rin_ctx* c, float ms[10])
+{
+    if (!c || !ms) return fail(RIN_ERR_ARG, "null argument");
+    for (int i = 0; i < 10; ++i) ms[i] = c->x_part_ms[i];
     return RIN_OK;
 }
 
@@ -2454,7 +2505,9 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         fg.f_tets = c->f_tets.as<uint32_t>();
         fg.f_funcs = c->f_funcs.as<uint32_t>();
         fg.overflow = &dctr->overflow;
-        const int face_grid = grid_for(a_est, 256, sm, 8);
+        // fused run + exchange: many short blocks instead of persistent ones, so that the high-priority exchange
+        // stream finds free SM slots while the face kernel runs
+        const int face_grid = c->fuse ? grid_for(a_est, 256, sm, 64) : grid_for(a_est, 256, sm, 8);
         faces_kernel<W, false><<<face_grid, 256, 0, s>>>(fg);
         CK(cudaGetLastError());
         ++c->launches;
@@ -2479,6 +2532,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             fr = finish_fused_exchange(c, my_ok);
             if (fr == X_NOT_FUSED || fr < 0) return fr;
             cudaEventElapsedTime(&c->x_chain_ms, c->ev_fork, c->ev_join);
+            for (int i = 0; i < 10; ++i) c->x_part_ms[i] = 0;
+            if (c->stage_timing)
+                for (int i = 0; i < c->x_parts; ++i)
+                    cudaEventElapsedTime(&c->x_part_ms[i], i ? c->ev_x[i - 1] : c->ev_fork, c->ev_x[i]);
         }
         if (!my_ok) {
             c->h_act = 0; // size the next attempt exactly
@@ -2624,26 +2681,44 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     EVREC(c->ev[ST_EVAL]);
     const uint32_t vf = c->v_count ? c->v_first : 0, vc = c->v_count ? c->v_count : (uint32_t)c->V;
     EVREC(c->kev[0]);
-    if (c->have_funcs) {
-        const size_t smem = F * sizeof(rin_func_desc);
-        const int g = grid_for((vc + EV_VPT - 1) / EV_VPT, 256, sm, 8);
+    c->launches = 0;
+    if (c->have_funcs && F <= (uint32_t)MI_EVAL_MAXF) {
+        // evaluation fused with the "highest func" loop: the values never come back from HBM
+        const size_t smem = mi_eval_smem(F);
+        CK(cudaFuncSetAttribute(eval_mi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi_eval_smem(MI_EVAL_MAXF)));
+        CK(cudaFuncSetAttribute(eval_mi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi_eval_smem(MI_EVAL_MAXF)));
+        const int g = grid_for((vc + MI_EVAL_VPT - 1) / MI_EVAL_VPT, 256, sm, 8);
         if (c->grid_R)
-            eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1,
-                make_fastdiv(c->grid_R + 1), vf, vc, V,
-                c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
-                &dctr->n_zero);
+            eval_mi_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1,
+                make_fastdiv(c->grid_R + 1), vf, vc, V, c->funcs.as<rin_func_desc>(), F, negate,
+                c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
         else
-            eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, FastDiv{}, vf, vc, V,
-                c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
-                &dctr->n_zero);
+            eval_mi_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, FastDiv{}, vf, vc, V,
+                c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), &dctr->n_zero);
+        ++c->launches;
     } else {
-        ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
-            negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr, &dctr->n_zero);
+        if (c->have_funcs) {
+            const size_t smem = F * sizeof(rin_func_desc);
+            const int g = grid_for((vc + EV_VPT - 1) / EV_VPT, 256, sm, 8);
+            if (c->grid_R)
+                eval_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1,
+                    make_fastdiv(c->grid_R + 1), vf, vc, V,
+                    c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
+                    &dctr->n_zero);
+            else
+                eval_kernel<false><<<g, 256, smem, s>>>(c->pts.as<double>(), nullptr, 0, FastDiv{}, vf, vc, V,
+                    c->funcs.as<rin_func_desc>(), F, negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr,
+                    &dctr->n_zero);
+        } else {
+            ingest_values_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->rowmajor.as<double>(), vf, vc, V, F,
+                negate, c->vals.as<double>(), c->vmask.as<uint2>(), nullptr, &dctr->n_zero);
+        }
+        // "highest func": masks of the maximal materials replace the sign masks
+        CK(cudaMemsetAsync(&dctr->n_zero, 0, 8, s));
+        highest_material_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->vals.as<double>(), vf, vc, V, F,
+            c->vmask.as<uint2>(), &dctr->n_zero);
+        c->launches += 2;
     }
-    // "highest func": masks of the maximal materials replace the sign masks
-    CK(cudaMemsetAsync(&dctr->n_zero, 0, 8, s));
-    highest_material_kernel<<<grid_for(vc, 256, sm, 8), 256, 0, s>>>(c->vals.as<double>(), vf, vc, V, F,
-        c->vmask.as<uint2>(), &dctr->n_zero);
     EVREC(c->kev[1]);
     CK(cudaGetLastError());
 
@@ -2673,6 +2748,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     EVREC(c->kev[3]);
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
+    c->launches += 2;
     CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const uint32_t A = h.filt.n_active;
@@ -2684,6 +2760,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, A, c->act_tet.as<uint32_t>(),
             c->act_mask.as<uint32_t>(), c->act_cap, tile_slots);
         CK(cudaGetLastError());
+        ++c->launches;
     }
 
     rin_counts& n = c->counts;
@@ -2711,11 +2788,15 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             use_secondary, c->rec_ref.as<uint32_t>(),
             c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_tie_faces);
         CK(cudaGetLastError());
+        ++c->launches;
     }
 
-    // ---- K4: general kernels (arena grows on overflow)
+    // ---- K4 + K5a: general kernels (arena grows on overflow), counts + offsets; ONE read-back for both
     EVREC(c->ev[ST_GENERAL]);
+    const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
+    unsigned n_gated = 0;
     if (A) {
+        CK(c->status.ensure((size_t)a_tiles * 16 + 64));
         const uint32_t est = use_lookup ? (h.filt.n_kmore + h.filt.n_k2) : A;
         const int small_blocks = (int)std::max<uint32_t>(
             1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
@@ -2736,7 +2817,18 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
                 c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
                 c->rec_ref.as<uint32_t>(), &dctr->gen);
             CK(cudaGetLastError());
+            // counts + offsets ride behind the general kernels (a record that did not fit reads as the empty record)
+            EVREC(c->ev[ST_SCAN]);
+            CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
+            if (attempt) CK(cudaMemsetAsync(&dctr->scan, 0, sizeof(ScanTotals), s));
+            count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
+                c->act_cap, A, c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
+                c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
+            CK(cudaGetLastError());
+            c->launches += 3;
             CK(cudaMemcpyAsync(&h.gen, &dctr->gen, sizeof(GeneralCounters), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(&h.scan, &dctr->scan, sizeof(ScanTotals), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(&n_gated, &dctr->n_tie_faces, 4, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             if (h.gen.err)
                 return fail(h.gen.err, "per-tet arrangement failed in tet " + std::to_string(h.gen.err_tet) +
@@ -2754,19 +2846,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     }
     n.num_general_tets = h.gen.n_general;
 
-    // ---- K5a: counts + offsets
-    EVREC(c->ev[ST_SCAN]);
-    const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
-    if (A) {
-        CK(c->status.ensure((size_t)a_tiles * 16 + 64));
-        CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
-        count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
-            c->act_cap, A, c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
-            c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h.scan, &dctr->scan, sizeof(ScanTotals), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-    }
+    if (!A) EVREC(c->ev[ST_SCAN]);
     const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
 
     // ---- K5b: emit
@@ -2777,14 +2857,9 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     CK(c->fv_ref.ensure((size_t)std::max(NFV, 1u) * 4));
     // tie tets exist: boundary faces carry the material set of their inside cell
     uint32_t* bf_mask = nullptr;
-    {
-        unsigned n_gated = 0;
-        CK(cudaMemcpyAsync(&n_gated, &dctr->n_tie_faces, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (n_gated) {
-            CK(c->bf_mask.ensure((size_t)std::max(NFc, 1u) * W * 4));
-            bf_mask = c->bf_mask.as<uint32_t>();
-        }
+    if (n_gated) {
+        CK(c->bf_mask.ensure((size_t)std::max(NFc, 1u) * W * 4));
+        bf_mask = c->bf_mask.as<uint32_t>();
     }
     if (A) {
         emit_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(), c->act_tet.as<uint32_t>(),
@@ -2793,6 +2868,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             c->cand_pay.as<uint4>(), c->face_hdr.as<uint4>(), c->fv_ref.as<uint32_t>(), bf_mask,
             &dctr->n_bndry_faces);
         CK(cudaGetLastError());
+        ++c->launches;
     }
 
     // ---- K6: dedup (hash-min + rank)
@@ -2808,10 +2884,13 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         CK(cudaMemsetAsync(c->table.p, 0xff, (size_t)tsize * 4, s));
         hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
             c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
-        // degenerate ties: reserved boundary-face slots exist -> match them across tets
+        // degenerate ties: reserved boundary-face slots exist -> match them across tets (only tie tets reserve
+        // slots: without them nothing has to be read back here)
         unsigned n_slots = 0;
-        CK(cudaMemcpyAsync(&n_slots, &dctr->n_bndry_faces, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        if (n_gated) {
+            CK(cudaMemcpyAsync(&n_slots, &dctr->n_bndry_faces, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
         h.n_bndry_faces = n_slots;
         if (n_slots) {
             uint32_t t2 = 1024;
@@ -2843,6 +2922,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             hash_insert_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
                 c->cand_pay.as<uint4>(), NC, c->table.as<uint32_t>(), tsize - 1, c->slot_of.as<uint32_t>());
             CK(cudaGetLastError());
+            c->launches += 5;
             unsigned bad = 0;
             CK(cudaMemcpyAsync(&bad, &dctr->n_unique, 4, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
@@ -2856,20 +2936,18 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), c->status.as<unsigned long long>(), &dctr->rank_tile,
             &dctr->n_unique);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        NV = h.n_unique;
+        c->launches += 2; // hash_insert, rank_reps
     }
 
-    // ---- K7: unique vertices + xyz
+    // ---- K7: unique vertices + xyz (their number arrives with the final read-back: sized for the candidates)
     EVREC(c->ev[ST_VERTS]);
-    CK(c->v_tet.ensure((size_t)std::max(NV, 1u) * 4));
-    CK(c->v_local.ensure(std::max(NV, 1u)));
-    CK(c->v_size.ensure(std::max(NV, 1u)));
-    CK(c->v_simplex.ensure((size_t)std::max(NV, 1u) * 16));
-    CK(c->v_funcs.ensure((size_t)std::max(NV, 1u) * 16));
-    CK(c->v_xyz.ensure((size_t)std::max(NV, 1u) * 24));
-    CK(c->v_key.ensure((size_t)std::max(NV, 1u) * 16));
+    CK(c->v_tet.ensure((size_t)std::max(NC, 1u) * 4));
+    CK(c->v_local.ensure(std::max(NC, 1u)));
+    CK(c->v_size.ensure(std::max(NC, 1u)));
+    CK(c->v_simplex.ensure((size_t)std::max(NC, 1u) * 16));
+    CK(c->v_funcs.ensure((size_t)std::max(NC, 1u) * 16));
+    CK(c->v_xyz.ensure((size_t)std::max(NC, 1u) * 24));
+    CK(c->v_key.ensure((size_t)std::max(NC, 1u) * 16));
     if (NC) {
         write_verts_mi_kernel<<<grid_for(NC, 256, sm, 8), 256, 0, s>>>(c->cand_key.as<uint4>(),
             c->cand_pay.as<uint4>(), c->rep.as<uint32_t>(), c->vid.as<uint32_t>(), NC, c->tets.as<uint4>(),
@@ -2877,6 +2955,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             c->v_size.as<uint8_t>(), c->v_simplex.as<uint4>(), c->v_funcs.as<uint4>(), c->v_xyz.as<double>(),
             c->v_key.as<uint4>());
         CK(cudaGetLastError());
+        ++c->launches;
     }
 
     // ---- faces
@@ -2895,6 +2974,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             NFV, c->f_off.as<uint32_t>(), c->f_toff.as<uint32_t>(), c->f_tets.as<uint32_t>(),
             c->f_funcs.as<uint32_t>());
         CK(cudaGetLastError());
+        c->launches += NFV ? 2 : 1;
     } else {
         // drop the boundary-face slots that were not switched on
         CK(c->tmp_fverts.ensure((size_t)std::max(NFV, 1u) * 4));
@@ -2913,6 +2993,7 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             c->f_off.as<uint32_t>(), c->f_verts.as<uint32_t>(), c->f_toff.as<uint32_t>(),
             c->f_tets.as<uint32_t>(), c->f_funcs.as<uint32_t>(), 1);
         CK(cudaGetLastError());
+        c->launches += 4;
         uint32_t ht[3];
         CK(cudaMemcpyAsync(ht, totals, 12, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -2921,7 +3002,14 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
         NFT = ht[2];
     }
     EVREC(c->ev[ST_COUNT]);
-    CK(cudaStreamSynchronize(s));
+    {
+        Counters* hp = static_cast<Counters*>(c->h_pinned);
+        CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (NC) NV = hp->n_unique;
+        h.n_exact_classify = hp->n_exact_classify;
+        h.gen.n_exact = hp->gen.n_exact;
+    }
     if (c->stage_timing) {
         for (int i = 0; i < ST_COUNT; ++i) CK(cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]));
         CK(cudaEventElapsedTime(&c->kernel_ms[0], c->kev[0], c->kev[1]));

@@ -86,6 +86,7 @@ def lib():
         L.rin_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.rin_exchange_nccl.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
         L.rin_get_exchange_time.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.rin_get_exchange_parts.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_run_exchange.argtypes = [C.c_void_p, C.c_int, C.c_uint32] + [C.POINTER(C.c_uint64)] * 4
         L.rin_get_exchange_offsets.argtypes = [C.c_void_p, C.c_void_p]
         L.rin_robust_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -292,6 +293,11 @@ class Context:
         ms = C.c_float()
         self._check(lib().rin_get_exchange_time(self._h, C.byref(ms)))
         return ms.value
+
+    def exchange_parts(self):
+        ms = (C.c_float * 10)()
+        self._check(lib().rin_get_exchange_parts(self._h, ms))
+        return [float(x) for x in ms]
 
     def get_complexes(self, mode, tet_ids):
         """Full per-tet complexes (layout in include/rin_b200.h) -> (offsets, words)."""

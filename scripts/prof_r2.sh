@@ -7,9 +7,9 @@ mkdir -p gpurun_out
 timeout 200 python bench.py --config $cfg --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_r2_$tag.json 2> gpurun_out/bench_r2_$tag.err; echo "bench rc=$?"
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r2_$tag.csv \
     python bench.py --config $cfg --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch.log 2>&1; echo "ncu list rc=$?"
-skip=24; [ "$cfg" = "C3" ] && skip=45
+skip=24; cnt=8; if [ "$cfg" = "C3" ]; then skip=38; cnt=13; fi
 timeout 300 ncu --set full --clock-control none --import-source on \
-    -k regex:"eval_kernel|filter_classify|general_ia_small|general_ia_mid|emit_kernel|insert_kernel|rank_verts|faces_kernel|filter_mi|highest|emit_mi|hash_insert|rank_reps|write_verts|general_mi|classify_mi|count_scan|write_faces_mi" --launch-skip $skip --launch-count ${NCU_COUNT:-8} \
+    -k regex:"eval_kernel|eval_mi|filter_classify|general_ia_small|general_ia_mid|emit_kernel|insert_kernel|rank_verts|faces_kernel|filter_mi|highest|emit_mi|hash_insert|rank_reps|write_verts|general_mi|classify_mi|count_scan|write_faces_mi" --launch-skip $skip --launch-count ${NCU_COUNT:-$cnt} \
     -f -o gpurun_out/ncu_r2_$tag python bench.py --config $cfg --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 (echo "# ncu --set full --clock-control none, config $cfg, one launch of each pipeline kernel (scripts/prof_r2.sh $tag $cfg)"; echo; python scripts/ncu_summary.py gpurun_out/ncu_r2_$tag.ncu-rep) > gpurun_out/ncu_r2_${tag}_summary.md
 python scripts/ncu_traffic.py gpurun_out/ncu_r2_$tag.ncu-rep $cfg "profiles/ncu_r2_${tag}_summary.md (ncu --set full, scripts/prof_r2.sh $tag $cfg)" > gpurun_out/ncu_traffic_$tag.json

@@ -131,14 +131,15 @@ def nested_components_case():
 
 def test_cell_grouping_mode_through_the_gpu_drop_in():
     """useTopoRayShooting = false: maps of the second extract_iso_mesh overload from the device
-    (rin_tet_maps), simplicial-cell grouping by the reference's own code; equal to the CPU reference in the same
+    (rin_tet_maps), simplicial-cell graph from host/cell_graph.h; equal to the CPU reference in the same
     mode, and the same number of cells as ray shooting (the reference's Fig. 14 differential check)."""
     pts, tets, vals = nested_components_case()
     gpu = ref_run("ia", pts, tets, vals, ray=False, lib=dropin_lib())
     assert gpu.error == "" and gpu["success"][0] == 1
     cpu = ref_run("ia", pts, tets, vals, ray=False)
     assert gpu.stats["num_components"] == cpu.stats["num_components"] == 4
-    assert crs(gpu, "cells") == crs(cpu, "cells")
+    # cells in the same order; the shells inside a cell come out of a hash set in the reference (unspecified order)
+    assert [sorted(c) for c in crs(gpu, "cells")] == [sorted(c) for c in crs(cpu, "cells")]
     assert np.array_equal(gpu["cell_function_label"], cpu["cell_function_label"])
     shot = ref_run("ia", pts, tets, vals, ray=True, lib=dropin_lib())
     assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 5
@@ -158,7 +159,8 @@ def test_mi_cell_grouping_mode_through_the_gpu_drop_in():
     assert gpu.error == "" and gpu["success"][0] == 1
     cpu = ref_run("mi", pts, tets, vals, ray=False)
     assert gpu.stats["num_components"] == cpu.stats["num_components"] == 2
-    assert crs(gpu, "cells") == crs(cpu, "cells")
+    # cells in the same order; the shells inside a cell come out of a hash set in the reference (unspecified order)
+    assert [sorted(c) for c in crs(gpu, "cells")] == [sorted(c) for c in crs(cpu, "cells")]
     assert np.array_equal(gpu["cell_function_label"], cpu["cell_function_label"])
     shot = ref_run("mi", pts, tets, vals, ray=True, lib=dropin_lib())
     assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 4
