@@ -388,15 +388,19 @@ template <class Caps, int W>
 __device__ bool general_mi_one_warp(MIComplex<Caps>& cx, MIWarpScratch<Caps>& sc, uint32_t a,
     const uint4* __restrict__ tets, const uint32_t* __restrict__ act_tet, const uint32_t* __restrict__ act_mask,
     uint32_t cap, const double* __restrict__ vals, uint32_t V, uint8_t* __restrict__ arena, uint32_t arena_cap,
-    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int lane)
+    uint32_t* __restrict__ rec_ref, GeneralCounters* __restrict__ gc, bool last_tier, int lane, int skip = 0)
 {
     const uint4 tv = __ldg(&tets[act_tet[a]]);
-    bool first = true;
+    bool first = skip == 0; // skip > 0: the complex already holds the first `skip` materials (tabulated start)
     for (int w = 0; w < W; ++w) {
         uint32_t mm = act_mask[(size_t)w * cap + a];
         while (mm) {
             const int f = w * 32 + __ffs(mm) - 1;
             mm &= mm - 1;
+            if (skip > 0) {
+                --skip;
+                continue;
+            }
             double pv[4];
             pv[0] = __ldg(&vals[(size_t)f * V + tv.x]);
             pv[1] = __ldg(&vals[(size_t)f * V + tv.y]);
@@ -444,6 +448,8 @@ __device__ bool general_mi_one_warp(MIComplex<Caps>& cx, MIWarpScratch<Caps>& sc
     return done != 0;
 }
 
+__device__ __forceinline__ int mi3_key(const double p0[4], const double p1[4], const double p2[4], unsigned* nex);
+
 struct alignas(16) MISmallSlot
 {
     MIComplex<MICapsSmall> cx;
@@ -456,7 +462,8 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_mi_small_kernel(
     const uint32_t* __restrict__ act_mask, uint32_t cap, const uint32_t* __restrict__ small_list,
     uint32_t* __restrict__ ovf_list, const double* __restrict__ vals, uint32_t V,
     uint8_t* __restrict__ arena, uint32_t arena_cap, uint32_t* __restrict__ rec_ref,
-    GeneralCounters* __restrict__ gc)
+    GeneralCounters* __restrict__ gc, const MIComplex<MICapsSmall>* __restrict__ cx3 = nullptr,
+    const uint32_t* __restrict__ lut3cx = nullptr)
 {
     extern __shared__ __align__(16) uint8_t s_raw_mi[];
     MISmallSlot* s_slot = reinterpret_cast<MISmallSlot*>(s_raw_mi);
@@ -464,9 +471,61 @@ __global__ void __launch_bounds__(GEN_SMALL_WARPS * 32) general_mi_small_kernel(
     const uint32_t n = gc->n_small;
     for (uint32_t g = blockIdx.x * GEN_SMALL_WARPS + warp; g < n; g += gridDim.x * GEN_SMALL_WARPS) {
         const uint32_t a = small_list[g];
+        int skip = 0;
+        if (cx3) {
+            // Tabulated start (the analogue of the 2-plane start of general_ia_small_kernel): a tet with >= 4 materials
+            // whose first three have a tabulated key starts from the complete complex of those three and inserts only
+            // the rest.  Every branch of an insertion depends on exact signs alone, which the key determines
+            // (mi3_key), so the state equals what the insertions would have produced; the values are the tet's own.
+            int entry = -1;
+            double p0[4], p1[4], p2[4];
+            if (lane == 0 && !(rec_ref[a] & REF_GATED)) {
+                uint32_t m[W];
+                int kk = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    m[w] = act_mask[(size_t)w * cap + a];
+                    kk += __popc(m[w]);
+                }
+                if (kk >= 4) {
+                    const uint4 tv = __ldg(&tets[act_tet[a]]);
+                    const uint32_t vv[4] = {tv.x, tv.y, tv.z, tv.w};
+                    const int f0 = nth_set_bit(m, W, 0), f1 = nth_set_bit(m, W, 1), f2 = nth_set_bit(m, W, 2);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        p0[c] = __ldg(&vals[(size_t)f0 * V + vv[c]]);
+                        p1[c] = __ldg(&vals[(size_t)f1 * V + vv[c]]);
+                        p2[c] = __ldg(&vals[(size_t)f2 * V + vv[c]]);
+                    }
+                    unsigned ex = 0;
+                    const int key = mi3_key(p0, p1, p2, &ex);
+                    if (ex) atomicAdd(&gc->n_exact, ex);
+                    if (key >= 0 && lut3cx[key] != 0xffffffffu) entry = (int)lut3cx[key];
+                }
+            }
+            entry = __shfl_sync(0xffffffffu, entry, 0);
+            if (entry >= 0) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(cx3 + entry);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&s_slot[warp].cx);
+                for (int i = lane; i < (int)(sizeof(MIComplex<MICapsSmall>) / 4); i += 32) dst[i] = src[i];
+                __syncwarp();
+                if (lane == 0) {
+                    MIComplex<MICapsSmall>& cx = s_slot[warp].cx;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        cx.mval[0][c] = p0[c];
+                        cx.mval[1][c] = p1[c];
+                        cx.mval[2][c] = p2[c];
+                    }
+                    cx.n_exact = 0;
+                    cx.err = 0;
+                }
+                skip = 3;
+            }
+        }
         __syncwarp();
         if (!general_mi_one_warp<MICapsSmall, W>(s_slot[warp].cx, s_slot[warp].sc, a, tets, act_tet, act_mask, cap,
-                vals, V, arena, arena_cap, rec_ref, gc, false, lane)) {
+                vals, V, arena, arena_cap, rec_ref, gc, false, lane, skip)) {
             if (lane == 0) ovf_list[atomicAdd(&gc->n_ovf, 1u)] = a;
         }
         __syncwarp();
@@ -526,6 +585,30 @@ __device__ __forceinline__ int mi3_key(const double p0[4], const double p1[4], c
 }
 constexpr uint32_t MI3_KEYS = 1u << 18;
 constexpr uint32_t LUT3_MISS = 0xffffffffu;
+
+// dumps the complete 3-material complexes of the chosen witnesses (table generation; witness w owns vertices
+// 4w..4w+3 and materials 0..2): the start state of general_mi_small_kernel for tets with more materials
+__global__ void __launch_bounds__(GEN_THREADS) dump_mi3_kernel(const uint32_t* __restrict__ witness, uint32_t n,
+    const double* __restrict__ vals, uint32_t V, MIComplex<MICapsSmall>* __restrict__ out, int* __restrict__ err)
+{
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const uint32_t w = witness[g];
+        MIComplex<MICapsSmall> cx;
+        for (int f = 0; f < 3; ++f) {
+            double pv[4];
+            for (int c = 0; c < 4; ++c) pv[c] = vals[(size_t)f * V + 4 * w + c];
+            if (f == 0)
+                cx.init(pv);
+            else
+                cx.insert(pv);
+        }
+        if (cx.err) *err = cx.err;
+        cx.n_exact = 0;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&cx);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + g);
+        for (int i = 0; i < (int)(sizeof(MIComplex<MICapsSmall>) / 4); ++i) dst[i] = src[i];
+    }
+}
 
 // table generation: witness w owns vertices 4w..4w+3 and materials 0..2 with hashed values in (0, 1)
 __global__ void __launch_bounds__(256) mi3_witness_kernel(uint32_t n, uint32_t Vw, double* __restrict__ vals,

@@ -110,6 +110,7 @@ struct Lut
 {
     DevBuf lut1, lut2, blob;
     DevBuf cx2, lut2cx; // complete 2-plane complexes (start state of the general kernel) + key -> entry
+    DevBuf cx3, lut3cx; // MI: complete 3-material complexes + key -> entry (uint32, 0xffffffff = none)
     uint32_t blob_bytes = 0;
     uint32_t n_keys3 = 0; // MI: realised keys of the 3-material table
     bool built = false;
@@ -336,8 +337,11 @@ void rin_destroy(rin_ctx* c)
         &c->fgids, &c->ftable, &c->bkeys, &c->bids, &c->x_send, &c->x_recv1, &c->x_recv2, &c->x_table, &c->x_small, &c->x_ids_up, &c->x_ids_low, &c->x_cnt, &c->e_key, &c->e_slot, &c->e_table, &c->e_verts, &c->e_of_face,
         &c->e_cnt, &c->e_off, &c->e_pairs, &c->cx_out, &c->f_off, &c->f_verts,
         &c->f_toff, &c->f_tets, &c->f_funcs, &c->lut_ia.lut1, &c->lut_ia.lut2, &c->lut_ia.blob, &c->lut_ia.cx2, &c->lut_ia.lut2cx,
-        &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob};
+        &c->lut_mi.lut1, &c->lut_mi.lut2, &c->lut_mi.blob, &c->lut_mi.cx3, &c->lut_mi.lut3cx, &c->g_off, &c->g_verts,
+        &c->g_toff, &c->g_tets, &c->g_funcs, &c->x_status, &c->p_stage};
     for (auto* b : bufs) b->release();
+    for (auto& e : c->ev_x)
+        if (e) cudaEventDestroy(e);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev)
@@ -2811,7 +2815,10 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             general_mi_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
                 c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
                 c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V,
-                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen);
+                c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen,
+                (use_lookup && c->lut_mi.cx3.p && !getenv("RIN_NO_MI3_START")) ? c->lut_mi.cx3.as<MIComplex<MICapsSmall>>()
+                                                                                : nullptr,
+                c->lut_mi.lut3cx.as<uint32_t>());
             general_mi_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
                 c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
                 c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
@@ -3420,6 +3427,33 @@ int build_mi_tables(rin_ctx* c)
         CK3(cudaMemcpyAsync(L.lut2.p, lut3.data(), (size_t)MI3_KEYS * 4, cudaMemcpyHostToDevice, s));
         CK3(cudaStreamSynchronize(s));
         L.n_keys3 = NCH;
+        // complete complexes of the same witnesses: tets with >= 4 materials start from them (general_mi_small_kernel)
+        if (NCH) {
+            std::vector<uint32_t> wit(NCH), lut3cx(MI3_KEYS, 0xffffffffu);
+            uint32_t j = 0;
+            for (auto& kv : first) {
+                wit[j] = kv.second;
+                if (lut3[kv.first] != LUT3_MISS) lut3cx[kv.first] = j;
+                ++j;
+            }
+            CK3(d_g3.ensure((size_t)NCH * 4));
+            CK3(cudaMemcpyAsync(d_g3.p, wit.data(), (size_t)NCH * 4, cudaMemcpyHostToDevice, s));
+            CK3(L.cx3.ensure((size_t)NCH * sizeof(MIComplex<MICapsSmall>)));
+            CK3(L.lut3cx.ensure((size_t)MI3_KEYS * 4));
+            int* d_err = reinterpret_cast<int*>(&dctr->gen.err);
+            CK3(cudaMemsetAsync(d_err, 0, 4, s));
+            dump_mi3_kernel<<<sm * 4, GEN_THREADS, 0, s>>>(d_g3.as<uint32_t>(), NCH, d_v3.as<double>(), Vw3,
+                L.cx3.as<MIComplex<MICapsSmall>>(), d_err);
+            CK3(cudaGetLastError());
+            int herr = 0;
+            CK3(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, s));
+            CK3(cudaMemcpyAsync(L.lut3cx.p, lut3cx.data(), (size_t)MI3_KEYS * 4, cudaMemcpyHostToDevice, s));
+            CK3(cudaStreamSynchronize(s));
+            if (herr) { // never seen; without the start complexes the general kernel inserts every material
+                L.cx3.release();
+                L.lut3cx.release();
+            }
+        }
         cleanup3();
 #undef CK3
     }

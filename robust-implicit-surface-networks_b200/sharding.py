@@ -65,6 +65,38 @@ def balanced_slab_planes(active_per_plane, world):
     return best
 
 
+def slabs_of_equal_cost(cost_per_plane, world):
+    """Boundaries 0 = b_0 < ... < b_world = R that minimise the largest slab cost for a given cost of every cube
+    plane (bisection on the limit, greedy filling; every slab keeps at least one plane)."""
+    cost = np.asarray(cost_per_plane, np.float64)
+    R = len(cost)
+    if world >= R:
+        return [min(i, R) for i in range(world + 1)][:world] + [R]
+    pre = np.concatenate([[0.0], np.cumsum(cost)])
+
+    def plan(limit):
+        b, i = [0], 0
+        for s in range(world):
+            left = world - s - 1
+            j = i + 1
+            while j < R - left and pre[j + 1] - pre[i] <= limit:
+                j += 1
+            b.append(j)
+            i = j
+        return b if b[-1] == R else None
+
+    lo, hi = float(cost.max()), float(pre[-1])
+    best = plan(hi)
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        p = plan(mid)
+        if p is not None:
+            best, hi = p, mid
+        else:
+            lo = mid
+    return best
+
+
 class ExchangeState:
     """Per-run cache: the shared vertex window does not change between passes over the same mesh."""
 
