@@ -343,6 +343,15 @@ def main():
     sampler.start()                # that a timed region of a few milliseconds still gets its samples
     for _ in range(args.warmup):
         step()
+    # further untimed passes for about 0.4 s (the same number on every rank) so that the clock sampler sees the load
+    tw = time.perf_counter()
+    step()
+    extra = torch.tensor([min(2000, int(0.4 / max(time.perf_counter() - tw, 1e-5)))], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.broadcast(extra, 0)
+    extra_warmup = int(extra.item())
+    for _ in range(extra_warmup):
+        step()
     barrier()
     dev_ms = []
     split.update(run=0.0, exchange=0.0, n=0)
@@ -559,7 +568,8 @@ def main():
         # kernels of the neighbour exchange: counted by the library when it rides behind the run (rin_run_exchange)
         x_launches = 10 if (world > 1 and args.two_call_exchange) else 0
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "warmup": args.warmup, "warmup_extra_for_clock_sampling": extra_warmup + 1,
+                "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_text(config, R, mi),
                            "baseline_config": config if world == 1 else ("C5" if R == 256 else "C2-weak"),

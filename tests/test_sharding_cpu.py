@@ -63,3 +63,25 @@ def test_two_rank_exchange_reproduces_single_run(tmp_path, world):
     assert np.array_equal(fv, ref["face_verts"])                # faces refer to the same global ids
     sizes = np.concatenate([np.diff(p["face_offsets"]) for p in parts])
     assert np.array_equal(sizes, np.diff(ref["face_offsets"]))
+
+
+def test_slabs_of_equal_cost_and_balanced_planes():
+    """Slab plans: every rank gets at least one cube plane, boundaries ascend, the largest slab cost is minimal
+    (checked against brute force on a small case)."""
+    import itertools
+    import sharding
+    rng = np.random.default_rng(5)
+    cost = rng.random(12) + 0.05
+    for world in (1, 2, 3, 5):
+        plan = sharding.slabs_of_equal_cost(cost, world)
+        assert plan[0] == 0 and plan[-1] == 12 and all(b > a for a, b in zip(plan, plan[1:])) and len(plan) == world + 1
+        worst = max(cost[a:b].sum() for a, b in zip(plan, plan[1:]))
+        best = min(max(cost[a:b].sum() for a, b in zip((0,) + cuts, cuts + (12,)))
+                   for cuts in itertools.combinations(range(1, 12), world - 1))
+        assert worst <= best * (1 + 1e-9)
+    assert sharding.slabs_of_equal_cost(np.ones(3), 5)[-1] == 3  # more ranks than planes: trailing ranks are empty
+    hist = np.zeros(16)
+    hist[6:10] = 1000.0  # the surface sits in the middle: the middle slabs get fewer planes
+    plan = sharding.balanced_slab_planes(hist, 4)
+    widths = np.diff(plan)
+    assert plan[0] == 0 and plan[-1] == 16 and widths.min() >= 1 and widths[0] > widths[1]
