@@ -259,11 +259,17 @@ __global__ void __launch_bounds__(256) eval_mi_kernel(const double* __restrict__
         for (int j = 0; j < MI_EVAL_VPT; ++j) {
             if (!ok[j]) continue;
             // "some two materials are exactly equal here" (tie gate of classify_mi_kernel)
+            // all pairs, fully unrolled; the slots of absent materials hold NaN, which equals nothing
+            double a[MI_EVAL_MAXF];
+#pragma unroll
+            for (int f = 0; f < MI_EVAL_MAXF; ++f)
+                a[f] = ((uint32_t)f < F) ? s_val[(f * MI_EVAL_VPT + j) * 256 + threadIdx.x]
+                                         : __longlong_as_double(0x7ff8000000000000ll);
             bool any_equal = false;
-            for (uint32_t f = 0; f + 1 < F; ++f) {
-                const double a = s_val[(f * MI_EVAL_VPT + j) * 256 + threadIdx.x];
-                for (uint32_t g = f + 1; g < F; ++g) any_equal |= (a == s_val[(g * MI_EVAL_VPT + j) * 256 + threadIdx.x]);
-            }
+#pragma unroll
+            for (int f = 0; f < MI_EVAL_MAXF; ++f)
+#pragma unroll
+                for (int g = f + 1; g < MI_EVAL_MAXF; ++g) any_equal |= (a[f] == a[g]);
             if (mx[j] != mx[j]) H[j] = 0; // every value NaN: nothing compares equal to the maximum
             vmask[v[j]] = make_uint2(H[j], any_equal ? 1u : 0u);
             tied += (__popc(H[j]) > 1);
