@@ -1,10 +1,10 @@
-// The implicit-arrangement pass as eight launches with no host synchronisation in between:
+// The implicit-arrangement pass as nine launches with no host synchronisation in between:
 //
 //   eval_*_kernel            K1  function values (SoA) + per-vertex sign masks
 //   filter_classify_kernel   K2  active-function filter + table dispatch, tile-local ordered compaction
 //   general_ia_small_kernel  K4  general per-tet arrangement, <= 4 functions (kernels_ia.cuh)
-//   general_ia_mid_kernel    K4  more functions / overflows (kernels_ia.cuh) + exclusive scan of the per-tile
-//                                totals in its last block
+//   general_ia_mid_kernel    K4  more functions / overflows (kernels_ia.cuh)
+//   scan_tiles5_kernel           exclusive scan of the per-tile totals (one block of 32 warps)
 //   emit_kernel              K5  ordered active list, canonical vertex keys
 //   insert_kernel            K6  hash-min insertion of the shareable candidates
 //   rank_verts_kernel        K6+K7  first-occurrence ranking, IsoVert records, coordinates

@@ -756,11 +756,12 @@ int rin_download_values(rin_ctx* c, double* out)
     CK(cudaSetDevice(c->device));
     const uint64_t V = c->run_V, VS = c->run_VS;
     const uint32_t F = c->run_F;
-    std::vector<double> soa((size_t)VS * F);
-    CK(cudaMemcpyAsync(soa.data(), c->vals.p, soa.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    // rows of V values at a pitch of VS (the padding between rows is never written)
+    std::vector<double> soa((size_t)V * F);
+    CK(cudaMemcpy2DAsync(soa.data(), V * 8, c->vals.p, VS * 8, V * 8, F, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (uint64_t v = 0; v < V; ++v)
-        for (uint32_t f = 0; f < F; ++f) out[v * F + f] = soa[(size_t)f * VS + v];
+        for (uint32_t f = 0; f < F; ++f) out[v * F + f] = soa[(size_t)f * V + v];
     return RIN_OK;
 }
 
@@ -2366,9 +2367,12 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             fa.vals, VS, c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
         general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
             (uint32_t)tl_stride, lists, lists + list_cap, nullptr, fa.vals, VS,
-            c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap, sa);
+            c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap, TileScanArgs{});
+        // exclusive scan of the per-tile totals: one block of 32 warps (the last block of the mid tier has four warps
+        // only: 13 us at 2048 tiles, 80 us at 16384)
+        scan_tiles5_kernel<<<1, 1024, 0, s>>>(sa);
         CK(cudaGetLastError());
-        c->launches += 2;
+        c->launches += 3;
         EVREC(c->ev[ST_SCAN]);
 
         auto check_general = [&](const Counters& hc, bool& again) -> int {
