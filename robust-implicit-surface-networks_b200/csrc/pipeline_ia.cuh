@@ -51,8 +51,8 @@ __device__ __forceinline__ uint4 grid_tet(uint32_t R, const FastDiv dR, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: evaluation + sign masks, EV_VPT vertices per thread and iteration: the function kind is branched
-// on once per function (warp-uniform), one descriptor fetch serves all the thread's vertices.
+// K1: evaluation + sign masks, EV_VPT consecutive vertices per thread (128-bit stores): the function kind is
+// branched on once per function (warp-uniform), one descriptor fetch serves all the thread's vertices.
 // GRID: coordinates come from the three axis tables, nothing else is read.
 // PACK (F <= 16): only the packed word P | N << 16 is written, else the (P, N) pairs per 32 functions.
 // VS = row stride of vals / vmask (V rounded up so that every row starts on a 128-byte boundary).
@@ -133,25 +133,48 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ pt
         reinterpret_cast<double*>(s_funcs)[i] = reinterpret_cast<const double*>(funcs)[i];
     __syncthreads();
     unsigned zeros = 0;
-    const uint32_t step = gridDim.x * blockDim.x * EV_VPT;
-    for (uint32_t i0 = blockIdx.x * blockDim.x * EV_VPT + threadIdx.x; i0 < v_count; i0 += step) {
+    // A thread owns EV_VPT = 4 CONSECUTIVE vertices starting at a multiple of 4: its values of one function are 32
+    // contiguous bytes of the row (two 128-bit stores, a warp writes 1 KB contiguously), its packed masks one 128-bit
+    // store; on a generated grid the four vertices share one index decomposition unless the run crosses a grid line.
+    const uint32_t v_end = v_first + v_count;
+    const uint32_t g_first = v_first / EV_VPT, g_end = (v_end + EV_VPT - 1) / EV_VPT;
+    for (uint32_t g = g_first + blockIdx.x * blockDim.x + threadIdx.x; g < g_end; g += gridDim.x * blockDim.x) {
+        const uint32_t vb = g * EV_VPT;
         double x[EV_VPT], y[EV_VPT], z[EV_VPT];
-        uint32_t v[EV_VPT];
         bool ok[EV_VPT];
+        bool all = true;
 #pragma unroll
         for (int j = 0; j < EV_VPT; ++j) {
-            const uint32_t idx = i0 + j * blockDim.x;
-            ok[j] = idx < v_count;
-            v[j] = v_first + (ok[j] ? idx : 0u);
-            if (GRID) {
-                const uint32_t ij = fd_div(v[j], dN), k = v[j] - ij * N, ii = fd_div(ij, dN), jj = ij - ii * N;
-                x[j] = __ldg(&axes[ii]);
-                y[j] = __ldg(&axes[N + jj]);
-                z[j] = __ldg(&axes[2 * N + k]);
+            ok[j] = vb + j >= v_first && vb + j < v_end;
+            all &= ok[j];
+        }
+        if (GRID) {
+            const uint32_t ij = fd_div(vb, dN), k = vb - ij * N, ii = fd_div(ij, dN), jj = ij - ii * N;
+            if (k + EV_VPT <= N) {
+                const double xs = __ldg(&axes[ii]), ys = __ldg(&axes[N + jj]);
+#pragma unroll
+                for (int j = 0; j < EV_VPT; ++j) {
+                    x[j] = xs;
+                    y[j] = ys;
+                    z[j] = __ldg(&axes[2 * N + k + j]);
+                }
             } else {
-                x[j] = __ldg(&pts[3 * (size_t)v[j]]);
-                y[j] = __ldg(&pts[3 * (size_t)v[j] + 1]);
-                z[j] = __ldg(&pts[3 * (size_t)v[j] + 2]);
+#pragma unroll
+                for (int j = 0; j < EV_VPT; ++j) {
+                    const uint32_t v = ok[j] ? vb + j : v_first;
+                    const uint32_t ij2 = fd_div(v, dN), k2 = v - ij2 * N, i2 = fd_div(ij2, dN), j2 = ij2 - i2 * N;
+                    x[j] = __ldg(&axes[i2]);
+                    y[j] = __ldg(&axes[N + j2]);
+                    z[j] = __ldg(&axes[2 * N + k2]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EV_VPT; ++j) {
+                const size_t v = ok[j] ? vb + j : v_first;
+                x[j] = __ldg(&pts[3 * v]);
+                y[j] = __ldg(&pts[3 * v + 1]);
+                z[j] = __ldg(&pts[3 * v + 2]);
             }
         }
         for (uint32_t w = 0; w * 32 < F; ++w) {
@@ -162,25 +185,40 @@ __global__ void __launch_bounds__(256) eval_kernel(const double* __restrict__ pt
             for (uint32_t f = w * 32; f < fe; ++f) {
                 double val[EV_VPT];
                 eval_func_n(s_funcs[f], x, y, z, val);
-                double* __restrict__ row = vals + (size_t)f * VS;
+                double* __restrict__ row = vals + (size_t)f * VS + vb;
                 const uint32_t bit = 1u << (f & 31);
 #pragma unroll
                 for (int j = 0; j < EV_VPT; ++j) {
                     if (negate) val[j] = val[j] * -1; // csg(): funcVals * -1 (src/csg.cpp:37)
-                    if (ok[j]) row[v[j]] = val[j];
                     if (val[j] > 0) P[j] |= bit;
                     if (val[j] < 0) Nn[j] |= bit;
                 }
+                if (all) {
+                    reinterpret_cast<double2*>(row)[0] = make_double2(val[0], val[1]);
+                    reinterpret_cast<double2*>(row)[1] = make_double2(val[2], val[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < EV_VPT; ++j)
+                        if (ok[j]) row[j] = val[j];
+                }
+            }
+            if (vmask16) {
+                if (all)
+                    *reinterpret_cast<uint4*>(vmask16 + vb) = make_uint4(P[0] | (Nn[0] << 16), P[1] | (Nn[1] << 16),
+                        P[2] | (Nn[2] << 16), P[3] | (Nn[3] << 16));
+                else {
+#pragma unroll
+                    for (int j = 0; j < EV_VPT; ++j)
+                        if (ok[j]) vmask16[vb + j] = P[j] | (Nn[j] << 16);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EV_VPT; ++j)
+                    if (ok[j]) vmask[(size_t)w * VS + vb + j] = make_uint2(P[j], Nn[j]);
             }
 #pragma unroll
             for (int j = 0; j < EV_VPT; ++j)
-                if (ok[j]) {
-                    if (vmask16)
-                        vmask16[v[j]] = P[j] | (Nn[j] << 16);
-                    else
-                        vmask[(size_t)w * VS + v[j]] = make_uint2(P[j], Nn[j]);
-                    zeros += (fe - w * 32) - __popc(P[j] | Nn[j]);
-                }
+                if (ok[j]) zeros += (fe - w * 32) - __popc(P[j] | Nn[j]);
         }
     }
     // num_degenerate_vertex counts (vertex, function) pairs with value 0 (src/implicit_arrangement.cpp:69-73)
