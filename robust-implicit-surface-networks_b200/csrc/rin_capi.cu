@@ -182,6 +182,7 @@ struct rin_ctx
     DevBuf tmp_fverts, bfkeys, frep, fdup, fpos, bf_mask; // degenerate boundary-face dedup
     DevBuf m_cnt, m_off, m_vmap, m_fmap, fpartner;        // cell-grouping maps (rin_tet_maps)
     bool ia_bndry_faces = false;                          // last run took the boundary-face path
+    bool skip_mid = false; // the last IA pass had no tet for the mid tier: its (empty) launch is left out, see run_ia_w
     uint64_t m_nv = 0, m_nf = 0;
     bool maps_ready = false;
     // outputs
@@ -2365,14 +2366,20 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             fa.tl_mask, (uint32_t)tl_stride, fa.small_list, lists + list_cap,
             c->lut_ia.built ? c->lut_ia.cx2.as<IAComplex<IACapsSmall>>() : nullptr, c->lut_ia.lut2cx.as<uint16_t>(),
             fa.vals, VS, c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap);
-        general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet, fa.tl_mask,
-            (uint32_t)tl_stride, lists, lists + list_cap, nullptr, fa.vals, VS,
-            c->arena.as<uint8_t>(), acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap, TileScanArgs{});
+        // The mid tier's launch costs ~10 us even when it has nothing to do (its shared-memory carve-out makes the SMs
+        // reconfigure twice).  When the previous pass had no tet for it, it is left out; the read-back tells whether
+        // this pass had one after all, and then the pass is repeated with it (never in a fused run + exchange, where
+        // every rank must take the same branch).
+        const bool skip_mid = c->skip_mid && !c->fuse && !sizing;
+        if (!skip_mid)
+            general_ia_mid_kernel<W><<<mid_blocks, GEN_MID_WARPS * 32, mid_smem, s>>>(c->tets.as<uint4>(), fa.tl_tet,
+                fa.tl_mask, (uint32_t)tl_stride, lists, lists + list_cap, nullptr, fa.vals, VS, c->arena.as<uint8_t>(),
+                acap, fa.tl_ref, &dctr->gen, fa.tile_tot, tile_slots, list_cap, TileScanArgs{});
         // exclusive scan of the per-tile totals: one block of 32 warps (the last block of the mid tier has four warps
         // only: 13 us at 2048 tiles, 80 us at 16384)
         scan_tiles5_kernel<<<1, 1024, 0, s>>>(sa);
         CK(cudaGetLastError());
-        c->launches += 3;
+        c->launches += skip_mid ? 2 : 3;
         EVREC(c->ev[ST_SCAN]);
 
         auto check_general = [&](const Counters& hc, bool& again) -> int {
@@ -2534,6 +2541,10 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
         bool again;
         int rc = check_general(h, again);
         if (rc) return rc;
+        if (skip_mid && (h.gen.n_big || h.gen.n_ovf)) { // the mid tier had work after all: once more, with it
+            c->skip_mid = false;
+            continue;
+        }
         const bool my_ok = !(again || h.overflow);
         int fr = RIN_OK;
         if (c->fuse) { // the same decision on every rank (it comes from the gathered records)
@@ -2623,6 +2634,7 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
             c->h_list = need + need / 8 + 1024;
         }
         c->table_size = tsize;
+        c->skip_mid = h.gen.n_big == 0 && h.gen.n_ovf == 0;
         c->h_unique = h.n_unique + h.n_unique / 8 + 1024;
         c->ia_bndry_faces = h.gen.n_bnd_faces != 0;
         const uint32_t NV = h.tot.n_cand ? h.n_unique : 0;
