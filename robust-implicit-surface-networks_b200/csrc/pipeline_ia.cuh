@@ -1120,7 +1120,7 @@ __device__ __forceinline__ void write_iso_vertex(const RankArgs& A, uint32_t c, 
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) rank_verts_kernel(const RankArgs A)
+__global__ void __launch_bounds__(256, 6) rank_verts_kernel(const RankArgs A)
 {
     __shared__ unsigned s_tile, s_base;
     __shared__ unsigned s_cnt[RV_ITEMS * 8];
