@@ -20,6 +20,7 @@
 #include "cell_graph.h"
 #include "rin_host.h"
 
+#include <chrono>
 #include <iostream>
 
 // the tables live inside the GPU library: the switches of the un-vendored library are no-ops here
@@ -32,6 +33,33 @@ void disable_lookup_table() {}
 namespace {
 
 using HalfFacePair = std::pair<std::pair<size_t, int>, std::pair<size_t, int>>;
+
+// One entry of the reference's timings.json: the label is pushed when the stage starts, the seconds when it ends
+// (also on an early return), like its ScopedTimer blocks (src/implicit_arrangement.cpp:408-623).
+struct StageTimer
+{
+    std::vector<double>& timings;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    StageTimer(const char* label, std::vector<std::string>& labels, std::vector<double>& timings_) : timings(timings_)
+    {
+        labels.emplace_back(label);
+    }
+    ~StageTimer() { timings.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
+};
+
+// the reference closes its cell stage with the total under "arrangement cells" / "material cells"; with several
+// components that entry becomes "...(other)" = total minus the sub-stages just recorded (:623-637)
+void close_cell_stage(bool mi, double total, size_t n_components, bool ray, std::vector<std::string>& labels,
+    std::vector<double>& timings)
+{
+    timings.push_back(total);
+    labels.emplace_back(mi ? "material cells" : "arrangement cells");
+    if (n_components > 1) {
+        labels.back() = mi ? "matCells(other)" : "arrCells(other)";
+        const size_t n = timings.size();
+        timings.back() = ray ? timings[n - 1] - timings[n - 2] : timings[n - 1] - timings[n - 2] - timings[n - 3];
+    }
+}
 
 template <typename Complex>
 void to_reference(const rin_host::TetComplex& in, Complex& out);
@@ -241,6 +269,7 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     Topology T;
     // N1 (edges on the device, patches / chains in the host layer of this repository, not the reference's)
     {
+        StageTimer st("isoEdge-face connectivity", timing_labels, timings);
         std::string err;
         if (!rin_host::mesh_edges(T.edges_of_face, iso_edges, err)) {
             std::cout << err << std::endl;
@@ -248,49 +277,67 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
         }
     }
     push_stat(stats_labels, stats, "num_iso_edges", iso_edges.size());
-    rin_host::mesh_patches(T.edges_of_face, iso_edges, iso_faces, patches, patch_function_label);
+    {
+        StageTimer st("patches", timing_labels, timings);
+        rin_host::mesh_patches(T.edges_of_face, iso_edges, iso_faces, patches, patch_function_label);
+    }
     push_stat(stats_labels, stats, "num_patches", patches.size());
-    T.patch_of_face.resize(iso_faces.size());
-    for (size_t p = 0; p < patches.size(); ++p)
-        for (size_t f : patches[p]) T.patch_of_face[f] = p;
-    rin_host::mesh_chains(iso_pts.size(), iso_edges, non_manifold_edges_of_vert, chains);
-    push_stat(stats_labels, stats, "num_chains", chains.size());
-    absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets;
-    if (hot.num_degenerate_vertex > 0) {
-        std::vector<bool> degenerate(pts.size(), false);
-        for (size_t v = 0; v < pts.size(); ++v)
-            for (size_t f = 0; f < n_func; ++f)
-                if (funcVals(v, f) == 0) degenerate[v] = true;
-        for (size_t t = 0; t < tets.size(); ++t)
-            for (size_t v : tets[t])
-                if (degenerate[v]) incident_tets[v].push_back(t);
+    {
+        StageTimer st("face-patch map", timing_labels, timings);
+        T.patch_of_face.resize(iso_faces.size());
+        for (size_t p = 0; p < patches.size(); ++p)
+            for (size_t f : patches[p]) T.patch_of_face[f] = p;
     }
     {
+        StageTimer st("chains", timing_labels, timings);
+        rin_host::mesh_chains(iso_pts.size(), iso_edges, non_manifold_edges_of_vert, chains);
+    }
+    push_stat(stats_labels, stats, "num_chains", chains.size());
+    absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets;
+    {
+        StageTimer st("vert-tet connectivity", timing_labels, timings);
+        if (hot.num_degenerate_vertex > 0) {
+            std::vector<bool> degenerate(pts.size(), false);
+            for (size_t v = 0; v < pts.size(); ++v)
+                for (size_t f = 0; f < n_func; ++f)
+                    if (funcVals(v, f) == 0) degenerate[v] = true;
+            for (size_t t = 0; t < tets.size(); ++t)
+                for (size_t v : tets[t])
+                    if (degenerate[v]) incident_tets[v].push_back(t);
+        }
+    }
+    {
+        StageTimer st("order patches around chains", timing_labels, timings);
         std::vector<size_t> wanted;
         for (size_t c = 0; c < chains.size(); ++c) face_order_tets(iso_edges[chains[c][0]], iso_faces, iso_verts, incident_tets, wanted);
         if (!lazy.need(std::move(wanted))) return false;
-    }
-    T.half_patch_pairs.resize(chains.size());
-    for (size_t c = 0; c < chains.size(); ++c) {
-        std::vector<HalfFacePair> face_pairs;
-        try {
-            compute_face_order(iso_edges[chains[c][0]], tets, iso_verts, iso_faces, cut_results, cut_result_index,
-                hot.func_in_tet, hot.start_index_of_tet, incident_tets, face_pairs);
-        } catch (std::exception& e) {
-            std::cout << "order patches failed: " << e.what() << std::endl;
-            return false;
+        T.half_patch_pairs.resize(chains.size());
+        for (size_t c = 0; c < chains.size(); ++c) {
+            std::vector<HalfFacePair> face_pairs;
+            try {
+                compute_face_order(iso_edges[chains[c][0]], tets, iso_verts, iso_faces, cut_results, cut_result_index,
+                    hot.func_in_tet, hot.start_index_of_tet, incident_tets, face_pairs);
+            } catch (std::exception& e) {
+                std::cout << "order patches failed: " << e.what() << std::endl;
+                return false;
+            }
+            for (const auto& fp : face_pairs)
+                T.half_patch_pairs[c].push_back({{T.patch_of_face[fp.first.first], fp.first.second},
+                    {T.patch_of_face[fp.second.first], fp.second.second}});
         }
-        for (const auto& fp : face_pairs)
-            T.half_patch_pairs[c].push_back({{T.patch_of_face[fp.first.first], fp.first.second},
-                {T.patch_of_face[fp.second.first], fp.second.second}});
     }
-    compute_shells_and_components(patches.size(), T.half_patch_pairs, shells, T.shell_of_half_patch, T.components,
-        T.component_of_patch);
+    {
+        StageTimer st("shells and components", timing_labels, timings);
+        compute_shells_and_components(patches.size(), T.half_patch_pairs, shells, T.shell_of_half_patch, T.components,
+            T.component_of_patch);
+    }
     push_stat(stats_labels, stats, "num_shells", shells.size());
     push_stat(stats_labels, stats, "num_components", T.components.size());
+    const auto cells_t0 = std::chrono::steady_clock::now();
     if (T.components.size() < 2) {
         for (size_t s = 0; s < shells.size(); ++s) arrangement_cells.push_back({s});
     } else if (use_topo_ray_shooting) {
+        StageTimer st("arrCells(ray shooting)", timing_labels, timings);
         std::vector<size_t> wanted;
         ray_shooting_tets(pts, tets, iso_verts, wanted);
         if (!lazy.need(std::move(wanted))) return false;
@@ -311,16 +358,24 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
         std::vector<std::pair<size_t, size_t>> tet_cell_of_simp_cell;
         std::vector<long long> simp_half_face_info;
         std::vector<size_t> simp_hFace_start_index;
-        rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
-            global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet, T.patch_of_face,
-            T.shell_of_half_patch,
-            [](const simplicial_arrangement::Arrangement<3>& cx, size_t f, size_t cell) {
-                return cx.faces[f].positive_cell == cell; // src/cell_connectivity.cpp:78
-            },
-            tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
-        rin_host::simplicial_cell_components(tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index,
-            arrangement_cells);
+        {
+            StageTimer st("arrCells(build simpCell graph)", timing_labels, timings);
+            rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
+                global_vId_start_index_of_tet, iso_fId_of_tet_face, iso_fId_start_index_of_tet, T.patch_of_face,
+                T.shell_of_half_patch,
+                [](const simplicial_arrangement::Arrangement<3>& cx, size_t f, size_t cell) {
+                    return cx.faces[f].positive_cell == cell; // src/cell_connectivity.cpp:78
+                },
+                tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
+        }
+        {
+            StageTimer st("arrCells(group simpCells into arrCells)", timing_labels, timings);
+            rin_host::simplicial_cell_components(tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index,
+                arrangement_cells);
+        }
     }
+    close_cell_stage(false, std::chrono::duration<double>(std::chrono::steady_clock::now() - cells_t0).count(),
+        T.components.size(), use_topo_ray_shooting, timing_labels, timings);
     push_stat(stats_labels, stats, "num_cells", arrangement_cells.size());
     lazy.report();
     std::vector<bool> sample(n_func);
@@ -362,6 +417,7 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     // ---- the reference's own host stages (src/material_interface.cpp:449-695)
     Topology T;
     {
+        StageTimer st("edge-face connectivity", timing_labels, timings);
         std::string err;
         if (!rin_host::mesh_edges(T.edges_of_face, MI_edges, err)) {
             std::cout << err << std::endl;
@@ -369,40 +425,58 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
         }
     }
     push_stat(stats_labels, stats, "num_MI_edges", MI_edges.size());
-    rin_host::mesh_patches(T.edges_of_face, MI_edges, MI_faces, patches, patch_function_label);
+    {
+        StageTimer st("patches", timing_labels, timings);
+        rin_host::mesh_patches(T.edges_of_face, MI_edges, MI_faces, patches, patch_function_label);
+    }
     push_stat(stats_labels, stats, "num_patches", patches.size());
-    T.patch_of_face.resize(MI_faces.size());
-    for (size_t p = 0; p < patches.size(); ++p)
-        for (size_t f : patches[p]) T.patch_of_face[f] = p;
-    rin_host::mesh_chains(MI_pts.size(), MI_edges, non_manifold_edges_of_vert, chains);
+    {
+        StageTimer st("face-patch map", timing_labels, timings);
+        T.patch_of_face.resize(MI_faces.size());
+        for (size_t p = 0; p < patches.size(); ++p)
+            for (size_t f : patches[p]) T.patch_of_face[f] = p;
+    }
+    {
+        StageTimer st("chains", timing_labels, timings);
+        rin_host::mesh_chains(MI_pts.size(), MI_edges, non_manifold_edges_of_vert, chains);
+    }
     push_stat(stats_labels, stats, "num_chains", chains.size());
     absl::flat_hash_map<size_t, std::vector<size_t>> incident_tets; // only filled for tied vertices upstream
     {
+        StageTimer st("vert-tet connectivity", timing_labels, timings);
+    }
+    {
+        StageTimer st("order patches around chains", timing_labels, timings);
         std::vector<size_t> wanted;
         for (size_t c = 0; c < chains.size(); ++c) face_order_tets(MI_edges[chains[c][0]], MI_faces, MI_verts, incident_tets, wanted);
         if (!lazy.need(std::move(wanted))) return false;
-    }
-    T.half_patch_pairs.resize(chains.size());
-    for (size_t c = 0; c < chains.size(); ++c) {
-        std::vector<HalfFacePair> face_pairs;
-        try {
-            compute_face_order(MI_edges[chains[c][0]], MI_faces, cut_results, cut_result_index, incident_tets, face_pairs);
-        } catch (std::exception& e) {
-            std::cout << "order patches failed: " << e.what() << std::endl;
-            return false;
+        T.half_patch_pairs.resize(chains.size());
+        for (size_t c = 0; c < chains.size(); ++c) {
+            std::vector<HalfFacePair> face_pairs;
+            try {
+                compute_face_order(MI_edges[chains[c][0]], MI_faces, cut_results, cut_result_index, incident_tets, face_pairs);
+            } catch (std::exception& e) {
+                std::cout << "order patches failed: " << e.what() << std::endl;
+                return false;
+            }
+            for (const auto& fp : face_pairs)
+                T.half_patch_pairs[c].push_back({{T.patch_of_face[fp.first.first], fp.first.second},
+                    {T.patch_of_face[fp.second.first], fp.second.second}});
         }
-        for (const auto& fp : face_pairs)
-            T.half_patch_pairs[c].push_back({{T.patch_of_face[fp.first.first], fp.first.second},
-                {T.patch_of_face[fp.second.first], fp.second.second}});
     }
-    compute_shells_and_components(patches.size(), T.half_patch_pairs, shells, T.shell_of_half_patch, T.components,
-        T.component_of_patch);
+    {
+        StageTimer st("shells and components", timing_labels, timings);
+        compute_shells_and_components(patches.size(), T.half_patch_pairs, shells, T.shell_of_half_patch, T.components,
+            T.component_of_patch);
+    }
     push_stat(stats_labels, stats, "num_shells", shells.size());
     push_stat(stats_labels, stats, "num_components", T.components.size());
+    const auto cells_t0 = std::chrono::steady_clock::now();
     if (T.components.size() < 2) {
         for (size_t s = 0; s < shells.size(); ++s) material_cells.push_back({s});
         if (material_cells.empty()) material_cells.push_back({Mesh_None}); // no interface at all (:619-623)
     } else if (use_topo_ray_shooting) {
+        StageTimer st("matCells(ray shooting)", timing_labels, timings);
         std::vector<size_t> wanted;
         ray_shooting_tets(pts, tets, MI_verts, wanted);
         if (!lazy.need(std::move(wanted))) return false;
@@ -423,16 +497,24 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
         std::vector<std::pair<size_t, size_t>> tet_cell_of_simp_cell;
         std::vector<long long> simp_half_face_info;
         std::vector<size_t> simp_hFace_start_index;
-        rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
-            global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet, T.patch_of_face,
-            T.shell_of_half_patch,
-            [](const simplicial_arrangement::MaterialInterface<3>& cx, size_t f, size_t cell) {
-                return cx.faces[f].positive_material_label == cx.cells[cell].material_label; // :227
-            },
-            tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
-        rin_host::simplicial_cell_components(tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index,
-            material_cells);
+        {
+            StageTimer st("matCells(build simpCell graph)", timing_labels, timings);
+            rin_host::simplicial_cell_adjacency(tets, cut_results, cut_result_index, global_vId_of_tet_vert,
+                global_vId_start_index_of_tet, MI_fId_of_tet_face, MI_fId_start_index_of_tet, T.patch_of_face,
+                T.shell_of_half_patch,
+                [](const simplicial_arrangement::MaterialInterface<3>& cx, size_t f, size_t cell) {
+                    return cx.faces[f].positive_material_label == cx.cells[cell].material_label; // :227
+                },
+                tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index);
+        }
+        {
+            StageTimer st("matCells(group simpCells into matCells)", timing_labels, timings);
+            rin_host::simplicial_cell_components(tet_cell_of_simp_cell, simp_half_face_info, simp_hFace_start_index,
+                material_cells);
+        }
     }
+    close_cell_stage(true, std::chrono::duration<double>(std::chrono::steady_clock::now() - cells_t0).count(),
+        T.components.size(), use_topo_ray_shooting, timing_labels, timings);
     push_stat(stats_labels, stats, "num_cells", material_cells.size());
     lazy.report();
     std::vector<double> sample(n_func);

@@ -2,22 +2,34 @@
 
 #include "../../include/rin_b200.h"
 
+#include <cstdlib>
 #include <iostream>
+#include <mutex>
 
 namespace rin_host {
 namespace {
 
+// One engine context per process, like the reference's process-global lookup tables (the entry points are not
+// re-entrant there either): created on first use on the device RIN_DEVICE names (default 0), destroyed at
+// exit.  Creation is guarded; calls that follow one another on different threads must be serialised by the caller.
 rin_ctx* g_ctx = nullptr;
+std::mutex g_ctx_mutex;
 size_t g_complexes_fetched = 0; // per-tet complexes fetched since the last hot-path call
 
 bool ensure_ctx(std::string& err)
 {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
     if (g_ctx) return true;
-    if (rin_create(0, &g_ctx) != RIN_OK) {
+    const char* dev = std::getenv("RIN_DEVICE");
+    if (rin_create(dev ? std::atoi(dev) : 0, &g_ctx) != RIN_OK) {
         err = rin_last_error();
         g_ctx = nullptr;
         return false;
     }
+    std::atexit([] {
+        if (g_ctx) rin_destroy(g_ctx);
+        g_ctx = nullptr;
+    });
     return true;
 }
 

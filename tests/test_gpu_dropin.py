@@ -144,6 +144,10 @@ def test_cell_grouping_mode_through_the_gpu_drop_in():
     shot = ref_run("ia", pts, tets, vals, ray=True, lib=dropin_lib())
     assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 5
     assert sorted(map(sorted, crs(shot, "cells"))) == sorted(map(sorted, crs(gpu, "cells")))
+    # timings.json keeps the reference's key set in both modes (src/implicit_arrangement.cpp:62-637)
+    assert list(gpu.timing_labels) == list(cpu.timing_labels)
+    assert list(shot.timing_labels) == list(ref_run("ia", pts, tets, vals, ray=True).timing_labels)
+    assert len(gpu["timings"]) == len(gpu.timing_labels) and (np.asarray(gpu["timings"]) >= 0).all()
 
 
 def test_mi_cell_grouping_mode_through_the_gpu_drop_in():
@@ -164,6 +168,9 @@ def test_mi_cell_grouping_mode_through_the_gpu_drop_in():
     assert np.array_equal(gpu["cell_function_label"], cpu["cell_function_label"])
     shot = ref_run("mi", pts, tets, vals, ray=True, lib=dropin_lib())
     assert shot.stats["num_cells"] == gpu.stats["num_cells"] == 4
+    assert list(gpu.timing_labels) == list(cpu.timing_labels)
+    assert list(shot.timing_labels) == list(ref_run("mi", pts, tets, vals, ray=True).timing_labels)
+    assert len(gpu["timings"]) == len(gpu.timing_labels)
 
 
 N1_CASES = [("ia", "C2", 24), ("ia", "3-sphere-3", 40), ("ia", "2-planesphere", 31), ("mi", "C3", 21),
