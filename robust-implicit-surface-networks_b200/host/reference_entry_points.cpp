@@ -253,8 +253,12 @@ bool implicit_arrangement(bool robust_test, bool use_lookup, bool use_secondary_
     std::vector<IsoVert> iso_verts;
     rin_host::HotPathOutput hot;
     if (!rin_host::implicit_arrangement_hot(use_lookup, use_secondary_lookup, pts, tets, funcVals.data(), n_func, false,
-            iso_pts, iso_faces, iso_verts, hot, timing_labels, timings, stats_labels, stats))
+            iso_pts, iso_faces, iso_verts, hot, timing_labels, timings, stats_labels, stats)) {
+        // -R: a per-tet computation that fails in the normal order is the reference's type 2 verdict (:330-332)
+        if (robust_test && hot.error.find("per-tet") != std::string::npos)
+            std::cout << "type 2 failure (crash in the normal order)." << std::endl;
         return false;
+    }
     if (robust_test) { // -R: verdict only, no mesh outputs (src/implicit_arrangement.cpp:329-343)
         iso_pts.clear();
         iso_faces.clear();
@@ -402,8 +406,11 @@ bool material_interface(bool robust_test, bool use_lookup, bool use_secondary_lo
     std::vector<MI_Vert> MI_verts;
     rin_host::HotPathOutput hot;
     if (!rin_host::material_interface_hot(use_lookup, use_secondary_lookup, pts, tets, funcVals.data(), n_func, MI_pts,
-            MI_faces, MI_verts, hot, timing_labels, timings, stats_labels, stats))
+            MI_faces, MI_verts, hot, timing_labels, timings, stats_labels, stats)) {
+        if (robust_test && hot.error.find("per-tet") != std::string::npos)
+            std::cout << "type 2 failure (crash in the normal order)." << std::endl;
         return false;
+    }
     if (robust_test) {
         MI_pts.clear();
         MI_faces.clear();
