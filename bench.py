@@ -148,20 +148,25 @@ CPU_LABELS = {"ia": ("func signs", "filter", "simp_arr(other)", "simp_arr(1 func
                      "compute xyz")}
 
 
+_CPU_SAMPLE = {}  # config -> (pts, tets) of the sample: built once, every step of the reference arm reuses it
+
+
 def cpu_reference_run(config):
     from helpers import make_funcs, orc_eval, orc_grid, orc_run, ref_lib, ref_run, synthetic_functions
     R, slabs = CPU_SLABS[config]
     mode = "mi" if config == "C3" else "ia"
     funcs = make_funcs(synthetic_functions(FUNCTION_SET[config]))
     N = R + 1
-    pts, tets = orc_grid(R)
     first = CPU_FIRST_SLAB.get(config, 0)
     n_t = slabs * 5 * R * R
     n_v = (slabs + 1) * N * N
-    v0, t0 = first * N * N, first * 5 * R * R
-    pts_s = pts[v0:v0 + n_v].copy()
-    tets_s = (tets[t0:t0 + n_t] - tets.dtype.type(v0)).copy()  # vertex ids relative to the sample's first plane
-    del pts, tets
+    if config not in _CPU_SAMPLE:
+        pts, tets = orc_grid(R)
+        v0, t0 = first * N * N, first * 5 * R * R
+        # vertex ids relative to the sample's first plane
+        _CPU_SAMPLE[config] = (pts[v0:v0 + n_v].copy(), (tets[t0:t0 + n_t] - tets.dtype.type(v0)).copy())
+        del pts, tets
+    pts_s, tets_s = _CPU_SAMPLE[config]
     t0 = time.perf_counter()
     vals = orc_eval(funcs, pts_s)  # load_functions restatement (stage 1 of the metric)
     t_eval = time.perf_counter() - t0
