@@ -406,8 +406,9 @@ template <int W>
 __global__ void __launch_bounds__(256) compact_active_kernel(const uint32_t* __restrict__ tl_tet,
     const uint32_t* __restrict__ tl_mask, size_t tl_stride, const uint2* __restrict__ tile_off,
     uint32_t n_tiles, uint32_t n_active, uint32_t* __restrict__ act_tet, uint32_t* __restrict__ act_mask,
-    uint32_t cap, uint32_t tile_slots = FILT_TILE)
+    uint32_t cap, uint32_t tile_slots = FILT_TILE, const unsigned* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) n_active = min(n_active, *n_dev); // launched for the capacity: the count is still on the device
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         // tile = last one with tile_off.x <= a
         uint32_t lo = 0, hi = n_tiles;
@@ -1042,14 +1043,16 @@ __global__ void __launch_bounds__(256) count_scan_kernel(const uint32_t* __restr
     const uint32_t* __restrict__ act_mask, uint32_t cap, uint32_t n_active,
     const uint8_t* __restrict__ lut_blob, const uint8_t* __restrict__ arena, uint4* __restrict__ offs,
     volatile unsigned long long* __restrict__ statusA, volatile unsigned long long* __restrict__ statusB,
-    ScanTotals* __restrict__ tot)
+    ScanTotals* __restrict__ tot, const unsigned* __restrict__ n_dev = nullptr)
 {
     __shared__ unsigned s_tile;
     __shared__ uint4 s_warp[8];
     __shared__ uint4 s_base;
+    if (n_dev) n_active = min(n_active, *n_dev); // launched for the capacity: the count is still on the device
     if (threadIdx.x == 0) s_tile = atomicAdd(&tot->tile_counter, 1u);
     __syncthreads();
     const unsigned tile = s_tile;
+    if ((size_t)tile * CS_TILE >= n_active) return; // beyond the count: no later tile looks back at this one
     const uint32_t a0 = tile * CS_TILE + threadIdx.x * CS_ITEMS; // CS_ITEMS consecutive active tets per thread
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 ci[CS_ITEMS];

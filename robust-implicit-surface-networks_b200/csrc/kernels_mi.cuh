@@ -643,8 +643,9 @@ __global__ void __launch_bounds__(256) classify_mi_kernel(const uint4* __restric
     uint32_t n_active, const double* __restrict__ vals, const uint2* __restrict__ vmask, uint32_t V, uint32_t F,
     const uint16_t* __restrict__ lut2, const uint32_t* __restrict__ lut3, int use_lookup, int use_secondary,
     uint32_t* __restrict__ rec_ref, uint32_t* __restrict__ small_list, uint32_t* __restrict__ big_list,
-    GeneralCounters* __restrict__ gc, unsigned* __restrict__ n_gated)
+    GeneralCounters* __restrict__ gc, unsigned* __restrict__ n_gated, const unsigned* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) n_active = min(n_active, *n_dev); // launched for the capacity: the count is still on the device
     unsigned exact = 0;
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_active; a += gridDim.x * blockDim.x) {
         uint32_t m[W];

@@ -175,6 +175,7 @@ struct rin_ctx
     DevBuf tl_ref, tile_tot, tile_pre;          // implicit-arrangement pass: record refs, tile totals / prefixes
     // sizes learnt from the previous pass (0 = unknown: the next pass sizes its buffers after the tile scan)
     uint32_t h_act = 0, h_list = 0, h_cand = 0, h_face = 0, h_fv = 0, h_unique = 0;
+    uint32_t h_act_mi = 0, h_gen_mi = 0; // material-interface pass: active / general tets of the previous pass (+ margin)
     uint32_t table_size = 0; // vertex hash table slots of the last IA pass
     DevBuf act_tet, act_mask, rec_ref, general_list, big_list, arena, offs;
     DevBuf cand_key, cand_pay, cand_src, face_hdr, fv_ref;
@@ -391,7 +392,7 @@ int rin_set_mesh_host(rin_ctx* c, const double* pts, uint64_t n_pts, const void*
     c->have_values = false;
     if (!same_shape) { // sizes learnt from the previous pass stay valid hints for a mesh of the same shape
         c->x_window = false;
-        c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+        c->h_act_mi = c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     }
     invalidate(c);
     return RIN_OK;
@@ -437,7 +438,7 @@ int rin_set_mesh_host_range(rin_ctx* c, uint64_t n_pts, uint64_t n_tets, const d
     c->have_values = false;
     if (!same_shape) {
         c->x_window = false;
-        c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+        c->h_act_mi = c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     }
     invalidate(c);
     return RIN_OK;
@@ -486,7 +487,7 @@ int rin_generate_grid(rin_ctx* c, uint32_t R, const double bmin[3], const double
     c->ghost_lo = c->ghost_hi = 0;
     c->v_first = c->v_count = 0;
     c->have_values = false;
-    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+    c->h_act_mi = c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     invalidate(c);
     return RIN_OK;
 }
@@ -504,7 +505,7 @@ int apply_tet_range(rin_ctx* c)
     c->v_first = 0;
     c->v_count = 0;
     c->x_window = false;
-    c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
+    c->h_act_mi = c->h_act = c->h_list = c->h_cand = c->h_face = c->h_fv = c->h_unique = 0;
     invalidate(c);
     if (c->t_count != 0 && (c->t_first != 0 || c->t_count != c->T)) {
         CK(cudaSetDevice(c->device));
@@ -2769,55 +2770,54 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     scan_tiles_kernel<<<1, 1024, 0, s>>>(c->tile_cnt.as<uint2>(), n_tiles, c->tile_off.as<uint2>(), &dctr->filt);
     CK(cudaGetLastError());
     c->launches += 2;
-    CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const uint32_t A = h.filt.n_active;
-    c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 16 + 1024);
+    // The number of active tets is read back here only when nothing is known about it; otherwise the kernels up to
+    // the count + scan are launched for the capacity learnt from the previous pass and read the count from device
+    // memory, and the first read-back of the pass is the merged one behind the count + scan.
+    const bool nosync = c->h_act_mi != 0 && c->act_cap >= c->h_act_mi && getenv("RIN_MI_SYNC") == nullptr;
+    const unsigned* dA = nosync ? &dctr->filt.n_active : nullptr;
+    uint32_t A = 0;  // active tets (exact once read back)
+    uint32_t An = 0; // launch bound and list stride until then
+    if (!nosync) {
+        CK(cudaMemcpyAsync(&h, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        A = An = h.filt.n_active;
+        c->act_cap = std::max<uint32_t>(c->act_cap, A + A / 8 + 1024);
+    } else
+        A = An = c->h_act_mi;
     CK(c->act_tet.ensure((size_t)c->act_cap * 4));
     CK(c->act_mask.ensure((size_t)c->act_cap * 4 * W));
-    if (A) {
-        compact_active_kernel<W><<<grid_for(A, 256, sm, 8), 256, 0, s>>>(c->tl_tet.as<uint32_t>(),
-            c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, A, c->act_tet.as<uint32_t>(),
-            c->act_mask.as<uint32_t>(), c->act_cap, tile_slots);
+    if (An) {
+        compact_active_kernel<W><<<grid_for(An, 256, sm, 8), 256, 0, s>>>(c->tl_tet.as<uint32_t>(),
+            c->tl_mask.as<uint32_t>(), tl_stride, c->tile_off.as<uint2>(), n_tiles, An, c->act_tet.as<uint32_t>(),
+            c->act_mask.as<uint32_t>(), c->act_cap, tile_slots, dA);
         CK(cudaGetLastError());
         ++c->launches;
     }
 
-    rin_counts& n = c->counts;
-    n = rin_counts{};
-    n.num_pts = c->V;
-    n.num_tets = c->t_count;
-    n.num_funcs = F;
-    n.num_degenerate_vertex = h.n_zero;
-    n.num_intersecting_tet = A;
-    n.num_k1 = h.filt.n_k1;
-    n.num_k2 = h.filt.n_k2;
-    n.num_kmore = h.filt.n_kmore;
-    n.num_active_funcs = h.filt.n_funcs;
-
     // ---- K3: classify
     EVREC(c->ev[ST_CLASSIFY]);
-    CK(c->rec_ref.ensure((size_t)std::max(A, 1u) * 4));
-    CK(c->general_list.ensure((size_t)std::max(A, 1u) * 4));
-    CK(c->big_list.ensure((size_t)std::max(A, 1u) * 8)); // [big | small-tier overflow]
-    CK(c->offs.ensure((size_t)std::max(A, 1u) * 16));
-    if (A) {
-        classify_mi_kernel<W><<<grid_for(A, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
-            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, A, c->vals.as<double>(),
+    CK(c->rec_ref.ensure((size_t)std::max(An, 1u) * 4));
+    CK(c->general_list.ensure((size_t)std::max(An, 1u) * 4));
+    CK(c->big_list.ensure((size_t)std::max(An, 1u) * 8)); // [big | small-tier overflow]
+    CK(c->offs.ensure((size_t)std::max(An, 1u) * 16));
+    if (An) {
+        classify_mi_kernel<W><<<grid_for(An, 256, sm, 4), 256, 0, s>>>(c->tets.as<uint4>(),
+            c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, An, c->vals.as<double>(),
             c->vmask.as<uint2>(), V, F, c->lut_mi.lut1.as<uint16_t>(), c->lut_mi.lut2.as<uint32_t>(), use_lookup,
             use_secondary, c->rec_ref.as<uint32_t>(),
-            c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_tie_faces);
+            c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>(), &dctr->gen, &dctr->n_tie_faces, dA);
         CK(cudaGetLastError());
         ++c->launches;
     }
 
     // ---- K4 + K5a: general kernels (arena grows on overflow), counts + offsets; ONE read-back for both
     EVREC(c->ev[ST_GENERAL]);
-    const uint32_t a_tiles = (A + CS_TILE - 1) / CS_TILE;
+    const uint32_t a_tiles = (An + CS_TILE - 1) / CS_TILE;
     unsigned n_gated = 0;
-    if (A) {
+    if (An) {
         CK(c->status.ensure((size_t)a_tiles * 16 + 64));
-        const uint32_t est = use_lookup ? (h.filt.n_kmore + h.filt.n_k2) : A;
+        const uint32_t est = nosync ? (use_lookup ? c->h_gen_mi : An)
+                                    : (use_lookup ? (h.filt.n_kmore + h.filt.n_k2) : An);
         const int small_blocks = (int)std::max<uint32_t>(
             1, std::min<uint32_t>((est + 64 + GEN_SMALL_WARPS - 1) / GEN_SMALL_WARPS, (uint32_t)sm * 14));
         const size_t small_smem = GEN_SMALL_WARPS * sizeof(MISmallSlot);
@@ -2830,14 +2830,14 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             // small tier: one tet per warp, complex in shared memory; capacity overflow -> ovf list
             general_mi_small_kernel<W><<<small_blocks, GEN_SMALL_WARPS * 32, small_smem, s>>>(
                 c->tets.as<uint4>(), c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap,
-                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V,
+                c->general_list.as<uint32_t>(), c->big_list.as<uint32_t>() + An, c->vals.as<double>(), V,
                 c->arena.as<uint8_t>(), acap, c->rec_ref.as<uint32_t>(), &dctr->gen,
                 (use_lookup && c->lut_mi.cx3.p && !getenv("RIN_NO_MI3_START")) ? c->lut_mi.cx3.as<MIComplex<MICapsSmall>>()
                                                                                 : nullptr,
                 c->lut_mi.lut3cx.as<uint32_t>());
             general_mi_big_kernel<W><<<sm * 4, GEN_THREADS, 0, s>>>(c->tets.as<uint4>(),
                 c->act_tet.as<uint32_t>(), c->act_mask.as<uint32_t>(), c->act_cap, c->big_list.as<uint32_t>(),
-                c->big_list.as<uint32_t>() + A, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
+                c->big_list.as<uint32_t>() + An, c->vals.as<double>(), V, c->arena.as<uint8_t>(), acap,
                 c->rec_ref.as<uint32_t>(), &dctr->gen);
             CK(cudaGetLastError());
             // counts + offsets ride behind the general kernels (a record that did not fit reads as the empty record)
@@ -2845,14 +2845,27 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             CK(cudaMemsetAsync(c->status.p, 0, (size_t)a_tiles * 16, s));
             if (attempt) CK(cudaMemsetAsync(&dctr->scan, 0, sizeof(ScanTotals), s));
             count_scan_kernel<W><<<a_tiles, 256, 0, s>>>(c->rec_ref.as<uint32_t>(), c->act_mask.as<uint32_t>(),
-                c->act_cap, A, c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
-                c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan);
+                c->act_cap, An, c->lut_mi.blob.as<uint8_t>(), c->arena.as<uint8_t>(), c->offs.as<uint4>(),
+                c->status.as<unsigned long long>(), c->status.as<unsigned long long>() + a_tiles, &dctr->scan, dA);
             CK(cudaGetLastError());
             c->launches += 3;
-            CK(cudaMemcpyAsync(&h.gen, &dctr->gen, sizeof(GeneralCounters), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(&h.scan, &dctr->scan, sizeof(ScanTotals), cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(&n_gated, &dctr->n_tie_faces, 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            {
+                // one copy of the whole counter block into pinned memory (copies into pageable memory serialise)
+                Counters* hp = static_cast<Counters*>(c->h_pinned);
+                CK(cudaMemcpyAsync(hp, dctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                h.gen = hp->gen;
+                h.scan = hp->scan;
+                n_gated = hp->n_tie_faces;
+                if (nosync) {
+                    h.filt = hp->filt;
+                    h.n_zero = hp->n_zero;
+                }
+            }
+            if (nosync && h.filt.n_active > An) { // more active tets than the learnt capacity: once more, sized exactly
+                c->h_act_mi = 0;
+                return run_mi_w<W>(c, flags);
+            }
             if (h.gen.err)
                 return fail(h.gen.err, "per-tet arrangement failed in tet " + std::to_string(h.gen.err_tet) +
                                            (h.gen.err == RIN_ERR_CAPACITY ? " (complex exceeds kernel capacity)"
@@ -2867,9 +2880,24 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
             CK(cudaMemcpyAsync(&dctr->gen, &z, sizeof(GeneralCounters), cudaMemcpyHostToDevice, s));
         }
     }
+    if (nosync) A = h.filt.n_active;
+    rin_counts& n = c->counts;
+    n = rin_counts{};
+    n.num_pts = c->V;
+    n.num_tets = c->t_count;
+    n.num_funcs = F;
+    n.num_degenerate_vertex = h.n_zero;
+    n.num_intersecting_tet = A;
+    n.num_k1 = h.filt.n_k1;
+    n.num_k2 = h.filt.n_k2;
+    n.num_kmore = h.filt.n_kmore;
+    n.num_active_funcs = h.filt.n_funcs;
     n.num_general_tets = h.gen.n_general;
+    c->h_act_mi = A + A / 8 + 1024;
+    c->h_gen_mi = h.gen.n_general + h.gen.n_general / 8 + 64;
+    c->act_cap = std::max<uint32_t>(c->act_cap, c->h_act_mi); // (the row stride only ever grows)
 
-    if (!A) EVREC(c->ev[ST_SCAN]);
+    if (!An) EVREC(c->ev[ST_SCAN]);
     const uint32_t NC = h.scan.n_cand, NFc = h.scan.n_faces, NFV = h.scan.n_fv;
 
     // ---- K5b: emit
