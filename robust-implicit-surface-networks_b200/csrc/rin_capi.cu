@@ -183,6 +183,7 @@ struct rin_ctx
     DevBuf tmp_fverts, bfkeys, frep, fdup, fpos, bf_mask; // degenerate boundary-face dedup
     DevBuf m_cnt, m_off, m_vmap, m_fmap, fpartner;        // cell-grouping maps (rin_tet_maps)
     bool ia_bndry_faces = false;                          // last run took the boundary-face path
+    uint32_t attr_set = 0; // kernel attributes already set on this context's device (bit W: mid tier, bit 16: eval_mi)
     bool skip_mid = false; // the last IA pass had no tet for the mid tier: its (empty) launch is left out, see run_ia_w
     uint64_t m_nv = 0, m_nf = 0;
     bool maps_ready = false;
@@ -2212,10 +2213,13 @@ int run_ia_w(rin_ctx* c, uint32_t flags)
     const size_t small_smem = GEN_SMALL_WARPS * sizeof(SmallSlot);
     const size_t mid_smem = GEN_MID_WARPS * sizeof(MidSlot);
     const int mid_per_sm = (int)std::max<size_t>(1, c->smem_per_sm / (mid_smem + 1024));
-    if (mid_smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
-    CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout,
-        (int)cudaSharedmemCarveoutMaxShared));
+    if (!(c->attr_set & (1u << W))) { // once per context and mask width (these calls sit in front of the first launch)
+        if (mid_smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
+        CK(cudaFuncSetAttribute(general_ia_mid_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            (int)cudaSharedmemCarveoutMaxShared));
+        c->attr_set |= 1u << W;
+    }
     if (c->arena.cap == 0) CK(c->arena.ensure(1u << 20));
 
     Counters h{};
@@ -2706,8 +2710,11 @@ int run_mi_w(rin_ctx* c, uint32_t flags)
     if (c->have_funcs && F <= (uint32_t)MI_EVAL_MAXF) {
         // evaluation fused with the "highest func" loop: the values never come back from HBM
         const size_t smem = mi_eval_smem(F);
-        CK(cudaFuncSetAttribute(eval_mi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi_eval_smem(MI_EVAL_MAXF)));
-        CK(cudaFuncSetAttribute(eval_mi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi_eval_smem(MI_EVAL_MAXF)));
+        if (!(c->attr_set & (1u << 16))) {
+            CK(cudaFuncSetAttribute(eval_mi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi_eval_smem(MI_EVAL_MAXF)));
+            CK(cudaFuncSetAttribute(eval_mi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi_eval_smem(MI_EVAL_MAXF)));
+            c->attr_set |= 1u << 16;
+        }
         const int g = grid_for((vc + MI_EVAL_VPT - 1) / MI_EVAL_VPT, 256, sm, 8);
         if (c->grid_R)
             eval_mi_kernel<true><<<g, 256, smem, s>>>(nullptr, c->axes.as<double>(), c->grid_R + 1,
